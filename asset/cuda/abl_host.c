@@ -1,0 +1,108 @@
+/* abl_host.c — see abl_host.h */
+#include "abl_host.h"
+
+#include <limits.h>
+#include <stdio.h>
+
+/* xorshift128+ (Vigna 2014) with the fixed seed the reference uses, so that the initial
+ * population of every model is the same as with the reference `c` backend. */
+static uint64_t rng_s0 = 0xdeadbeefULL, rng_s1 = 0xbeefdeadULL;
+
+void abl_host_rng_reset(void) { rng_s0 = 0xdeadbeefULL; rng_s1 = 0xbeefdeadULL; }
+
+static uint64_t rng_next(void) {
+  uint64_t a = rng_s0;
+  const uint64_t b = rng_s1;
+  rng_s0 = b;
+  a ^= a << 23;
+  rng_s1 = a ^ b ^ (a >> 17) ^ (b >> 26);
+  return rng_s1 + b;
+}
+
+abl_real random_float(abl_real lo, abl_real hi) {
+  uint64_t x = rng_next();
+  return lo + (abl_real)x / (abl_real)(UINT64_MAX / (hi - lo));
+}
+
+int random_int(int lo, int hi) {
+  unsigned n = hi - lo + 1;
+  if ((n & (n - 1)) == 0) return rng_next() & (n - 1); /* power of two: `lo` is not added */
+  unsigned r = UINT_MAX % n;
+  unsigned x;
+  do {
+    x = rng_next();
+  } while (x >= UINT_MAX - r);
+  return lo + x % n;
+}
+
+void abl_host_check(int rc, const char *what) {
+  if (rc == 0) return;
+  fprintf(stderr, "abl_cuda: %s failed (%d): %s\n", what, rc, abl_cuda_last_error());
+  exit(1);
+}
+
+static void json_member(FILE *f, const char *rec, const abl_member_desc *m) {
+  const char *p = rec + m->offset;
+  fprintf(f, "\"%s\":", m->name);
+  switch (m->type) {
+    case ABL_TYPE_BOOL: fputs(*(const bool *)p ? "true" : "false", f); break;
+    case ABL_TYPE_INT: fprintf(f, "%d", *(const int *)p); break;
+    case ABL_TYPE_FLOAT: fprintf(f, "%f", (double)*(const abl_real *)p); break;
+    case ABL_TYPE_FLOAT2: {
+      const abl_real *v = (const abl_real *)p;
+      fprintf(f, "[%f,%f]", (double)v[0], (double)v[1]);
+      break;
+    }
+    case ABL_TYPE_FLOAT3: {
+      const abl_real *v = (const abl_real *)p;
+      fprintf(f, "[%f,%f,%f]", (double)v[0], (double)v[1], (double)v[2]);
+      break;
+    }
+    default: break;
+  }
+}
+
+int abl_host_save_json(const abl_host_type *types, int n_types, const char *path) {
+  FILE *f = fopen(path, "w");
+  if (!f) { fprintf(stderr, "save: cannot open %s\n", path); return 1; }
+  fputc('{', f);
+  for (int t = 0; t < n_types; t++) {
+    const abl_host_type *ty = &types[t];
+    if (t) fputc(',', f);
+    fprintf(f, "\"%s\":[", ty->desc.name);
+    const char *rec = (const char *)ty->agents->data;
+    for (size_t i = 0; i < ty->agents->len; i++, rec += ty->desc.stride) {
+      if (i) fputs(",\n", f);
+      fputc('{', f);
+      for (int m = 0; m < ty->desc.n_members; m++) {
+        if (m) fputc(',', f);
+        json_member(f, rec, &ty->desc.members[m]);
+      }
+      fputc('}', f);
+    }
+    fputc(']', f);
+  }
+  fputc('}', f);
+  fclose(f);
+  return 0;
+}
+
+int abl_host_save_raw(const abl_host_type *types, int n_types, const char *path) {
+  FILE *f = fopen(path, "wb");
+  if (!f) return 1;
+  for (int t = 0; t < n_types; t++) {
+    uint64_t n = types[t].agents->len;
+    uint32_t stride = types[t].desc.stride;
+    fwrite(&n, sizeof n, 1, f);
+    fwrite(&stride, sizeof stride, 1, f);
+    fwrite(types[t].agents->data, stride, n, f);
+  }
+  fclose(f);
+  return 0;
+}
+
+static FILE *log_file = NULL;
+void abl_host_log_open(const char *path) { if (!log_file) log_file = fopen(path, "w"); }
+void abl_host_log_int(int first, int v) { if (log_file) fprintf(log_file, first ? "%d" : ",%d", v); }
+void abl_host_log_float(int first, double v) { if (log_file) fprintf(log_file, first ? "%f" : ",%f", v); }
+void abl_host_log_end(void) { if (log_file) { fputc('\n', log_file); fflush(log_file); } }

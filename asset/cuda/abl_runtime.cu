@@ -1,0 +1,1311 @@
+// abl_runtime.cu — B200-native OpenABL runtime (libabl_cuda.so), C ABI in abl_cuda.h.
+//
+// Owns: SoA agent pools with per-column ping-pong buffers in HBM, uniform-grid binning
+// (single-digit radix = counting sort over the cell key, ties ordered by agent id), the
+// step-function launch protocol, stream compaction for removeCurrent()/add(), reductions,
+// and host AoS <-> device SoA transfer.  Generated step kernels (abl_device.cuh) are
+// launched through the launcher registered with each step.
+//
+// Reference constructs replaced (see include/abl_cuda.h for the per-function mapping):
+// dyn_array storage + double buffer (asset/c/libabl.h:11-57, CPrinter.cpp:210-228) and the
+// brute-force neighbour scan (CPrinter.cpp:160-171).
+//
+// Kernel inventory (all HBM/L2-bound integer/byte work; no tensor cores by design):
+//   k_aos_to_soa / k_soa_to_aos   host record transpose (upload / download)
+//   k_bin_count                   cell key + per-cell histogram (returns arrival rank)
+//   k_scan<...>                   single-pass decoupled-look-back exclusive scan
+//   k_bin_scatter                 (id, source index) pairs into cell segments
+//   k_bin_rank_move               rank by id inside the segment + gather all columns
+//   k_compact_move / k_append     stream compaction for remove / add
+//   k_reduce_*                    count / sum reductions
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "abl_cuda.h"
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+typedef unsigned char u8;
+
+// ---------------------------------------------------------------------------------------
+// error handling
+// ---------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t e_ = (call);                                                              \
+    if (e_ != cudaSuccess)                                                                \
+      return fail(ABL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+                  __FILE__, __LINE__);                                                    \
+  } while (0)
+
+#define TRY(call)              \
+  do {                         \
+    int r_ = (call);           \
+    if (r_ != ABL_OK) return r_; \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// data structures
+// ---------------------------------------------------------------------------------------
+struct Column {
+  int elem = 0;       // bytes per agent in this column (1, 4, 8 or 16)
+  int comp = 0;       // bytes per scalar component
+  int ncomp = 0;      // components packed in one element
+  int host_off = -1;  // byte offset inside the host AoS record (-1: not part of it, i.e. ids)
+  void *buf[2] = {nullptr, nullptr};
+  int cur = 0;
+};
+
+struct Member {
+  int type = 0;
+  int first_col = 0;
+  int ncols = 0;
+  std::string name;
+};
+
+struct Pool {
+  std::string name;
+  std::vector<Member> members;
+  std::vector<Column> cols;  // user columns followed by the id column
+  int id_col = -1;
+  int pos_member = -1;
+  unsigned stride = 0;
+  size_t n = 0, cap = 0;
+  u32 next_id = 0;
+  bool binned = false;
+  bool ever_removed = false;
+  // binning scratch (per pool so that pools can be binned independently)
+  u32 *key = nullptr, *local = nullptr;
+  u64 *pairs = nullptr;
+  u32 *cell_count = nullptr, *cell_start = nullptr;
+  // remove / add scratch
+  u8 *dead = nullptr;
+  u8 *add_flag = nullptr;
+  u32 *offsets = nullptr;
+  size_t scratch_cap = 0;
+};
+
+struct ScanState {
+  u64 *desc = nullptr;   // one descriptor per tile: (epoch<<2 | status) << 32 | value
+  u32 *ctrl = nullptr;   // [0] dynamic tile counter, [1] finished tiles, [2] epoch
+  size_t max_tiles = 0;
+};
+
+struct Step {
+  abl_step_desc desc;
+  std::string name;
+  int reach = 1;
+};
+
+struct ColTable {
+  int ncols;
+  int elem[ABL_MAX_COLUMNS + 1];
+  int comp[ABL_MAX_COLUMNS + 1];
+  int ncomp[ABL_MAX_COLUMNS + 1];
+  int host_off[ABL_MAX_COLUMNS + 1];
+  const void *in[ABL_MAX_COLUMNS + 1];
+  void *out[ABL_MAX_COLUMNS + 1];
+};
+
+struct GridParams {
+  int dim;
+  int n_cell[3];
+  double origin[3];
+  double cell;
+  u32 n_cells;
+};
+
+struct abl_runtime {
+  abl_config cfg;
+  int device = 0;
+  int real_size = 8;
+  cudaStream_t stream = nullptr;
+  bool env_set = false;
+  GridParams grid;
+  std::vector<Pool> pools;
+  std::vector<Step> steps;
+  ScanState scan;
+  void *stage = nullptr;       // device staging for AoS transfers
+  size_t stage_cap = 0;
+  void *pinned = nullptr;      // pinned host bounce buffer
+  size_t pinned_cap = 0;
+  u32 *d_scalar = nullptr;     // small device scratch for totals / reductions
+  u32 *h_scalar = nullptr;     // pinned mirror
+  unsigned timestep = 0;
+  bool timing = false;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t ev_ts[2] = {nullptr, nullptr};
+  bool ts_open = false;
+  double last_ts_seconds = 0;
+  abl_step_timing last = {0, 0, 0, 0};
+  unsigned launches = 0;
+};
+
+static const int kScanBlock = 256;
+static const int kScanItems = 16;                      // per thread
+static const int kScanTile = kScanBlock * kScanItems;  // 4096
+
+static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// ---------------------------------------------------------------------------------------
+// kernels: transpose between host records and columns
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void copy_scalar(void *dst, const void *src, int bytes) {
+  switch (bytes) {
+    case 1: *(u8 *)dst = *(const u8 *)src; break;
+    case 4: *(u32 *)dst = *(const u32 *)src; break;
+    default: *(u64 *)dst = *(const u64 *)src; break;
+  }
+}
+
+__global__ void k_aos_to_soa(ColTable t, const u8 *aos, u32 stride, u32 n, u32 first_id) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8 *rec = aos + (size_t)i * stride;
+  for (int c = 0; c < t.ncols; c++) {
+    u8 *dst = (u8 *)t.out[c] + (size_t)i * t.elem[c];
+    if (t.host_off[c] < 0) { *(u32 *)dst = first_id + i; continue; }
+    for (int k = 0; k < t.ncomp[c]; k++)
+      copy_scalar(dst + k * t.comp[c], rec + t.host_off[c] + k * t.comp[c], t.comp[c]);
+  }
+}
+
+// dest_rank == nullptr: record i goes to slot id[i]; otherwise to dest_rank[id[i]]
+__global__ void k_soa_to_aos(ColTable t, u8 *aos, u32 stride, u32 n, const u32 *ids,
+                             const u32 *dest_rank) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 slot = ids[i];
+  if (dest_rank) slot = dest_rank[slot];
+  u8 *rec = aos + (size_t)slot * stride;
+  for (int c = 0; c < t.ncols; c++) {
+    if (t.host_off[c] < 0) continue;
+    const u8 *src = (const u8 *)t.in[c] + (size_t)i * t.elem[c];
+    for (int k = 0; k < t.ncomp[c]; k++)
+      copy_scalar(rec + t.host_off[c] + k * t.comp[c], src + k * t.comp[c], t.comp[c]);
+  }
+}
+
+__global__ void k_mark_present(const u32 *ids, u32 n, u32 *present) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) present[ids[i]] = 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels: single-pass exclusive scan (decoupled look-back)
+// ---------------------------------------------------------------------------------------
+// Each CTA takes the next tile (dynamic tile index => earlier tiles are always running or
+// done, so spinning on them cannot deadlock), scans it locally, publishes its aggregate,
+// looks back over predecessors' descriptors to obtain its exclusive prefix, then publishes
+// its inclusive prefix.  Descriptors carry an epoch so the array never needs clearing; the
+// last CTA to finish resets the tile counter and bumps the epoch, which keeps the kernel
+// re-launchable without any host-side memset (CUDA-graph friendly).
+enum { SCAN_INVALID = 0, SCAN_AGGREGATE = 1, SCAN_PREFIX = 2 };
+
+template <typename T> struct ScanLoad;
+template <> struct ScanLoad<u32> {
+  static __device__ __forceinline__ void load4(const u32 *in, size_t i, u32 v[4]) {
+    uint4 q = *reinterpret_cast<const uint4 *>(in + i);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+template <> struct ScanLoad<u8> {
+  static __device__ __forceinline__ void load4(const u8 *in, size_t i, u32 v[4]) {
+    uchar4 q = *reinterpret_cast<const uchar4 *>(in + i);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  }
+};
+
+// MODE 0: out[i] = exclusive prefix of in[i]
+// MODE 1: in[] holds "dead" flags; scans (in[i] == 0), i.e. survivors
+template <typename T, int MODE, bool ZERO_INPUT>
+__global__ void __launch_bounds__(kScanBlock)
+k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
+  __shared__ u32 s_tile;
+  __shared__ u32 s_warp[kScanBlock / 32];
+  __shared__ u32 s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(&ctrl[0], 1u);
+  __syncthreads();
+  const u32 tile = s_tile;
+  const u32 epoch = *((volatile u32 *)&ctrl[2]);
+  const size_t base = (size_t)tile * kScanTile;
+
+  // local scan: 4 chunks of (256 threads x 4 items), items of a thread are consecutive
+  u32 vals[kScanItems];
+  u32 chunk_excl[4];
+  u32 running = 0;
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    size_t i0 = base + (size_t)c * (kScanBlock * 4) + (size_t)tid * 4;
+    u32 v[4] = {0, 0, 0, 0};
+    if (i0 < n) {  // arrays are padded to a multiple of the tile, reads past n are in bounds
+      ScanLoad<T>::load4(in, i0, v);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        if (MODE == 1) v[k] = v[k] ? 0u : 1u;
+        if (i0 + k >= n) v[k] = 0;
+      }
+      if (ZERO_INPUT) {
+        if (sizeof(T) == 4) *reinterpret_cast<uint4 *>(in + i0) = make_uint4(0, 0, 0, 0);
+        else *reinterpret_cast<u32 *>(in + i0) = 0;
+      }
+    }
+    u32 t = v[0] + v[1] + v[2] + v[3];
+    u32 inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += y;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    u32 wsum = lane < kScanBlock / 32 ? s_warp[lane] : 0;
+    u32 winc = wsum;
+#pragma unroll
+    for (int d = 1; d < kScanBlock / 32; d <<= 1) {
+      u32 y = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += y;
+    }
+    u32 warp_excl = __shfl_sync(0xffffffffu, winc - wsum, warp);
+    u32 chunk_total = __shfl_sync(0xffffffffu, winc, kScanBlock / 32 - 1);
+    u32 excl = running + warp_excl + inc - t;
+    chunk_excl[c] = excl;
+    vals[c * 4 + 0] = excl;
+    vals[c * 4 + 1] = excl + v[0];
+    vals[c * 4 + 2] = excl + v[0] + v[1];
+    vals[c * 4 + 3] = excl + v[0] + v[1] + v[2];
+    running += chunk_total;
+    __syncthreads();
+  }
+  (void)chunk_excl;
+  const u32 aggregate = running;
+
+  // look-back (warp 0)
+  if (warp == 0) {
+    u32 prefix = 0;
+    if (tile == 0) {
+      if (lane == 0)
+        *((volatile u64 *)&desc[0]) = ((u64)((epoch << 2) | SCAN_PREFIX) << 32) | aggregate;
+    } else {
+      if (lane == 0)
+        *((volatile u64 *)&desc[tile]) = ((u64)((epoch << 2) | SCAN_AGGREGATE) << 32) | aggregate;
+      int idx = (int)tile - 1;
+      for (;;) {
+        int my = idx - lane;
+        u32 status = SCAN_PREFIX, value = 0;  // tiles before 0 behave as prefix 0
+        if (my >= 0) {
+          for (;;) {
+            u64 d = *((volatile u64 *)&desc[my]);
+            u32 hi = (u32)(d >> 32);
+            if ((hi >> 2) == epoch && (hi & 3u) != SCAN_INVALID) {
+              status = hi & 3u;
+              value = (u32)d;
+              break;
+            }
+          }
+        }
+        u32 pm = __ballot_sync(0xffffffffu, status == SCAN_PREFIX);
+        int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor with a full prefix
+        u32 contrib = lane <= first ? value : 0;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+        prefix += contrib;
+        if (pm) break;
+        idx -= 32;
+      }
+      if (lane == 0)
+        *((volatile u64 *)&desc[tile]) =
+            ((u64)((epoch << 2) | SCAN_PREFIX) << 32) | (u32)(prefix + aggregate);
+    }
+    if (lane == 0) s_prefix = prefix;
+  }
+  __syncthreads();
+  const u32 prefix = s_prefix;
+
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    size_t i0 = base + (size_t)c * (kScanBlock * 4) + (size_t)tid * 4;
+    if (i0 < n) {
+      uint4 q = make_uint4(vals[c * 4] + prefix, vals[c * 4 + 1] + prefix,
+                           vals[c * 4 + 2] + prefix, vals[c * 4 + 3] + prefix);
+      *reinterpret_cast<uint4 *>(out + i0) = q;  // out is padded like in
+    }
+  }
+
+  // bookkeeping: total + self-reset by the last CTA
+  const u32 ntiles = gridDim.x;
+  if (tid == 0) {
+    if (tile == ntiles - 1 && total_out) *total_out = prefix + aggregate;
+    __threadfence();
+    u32 done = atomicAdd(&ctrl[1], 1u);
+    if (done == ntiles - 1) {
+      ctrl[0] = 0;
+      ctrl[1] = 0;
+      ctrl[2] = (epoch + 1) & 0x3fffffffu;
+      __threadfence();
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels: binning
+// ---------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ int cell_coord(R p, R origin, R cell, int n) {
+  int c = (int)floor((p - origin) / cell);
+  return c < 0 ? 0 : (c >= n ? n - 1 : c);
+}
+
+// POS2: position is one packed 2-vector column; otherwise three scalar columns.
+template <typename R, int DIM>
+__global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, GridParams g,
+                            u32 *key, u32 *local, u32 *cell_count) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R x, y, z = 0;
+  if (DIM == 2) {
+    x = ((const R *)px)[2 * (size_t)i];
+    y = ((const R *)px)[2 * (size_t)i + 1];
+  } else {
+    x = ((const R *)px)[i];
+    y = ((const R *)py)[i];
+    z = ((const R *)pz)[i];
+  }
+  int cx = cell_coord<R>(x, (R)g.origin[0], (R)g.cell, g.n_cell[0]);
+  int cy = cell_coord<R>(y, (R)g.origin[1], (R)g.cell, g.n_cell[1]);
+  u32 c = (u32)cy * (u32)g.n_cell[0] + (u32)cx;
+  if (DIM == 3) {
+    int cz = cell_coord<R>(z, (R)g.origin[2], (R)g.cell, g.n_cell[2]);
+    c += (u32)cz * (u32)g.n_cell[0] * (u32)g.n_cell[1];
+  }
+  key[i] = c;
+  local[i] = atomicAdd(&cell_count[c], 1u);
+}
+
+__global__ void k_bin_scatter(const u32 *key, const u32 *local, const u32 *ids, u32 n,
+                              const u32 *cell_start, u64 *pairs) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  u32 slot = cell_start[key[i]] + local[i];
+  pairs[slot] = ((u64)ids[i] << 32) | i;
+}
+
+__device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src, size_t si, int elem) {
+  switch (elem) {
+    case 1: ((u8 *)dst)[di] = ((const u8 *)src)[si]; break;
+    case 4: ((u32 *)dst)[di] = ((const u32 *)src)[si]; break;
+    case 8: ((uint2 *)dst)[di] = ((const uint2 *)src)[si]; break;
+    default: ((uint4 *)dst)[di] = ((const uint4 *)src)[si]; break;
+  }
+}
+
+// Slot s holds one (id, src) pair of its cell segment in arrival order.  The final place of
+// that agent is segment_begin + (number of ids in the segment smaller than its id); the
+// segment is contiguous, so the rank is a short coalesced scan.  The agent's whole record is
+// then moved column by column (gather read, near-coalesced write).
+__global__ void k_bin_rank_move(ColTable t, const u64 *pairs, const u32 *key, u32 n,
+                                const u32 *cell_start) {
+  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  u64 mine = pairs[s];
+  u32 src = (u32)mine;
+  u32 c = key[src];
+  u32 b = cell_start[c], e = cell_start[c + 1];
+  u32 rank = 0;
+  for (u32 q = b; q < e; q++) rank += (pairs[q] < mine) ? 1u : 0u;  // ids are unique
+  u32 dst = b + rank;
+  for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels: compaction (remove) and append (add)
+// ---------------------------------------------------------------------------------------
+__global__ void k_compact_move(ColTable t, const u8 *dead, const u32 *offsets, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || dead[i]) return;
+  u32 dst = offsets[i];
+  for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], i, t.elem[k]);
+}
+
+// list[rank] = (parent id << 32 | parent slot) for every flagged parent
+__global__ void k_collect_adds(const u8 *flag, const u32 *offsets, const u32 *parent_ids, u32 n,
+                               u64 *list) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  list[offsets[i]] = ((u64)parent_ids[i] << 32) | i;
+}
+
+// New agents are appended in ascending parent-id order (canonical, independent of the
+// current memory order of the parents).  m is small compared to n, rank by counting.
+__global__ void k_append(ColTable t, const u64 *list, u32 m, u32 base, u32 first_id) {
+  u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  u64 mine = list[a];
+  u32 rank = 0;
+  for (u32 q = 0; q < m; q++) rank += (list[q] < mine) ? 1u : 0u;
+  u32 src = (u32)mine;
+  u32 dst = base + rank;
+  for (int k = 0; k < t.ncols; k++) {
+    if (t.host_off[k] < 0) ((u32 *)t.out[k])[dst] = first_id + rank;  // id column
+    else copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// kernels: reductions (integer results are exact; float sums use a fixed two-level tree)
+// ---------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ T block_sum(T v, T *smem) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  v = threadIdx.x < blockDim.x / 32 ? smem[threadIdx.x] : (T)0;
+  if (warp == 0) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_down_sync(0xffffffffu, v, d);
+  }
+  return v;
+}
+
+// KIND 0: sum of int column, 1: sum of bool column, 2: count int == value, 3: count bool == value
+template <int KIND>
+__global__ void k_reduce_int(const void *col, u32 n, int value, int *result) {
+  __shared__ int smem[32];
+  int acc = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    if (KIND == 0) acc += ((const int *)col)[i];
+    else if (KIND == 1) acc += ((const u8 *)col)[i] ? 1 : 0;
+    else if (KIND == 2) acc += ((const int *)col)[i] == value ? 1 : 0;
+    else acc += (((const u8 *)col)[i] ? 1 : 0) == value ? 1 : 0;
+  }
+  acc = block_sum<int>(acc, smem);
+  if (threadIdx.x == 0) atomicAdd(result, acc);  // integer addition: order-independent
+}
+
+template <typename R>
+__global__ void k_reduce_real_partial(const R *col, int stride, int comp, u32 n, double *partial) {
+  __shared__ double smem[32];
+  double acc = 0;
+  // fixed assignment of elements to threads and a fixed tree => deterministic result
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    acc += (double)col[(size_t)i * stride + comp];
+  acc = block_sum<double>(acc, smem);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+template <typename R>
+__global__ void k_count_real(const R *col, u32 n, R value, int *result) {
+  __shared__ int smem[32];
+  int acc = 0;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    acc += col[i] == value ? 1 : 0;
+  acc = block_sum<int>(acc, smem);
+  if (threadIdx.x == 0) atomicAdd(result, acc);
+}
+
+__global__ void k_final_sum(const double *partial, int m, double *out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double s = 0;
+    for (int i = 0; i < m; i++) s += partial[i];
+    *out = s;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------
+static inline u32 blocks_for(size_t n, int bs) { return (u32)((n + bs - 1) / bs); }
+
+static int ensure_stage(abl_runtime *rt, size_t bytes) {
+  if (rt->stage_cap >= bytes) return ABL_OK;
+  if (rt->stage) CU(cudaFree(rt->stage));
+  rt->stage = nullptr;
+  size_t cap = round_up(bytes + bytes / 8, 1 << 20);
+  CU(cudaMalloc(&rt->stage, cap));
+  rt->stage_cap = cap;
+  return ABL_OK;
+}
+
+static int ensure_scan(abl_runtime *rt, size_t n) {
+  size_t tiles = (n + kScanTile - 1) / kScanTile + 1;
+  if (!rt->scan.ctrl) {
+    CU(cudaMalloc(&rt->scan.ctrl, 4 * sizeof(u32)));
+    u32 init[4] = {0, 0, 1, 0};  // epoch starts at 1 so zeroed descriptors are invalid
+    CU(cudaMemcpyAsync(rt->scan.ctrl, init, sizeof init, cudaMemcpyHostToDevice, rt->stream));
+    CU(cudaStreamSynchronize(rt->stream));
+  }
+  if (rt->scan.max_tiles >= tiles) return ABL_OK;
+  CU(cudaStreamSynchronize(rt->stream));
+  if (rt->scan.desc) CU(cudaFree(rt->scan.desc));
+  size_t cap = tiles * 2;
+  CU(cudaMalloc(&rt->scan.desc, cap * sizeof(u64)));
+  CU(cudaMemsetAsync(rt->scan.desc, 0, cap * sizeof(u64), rt->stream));
+  rt->scan.max_tiles = cap;
+  return ABL_OK;
+}
+
+// Exclusive scan of `n` items; arrays must be padded to a multiple of kScanTile.
+template <typename T, int MODE, bool ZERO>
+static int run_scan(abl_runtime *rt, T *in, u32 *out, size_t n, u32 *total_out) {
+  if (n == 0) {
+    if (total_out) CU(cudaMemsetAsync(total_out, 0, sizeof(u32), rt->stream));
+    return ABL_OK;
+  }
+  TRY(ensure_scan(rt, n));
+  u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
+  k_scan<T, MODE, ZERO><<<tiles, kScanBlock, 0, rt->stream>>>(in, out, (u32)n, rt->scan.desc,
+                                                            rt->scan.ctrl, total_out);
+  rt->launches++;
+  CU(cudaGetLastError());
+  return ABL_OK;
+}
+
+static int free_pool_scratch(Pool &p) {
+  void *ptrs[] = {p.key, p.local, p.pairs, p.dead, p.add_flag, p.offsets};
+  for (void *q : ptrs) if (q) CU(cudaFree(q));
+  p.key = p.local = nullptr; p.pairs = nullptr; p.dead = p.add_flag = nullptr; p.offsets = nullptr;
+  p.scratch_cap = 0;
+  return ABL_OK;
+}
+
+// Grows a pool (columns + scratch) to hold at least `want` agents, preserving contents.
+static int reserve_pool(abl_runtime *rt, Pool &p, size_t want) {
+  if (want <= p.cap && p.scratch_cap >= p.cap && p.cap > 0) return ABL_OK;
+  size_t cap = p.cap;
+  if (want > cap) {
+    cap = round_up(std::max(want + want / 4, (size_t)kScanTile), kScanTile);
+    CU(cudaStreamSynchronize(rt->stream));
+    for (Column &c : p.cols) {
+      for (int b = 0; b < 2; b++) {
+        void *nb = nullptr;
+        CU(cudaMalloc(&nb, cap * (size_t)c.elem));
+        if (c.buf[b]) {
+          if (b == c.cur && p.n)
+            CU(cudaMemcpy(nb, c.buf[b], p.n * (size_t)c.elem, cudaMemcpyDeviceToDevice));
+          CU(cudaFree(c.buf[b]));
+        }
+        c.buf[b] = nb;
+      }
+    }
+    p.cap = cap;
+  }
+  if (p.scratch_cap < p.cap) {
+    // dead / add flags may hold live data (set by a step kernel that has not been committed)
+    u8 *dead = nullptr, *add_flag = nullptr;
+    CU(cudaMalloc(&dead, p.cap));
+    CU(cudaMalloc(&add_flag, p.cap));
+    CU(cudaMemset(dead, 0, p.cap));
+    CU(cudaMemset(add_flag, 0, p.cap));
+    if (p.scratch_cap) {
+      CU(cudaMemcpy(dead, p.dead, p.scratch_cap, cudaMemcpyDeviceToDevice));
+      CU(cudaMemcpy(add_flag, p.add_flag, p.scratch_cap, cudaMemcpyDeviceToDevice));
+    }
+    TRY(free_pool_scratch(p));
+    p.dead = dead;
+    p.add_flag = add_flag;
+    CU(cudaMalloc(&p.key, p.cap * sizeof(u32)));
+    CU(cudaMalloc(&p.local, p.cap * sizeof(u32)));
+    CU(cudaMalloc(&p.pairs, p.cap * sizeof(u64)));
+    CU(cudaMalloc(&p.offsets, (p.cap + kScanTile) * sizeof(u32)));
+    p.scratch_cap = p.cap;
+  }
+  return ABL_OK;
+}
+
+static void fill_table(const Pool &p, ColTable &t, bool out_is_alt) {
+  t.ncols = (int)p.cols.size();
+  for (int c = 0; c < t.ncols; c++) {
+    const Column &col = p.cols[c];
+    t.elem[c] = col.elem; t.comp[c] = col.comp; t.ncomp[c] = col.ncomp;
+    t.host_off[c] = col.host_off;
+    t.in[c] = col.buf[col.cur];
+    t.out[c] = out_is_alt ? col.buf[col.cur ^ 1] : col.buf[col.cur];
+  }
+}
+
+static void flip_all(Pool &p) { for (Column &c : p.cols) c.cur ^= 1; }
+
+// ---------------------------------------------------------------------------------------
+// C ABI: life cycle
+// ---------------------------------------------------------------------------------------
+extern "C" int abl_cuda_abi_version(void) { return ABL_CUDA_ABI_VERSION; }
+
+extern "C" const char *abl_cuda_last_error(void) { return g_err; }
+
+extern "C" void abl_cuda_default_config(abl_config *cfg) {
+  memset(cfg, 0, sizeof *cfg);
+  cfg->device = -1;
+  cfg->use_float = 0;
+  cfg->seed = 0x0123456789abcdefull;
+  cfg->deterministic = 1;
+  cfg->tile_neighbours = 1;
+  cfg->block_size = 128;
+}
+
+extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
+  if (!out) return fail(ABL_ERR_ARGUMENT, "abl_cuda_create: null output handle");
+  *out = nullptr;
+  abl_config c;
+  if (cfg) c = *cfg; else abl_cuda_default_config(&c);
+  int count = 0;
+  CU(cudaGetDeviceCount(&count));
+  if (count == 0) return fail(ABL_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+  if (c.device >= 0) CU(cudaSetDevice(c.device));
+  abl_runtime *rt = new abl_runtime;
+  rt->cfg = c;
+  if (rt->cfg.block_size <= 0) rt->cfg.block_size = 128;
+  CU(cudaGetDevice(&rt->device));
+  rt->real_size = c.use_float ? 4 : 8;
+  CU(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
+  CU(cudaMalloc(&rt->d_scalar, 4096));
+  CU(cudaMemset(rt->d_scalar, 0, 4096));
+  CU(cudaMallocHost(&rt->h_scalar, 4096));
+  for (int i = 0; i < 4; i++) CU(cudaEventCreate(&rt->ev[i]));
+  for (int i = 0; i < 2; i++) CU(cudaEventCreate(&rt->ev_ts[i]));
+  memset(&rt->grid, 0, sizeof rt->grid);
+  *out = rt;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_destroy(abl_runtime *rt) {
+  if (!rt) return ABL_OK;
+  cudaSetDevice(rt->device);
+  cudaStreamSynchronize(rt->stream);
+  for (Pool &p : rt->pools) {
+    for (Column &c : p.cols) for (int b = 0; b < 2; b++) if (c.buf[b]) cudaFree(c.buf[b]);
+    free_pool_scratch(p);
+    if (p.cell_count) cudaFree(p.cell_count);
+    if (p.cell_start) cudaFree(p.cell_start);
+  }
+  if (rt->scan.desc) cudaFree(rt->scan.desc);
+  if (rt->scan.ctrl) cudaFree(rt->scan.ctrl);
+  if (rt->stage) cudaFree(rt->stage);
+  if (rt->pinned) cudaFreeHost(rt->pinned);
+  if (rt->d_scalar) cudaFree(rt->d_scalar);
+  if (rt->h_scalar) cudaFreeHost(rt->h_scalar);
+  for (int i = 0; i < 4; i++) if (rt->ev[i]) cudaEventDestroy(rt->ev[i]);
+  for (int i = 0; i < 2; i++) if (rt->ev_ts[i]) cudaEventDestroy(rt->ev_ts[i]);
+  cudaStreamDestroy(rt->stream);
+  delete rt;
+  return ABL_OK;
+}
+
+extern "C" void *abl_cuda_stream(abl_runtime *rt) { return rt ? (void *)rt->stream : nullptr; }
+
+extern "C" int abl_cuda_synchronize(abl_runtime *rt) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  CU(cudaStreamSynchronize(rt->stream));
+  return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// C ABI: environment and pools
+// ---------------------------------------------------------------------------------------
+extern "C" int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *env_min,
+                                        const double *env_max, double granularity) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (dim != 2 && dim != 3) return fail(ABL_ERR_ARGUMENT, "environment dimension must be 2 or 3");
+  if (!(granularity > 0)) return fail(ABL_ERR_ARGUMENT, "granularity must be positive");
+  GridParams &g = rt->grid;
+  g.dim = dim;
+  g.cell = granularity;
+  u64 cells = 1;
+  for (int a = 0; a < 3; a++) {
+    if (a < dim) {
+      double size = env_max[a] - env_min[a];
+      if (size < 0) return fail(ABL_ERR_ARGUMENT, "environment max < min");
+      long nc = (long)ceil(size / granularity);
+      if (nc < 1) nc = 1;
+      g.n_cell[a] = (int)nc;
+      g.origin[a] = env_min[a];
+    } else {
+      g.n_cell[a] = 1;
+      g.origin[a] = 0;
+    }
+    cells *= (u64)g.n_cell[a];
+  }
+  if (cells > 0x7fffffffull)
+    return fail(ABL_ERR_ARGUMENT, "grid of %llu cells exceeds 2^31; increase the granularity", cells);
+  g.n_cells = (u32)cells;
+  rt->env_set = true;
+  for (Pool &p : rt->pools) p.binned = false;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_grid_cells(abl_runtime *rt, unsigned *n_cells, int n_cell_axis[3]) {
+  if (!rt || !rt->env_set) return fail(ABL_ERR_STATE, "environment not set");
+  if (n_cells) *n_cells = rt->grid.n_cells;
+  if (n_cell_axis) for (int a = 0; a < 3; a++) n_cell_axis[a] = rt->grid.n_cell[a];
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_add_pool(abl_runtime *rt, const abl_agent_desc *desc, int *pool) {
+  if (!rt || !desc) return fail(ABL_ERR_ARGUMENT, "null argument");
+  if (desc->n_members > ABL_MAX_MEMBERS) return fail(ABL_ERR_ARGUMENT, "too many members");
+  Pool p;
+  p.name = desc->name ? desc->name : "";
+  p.stride = desc->stride;
+  const int rs = rt->real_size;
+  for (int m = 0; m < desc->n_members; m++) {
+    const abl_member_desc &md = desc->members[m];
+    Member mem;
+    mem.type = md.type;
+    mem.name = md.name ? md.name : "";
+    mem.first_col = (int)p.cols.size();
+    auto add_col = [&](int comp, int ncomp, int off) {
+      Column c;
+      c.comp = comp; c.ncomp = ncomp; c.elem = comp * ncomp; c.host_off = off;
+      p.cols.push_back(c);
+    };
+    switch (md.type) {
+      case ABL_TYPE_BOOL: add_col(1, 1, (int)md.offset); break;
+      case ABL_TYPE_INT: add_col(4, 1, (int)md.offset); break;
+      case ABL_TYPE_FLOAT: add_col(rs, 1, (int)md.offset); break;
+      case ABL_TYPE_FLOAT2: add_col(rs, 2, (int)md.offset); break;
+      case ABL_TYPE_FLOAT3:
+        for (int k = 0; k < 3; k++) add_col(rs, 1, (int)md.offset + k * rs);
+        break;
+      default: return fail(ABL_ERR_ARGUMENT, "member %s: unsupported type %d", mem.name.c_str(), md.type);
+    }
+    mem.ncols = (int)p.cols.size() - mem.first_col;
+    if (md.is_pos) p.pos_member = m;
+    p.members.push_back(mem);
+  }
+  if ((int)p.cols.size() > ABL_MAX_COLUMNS) return fail(ABL_ERR_ARGUMENT, "too many columns");
+  Column idc;
+  idc.comp = 4; idc.ncomp = 1; idc.elem = 4; idc.host_off = -1;
+  p.id_col = (int)p.cols.size();
+  p.cols.push_back(idc);
+  rt->pools.push_back(p);
+  if (pool) *pool = (int)rt->pools.size() - 1;
+  return ABL_OK;
+}
+
+static int get_pool(abl_runtime *rt, int pool, Pool **out) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (pool < 0 || pool >= (int)rt->pools.size()) return fail(ABL_ERR_ARGUMENT, "bad pool index %d", pool);
+  *out = &rt->pools[pool];
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  if (n) *n = p->n;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  CU(cudaSetDevice(rt->device));
+  if (n > 0x7fffffffu) return fail(ABL_ERR_ARGUMENT, "pool too large");
+  p->n = 0;
+  TRY(reserve_pool(rt, *p, std::max(n, (size_t)1)));
+  size_t bytes = n * (size_t)p->stride;
+  if (n) {
+    TRY(ensure_stage(rt, bytes));
+    CU(cudaMemcpyAsync(rt->stage, host_aos, bytes, cudaMemcpyHostToDevice, rt->stream));
+    ColTable t;
+    fill_table(*p, t, false);
+    k_aos_to_soa<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->stage, p->stride,
+                                                             (u32)n, 0u);
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  p->n = n;
+  p->next_id = (u32)n;
+  p->binned = false;
+  p->ever_removed = false;
+  CU(cudaStreamSynchronize(rt->stream));  // host buffer may be reused by the caller
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity,
+                                 size_t *n_out) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  CU(cudaSetDevice(rt->device));
+  if (n_out) *n_out = p->n;
+  if (capacity < p->n) return fail(ABL_ERR_CAPACITY, "download: buffer holds %zu agents, pool has %zu", capacity, p->n);
+  if (p->n == 0) return ABL_OK;
+  size_t bytes = p->n * (size_t)p->stride;
+  size_t rank_bytes = 0;
+  const bool dense = p->next_id == p->n;  // ids are a permutation of 0..n-1
+  if (!dense) rank_bytes = round_up((size_t)p->next_id + 1, kScanTile) * sizeof(u32) * 2;
+  TRY(ensure_stage(rt, round_up(bytes, 256) + rank_bytes));
+  const u32 *ids = (const u32 *)p->cols[p->id_col].buf[p->cols[p->id_col].cur];
+  u32 *rank = nullptr;
+  if (!dense) {
+    u32 *present = (u32 *)((u8 *)rt->stage + round_up(bytes, 256));
+    size_t padded = round_up((size_t)p->next_id + 1, kScanTile);
+    rank = present + padded;
+    CU(cudaMemsetAsync(present, 0, padded * sizeof(u32), rt->stream));
+    k_mark_present<<<blocks_for(p->n, 256), 256, 0, rt->stream>>>(ids, (u32)p->n, present);
+    rt->launches++;
+    TRY((run_scan<u32, 0, false>(rt, present, rank, (size_t)p->next_id, nullptr)));
+  }
+  // padding bytes of the host records are zeroed for reproducible raw dumps
+  CU(cudaMemsetAsync(rt->stage, 0, bytes, rt->stream));
+  ColTable t;
+  fill_table(*p, t, false);
+  k_soa_to_aos<<<blocks_for(p->n, 256), 256, 0, rt->stream>>>(t, (u8 *)rt->stage, p->stride,
+                                                              (u32)p->n, ids, rank);
+  rt->launches++;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(host_aos, rt->stage, bytes, cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// binning
+// ---------------------------------------------------------------------------------------
+static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
+  if (p.cell_count) return ABL_OK;
+  size_t padded = round_up((size_t)rt->grid.n_cells + 1, kScanTile);
+  CU(cudaMalloc(&p.cell_count, padded * sizeof(u32)));
+  CU(cudaMalloc(&p.cell_start, padded * sizeof(u32)));
+  CU(cudaMemsetAsync(p.cell_count, 0, padded * sizeof(u32), rt->stream));
+  CU(cudaMemsetAsync(p.cell_start, 0, padded * sizeof(u32), rt->stream));
+  return ABL_OK;
+}
+
+static int bin_pool(abl_runtime *rt, Pool &p) {
+  if (!rt->env_set) return fail(ABL_ERR_STATE, "binning requires an environment");
+  if (p.pos_member < 0) return fail(ABL_ERR_STATE, "pool %s has no position member", p.name.c_str());
+  TRY(reserve_pool(rt, p, std::max(p.n, (size_t)1)));
+  TRY(ensure_grid_arrays(rt, p));
+  const GridParams &g = rt->grid;
+  const Member &pm = p.members[p.pos_member];
+  const u32 n = (u32)p.n;
+  const int bs = 256;
+  if (n) {
+    const void *px = p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
+    const void *py = nullptr, *pz = nullptr;
+    if (g.dim == 3) {
+      py = p.cols[pm.first_col + 1].buf[p.cols[pm.first_col + 1].cur];
+      pz = p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
+    }
+    u32 nb = blocks_for(n, bs);
+    if (rt->real_size == 8) {
+      if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+      else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    } else {
+      if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+      else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    }
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  // cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also clears
+  // the histogram for the next binning.
+  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_cells + 1, nullptr)));
+  if (n) {
+    const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
+    u32 nb = blocks_for(n, bs);
+    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, p.cell_start, p.pairs);
+    ColTable t;
+    fill_table(p, t, true);
+    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, p.pairs, p.key, n, p.cell_start);
+    rt->launches += 2;
+    CU(cudaGetLastError());
+    flip_all(p);
+  }
+  p.binned = true;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_bin(abl_runtime *rt, int pool) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  CU(cudaSetDevice(rt->device));
+  if (rt->timing) CU(cudaEventRecord(rt->ev[0], rt->stream));
+  TRY(bin_pool(rt, *p));
+  if (rt->timing) {
+    CU(cudaEventRecord(rt->ev[1], rt->stream));
+    CU(cudaEventSynchronize(rt->ev[1]));
+    CU(cudaEventElapsedTime(&rt->last.bin_ms, rt->ev[0], rt->ev[1]));
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_debug_binning(abl_runtime *rt, int pool, unsigned *cell_start,
+                                      size_t n_cells_plus_1, unsigned *ids, size_t n_ids) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  if (!p->binned) return fail(ABL_ERR_STATE, "pool is not binned");
+  CU(cudaStreamSynchronize(rt->stream));
+  if (cell_start) {
+    size_t m = std::min(n_cells_plus_1, (size_t)rt->grid.n_cells + 1);
+    CU(cudaMemcpy(cell_start, p->cell_start, m * sizeof(u32), cudaMemcpyDeviceToHost));
+  }
+  if (ids) {
+    size_t m = std::min(n_ids, p->n);
+    CU(cudaMemcpy(ids, p->cols[p->id_col].buf[p->cols[p->id_col].cur], m * sizeof(u32),
+                  cudaMemcpyDeviceToHost));
+  }
+  return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// step functions
+// ---------------------------------------------------------------------------------------
+extern "C" int abl_cuda_register_step(abl_runtime *rt, const abl_step_desc *desc, int *step) {
+  if (!rt || !desc || !desc->launch) return fail(ABL_ERR_ARGUMENT, "bad step descriptor");
+  Pool *p;
+  TRY(get_pool(rt, desc->self_pool, &p));
+  if (desc->nbr_pool >= 0) {
+    Pool *q;
+    TRY(get_pool(rt, desc->nbr_pool, &q));
+    if (q->pos_member < 0) return fail(ABL_ERR_ARGUMENT, "step %s: neighbour pool has no position", desc->name);
+    if (!rt->env_set) return fail(ABL_ERR_STATE, "register_step before set_environment");
+  }
+  if (desc->added_pool >= 0) {
+    Pool *q;
+    TRY(get_pool(rt, desc->added_pool, &q));
+  }
+  Step s;
+  s.desc = *desc;
+  s.name = desc->name ? desc->name : "";
+  s.desc.name = nullptr;
+  s.reach = 1;
+  if (desc->nbr_pool >= 0) {
+    double r = desc->radius / rt->grid.cell;
+    int reach = (int)ceil(r - 1e-12);
+    s.reach = reach < 1 ? 1 : reach;
+  }
+  rt->steps.push_back(s);
+  if (step) *step = (int)rt->steps.size() - 1;
+  return ABL_OK;
+}
+
+static void fill_view(const Pool &p, abl_pool_view &v, uint32_t written_members, bool self) {
+  memset(&v, 0, sizeof v);
+  v.n = (unsigned)p.n;
+  int ncols = (int)p.cols.size() - 1;
+  for (int c = 0; c < ncols; c++) {
+    v.in[c] = p.cols[c].buf[p.cols[c].cur];
+    v.out[c] = p.cols[c].buf[p.cols[c].cur];
+  }
+  if (self) {
+    for (size_t m = 0; m < p.members.size(); m++) {
+      if (!(written_members >> m & 1u)) continue;
+      const Member &mem = p.members[m];
+      for (int c = mem.first_col; c < mem.first_col + mem.ncols; c++)
+        v.out[c] = p.cols[c].buf[p.cols[c].cur ^ 1];
+    }
+  }
+  v.id = (const unsigned *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
+  v.cell_start = p.binned ? p.cell_start : nullptr;
+}
+
+static int read_scalar(abl_runtime *rt, const u32 *d, u32 *out) {
+  CU(cudaMemcpyAsync(rt->h_scalar, d, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  *out = rt->h_scalar[0];
+  return ABL_OK;
+}
+
+static int commit_removals(abl_runtime *rt, Pool &p) {
+  const u32 n = (u32)p.n;
+  if (!n) return ABL_OK;
+  TRY((run_scan<u8, 1, false>(rt, p.dead, p.offsets, n, rt->d_scalar)));
+  u32 survivors = 0;
+  TRY(read_scalar(rt, rt->d_scalar, &survivors));
+  if (survivors == n) return ABL_OK;  // nobody died: nothing to move
+  ColTable t;
+  fill_table(p, t, true);
+  k_compact_move<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, p.dead, p.offsets, n);
+  rt->launches++;
+  CU(cudaGetLastError());
+  flip_all(p);
+  p.ever_removed = true;
+  p.binned = false;  // stable compaction keeps cell order, but cell_start is stale
+  p.n = survivors;
+  return ABL_OK;
+}
+
+static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const *staging) {
+  const u32 n = (u32)parent.n;
+  if (!n) return ABL_OK;
+  TRY((run_scan<u8, 0, false>(rt, parent.add_flag, parent.offsets, n, rt->d_scalar)));
+  u32 m = 0;
+  TRY(read_scalar(rt, rt->d_scalar, &m));
+  if (!m) return ABL_OK;
+  const u32 *pids = (const u32 *)parent.cols[parent.id_col].buf[parent.cols[parent.id_col].cur];
+  u64 *list = parent.pairs;  // free between binnings
+  k_collect_adds<<<blocks_for(n, 256), 256, 0, rt->stream>>>(parent.add_flag, parent.offsets, pids, n, list);
+  rt->launches++;
+  CU(cudaGetLastError());
+  u64 *tmp = nullptr;
+  if (target.n + m > target.cap) {
+    // growing the target reallocates its scratch (which holds `list` when parent == target)
+    CU(cudaMalloc(&tmp, (size_t)m * sizeof(u64)));
+    CU(cudaMemcpyAsync(tmp, list, (size_t)m * sizeof(u64), cudaMemcpyDeviceToDevice, rt->stream));
+    CU(cudaStreamSynchronize(rt->stream));
+    TRY(reserve_pool(rt, target, target.n + m));
+    list = tmp;
+  }
+  ColTable t;
+  fill_table(target, t, false);
+  for (int c = 0; c < t.ncols; c++) t.in[c] = t.host_off[c] < 0 ? nullptr : staging[c];
+  k_append<<<blocks_for(m, 128), 128, 0, rt->stream>>>(t, list, m, (u32)target.n, target.next_id);
+  rt->launches++;
+  CU(cudaGetLastError());
+  if (tmp) {
+    CU(cudaStreamSynchronize(rt->stream));
+    CU(cudaFree(tmp));
+  }
+  target.n += m;
+  target.next_id += m;
+  target.binned = false;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (step < 0 || step >= (int)rt->steps.size()) return fail(ABL_ERR_ARGUMENT, "bad step index %d", step);
+  CU(cudaSetDevice(rt->device));
+  Step &s = rt->steps[step];
+  Pool &self = rt->pools[s.desc.self_pool];
+  Pool *nbr = s.desc.nbr_pool >= 0 ? &rt->pools[s.desc.nbr_pool] : nullptr;
+  Pool *added = s.desc.added_pool >= 0 ? &rt->pools[s.desc.added_pool] : nullptr;
+
+  if (rt->timing) CU(cudaEventRecord(rt->ev[0], rt->stream));
+  if (nbr) {
+    if (!nbr->binned) TRY(bin_pool(rt, *nbr));
+    // keep the iterating pool in cell order too: neighbouring threads then walk
+    // neighbouring cells (coalescing / L1 reuse)
+    if (&self != nbr && self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self));
+  }
+  if (rt->timing) CU(cudaEventRecord(rt->ev[1], rt->stream));
+
+  if (self.n) {
+    TRY(reserve_pool(rt, self, self.n));
+    abl_step_launch a;
+    memset(&a, 0, sizeof a);
+    fill_view(self, a.self, s.desc.written_members, true);
+    if (nbr) fill_view(*nbr, a.nbr, 0, false);
+    a.grid.dim = rt->grid.dim;
+    for (int k = 0; k < 3; k++) { a.grid.n_cell[k] = rt->grid.n_cell[k]; a.grid.origin[k] = rt->grid.origin[k]; }
+    a.grid.cell_size = rt->grid.cell;
+    a.grid.n_cells = rt->grid.n_cells;
+    a.reach = s.reach;
+    a.dead = s.desc.uses_removal ? self.dead : nullptr;
+    void *staging[ABL_MAX_COLUMNS + 1];
+    memset(staging, 0, sizeof staging);
+    if (added) {
+      // staging for one new agent per parent: the alternate buffers of the *target* pool
+      // cannot be used (target may be the parent itself and be written by this step), so
+      // dedicated staging columns are carved out of the transfer staging buffer.
+      size_t bytes = 0;
+      int ncols = (int)added->cols.size() - 1;
+      for (int c = 0; c < ncols; c++) bytes += round_up(self.n * (size_t)added->cols[c].elem, 256);
+      TRY(ensure_stage(rt, bytes));
+      size_t off = 0;
+      for (int c = 0; c < ncols; c++) {
+        staging[c] = (u8 *)rt->stage + off;
+        a.add_cols[c] = staging[c];
+        off += round_up(self.n * (size_t)added->cols[c].elem, 256);
+      }
+      a.add_flag = self.add_flag;
+    }
+    a.seed = rt->cfg.seed;
+    a.timestep = rt->timestep;
+    a.step_index = (unsigned)step;
+    a.block_size = rt->cfg.block_size;
+    a.tile_neighbours = rt->cfg.tile_neighbours;
+    a.stream = (void *)rt->stream;
+    int rc = s.desc.launch(&a);
+    rt->launches++;
+    if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: kernel launch failed: %s", s.name.c_str(),
+                             cudaGetErrorString((cudaError_t)rc));
+    if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
+
+    // commit: flip written columns
+    for (size_t m = 0; m < self.members.size(); m++) {
+      if (!(s.desc.written_members >> m & 1u)) continue;
+      const Member &mem = self.members[m];
+      for (int c = mem.first_col; c < mem.first_col + mem.ncols; c++) self.cols[c].cur ^= 1;
+      if ((int)m == self.pos_member) self.binned = false;
+    }
+    if (added) TRY(commit_adds(rt, self, *added, staging));
+    if (s.desc.uses_removal) TRY(commit_removals(rt, self));
+  } else if (rt->timing) {
+    CU(cudaEventRecord(rt->ev[2], rt->stream));
+  }
+  if (rt->timing) {
+    CU(cudaEventRecord(rt->ev[3], rt->stream));
+    CU(cudaEventSynchronize(rt->ev[3]));
+    CU(cudaEventElapsedTime(&rt->last.bin_ms, rt->ev[0], rt->ev[1]));
+    CU(cudaEventElapsedTime(&rt->last.kernel_ms, rt->ev[1], rt->ev[2]));
+    CU(cudaEventElapsedTime(&rt->last.commit_ms, rt->ev[2], rt->ev[3]));
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_begin_timestep(abl_runtime *rt) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  CU(cudaEventRecord(rt->ev_ts[0], rt->stream));
+  rt->ts_open = true;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_end_timestep(abl_runtime *rt) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  rt->timestep++;
+  if (rt->ts_open) {
+    CU(cudaEventRecord(rt->ev_ts[1], rt->stream));
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_last_exec_time(abl_runtime *rt, double *seconds) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  // time of the parallel part of the current timestep so far (the sequential step runs
+  // after all step functions, reference MasonPrinter.cpp:535-541)
+  float ms = 0;
+  if (rt->ts_open) {
+    CU(cudaEventRecord(rt->ev_ts[1], rt->stream));
+    CU(cudaEventSynchronize(rt->ev_ts[1]));
+    CU(cudaEventElapsedTime(&ms, rt->ev_ts[0], rt->ev_ts[1]));
+  }
+  if (seconds) *seconds = ms / 1000.0;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_enable_timing(abl_runtime *rt, int on) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  rt->timing = on != 0;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t) {
+  if (!rt || !t) return fail(ABL_ERR_ARGUMENT, "null argument");
+  *t = rt->last;
+  t->launches = rt->launches;
+  return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// reductions
+// ---------------------------------------------------------------------------------------
+extern "C" int abl_cuda_count(abl_runtime *rt, int pool, int *result) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  if (result) *result = (int)p->n;
+  return ABL_OK;
+}
+
+static int get_member(abl_runtime *rt, int pool, int member, Pool **p, Member **m) {
+  TRY(get_pool(rt, pool, p));
+  if (member < 0 || member >= (int)(*p)->members.size()) return fail(ABL_ERR_ARGUMENT, "bad member index %d", member);
+  *m = &(*p)->members[member];
+  return ABL_OK;
+}
+
+static int reduce_int(abl_runtime *rt, Pool &p, Member &m, int kind, int value, int *result) {
+  int *d = (int *)rt->d_scalar;
+  CU(cudaMemsetAsync(d, 0, sizeof(int), rt->stream));
+  const void *col = p.cols[m.first_col].buf[p.cols[m.first_col].cur];
+  u32 n = (u32)p.n;
+  if (n) {
+    u32 nb = std::min(blocks_for(n, 256), 148u * 8u);
+    switch (kind) {
+      case 0: k_reduce_int<0><<<nb, 256, 0, rt->stream>>>(col, n, value, d); break;
+      case 1: k_reduce_int<1><<<nb, 256, 0, rt->stream>>>(col, n, value, d); break;
+      case 2: k_reduce_int<2><<<nb, 256, 0, rt->stream>>>(col, n, value, d); break;
+      default: k_reduce_int<3><<<nb, 256, 0, rt->stream>>>(col, n, value, d); break;
+    }
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  u32 out = 0;
+  TRY(read_scalar(rt, rt->d_scalar, &out));
+  if (result) *result = (int)out;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_sum_int(abl_runtime *rt, int pool, int member, int *result) {
+  Pool *p; Member *m;
+  TRY(get_member(rt, pool, member, &p, &m));
+  if (m->type == ABL_TYPE_INT) return reduce_int(rt, *p, *m, 0, 0, result);
+  if (m->type == ABL_TYPE_BOOL) return reduce_int(rt, *p, *m, 1, 0, result);
+  return fail(ABL_ERR_ARGUMENT, "sum_int on non-integer member %s", m->name.c_str());
+}
+
+extern "C" int abl_cuda_count_member_int(abl_runtime *rt, int pool, int member, int value, int *result) {
+  Pool *p; Member *m;
+  TRY(get_member(rt, pool, member, &p, &m));
+  if (m->type == ABL_TYPE_INT) return reduce_int(rt, *p, *m, 2, value, result);
+  if (m->type == ABL_TYPE_BOOL) return reduce_int(rt, *p, *m, 3, value ? 1 : 0, result);
+  return fail(ABL_ERR_ARGUMENT, "count_member_int on non-integer member %s", m->name.c_str());
+}
+
+extern "C" int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member, double value, int *result) {
+  Pool *p; Member *m;
+  TRY(get_member(rt, pool, member, &p, &m));
+  if (m->type != ABL_TYPE_FLOAT) return fail(ABL_ERR_ARGUMENT, "count_member_float on non-float member");
+  int *d = (int *)rt->d_scalar;
+  CU(cudaMemsetAsync(d, 0, sizeof(int), rt->stream));
+  const void *col = p->cols[m->first_col].buf[p->cols[m->first_col].cur];
+  u32 n = (u32)p->n;
+  if (n) {
+    u32 nb = std::min(blocks_for(n, 256), 148u * 8u);
+    if (rt->real_size == 8) k_count_real<double><<<nb, 256, 0, rt->stream>>>((const double *)col, n, value, d);
+    else k_count_real<float><<<nb, 256, 0, rt->stream>>>((const float *)col, n, (float)value, d);
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  u32 out = 0;
+  TRY(read_scalar(rt, rt->d_scalar, &out));
+  if (result) *result = (int)out;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int component, double *result) {
+  Pool *p; Member *m;
+  TRY(get_member(rt, pool, member, &p, &m));
+  int col_index = m->first_col, stride = 1, comp = 0;
+  if (m->type == ABL_TYPE_FLOAT2) { stride = 2; comp = component; }
+  else if (m->type == ABL_TYPE_FLOAT3) { col_index += component; }
+  else if (m->type != ABL_TYPE_FLOAT) return fail(ABL_ERR_ARGUMENT, "sum_float on non-float member");
+  if (comp < 0 || comp > 1 || component < 0 || component > 2) return fail(ABL_ERR_ARGUMENT, "bad component");
+  const void *col = p->cols[col_index].buf[p->cols[col_index].cur];
+  u32 n = (u32)p->n;
+  const u32 nb = 148 * 2;
+  double *partial = (double *)(rt->d_scalar + 16);  // 8-byte aligned region inside scratch
+  double *d_out = (double *)(rt->d_scalar + 2);
+  if (rt->real_size == 8) k_reduce_real_partial<double><<<nb, 256, 0, rt->stream>>>((const double *)col, stride, comp, n, partial);
+  else k_reduce_real_partial<float><<<nb, 256, 0, rt->stream>>>((const float *)col, stride, comp, n, partial);
+  k_final_sum<<<1, 32, 0, rt->stream>>>(partial, (int)nb, d_out);
+  rt->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(rt->h_scalar, d_out, sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  if (result) memcpy(result, rt->h_scalar, sizeof(double));
+  return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// multi-GPU (slab decomposition): implemented in abl_exchange.cu
+// ---------------------------------------------------------------------------------------

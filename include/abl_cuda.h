@@ -1,0 +1,212 @@
+/* abl_cuda.h — C ABI of the B200-native OpenABL runtime (asset/cuda, libabl_cuda.so).
+ *
+ * This is the drop-in boundary on the run-time side.  The reference `c` backend has no
+ * FFI: its generated main.c owns agent storage (`dyn_array`, reference
+ * asset/c/libabl.h:11-57) and runs the simulate loop inline (reference
+ * src/backend/CPrinter.cpp:189-233).  The `cuda` backend keeps that host program shape
+ * and replaces exactly those two pieces by calls into this library; every entry point
+ * below cites the reference construct it stands in for.
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a non-zero
+ * ABL_ERR_* code, with a human-readable message available from abl_cuda_last_error().
+ * One host thread drives one runtime; one runtime drives one CUDA device.  Device memory
+ * is owned by the runtime, host buffers stay owned by the caller.
+ *
+ * There is NO CPU fallback: if no CUDA device is usable abl_cuda_create() fails.
+ */
+#ifndef ABL_CUDA_H
+#define ABL_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABL_CUDA_ABI_VERSION 1
+#define ABL_MAX_MEMBERS 16   /* members per agent type */
+#define ABL_MAX_COLUMNS 32   /* SoA columns per agent type (a float3 member is 3 columns) */
+
+enum {
+  ABL_OK = 0,
+  ABL_ERR_CUDA = 1,        /* a CUDA call failed / no device */
+  ABL_ERR_ARGUMENT = 2,    /* bad handle, index or descriptor */
+  ABL_ERR_STATE = 3,       /* call order violated (e.g. step before environment) */
+  ABL_ERR_CAPACITY = 4,    /* host buffer too small */
+  ABL_ERR_COMM = 5         /* multi-GPU exchange failed */
+};
+
+/* Member kinds.  Numbering equals the reference's type_id (asset/c/libabl.h:188-196) so a
+ * generated type table can be passed through unchanged. */
+enum {
+  ABL_TYPE_END = 0,
+  ABL_TYPE_BOOL = 1,
+  ABL_TYPE_INT = 2,
+  ABL_TYPE_FLOAT = 3,
+  ABL_TYPE_STRING = 4, /* not storable in agents */
+  ABL_TYPE_FLOAT2 = 5,
+  ABL_TYPE_FLOAT3 = 6
+};
+
+/* One agent member inside the host AoS record; mirrors `type_info`
+ * (reference asset/c/libabl.h:198-203). */
+typedef struct {
+  int type;            /* ABL_TYPE_* */
+  unsigned offset;     /* byte offset inside the host record */
+  const char *name;
+  int is_pos;          /* the `position` member */
+} abl_member_desc;
+
+/* One agent type; mirrors the per-agent `type_info[]` + `agent_info` pair
+ * (reference src/backend/CPrinter.cpp:250-265, 286-302). */
+typedef struct {
+  const char *name;
+  const abl_member_desc *members;
+  int n_members;
+  unsigned stride;     /* sizeof(host record) */
+} abl_agent_desc;
+
+typedef struct abl_runtime abl_runtime;
+
+typedef struct {
+  int device;            /* CUDA device ordinal; -1 = current device */
+  int use_float;         /* 1: abl_float is float (reference -DLIBABL_USE_FLOAT=1), 0: double */
+  uint64_t seed;         /* seed of the in-step counter-based RNG */
+  int deterministic;     /* reserved, must be 1: neighbour order = (cell, agent id) */
+  int tile_neighbours;   /* 1: step kernels stage neighbour cell ranges in shared memory */
+  int block_size;        /* threads per CTA for step kernels (0 = default 128) */
+} abl_config;
+
+/* ---- life cycle -------------------------------------------------------------------- */
+int abl_cuda_abi_version(void);
+void abl_cuda_default_config(abl_config *cfg);
+int abl_cuda_create(abl_runtime **rt, const abl_config *cfg);
+int abl_cuda_destroy(abl_runtime *rt);
+const char *abl_cuda_last_error(void);
+
+/* ---- environment (reference EnvironmentDeclaration: envMin/envMax/envGranularity,
+ *      src/AST.hpp:658-662; grid sizing rule ceil(size/granularity) per axis) ----------- */
+int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *env_min,
+                             const double *env_max, double granularity);
+
+/* ---- agent pools: SoA, per-column double buffered, replaces `agents_T` / `agents_T_dbuf`
+ *      dyn_arrays (reference src/backend/CPrinter.cpp:286-302) --------------------------- */
+int abl_cuda_add_pool(abl_runtime *rt, const abl_agent_desc *desc, int *pool);
+/* Host AoS -> device SoA.  Agent i receives id i (ids are the tie-break of the cell sort
+ * and the order of every download). */
+int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n);
+/* Device SoA -> host AoS in ascending agent-id order (= original index order while no agent
+ * has been removed; reference save() order, asset/c/libabl.c:96-109). */
+int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity, size_t *n);
+int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
+
+/* ---- step functions ------------------------------------------------------------------ */
+
+/* Everything a generated step kernel needs, passed by value at launch. */
+typedef struct {
+  unsigned n;                              /* live agents */
+  const void *in[ABL_MAX_COLUMNS];         /* current column base pointers */
+  void *out[ABL_MAX_COLUMNS];              /* where this step writes (== in[] if unwritten) */
+  const unsigned *id;                      /* agent ids, same order as the columns */
+  const unsigned *cell_start;              /* [n_cells + 1] exclusive prefix, NULL if unbinned */
+} abl_pool_view;
+
+typedef struct {
+  int dim;
+  int n_cell[3];
+  double origin[3];
+  double cell_size;
+  unsigned n_cells;
+} abl_grid_view;
+
+typedef struct {
+  abl_pool_view self;                      /* pool the step function iterates */
+  abl_pool_view nbr;                       /* pool of its for-near loop (n = 0 if none) */
+  abl_grid_view grid;
+  int reach;                               /* cells to visit on each side: ceil(radius/cell) */
+  unsigned char *dead;                     /* [self.n] removeCurrent() flags, or NULL */
+  unsigned char *add_flag;                 /* [self.n] add() flags, or NULL */
+  void *add_cols[ABL_MAX_COLUMNS];         /* staging columns of the added type, [self.n] */
+  uint64_t seed;
+  unsigned timestep;
+  unsigned step_index;
+  int block_size;
+  int tile_neighbours;
+  void *stream;                            /* cudaStream_t */
+} abl_step_launch;
+
+typedef int (*abl_step_launcher)(const abl_step_launch *args);
+
+/* Static facts about one `step` function — the analysis products a GPU backend consumes
+ * (reference FunctionDeclaration::accessedAgent/accessedMembers/usesRuntimeRemoval/
+ * runtimeAddedAgent, src/AST.hpp:536-544). */
+typedef struct {
+  const char *name;
+  int self_pool;
+  int nbr_pool;              /* -1: no for-near loop */
+  double radius;             /* folded for-near radius */
+  uint32_t written_members;  /* bit m set: member m of `out` is assigned */
+  int uses_removal;
+  int added_pool;            /* -1: no run-time add() */
+  abl_step_launcher launch;
+} abl_step_desc;
+
+int abl_cuda_register_step(abl_runtime *rt, const abl_step_desc *desc, int *step);
+/* One parallel step function over its pool: (re)bin the neighbour pool if its positions
+ * changed, launch the kernel, flip the written columns, compact removals / append adds.
+ * Replaces one `#pragma omp parallel for` block + buffer swap of the reference simulate
+ * loop (src/backend/CPrinter.cpp:207-228). */
+int abl_cuda_step(abl_runtime *rt, int step);
+/* Marks the start of a new timestep (advances the RNG counter, starts the timer used by
+ * getLastExecTime()). */
+int abl_cuda_begin_timestep(abl_runtime *rt);
+int abl_cuda_end_timestep(abl_runtime *rt);
+int abl_cuda_synchronize(abl_runtime *rt);
+
+/* ---- reductions for `sequential step` functions (semantics: reference
+ *      src/backend/MasonPrinter.cpp:623-682; absent from the `c` backend) ---------------- */
+int abl_cuda_count(abl_runtime *rt, int pool, int *result);
+int abl_cuda_count_member_int(abl_runtime *rt, int pool, int member, int value, int *result);
+int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member, double value, int *result);
+int abl_cuda_sum_int(abl_runtime *rt, int pool, int member, int *result);        /* int and bool */
+int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int component, double *result);
+int abl_cuda_last_exec_time(abl_runtime *rt, double *seconds);
+
+/* ---- introspection used by tests / bench (binning is an internal stage of abl_cuda_step) */
+/* Forces binning of `pool` now. */
+int abl_cuda_bin(abl_runtime *rt, int pool);
+/* Copies the pool's current cell_start (n_cells+1 entries) and agent ids in device order. */
+int abl_cuda_debug_binning(abl_runtime *rt, int pool, unsigned *cell_start, size_t n_cells_plus_1,
+                           unsigned *ids, size_t n_ids);
+int abl_cuda_grid_cells(abl_runtime *rt, unsigned *n_cells, int n_cell_axis[3]);
+/* Device time of the most recent abl_cuda_step / abl_cuda_bin stages, CUDA events, ms. */
+typedef struct {
+  float bin_ms;
+  float kernel_ms;
+  float commit_ms;
+  unsigned launches;       /* kernels launched by the runtime since creation */
+} abl_step_timing;
+int abl_cuda_enable_timing(abl_runtime *rt, int on);
+int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t);
+void *abl_cuda_stream(abl_runtime *rt);
+
+/* ---- multi-GPU slab decomposition (one runtime per GPU, one process per GPU) ----------
+ * The population is split into slabs of whole cell layers along the slowest-varying grid
+ * axis.  Each runtime owns the agents whose cell layer lies in [layer_begin, layer_end) and
+ * keeps read-only ghost copies of the adjacent layer(s) on each side.  The transport is
+ * supplied by the caller as NCCL (abl_cuda_comm_init_nccl) — the runtime issues grouped
+ * ncclSend/ncclRecv on its own stream. */
+int abl_cuda_nccl_unique_id(void *id128);   /* 128-byte ncclUniqueId, to be broadcast by the caller */
+int abl_cuda_comm_init_nccl(abl_runtime *rt, const void *id128, int rank, int world);
+int abl_cuda_set_slab(abl_runtime *rt, int layer_begin, int layer_end);
+int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers);
+/* After a step (or upload): send agents that left the slab to the neighbour ranks, receive
+ * arrivals, then refresh ghost layers of `pool`.  Collective over neighbouring ranks. */
+int abl_cuda_exchange(abl_runtime *rt, int pool);
+int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABL_CUDA_H */

@@ -1,0 +1,206 @@
+"""ctypes binding of the runtime C ABI (include/abl_cuda.h).
+
+Fails loudly when the CUDA library is missing or no device is present: there is no CPU
+fallback on the product path.
+"""
+import ctypes as C
+import os
+
+from .paths import RUNTIME_LIB
+
+ABL_MAX_COLUMNS = 32
+
+
+class AblError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int), ("use_float", C.c_int), ("seed", C.c_uint64),
+                ("deterministic", C.c_int), ("tile_neighbours", C.c_int), ("block_size", C.c_int)]
+
+
+class MemberDesc(C.Structure):
+    _fields_ = [("type", C.c_int), ("offset", C.c_uint), ("name", C.c_char_p), ("is_pos", C.c_int)]
+
+
+class AgentDesc(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("members", C.POINTER(MemberDesc)), ("n_members", C.c_int),
+                ("stride", C.c_uint)]
+
+
+class StepTiming(C.Structure):
+    _fields_ = [("bin_ms", C.c_float), ("kernel_ms", C.c_float), ("commit_ms", C.c_float),
+                ("launches", C.c_uint)]
+
+
+# every symbol include/abl_cuda.h declares: name -> (restype, argtypes)
+_VP = C.c_void_p
+ABI = {
+    "abl_cuda_abi_version": (C.c_int, []),
+    "abl_cuda_default_config": (None, [C.POINTER(Config)]),
+    "abl_cuda_create": (C.c_int, [C.POINTER(_VP), C.POINTER(Config)]),
+    "abl_cuda_destroy": (C.c_int, [_VP]),
+    "abl_cuda_last_error": (C.c_char_p, []),
+    "abl_cuda_set_environment": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]),
+    "abl_cuda_add_pool": (C.c_int, [_VP, C.POINTER(AgentDesc), C.POINTER(C.c_int)]),
+    "abl_cuda_upload": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t]),
+    "abl_cuda_download": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "abl_cuda_pool_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_register_step": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
+    "abl_cuda_step": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_begin_timestep": (C.c_int, [_VP]),
+    "abl_cuda_end_timestep": (C.c_int, [_VP]),
+    "abl_cuda_synchronize": (C.c_int, [_VP]),
+    "abl_cuda_count": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_int)]),
+    "abl_cuda_count_member_int": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "abl_cuda_count_member_float": (C.c_int, [_VP, C.c_int, C.c_int, C.c_double, C.POINTER(C.c_int)]),
+    "abl_cuda_sum_int": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "abl_cuda_sum_float": (C.c_int, [_VP, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]),
+    "abl_cuda_last_exec_time": (C.c_int, [_VP, C.POINTER(C.c_double)]),
+    "abl_cuda_bin": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_debug_binning": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, _VP, C.c_size_t]),
+    "abl_cuda_grid_cells": (C.c_int, [_VP, C.POINTER(C.c_uint), C.POINTER(C.c_int * 3)]),
+    "abl_cuda_enable_timing": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_last_timing": (C.c_int, [_VP, C.POINTER(StepTiming)]),
+    "abl_cuda_stream": (_VP, [_VP]),
+    "abl_cuda_nccl_unique_id": (C.c_int, [_VP]),
+    "abl_cuda_comm_init_nccl": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
+    "abl_cuda_set_slab": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "abl_cuda_slab_axis_layers": (C.c_int, [_VP, C.POINTER(C.c_int)]),
+    "abl_cuda_exchange": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_owned_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+}
+
+_lib = None
+
+
+def load_library(path=None):
+    """Loads libabl_cuda.so (RTLD_GLOBAL so model libraries resolve against it)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = path or RUNTIME_LIB
+    if not os.path.exists(path):
+        raise AblError("CUDA runtime library %s is missing — run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load_library().abl_cuda_last_error().decode(errors="replace")
+        raise AblError("%s failed (code %d): %s" % (what or "abl_cuda call", rc, msg))
+
+
+class Runtime:
+    """One device runtime (one GPU)."""
+
+    def __init__(self, use_float=False, device=-1, block_size=128, tile=True, seed=None):
+        self.lib = load_library()
+        cfg = Config()
+        self.lib.abl_cuda_default_config(C.byref(cfg))
+        cfg.device = device
+        cfg.use_float = 1 if use_float else 0
+        cfg.block_size = block_size
+        cfg.tile_neighbours = 1 if tile else 0
+        if seed is not None:
+            cfg.seed = seed
+        self.handle = _VP()
+        check(self.lib.abl_cuda_create(C.byref(self.handle), C.byref(cfg)), "abl_cuda_create")
+        self.use_float = use_float
+
+    def close(self):
+        if self.handle:
+            check(self.lib.abl_cuda_destroy(self.handle), "abl_cuda_destroy")
+            self.handle = _VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # thin wrappers -------------------------------------------------------------------
+    def set_environment(self, env_min, env_max, granularity):
+        dim = len(env_max)
+        lo = (C.c_double * 3)(*(list(env_min) + [0.0] * (3 - dim)))
+        hi = (C.c_double * 3)(*(list(env_max) + [0.0] * (3 - dim)))
+        check(self.lib.abl_cuda_set_environment(self.handle, dim, lo, hi, granularity), "set_environment")
+
+    def upload(self, pool, array):
+        check(self.lib.abl_cuda_upload(self.handle, pool, array.ctypes.data_as(_VP), len(array)), "upload")
+
+    def pool_size(self, pool):
+        n = C.c_size_t()
+        check(self.lib.abl_cuda_pool_size(self.handle, pool, C.byref(n)), "pool_size")
+        return n.value
+
+    def download(self, pool, dtype):
+        import numpy as np
+        n = self.pool_size(pool)
+        out = np.zeros(n, dtype=dtype)
+        got = C.c_size_t()
+        check(self.lib.abl_cuda_download(self.handle, pool, out.ctypes.data_as(_VP), n, C.byref(got)), "download")
+        return out
+
+    def step(self, step_id):
+        check(self.lib.abl_cuda_step(self.handle, step_id), "step")
+
+    def bin(self, pool):
+        check(self.lib.abl_cuda_bin(self.handle, pool), "bin")
+
+    def synchronize(self):
+        check(self.lib.abl_cuda_synchronize(self.handle), "synchronize")
+
+    def grid_cells(self):
+        n = C.c_uint()
+        axes = (C.c_int * 3)()
+        check(self.lib.abl_cuda_grid_cells(self.handle, C.byref(n), C.byref(axes)), "grid_cells")
+        return n.value, list(axes)
+
+    def debug_binning(self, pool):
+        import numpy as np
+        ncells, _ = self.grid_cells()
+        n = self.pool_size(pool)
+        cs = np.zeros(ncells + 1, dtype=np.uint32)
+        ids = np.zeros(n, dtype=np.uint32)
+        check(self.lib.abl_cuda_debug_binning(self.handle, pool, cs.ctypes.data_as(_VP), len(cs),
+                                              ids.ctypes.data_as(_VP), len(ids)), "debug_binning")
+        return cs, ids
+
+    def enable_timing(self, on=True):
+        check(self.lib.abl_cuda_enable_timing(self.handle, 1 if on else 0), "enable_timing")
+
+    def last_timing(self):
+        t = StepTiming()
+        check(self.lib.abl_cuda_last_timing(self.handle, C.byref(t)), "last_timing")
+        return {"bin_ms": t.bin_ms, "kernel_ms": t.kernel_ms, "commit_ms": t.commit_ms, "launches": t.launches}
+
+    def stream(self):
+        return self.lib.abl_cuda_stream(self.handle)
+
+    def count(self, pool):
+        r = C.c_int()
+        check(self.lib.abl_cuda_count(self.handle, pool, C.byref(r)), "count")
+        return r.value
+
+    def sum_int(self, pool, member):
+        r = C.c_int()
+        check(self.lib.abl_cuda_sum_int(self.handle, pool, member, C.byref(r)), "sum_int")
+        return r.value
+
+    def count_member_int(self, pool, member, value):
+        r = C.c_int()
+        check(self.lib.abl_cuda_count_member_int(self.handle, pool, member, int(value), C.byref(r)), "count_member_int")
+        return r.value
+
+    def sum_float(self, pool, member, component=0):
+        r = C.c_double()
+        check(self.lib.abl_cuda_sum_float(self.handle, pool, member, component, C.byref(r)), "sum_float")
+        return r.value

@@ -1,0 +1,116 @@
+"""Runs the REAL reference (`oracle/_ref/OpenABL_ref -b c` + the reference's own libabl,
+compiled by gcc with the reference's build line) and collects raw agent state.
+
+TEST INFRASTRUCTURE ONLY.  Works only where /root/reference exists (the build container);
+the GPU box uses the fixtures this script commits under tests/golden/ and the prebuilt
+binaries under oracle/_ref/.
+
+    python oracle/refgen.py            # (re)generate every fixture listed in FIXTURES
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = os.environ.get("OPENABL_REFERENCE", "/root/reference")
+REF_BIN = os.path.join(HERE, "_ref", "OpenABL_ref")
+GOLDEN = os.path.join(REPO, "tests", "golden")
+
+sys.path.insert(0, REPO)
+from openabl_b200.state import agent_dtype, parse_agents, read_raw  # noqa: E402
+
+
+def reference_available():
+    return os.path.isdir(REF) and os.path.exists(REF_BIN)
+
+
+def build_reference_program(model, params, use_float, out_dir, threads_flag=True):
+    """Generates C with the reference compiler and builds it with the reference's build line
+    plus the save() wrapper that dumps raw state.  Returns the path of the executable."""
+    os.makedirs(out_dir, exist_ok=True)
+    cmd = [REF_BIN, "-A", os.path.join(REF, "asset"), "-i", model, "-b", "c", "-o", out_dir]
+    for k, v in params.items():
+        cmd += ["-P", "%s=%s" % (k, v)]
+    if use_float:
+        cmd += ["-C", "use_float=true"]
+    subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)
+    # reference build line (src/backend/CBackend.cpp:21-27) + wrapper object
+    gcc = ["gcc", "-O2", "-std=c99"] + (["-DLIBABL_USE_FLOAT=1"] if use_float else []) + [
+        "main.c", "libabl.c", os.path.join(HERE, "shim", "save_wrap.c"), "-I.", "-lm", "-fopenmp",
+        "-Wl,--wrap=save", "-o", "main"]
+    subprocess.run(gcc, cwd=out_dir, check=True)
+    return os.path.join(out_dir, "main")
+
+
+def run_reference(model, params, use_float=False, keep=None):
+    """-> (list of structured arrays per agent type, json text)"""
+    tmp = keep or tempfile.mkdtemp(prefix="ablref_")
+    try:
+        exe = build_reference_program(model, params, use_float, tmp)
+        subprocess.run([exe], cwd=tmp, check=True)
+        with open(model) as f:
+            agents = parse_agents(f.read())
+        dtypes = [agent_dtype(m, use_float) for _, m in agents]
+        raw = [p for p in os.listdir(tmp) if p.endswith(".bin")]
+        assert len(raw) == 1, raw
+        state = read_raw(os.path.join(tmp, raw[0]), dtypes)
+        with open(os.path.join(tmp, raw[0][:-4])) as f:
+            text = f.read()
+        return state, text
+    finally:
+        if not keep:
+            shutil.rmtree(tmp, ignore_errors=True)
+
+
+# name -> (model file under examples/, params, use_float)
+FIXTURES = {
+    "circle_n1000_t100": ("circle.abl", {"num_agents": 1000, "num_timesteps": 100}, False),
+    "circle_n1000_t0": ("circle.abl", {"num_agents": 1000, "num_timesteps": 0}, False),
+    "circle_n2000_t10_f32": ("circle.abl", {"num_agents": 2000, "num_timesteps": 10}, True),
+    "circle3d_n2000_t10": ("circle3d.abl", {"num_agents": 2000, "num_timesteps": 10}, False),
+    "circle3d_n2000_t0": ("circle3d.abl", {"num_agents": 2000, "num_timesteps": 0}, False),
+    "boids2d_n4000_t10": ("boids2d.abl", {"num_agents": 4000, "num_timesteps": 10}, False),
+    "boids2d_n4000_t0": ("boids2d.abl", {"num_agents": 4000, "num_timesteps": 0}, False),
+    "boids2d_n4000_t10_f32": ("boids2d.abl", {"num_agents": 4000, "num_timesteps": 10}, True),
+    "game_of_life_n4096_t10": ("game_of_life.abl", {"num_agents": 4096, "num_timesteps": 10}, False),
+    "game_of_life_n4096_t0": ("game_of_life.abl", {"num_agents": 4096, "num_timesteps": 0}, False),
+}
+
+
+def fixture_paths(name):
+    return os.path.join(GOLDEN, name + ".npz"), os.path.join(GOLDEN, name + ".json")
+
+
+def load_fixture(name):
+    npz, meta = fixture_paths(name)
+    with open(meta) as f:
+        info = json.load(f)
+    data = np.load(npz)
+    return info, [data["type%d" % i] for i in range(info["n_types"])]
+
+
+def main():
+    if not reference_available():
+        sys.exit("reference not available: build oracle/_ref first (make -C oracle ref)")
+    os.makedirs(GOLDEN, exist_ok=True)
+    for name, (model, params, use_float) in FIXTURES.items():
+        path = os.path.join(REPO, "examples", model)
+        state, text = run_reference(path, params, use_float)
+        npz, meta = fixture_paths(name)
+        np.savez_compressed(npz, **{"type%d" % i: s for i, s in enumerate(state)})
+        with open(meta, "w") as f:
+            json.dump({"model": model, "params": params, "use_float": use_float,
+                       "n_types": len(state), "counts": [len(s) for s in state],
+                       "generator": "oracle/refgen.py (reference c backend, gcc -O2 -std=c99 -fopenmp)"},
+                      f, indent=1)
+        print(name, [len(s) for s in state])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,1151 @@
+// The B200-native `cuda` backend: code printer + build script generation.
+//
+// Replaces reference src/backend/CBackend.cpp + CPrinter.cpp for `-b cuda`.  From the
+// analysed script it writes into outputDir:
+//   model_host.c     C99 host program: agent records + type tables, folded constants,
+//                    library/user functions, main() whose `simulate` hands the population
+//                    to the device runtime (include/abl_cuda.h).  Everything outside
+//                    `simulate` is lowered with the same expression shapes and literal
+//                    formatting as the reference C printer (GenericPrinter.cpp:39-58 float
+//                    literals with 6 significant digits, GenericCPrinter.cpp:20-75 vector
+//                    operator lowering, CPrinter.cpp:64-173), because initial state and
+//                    arithmetic must match the `c` backend bit for bit.
+//   model_kernels.cu one __global__ kernel per `step` function (sm_100a) + launcher +
+//                    registration of pools and steps with the runtime.
+//   build.sh/run.sh  nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false + gcc -O2 -std=c99.
 #include "Backend.hpp"
+
+#include <cmath>
+#include <functional>
+#include <sstream>
+
+#include "../FileUtil.hpp"
+
 namespace abl {
-void CudaBackend::generate(Script &, const BackendContext &) { throw BackendError("cuda backend: not implemented yet"); }
+
+namespace {
+
+enum class Target { Host, Device };
+
+// Float literal text: what `std::ostream << double` prints (6 significant digits), with
+// ".0" appended when the text has no '.', as the reference does (GenericPrinter.cpp:42-50).
+// Deviation: the reference appends ".0" also to exponent forms ("1e+06.0", which is not
+// valid C); exponent forms are left untouched here.
+std::string floatText(double v) {
+  std::ostringstream s;
+  s << v;
+  std::string t = s.str();
+  if (t.find('.') == std::string::npos && t.find('e') == std::string::npos && std::isfinite(v))
+    t += ".0";
+  return t;
 }
+
+std::string quoted(const std::string &s) {
+  std::string out = "\"";
+  for (char c : s) {
+    if (c == '"' || c == '\\') out.push_back('\\');
+    out.push_back(c);
+  }
+  return out + "\"";
+}
+
+class Writer {
+public:
+  Writer &operator<<(const std::string &s) { buf << s; return *this; }
+  Writer &operator<<(const char *s) { buf << s; return *this; }
+  Writer &operator<<(char c) { buf << c; return *this; }
+  Writer &operator<<(long v) { buf << v; return *this; }
+  Writer &operator<<(int v) { buf << v; return *this; }
+  Writer &operator<<(unsigned v) { buf << v; return *this; }
+  Writer &operator<<(size_t v) { buf << v; return *this; }
+  void nl() { buf << "\n" << std::string(4 * depth, ' '); }
+  void indent() { depth++; }
+  void outdent() { depth--; }
+  std::string str() const { return buf.str(); }
+private:
+  std::ostringstream buf;
+  int depth = 0;
+};
+
+struct StepInfo {
+  FuncDecl *fn;
+  AgentDecl *self;
+  std::set<std::string> reads;   // members of `in` read
+  std::set<std::string> writes;  // members of `out` assigned (identity copies excluded)
+  bool wholeIn = false, wholeOut = false;
+};
+
+class CudaPrinter {
+public:
+  CudaPrinter(Script &script, bool useFloat, const Config &config)
+      : script(script), useFloat(useFloat), config(config) {}
+
+  std::string hostSource();
+  std::string kernelSource();
+
+private:
+  Script &script;
+  bool useFloat;
+  const Config &config;
+  Writer w;
+  Target target = Target::Host;
+  int anon = 0;
+  // device-function context
+  const FuncDecl *curFn = nullptr;
+  const StepInfo *curStep = nullptr;
+  std::vector<StepInfo> steps;
+
+  std::string label() { return "_var" + std::to_string(anon++); }
+  bool dev() const { return target == Target::Device; }
+
+  int agentIndex(const AgentDecl *a) const {
+    for (size_t i = 0; i < script.agents.size(); i++) if (script.agents[i] == a) return (int)i;
+    return -1;
+  }
+  // first SoA column of member m (float3 members take three columns)
+  static int columnOf(const AgentDecl &a, int member) {
+    int c = 0;
+    for (int i = 0; i < member; i++) c += a.members[i]->type.k == TK::Vec3 ? 3 : 1;
+    return c;
+  }
+  static int columnCount(const AgentDecl &a) { return columnOf(a, (int)a.members.size()); }
+
+  std::string typeName(const Ty &t) const;
+  std::string storageName(const Ty &t) const;
+  static const char *typeTag(const Ty &t);
+
+  void expr(const Expr &e);
+  std::string exprText(const Expr &e) {
+    Writer tmp;
+    std::swap(w, tmp);
+    expr(e);
+    std::string text = w.str();
+    std::swap(w, tmp);
+    return text;
+  }
+  void args(const Expr &call);
+  void vecBinary(Op op, const Expr &l, const Expr &r);
+  void callExpr(const Expr &e);
+  void stmt(const Stmt &s);
+  void stmts(const std::vector<StmtP> &v);
+  void forStmt(const Stmt &s);
+  void nearLoop(const Stmt &s);
+  void constDecl(const ConstDecl &c);
+  void function(const FuncDecl &f);
+  void agentStruct(const AgentDecl &a);
+
+  void analyseSteps();
+  void scanStepExpr(const Expr &e, StepInfo &si, const FuncDecl &f);
+  void scanStepStmt(const Stmt &s, StepInfo &si, const FuncDecl &f);
+  void reachable(const FuncDecl *f, std::set<const FuncDecl *> &seen);
+  void reachableExpr(const Expr &e, std::set<const FuncDecl *> &seen);
+  void reachableStmt(const Stmt &s, std::set<const FuncDecl *> &seen);
+
+  void stepKernel(const StepInfo &si, int index);
+  void loadMember(const AgentDecl &a, int m, const std::string &dst, const std::string &view,
+                  const std::string &idx);
+  void storeMember(const AgentDecl &a, int m, const std::string &cols, const std::string &idx,
+                   const std::string &value);
+  void hostSimulate();
+  void hostSeqSupport();
+};
+
+// ---------------------------------------------------------------------------------------
+// types
+// ---------------------------------------------------------------------------------------
+std::string CudaPrinter::typeName(const Ty &t) const {
+  switch (t.k) {
+    case TK::Void: return "void";
+    case TK::Bool: return "bool";
+    case TK::Int: return "int";
+    case TK::Float: return "abl_real";
+    case TK::String: return "const char*";
+    case TK::Vec2: return "abl_float2";
+    case TK::Vec3: return "abl_float3";
+    case TK::Agent: return dev() ? t.agent->name : t.agent->name + "*";
+    case TK::Array: return dev() ? storageName(t.elem()) : "abl_array*";
+    default: throw BackendError("cuda backend: unsupported type " + t.str());
+  }
+}
+
+std::string CudaPrinter::storageName(const Ty &t) const {
+  if (t.isAgent()) return t.agent->name;
+  return typeName(t);
+}
+
+const char *CudaPrinter::typeTag(const Ty &t) {
+  switch (t.k) {
+    case TK::Bool: return "ABL_TYPE_BOOL";
+    case TK::Int: return "ABL_TYPE_INT";
+    case TK::Float: return "ABL_TYPE_FLOAT";
+    case TK::Vec2: return "ABL_TYPE_FLOAT2";
+    case TK::Vec3: return "ABL_TYPE_FLOAT3";
+    default: throw BackendError("cuda backend: agent members must be bool, int, float, float2 or float3");
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// expressions
+// ---------------------------------------------------------------------------------------
+void CudaPrinter::args(const Expr &call) {
+  for (size_t i = 0; i < call.kids.size(); i++) {
+    if (i) w << ", ";
+    expr(*call.kids[i]);
+  }
+}
+
+void CudaPrinter::vecBinary(Op op, const Expr &l, const Expr &r) {
+  const Ty &v = l.type.isVec() ? l.type : r.type;
+  w << "float" << v.vecLen() << "_";
+  switch (op) {
+    case Op::Add: w << "add"; break;
+    case Op::Sub: w << "sub"; break;
+    case Op::Div: w << "div_scalar"; break;
+    case Op::Mul: w << "mul_scalar"; break;
+    case Op::Eq: w << "equals"; break;
+    case Op::Ne: w << "not_equals"; break;
+    default: throw BackendError("cuda backend: unsupported vector operator");
+  }
+  w << "(";
+  expr(l);
+  w << ", ";
+  expr(r);
+  w << ")";
+}
+
+void CudaPrinter::expr(const Expr &e) {
+  switch (e.kind) {
+    case Expr::BoolLit: w << (e.bval ? "true" : "false"); return;
+    case Expr::IntLit: w << e.ival; return;
+    case Expr::FloatLit:
+      if (dev()) w << "ABL_R(" << floatText(e.fval) << ")";
+      else w << floatText(e.fval);
+      return;
+    case Expr::StrLit: w << quoted(e.name); return;
+    case Expr::Var: w << e.name; return;
+
+    case Expr::Unary:
+      if (e.kids[0]->type.isVec()) {
+        if (e.op == Op::Pos) { expr(*e.kids[0]); return; }
+        // -v is v * -1.0, exactly like the reference lowering
+        w << "float" << e.kids[0]->type.vecLen() << "_mul_scalar(";
+        expr(*e.kids[0]);
+        w << ", " << (dev() ? "ABL_R(-1.0)" : "-1.0") << ")";
+        return;
+      }
+      w << "(" << opSigil(e.op);
+      expr(*e.kids[0]);
+      w << ")";
+      return;
+
+    case Expr::Binary: {
+      const Expr &l = *e.kids[0], &r = *e.kids[1];
+      if (l.type.isVec() || r.type.isVec()) { vecBinary(e.op, l, r); return; }
+      if (e.op == Op::Mod && !(l.type.isInt() && r.type.isInt())) {
+        w << (dev() ? "abl_fmod(" : "fmod(");
+        expr(l); w << ", "; expr(r); w << ")";
+        return;
+      }
+      w << "("; expr(l); w << " " << opSigil(e.op) << " "; expr(r); w << ")";
+      return;
+    }
+
+    case Expr::Ternary:
+      w << "("; expr(*e.kids[0]); w << " ? "; expr(*e.kids[1]); w << " : "; expr(*e.kids[2]); w << ")";
+      return;
+
+    case Expr::Member:
+      expr(*e.kids[0]);
+      w << ((e.kids[0]->type.isAgent() && !dev()) ? "->" : ".") << e.name;
+      return;
+
+    case Expr::Index:
+      if (!dev() && e.kids[0]->type.isArray() && e.kids[0]->kind == Expr::Var &&
+          e.kids[0]->sym && !e.kids[0]->sym->global) {
+        // local arrays on the host are abl_array handles
+        w << "(*ABL_AT("; expr(*e.kids[0]); w << ", " << storageName(e.type) << ", ";
+        expr(*e.kids[1]); w << "))";
+        return;
+      }
+      expr(*e.kids[0]); w << "["; expr(*e.kids[1]); w << "]";
+      return;
+
+    case Expr::Call: callExpr(e); return;
+
+    case Expr::AgentCreate:
+      if (dev()) {
+        // only reachable as the argument of add(), handled in callExpr
+        throw BackendError("cuda backend: agent creation outside add() is not supported in step functions");
+      }
+      w << "(" << e.name << ") {";
+      w.indent();
+      for (size_t i = 0; i < e.kids.size(); i++) {
+        w.nl();
+        w << "." << e.initNames[i] << " = ";
+        expr(*e.kids[i]);
+        w << ",";
+      }
+      w.outdent();
+      w.nl();
+      w << "}";
+      return;
+
+    case Expr::ArrayInit:
+      w << "{ ";
+      args(e);
+      w << " }";
+      return;
+
+    case Expr::NewArray:
+      if (dev()) throw BackendError("cuda backend: `new` arrays are not supported in step functions");
+      w << "abl_array_zeroed(sizeof(" << storageName(e.elemTy) << "), ";
+      expr(*e.kids[0]);
+      w << ")";
+      return;
+
+    case Expr::EnvAccess:
+      throw BackendError("cuda backend: unresolved environment access");
+  }
+}
+
+void CudaPrinter::callExpr(const Expr &e) {
+  if (e.ckind == Expr::Ctor) {
+    if (e.type.isVec()) {
+      w << "float" << e.type.vecLen() << "_" << (e.kids.size() == 1 ? "fill" : "create") << "(";
+      args(e);
+      w << ")";
+    } else {
+      w << "(" << typeName(e.type) << ") ";
+      expr(*e.kids[0]);
+    }
+    return;
+  }
+
+  const std::string &t = e.target;
+  if (e.ckind == Expr::Builtin) {
+    if (t == "add") {
+      AgentDecl *agent = e.paramTys[0].agent;
+      if (!dev()) {
+        w << "*(" << agent->name << " *)abl_array_push(&agents_" << agent->name << ", sizeof("
+          << agent->name << ")) = ";
+        expr(*e.kids[0]);
+        return;
+      }
+      // device: stage the new agent in the per-parent slot; the runtime appends it at commit
+      const Expr &c = *e.kids[0];
+      w << "{ _ctx.added = true;";
+      for (size_t m = 0; m < agent->members.size(); m++) {
+        const Expr *init = c.init(agent->members[m]->name);
+        w << " ";
+        storeMember(*agent, (int)m, "_a.add_cols", "_i", exprText(*init));
+      }
+      w << " }";
+      return;
+    }
+    if (t == "save") {
+      w << "abl_model_save(";
+      args(e);
+      w << ")";
+      return;
+    }
+    if (t == "removeCurrent") {
+      if (!dev()) throw BackendError("cuda backend: removeCurrent() outside a step function");
+      w << "_ctx.dead = true";
+      return;
+    }
+    if (t == "count") {
+      w << "abl_model_count(" << agentIndex(e.paramTys[0].agent) << ")";
+      return;
+    }
+    if (t == "count_member") {
+      const Ty &mt = e.paramTys[0];
+      int mi = mt.agent->memberIndex(mt.member->name);
+      bool isFloat = mt.member->type.isFloat();
+      w << (isFloat ? "abl_model_count_member_float(" : "abl_model_count_member_int(")
+        << agentIndex(mt.agent) << ", " << mi << ", ";
+      expr(*e.kids[1]);
+      w << ")";
+      return;
+    }
+    if (t == "sum") {
+      const Ty &mt = e.paramTys[0];
+      int mi = mt.agent->memberIndex(mt.member->name);
+      const Ty &ty = mt.member->type;
+      if (ty.isInt() || ty.isBool()) w << "abl_model_sum_int(" << agentIndex(mt.agent) << ", " << mi << ")";
+      else if (ty.isFloat()) w << "abl_model_sum_float(" << agentIndex(mt.agent) << ", " << mi << ")";
+      else if (ty.k == TK::Vec2) w << "abl_model_sum_float2(" << agentIndex(mt.agent) << ", " << mi << ")";
+      else w << "abl_model_sum_float3(" << agentIndex(mt.agent) << ", " << mi << ")";
+      return;
+    }
+    if (t == "log_csv") {
+      w << "{ abl_host_log_open(\"log.csv\");";
+      for (size_t i = 0; i < e.kids.size(); i++) {
+        w << (e.kids[i]->type.isInt() ? " abl_host_log_int(" : " abl_host_log_float(")
+          << (i == 0 ? 1 : 0) << ", ";
+        expr(*e.kids[i]);
+        w << ");";
+      }
+      w << " abl_host_log_end(); }";
+      return;
+    }
+    if (t == "getLastExecTime") { w << "abl_model_last_exec_time()"; return; }
+    if (t == "near") throw BackendError("cuda backend: near() is only supported as a for-loop range");
+    if (t == "random_float" || t == "random_int") {
+      w << t << "(";
+      if (dev()) w << "_ctx, ";
+      args(e);
+      w << ")";
+      return;
+    }
+    if (t == "min" || t == "max") {
+      w << "abl_" << t << "(";
+      args(e);
+      w << ")";
+      return;
+    }
+    w << t << "(";
+    args(e);
+    w << ")";
+    return;
+  }
+
+  // user function
+  w << t << "(";
+  if (dev()) { w << "_ctx"; if (!e.kids.empty()) w << ", "; }
+  args(e);
+  w << ")";
+}
+
+// ---------------------------------------------------------------------------------------
+// statements
+// ---------------------------------------------------------------------------------------
+void CudaPrinter::stmts(const std::vector<StmtP> &v) {
+  for (const StmtP &s : v) { w.nl(); stmt(*s); }
+}
+
+void CudaPrinter::stmt(const Stmt &s) {
+  switch (s.kind) {
+    case Stmt::ExprS: {
+      const Expr &e = *s.e[0];
+      expr(e);
+      bool braced = e.kind == Expr::Call && e.ckind == Expr::Builtin &&
+                    (e.target == "log_csv" || (dev() && e.target == "add"));
+      if (!braced) w << ";";
+      return;
+    }
+    case Stmt::Block:
+      w << "{";
+      w.indent(); stmts(s.body); w.outdent();
+      w.nl();
+      w << "}";
+      return;
+    case Stmt::VarDecl: {
+      const Ty &t = s.declTy;
+      if (!dev() && (t.isAgent() || t.isArray())) {
+        // host: agents and arrays live in a storage variable, the name is a pointer to it
+        std::string store = label();
+        w << (t.isArray() ? "abl_array" : t.agent->name) << " " << store;
+        if (!s.e.empty()) {
+          w << " = ";
+          if (s.e[0]->type.isAgent() && s.e[0]->kind != Expr::AgentCreate) w << "*";
+          expr(*s.e[0]);
+        }
+        w << ";";
+        w.nl();
+        w << typeName(t) << " " << s.varName << " = &" << store << ";";
+        return;
+      }
+      w << typeName(t) << " " << s.varName;
+      if (!s.e.empty()) { w << " = "; expr(*s.e[0]); }
+      w << ";";
+      return;
+    }
+    case Stmt::Assign:
+      if (s.e[1]->type.isAgent() && !dev()) {
+        w << "*"; expr(*s.e[0]); w << " = *"; expr(*s.e[1]); w << ";";
+        return;
+      }
+      expr(*s.e[0]); w << " = "; expr(*s.e[1]); w << ";";
+      return;
+    case Stmt::AssignOp: {
+      const Expr &l = *s.e[0], &r = *s.e[1];
+      bool special = l.type.isVec() || r.type.isVec() ||
+                     (s.op == Op::Mod && !(l.type.isInt() && r.type.isInt()));
+      if (special) {
+        expr(l);
+        w << " = ";
+        if (l.type.isVec() || r.type.isVec()) vecBinary(s.op, l, r);
+        else { w << (dev() ? "abl_fmod(" : "fmod("); expr(l); w << ", "; expr(r); w << ")"; }
+        w << ";";
+        return;
+      }
+      expr(l); w << " " << opSigil(s.op) << "= "; expr(r); w << ";";
+      return;
+    }
+    case Stmt::If:
+      w << "if ("; expr(*s.e[0]); w << ") ";
+      stmt(*s.body[0]);
+      if (s.body.size() > 1) { w << " else "; stmt(*s.body[1]); }
+      return;
+    case Stmt::While:
+      w << "while ("; expr(*s.e[0]); w << ") ";
+      stmt(*s.body[0]);
+      return;
+    case Stmt::For: forStmt(s); return;
+    case Stmt::Return:
+      if (s.e.empty()) w << "return;";
+      else { w << "return "; expr(*s.e[0]); w << ";"; }
+      return;
+    case Stmt::Break: w << "break;"; return;
+    case Stmt::Continue: w << "continue;"; return;
+    case Stmt::Simulate:
+      if (dev()) throw BackendError("cuda backend: simulate inside device code");
+      w << "abl_model_simulate("; expr(*s.e[0]); w << ");";
+      return;
+  }
+}
+
+void CudaPrinter::forStmt(const Stmt &s) {
+  if (s.forKind == Stmt::ForRange) {
+    std::string end = label();
+    const Expr &range = *s.e[0];
+    w << "for (int " << s.varName << " = "; expr(*range.kids[0]);
+    w << ", " << end << " = "; expr(*range.kids[1]);
+    w << "; " << s.varName << " < " << end << "; ++" << s.varName << ") ";
+    stmt(*s.body[0]);
+    return;
+  }
+  if (s.forKind == Stmt::ForNear) { nearLoop(s); return; }
+
+  // array iteration
+  const Expr &arr = *s.e[0];
+  std::string idx = label();
+  if (dev() || (arr.kind == Expr::Var && arr.sym && arr.sym->global)) {
+    // global constant array with a compile-time length
+    w << "for (int " << idx << " = 0; " << idx << " < (int)(sizeof("; expr(arr);
+    w << ") / sizeof(("; expr(arr); w << ")[0])); " << idx << "++) {";
+    w.indent(); w.nl();
+    w << typeName(s.declTy) << " " << s.varName << " = "; expr(arr); w << "[" << idx << "];";
+    w.nl(); stmt(*s.body[0]);
+    w.outdent(); w.nl(); w << "}";
+    return;
+  }
+  std::string handle = label();
+  w << "abl_array* " << handle << " = "; expr(arr); w << ";";
+  w.nl();
+  w << "for (size_t " << idx << " = 0; " << idx << " < " << handle << "->len; " << idx << "++) {";
+  w.indent(); w.nl();
+  if (s.declTy.isAgent())
+    w << s.declTy.agent->name << "* " << s.varName << " = ABL_AT(" << handle << ", "
+      << s.declTy.agent->name << ", " << idx << ");";
+  else
+    w << typeName(s.declTy) << " " << s.varName << " = *ABL_AT(" << handle << ", "
+      << storageName(s.declTy) << ", " << idx << ");";
+  w.nl(); stmt(*s.body[0]);
+  w.outdent(); w.nl(); w << "}";
+}
+
+// for (T nx : near(agent, radius)) body   — device only
+void CudaPrinter::nearLoop(const Stmt &s) {
+  if (!dev() || !curStep)
+    throw BackendError("cuda backend: for-near loops are only supported directly inside step functions");
+  const Expr &call = *s.e[0];
+  const Expr &agentExpr = *call.kids[0];
+  const Expr &radius = *call.kids[1];
+  AgentDecl *nbr = s.declTy.agent;
+  AgentMember *pos = nbr->position();
+  AgentDecl *selfTy = agentExpr.type.agent;
+  AgentMember *selfPos = selfTy ? selfTy->position() : nullptr;
+  if (!selfPos) throw BackendError("cuda backend: near() needs an agent with a position");
+  int dim = pos->type.vecLen();
+  std::string it = label();
+
+  w << "{";
+  w.indent(); w.nl();
+  w << "abl_near_iter " << it << ";";
+  w.nl();
+  w << it << ".init" << dim << "(_a, "; expr(agentExpr); w << "." << selfPos->name << ", true);";
+  w.nl();
+  w << "for (; " << it << ".valid(); " << it << ".next()) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "j = " << it << ".index();";
+  w.nl();
+  w << nbr->name << " " << s.varName << ";";
+  // position first (needed by the radius filter), then the members the body reads
+  std::set<std::string> members = curFn->nearMembers;
+  members.insert(pos->name);
+  for (size_t m = 0; m < nbr->members.size(); m++) {
+    if (!members.count(nbr->members[m]->name)) continue;
+    w.nl();
+    loadMember(*nbr, (int)m, s.varName + "." + nbr->members[m]->name, "_a.nbr.in", it + "j");
+  }
+  w.nl();
+  // inclusive radius, self included, same operand order as the reference's filter
+  // (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip
+  w << "if (dist_float" << dim << "(" << s.varName << "." << pos->name << ", ";
+  expr(agentExpr);
+  w << "." << selfPos->name << ") > ";
+  expr(radius);
+  w << ") continue;";
+  w.nl();
+  stmt(*s.body[0]);
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "}";
+}
+
+// ---------------------------------------------------------------------------------------
+// declarations
+// ---------------------------------------------------------------------------------------
+void CudaPrinter::constDecl(const ConstDecl &c) {
+  const Ty &t = c.type;
+  if (!dev()) {
+    // same text as the reference: `double W = 141.421;`, vectors as brace initialisers
+    Ty base = c.isArray ? t.elem() : t;
+    w << typeName(base) << " " << c.name << (c.isArray ? "[]" : "") << " = ";
+    if (base.isVec() && !c.isArray) {
+      w << "{";
+      args(*c.init);
+      w << "};";
+    } else {
+      expr(*c.init);
+      w << ";";
+    }
+    return;
+  }
+  if (c.isArray) {
+    Ty base = t.elem();
+    w << "__device__ const " << typeName(base) << " " << c.name << "[] = ";
+    if (base.isVec()) throw BackendError("cuda backend: vector constant arrays are not supported");
+    expr(*c.init);
+    w << ";";
+    return;
+  }
+  if (t.isVec()) {
+    w << "__device__ const " << typeName(t) << " " << c.name << " = {";
+    args(*c.init);
+    w << "};";
+    return;
+  }
+  if (t.isString()) return;
+  w << "static constexpr " << typeName(t) << " " << c.name << " = ";
+  expr(*c.init);
+  w << ";";
+}
+
+void CudaPrinter::function(const FuncDecl &f) {
+  curFn = &f;
+  if (dev()) {
+    w << "__device__ " << typeName(f.retTy) << " " << f.emitName << "(abl_ctx& _ctx";
+    for (const Param &p : f.params) {
+      w << ", ";
+      if (p.type.isAgent()) w << "const " << p.type.agent->name << "& " << p.name;
+      else w << typeName(p.type) << " " << p.name;
+    }
+    w << ") {";
+  } else {
+    w << typeName(f.retTy) << " " << f.emitName << "(";
+    for (size_t i = 0; i < f.params.size(); i++) {
+      if (i) w << ", ";
+      w << typeName(f.params[i].type) << " " << f.params[i].name;
+    }
+    if (f.params.empty()) w << "void";
+    w << ") {";
+  }
+  w.indent(); stmts(f.body); w.outdent();
+  w.nl();
+  w << "}";
+  curFn = nullptr;
+}
+
+void CudaPrinter::agentStruct(const AgentDecl &a) {
+  w << "typedef struct {";
+  w.indent();
+  for (auto &m : a.members) { w.nl(); w << typeName(m->type) << " " << m->name << ";"; }
+  w.outdent();
+  w.nl();
+  w << "} " << a.name << ";";
+}
+
+// ---------------------------------------------------------------------------------------
+// step analysis: which members of `in` are read / of `out` are written
+// ---------------------------------------------------------------------------------------
+void CudaPrinter::scanStepExpr(const Expr &e, StepInfo &si, const FuncDecl &f) {
+  const Param &p = f.params[0];
+  if (e.kind == Expr::Member && e.kids[0]->kind == Expr::Var) {
+    const Expr &base = *e.kids[0];
+    if (base.sym && base.sym == p.sym) { si.reads.insert(e.name); return; }
+    if (base.sym && base.sym == p.outSym) { si.reads.insert(e.name); return; }  // reads copy-through value
+  }
+  if (e.kind == Expr::Var && e.sym && (e.sym == p.sym)) si.wholeIn = true;
+  if (e.kind == Expr::Var && e.sym && (e.sym == p.outSym)) { si.wholeOut = true; si.wholeIn = true; }
+  if (e.kind == Expr::Call && e.ckind == Expr::Builtin && e.target == "near") {
+    // near(in, r): only the position is needed, not the whole record
+    const Expr &a = *e.kids[0];
+    if (a.kind == Expr::Var && a.sym == p.sym) {
+      if (AgentMember *pm = p.type.agent->position()) si.reads.insert(pm->name);
+      scanStepExpr(*e.kids[1], si, f);
+      return;
+    }
+  }
+  for (const ExprP &k : e.kids) scanStepExpr(*k, si, f);
+}
+
+static const Expr *outMemberRoot(const Expr &lhs, const Param &p) {
+  // out.m, out.m.x -> the Member node directly on `out`
+  const Expr *e = &lhs;
+  while (e->kind == Expr::Member || e->kind == Expr::Index) {
+    const Expr &base = *e->kids[0];
+    if (e->kind == Expr::Member && base.kind == Expr::Var && base.sym && base.sym == p.outSym) return e;
+    e = &base;
+  }
+  return nullptr;
+}
+
+void CudaPrinter::scanStepStmt(const Stmt &s, StepInfo &si, const FuncDecl &f) {
+  const Param &p = f.params[0];
+  if (s.kind == Stmt::Assign || s.kind == Stmt::AssignOp) {
+    const Expr *root = outMemberRoot(*s.e[0], p);
+    if (root) {
+      bool identity = false;
+      if (s.kind == Stmt::Assign && root == s.e[0].get()) {
+        const Expr &r = *s.e[1];
+        identity = r.kind == Expr::Member && r.name == root->name && r.kids[0]->kind == Expr::Var &&
+                   r.kids[0]->sym == p.sym;
+      }
+      if (!identity) si.writes.insert(root->name);
+      if (s.kind == Stmt::AssignOp || root != s.e[0].get()) si.reads.insert(root->name);
+      scanStepExpr(*s.e[1], si, f);
+      return;
+    }
+    if (s.e[0]->kind == Expr::Var && s.e[0]->sym == p.outSym) {
+      si.wholeOut = true;
+      scanStepExpr(*s.e[1], si, f);
+      return;
+    }
+  }
+  for (const ExprP &e : s.e) scanStepExpr(*e, si, f);
+  for (const StmtP &b : s.body) scanStepStmt(*b, si, f);
+}
+
+void CudaPrinter::analyseSteps() {
+  steps.clear();
+  if (!script.simulate) return;
+  for (FuncDecl *f : script.simulate->steps) {
+    StepInfo si;
+    si.fn = f;
+    si.self = f->stepAgent();
+    for (const StmtP &s : f->body) scanStepStmt(*s, si, *f);
+    if (si.wholeIn) for (auto &m : si.self->members) si.reads.insert(m->name);
+    if (si.wholeOut) for (auto &m : si.self->members) si.writes.insert(m->name);
+    f->writtenMembers = si.writes;
+    steps.push_back(si);
+  }
+}
+
+void CudaPrinter::reachableExpr(const Expr &e, std::set<const FuncDecl *> &seen) {
+  if (e.kind == Expr::Call && e.ckind == Expr::User && e.callee) reachable(e.callee, seen);
+  for (const ExprP &k : e.kids) reachableExpr(*k, seen);
+}
+void CudaPrinter::reachableStmt(const Stmt &s, std::set<const FuncDecl *> &seen) {
+  for (const ExprP &e : s.e) reachableExpr(*e, seen);
+  for (const StmtP &b : s.body) reachableStmt(*b, seen);
+}
+void CudaPrinter::reachable(const FuncDecl *f, std::set<const FuncDecl *> &seen) {
+  if (!seen.insert(f).second) return;
+  for (const StmtP &s : f->body) reachableStmt(*s, seen);
+}
+
+// ---------------------------------------------------------------------------------------
+// host program
+// ---------------------------------------------------------------------------------------
+std::string CudaPrinter::hostSource() {
+  target = Target::Host;
+  w = Writer();
+  anon = 0;
+  analyseSteps();
+  w << "/* Generated by OpenABL (cuda backend, sm_100a). Host program. */";
+  w.nl();
+  w << "#include <stdio.h>"; w.nl();
+  w << "#include \"abl_host.h\""; w.nl(); w.nl();
+
+  for (AgentDecl *a : script.agents) {
+    agentStruct(*a);
+    w.nl();
+    w << "static const abl_member_desc " << a->name << "_members[] = {";
+    w.indent();
+    for (auto &m : a->members) {
+      w.nl();
+      w << "{ " << typeTag(m->type) << ", offsetof(" << a->name << ", " << m->name << "), \""
+        << m->name << "\", " << (m->isPosition ? 1 : 0) << " },";
+    }
+    w.nl();
+    w << "{ ABL_TYPE_END, 0, NULL, 0 }";
+    w.outdent(); w.nl();
+    w << "};"; w.nl();
+    w << "abl_array agents_" << a->name << ";"; w.nl(); w.nl();
+  }
+  w << "abl_host_type abl_model_types[] = {";
+  w.indent();
+  for (AgentDecl *a : script.agents) {
+    w.nl();
+    w << "{ { \"" << a->name << "\", " << a->name << "_members, " << a->members.size()
+      << ", sizeof(" << a->name << ") }, &agents_" << a->name << ", -1 },";
+  }
+  w.nl();
+  w << "{ { NULL, NULL, 0, 0 }, NULL, -1 }";
+  w.outdent(); w.nl();
+  w << "};"; w.nl();
+  w << "const int abl_model_n_types = " << script.agents.size() << ";"; w.nl();
+  w << "const int abl_model_use_float = " << (useFloat ? 1 : 0) << ";"; w.nl(); w.nl();
+
+  hostSeqSupport();
+
+  for (ConstDecl *c : script.consts) { constDecl(*c); w.nl(); }
+  w.nl();
+
+  FuncDecl *mainFn = script.mainFunc;
+  for (FuncDecl *f : script.funcs) {
+    if (f->isStep() || f == mainFn) continue;
+    function(*f);
+    w.nl();
+  }
+  w.nl();
+  hostSimulate();
+
+  // main(): whole user main as abl_model_main, plus the pre-simulate part on its own
+  curFn = mainFn;
+  w << "int abl_model_main(void) {";
+  w.indent(); stmts(mainFn->body); w.nl();
+  w << "return 0;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "/* statements of main() that precede `simulate` (population set-up only) */"; w.nl();
+  w << "int abl_model_populate(void) {";
+  w.indent();
+  for (const StmtP &s : mainFn->body) {
+    if (s->kind == Stmt::Simulate) break;
+    w.nl(); stmt(*s);
+  }
+  w.nl();
+  w << "return 0;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl(); w.nl();
+  curFn = nullptr;
+
+  w << "#ifndef ABL_MODEL_NO_MAIN"; w.nl();
+  w << "int main(void) { return abl_model_main(); }"; w.nl();
+  w << "#endif"; w.nl();
+  return w.str();
+}
+
+void CudaPrinter::hostSeqSupport() {
+  w << "/* runtime handle used by `simulate` and by reductions in the sequential step */"; w.nl();
+  w << "static abl_runtime *abl_rt = NULL;"; w.nl();
+  w << "void abl_model_set_runtime(abl_runtime *rt) { abl_rt = rt; }"; w.nl();
+  w << "abl_runtime *abl_model_runtime(void) { return abl_rt; }"; w.nl();
+  w << "extern int abl_model_setup(abl_runtime *rt);"; w.nl();
+  w << "extern int abl_model_parallel_steps(abl_runtime *rt);"; w.nl();
+  w << "#define ABL_UNUSED __attribute__((unused))"; w.nl();
+  w << "static ABL_UNUSED int abl_model_count(int t) { int r = 0; abl_host_check(abl_cuda_count(abl_rt, abl_model_types[t].pool, &r), \"count\"); return r; }"; w.nl();
+  w << "static ABL_UNUSED int abl_model_count_member_int(int t, int m, int v) { int r = 0; abl_host_check(abl_cuda_count_member_int(abl_rt, abl_model_types[t].pool, m, v, &r), \"count\"); return r; }"; w.nl();
+  w << "static ABL_UNUSED int abl_model_count_member_float(int t, int m, double v) { int r = 0; abl_host_check(abl_cuda_count_member_float(abl_rt, abl_model_types[t].pool, m, v, &r), \"count\"); return r; }"; w.nl();
+  w << "static ABL_UNUSED int abl_model_sum_int(int t, int m) { int r = 0; abl_host_check(abl_cuda_sum_int(abl_rt, abl_model_types[t].pool, m, &r), \"sum\"); return r; }"; w.nl();
+  w << "static ABL_UNUSED abl_real abl_model_sum_float(int t, int m) { double r = 0; abl_host_check(abl_cuda_sum_float(abl_rt, abl_model_types[t].pool, m, 0, &r), \"sum\"); return (abl_real)r; }"; w.nl();
+  w << "static ABL_UNUSED abl_float2 abl_model_sum_float2(int t, int m) { double x = 0, y = 0; abl_host_check(abl_cuda_sum_float(abl_rt, abl_model_types[t].pool, m, 0, &x), \"sum\"); abl_host_check(abl_cuda_sum_float(abl_rt, abl_model_types[t].pool, m, 1, &y), \"sum\"); return float2_create((abl_real)x, (abl_real)y); }"; w.nl();
+  w << "static ABL_UNUSED abl_float3 abl_model_sum_float3(int t, int m) { double v[3] = {0, 0, 0}; for (int k = 0; k < 3; k++) abl_host_check(abl_cuda_sum_float(abl_rt, abl_model_types[t].pool, m, k, &v[k]), \"sum\"); return float3_create((abl_real)v[0], (abl_real)v[1], (abl_real)v[2]); }"; w.nl();
+  w << "static ABL_UNUSED abl_real abl_model_last_exec_time(void) { double s = 0; abl_host_check(abl_cuda_last_exec_time(abl_rt, &s), \"getLastExecTime\"); return (abl_real)s; }"; w.nl();
+  w << "static ABL_UNUSED void abl_model_save(const char *path) {"; w.nl();
+  w << "    abl_host_save_json(abl_model_types, abl_model_n_types, path);"; w.nl();
+  w << "    if (getenv(\"ABL_DUMP_STATE\")) { char raw[4096]; snprintf(raw, sizeof raw, \"%s.bin\", path); abl_host_save_raw(abl_model_types, abl_model_n_types, raw); }"; w.nl();
+  w << "}"; w.nl();
+  w.nl();
+}
+
+void CudaPrinter::hostSimulate() {
+  FuncDecl *seq = script.simulate ? script.simulate->seqStep : nullptr;
+  w << "/* one timestep: all parallel step functions in order, then the sequential step */"; w.nl();
+  w << "int abl_model_timestep(abl_runtime *rt) {"; w.nl();
+  w << "    abl_rt = rt;"; w.nl();
+  w << "    abl_host_check(abl_cuda_begin_timestep(rt), \"begin_timestep\");"; w.nl();
+  w << "    abl_host_check(abl_model_parallel_steps(rt), \"step\");"; w.nl();
+  if (seq) { w << "    " << seq->emitName << "();"; w.nl(); }
+  w << "    abl_host_check(abl_cuda_end_timestep(rt), \"end_timestep\");"; w.nl();
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "int abl_model_upload(abl_runtime *rt) {"; w.nl();
+  w << "    for (int t = 0; t < abl_model_n_types; t++)"; w.nl();
+  w << "        abl_host_check(abl_cuda_upload(rt, abl_model_types[t].pool, abl_model_types[t].agents->data, abl_model_types[t].agents->len), \"upload\");"; w.nl();
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl();
+  w << "int abl_model_download(abl_runtime *rt) {"; w.nl();
+  w << "    for (int t = 0; t < abl_model_n_types; t++) {"; w.nl();
+  w << "        size_t n = 0;"; w.nl();
+  w << "        abl_host_check(abl_cuda_pool_size(rt, abl_model_types[t].pool, &n), \"pool_size\");"; w.nl();
+  w << "        abl_array_resize(abl_model_types[t].agents, abl_model_types[t].desc.stride, n);"; w.nl();
+  w << "        abl_host_check(abl_cuda_download(rt, abl_model_types[t].pool, abl_model_types[t].agents->data, n, &n), \"download\");"; w.nl();
+  w << "    }"; w.nl();
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "/* the `simulate` statement: upload, run, download (replaces the reference's inline"; w.nl();
+  w << "   double-buffered OpenMP loop) */"; w.nl();
+  w << "static void abl_model_simulate(int timesteps) {"; w.nl();
+  w << "    abl_config cfg;"; w.nl();
+  w << "    abl_cuda_default_config(&cfg);"; w.nl();
+  w << "    cfg.use_float = abl_model_use_float;"; w.nl();
+  w << "    cfg.block_size = " << config.getInt("cuda.block_size", 128) << ";"; w.nl();
+  w << "    cfg.tile_neighbours = " << (config.getBool("cuda.tile", true) ? 1 : 0) << ";"; w.nl();
+  w << "    if (getenv(\"ABL_CUDA_DEVICE\")) cfg.device = atoi(getenv(\"ABL_CUDA_DEVICE\"));"; w.nl();
+  w << "    abl_runtime *rt = NULL;"; w.nl();
+  w << "    abl_host_check(abl_cuda_create(&rt, &cfg), \"create\");"; w.nl();
+  w << "    abl_host_check(abl_model_setup(rt), \"setup\");"; w.nl();
+  w << "    abl_model_upload(rt);"; w.nl();
+  w << "    for (int t = 0; t < timesteps; t++) abl_model_timestep(rt);"; w.nl();
+  w << "    abl_model_download(rt);"; w.nl();
+  w << "    abl_rt = NULL;"; w.nl();
+  w << "    abl_host_check(abl_cuda_destroy(rt), \"destroy\");"; w.nl();
+  w << "}"; w.nl(); w.nl();
+}
+
+// ---------------------------------------------------------------------------------------
+// device program
+// ---------------------------------------------------------------------------------------
+void CudaPrinter::loadMember(const AgentDecl &a, int m, const std::string &dst,
+                             const std::string &view, const std::string &idx) {
+  const Ty &t = a.members[m]->type;
+  int c = columnOf(a, m);
+  if (t.k == TK::Vec3) w << dst << " = abl_ld3(" << view << ", " << c << ", " << idx << ");";
+  else w << dst << " = abl_ld<" << typeName(t) << ">(" << view << "[" << c << "], " << idx << ");";
+}
+
+void CudaPrinter::storeMember(const AgentDecl &a, int m, const std::string &cols,
+                              const std::string &idx, const std::string &value) {
+  const Ty &t = a.members[m]->type;
+  int c = columnOf(a, m);
+  if (t.k == TK::Vec3) w << "abl_st3(" << cols << ", " << c << ", " << idx << ", " << value << ");";
+  else w << "abl_st<" << typeName(t) << ">(" << cols << "[" << c << "], " << idx << ", " << value << ");";
+}
+
+void CudaPrinter::stepKernel(const StepInfo &si, int index) {
+  FuncDecl &f = *si.fn;
+  AgentDecl &self = *si.self;
+  const Param &p = f.params[0];
+  curFn = &f;
+  curStep = &si;
+
+  // the user's step function
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const "
+    << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
+  w.indent(); stmts(f.body); w.outdent();
+  w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
+    << "(const __grid_constant__ abl_step_launch _a) {";
+  w.indent(); w.nl();
+  w << "const unsigned _i = blockIdx.x * blockDim.x + threadIdx.x;"; w.nl();
+  w << "if (_i >= _a.self.n) return;"; w.nl();
+  w << self.name << " " << p.name << ";";
+  std::set<std::string> loads = si.reads;
+  for (const std::string &m : si.writes) loads.insert(m);
+  for (size_t m = 0; m < self.members.size(); m++) {
+    if (!loads.count(self.members[m]->name)) continue;
+    w.nl();
+    loadMember(self, (int)m, p.name + "." + self.members[m]->name, "_a.self.in", "_i");
+  }
+  w.nl();
+  w << self.name << " " << p.outName << " = " << p.name << ";"; w.nl();
+  w << "abl_ctx _ctx;"; w.nl();
+  w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, " << (f.usesRng ? "_a.self.id[_i]" : "0u") << ");"; w.nl();
+  w << f.emitName << "(_ctx, _a, _i, " << p.name << ", " << p.outName << ");";
+  for (size_t m = 0; m < self.members.size(); m++) {
+    if (!si.writes.count(self.members[m]->name)) continue;
+    w.nl();
+    storeMember(self, (int)m, "_a.self.out", "_i", p.outName + "." + self.members[m]->name);
+  }
+  if (f.usesRemoval) { w.nl(); w << "_a.dead[_i] = _ctx.dead ? 1 : 0;"; }
+  if (f.addedAgent) { w.nl(); w << "_a.add_flag[_i] = _ctx.added ? 1 : 0;"; }
+  w.outdent(); w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *a) {"; w.nl();
+  w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 128;"; w.nl();
+  w << "    unsigned grid = (a->self.n + bs - 1) / bs;"; w.nl();
+  w << "    abl_kernel_" << f.emitName << "<<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a);"; w.nl();
+  w << "    return (int)cudaGetLastError();"; w.nl();
+  w << "}"; w.nl(); w.nl();
+  (void)index;
+  curFn = nullptr;
+  curStep = nullptr;
+}
+
+std::string CudaPrinter::kernelSource() {
+  target = Target::Device;
+  w = Writer();
+  anon = 0;
+  analyseSteps();
+  w << "// Generated by OpenABL (cuda backend, sm_100a). Device program."; w.nl();
+  if (useFloat) { w << "#ifndef ABL_USE_FLOAT"; w.nl(); w << "#define ABL_USE_FLOAT 1"; w.nl(); w << "#endif"; w.nl(); }
+  w << "#include <cuda_runtime.h>"; w.nl();
+  w << "#include \"abl_device.cuh\""; w.nl(); w.nl();
+
+  for (AgentDecl *a : script.agents) {
+    w << "struct " << a->name << " {";
+    w.indent();
+    for (auto &m : a->members) { w.nl(); w << typeName(m->type) << " " << m->name << ";"; }
+    w.outdent(); w.nl();
+    w << "};"; w.nl();
+  }
+  w.nl();
+  for (ConstDecl *c : script.consts) {
+    if (c->type.isString()) continue;
+    constDecl(*c);
+    w.nl();
+  }
+  w.nl();
+
+  // device functions reachable from step functions, in declaration order
+  std::set<const FuncDecl *> used;
+  for (const StepInfo &si : steps) reachable(si.fn, used);
+  for (FuncDecl *f : script.funcs) {
+    if (f->isStep() || f->isSeqStep() || f->isMain() || !used.count(f)) continue;
+    function(*f);
+    w.nl();
+  }
+  w.nl();
+  for (size_t i = 0; i < steps.size(); i++) stepKernel(steps[i], (int)i);
+
+  // registration with the runtime
+  EnvDecl *env = script.env;
+  w << "struct abl_host_type_ { abl_agent_desc desc; void *agents; int pool; };"; w.nl();
+  w << "extern \"C\" abl_host_type_ abl_model_types[];"; w.nl();
+  w << "static int abl_model_step_ids[" << (steps.empty() ? 1 : steps.size()) << "];"; w.nl();
+  w << "extern \"C\" const int abl_model_n_steps = " << steps.size() << ";"; w.nl();
+  w << "extern \"C\" const char *abl_model_step_name(int s) {"; w.nl();
+  w << "    static const char *names[] = {";
+  for (const StepInfo &si : steps) w << " \"" << si.fn->name << "\",";
+  w << " \"\" };"; w.nl();
+  w << "    return names[s];"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "extern \"C\" int abl_model_setup(abl_runtime *rt) {"; w.nl();
+  w << "    int rc;"; w.nl();
+  if (env && env->dim > 0) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "    const double env_min[3] = { %.17g, %.17g, %.17g };", env->envMin.v[0],
+             env->envMin.v[1], env->dim == 3 ? env->envMin.v[2] : 0.0);
+    w << buf; w.nl();
+    snprintf(buf, sizeof buf, "    const double env_max[3] = { %.17g, %.17g, %.17g };", env->envMax.v[0],
+             env->envMax.v[1], env->dim == 3 ? env->envMax.v[2] : 0.0);
+    w << buf; w.nl();
+    snprintf(buf, sizeof buf, "    if ((rc = abl_cuda_set_environment(rt, %d, env_min, env_max, %.17g))) return rc;",
+             env->dim, env->granularity.valid() ? env->granularity.num() : 1.0);
+    w << buf; w.nl();
+  }
+  w << "    for (int t = 0; abl_model_types[t].desc.name; t++)"; w.nl();
+  w << "        if ((rc = abl_cuda_add_pool(rt, &abl_model_types[t].desc, &abl_model_types[t].pool))) return rc;"; w.nl();
+  for (size_t i = 0; i < steps.size(); i++) {
+    const StepInfo &si = steps[i];
+    FuncDecl &f = *si.fn;
+    unsigned mask = 0;
+    for (size_t m = 0; m < si.self->members.size(); m++)
+      if (si.writes.count(si.self->members[m]->name)) mask |= 1u << m;
+    double radius = f.nearRadius.valid() && f.nearRadius.isNum() ? f.nearRadius.num() : 0.0;
+    if (f.nearAgent && !(f.nearRadius.valid() && f.nearRadius.isNum())) {
+      // dynamic radius: cover it with the cell size (it must not exceed the granularity)
+      radius = env && env->granularity.valid() ? env->granularity.num() : 0.0;
+    }
+    char buf[256];
+    w << "    {"; w.nl();
+    w << "        abl_step_desc d;"; w.nl();
+    w << "        d.name = \"" << f.name << "\";"; w.nl();
+    w << "        d.self_pool = abl_model_types[" << agentIndex(si.self) << "].pool;"; w.nl();
+    if (f.nearAgent) w << "        d.nbr_pool = abl_model_types[" << agentIndex(f.nearAgent) << "].pool;";
+    else w << "        d.nbr_pool = -1;";
+    w.nl();
+    snprintf(buf, sizeof buf, "        d.radius = %.17g;", radius);
+    w << buf; w.nl();
+    w << "        d.written_members = " << mask << "u;"; w.nl();
+    w << "        d.uses_removal = " << (f.usesRemoval ? 1 : 0) << ";"; w.nl();
+    if (f.addedAgent) w << "        d.added_pool = abl_model_types[" << agentIndex(f.addedAgent) << "].pool;";
+    else w << "        d.added_pool = -1;";
+    w.nl();
+    w << "        d.launch = abl_launch_" << f.emitName << ";"; w.nl();
+    w << "        if ((rc = abl_cuda_register_step(rt, &d, &abl_model_step_ids[" << i << "]))) return rc;"; w.nl();
+    w << "    }"; w.nl();
+  }
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "extern \"C\" int abl_model_run_step(abl_runtime *rt, int s) { return abl_cuda_step(rt, abl_model_step_ids[s]); }"; w.nl();
+  w << "extern \"C\" int abl_model_parallel_steps(abl_runtime *rt) {"; w.nl();
+  w << "    int rc;"; w.nl();
+  w << "    for (int s = 0; s < abl_model_n_steps; s++)"; w.nl();
+  w << "        if ((rc = abl_cuda_step(rt, abl_model_step_ids[s]))) return rc;"; w.nl();
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl();
+  return w.str();
+}
+
+std::string buildScript(const BackendContext &ctx, bool useFloat) {
+  std::string asset = ctx.assetDir + "/cuda";
+  std::string def = useFloat ? " -DABL_USE_FLOAT=1" : "";
+  std::ostringstream s;
+  s << "#!/bin/sh\n"
+       "# Generated by OpenABL (cuda backend). Builds libmodel.so (+ ./main) for NVIDIA B200.\n"
+       "set -e\n"
+       "cd \"$(dirname \"$0\")\"\n"
+       "NVCC=${NVCC:-nvcc}\n"
+       "CC=${CC:-gcc}\n"
+       "ASSET=\"" << asset << "\"\n"
+       "CUDA_LIB=${CUDA_LIB:-/usr/local/cuda/lib64}\n"
+       "ARCH=\"-gencode arch=compute_100a,code=sm_100a\"\n"
+       "# -fmad=false: the reference C path has no FMA contraction; results must match it\n"
+       "$NVCC $ARCH -O3 -lineinfo -fmad=false -std=c++17 -diag-suppress 177" << def << " -Xcompiler -fPIC -I. -c model_kernels.cu -o model_kernels.o\n"
+       "$CC -O2 -std=c99" << def << " -fPIC -I. -c model_host.c -o model_host.o\n"
+       "$CC -O2 -std=c99" << def << " -fPIC -I. -DABL_MODEL_NO_MAIN -c model_host.c -o model_host_lib.o\n"
+       "$CC -O2 -std=c99" << def << " -fPIC -I. -c abl_host.c -o abl_host.o\n"
+       "if [ -f \"$ASSET/libabl_cuda.so\" ]; then\n"
+       "  RT_DIR=\"$ASSET\"\n"
+       "else\n"
+       "  $NVCC $ARCH -O3 -lineinfo -std=c++17 --cudart shared -Xcompiler -fPIC -I. -shared -o libabl_cuda.so \"$ASSET/abl_runtime.cu\" \"$ASSET/abl_exchange.cu\" -lnccl\n"
+       "  RT_DIR=\"$(pwd)\"\n"
+       "fi\n"
+       "$NVCC $ARCH --cudart shared -shared -o libmodel.so model_kernels.o model_host_lib.o abl_host.o -L\"$RT_DIR\" -labl_cuda -Xlinker -rpath -Xlinker \"$RT_DIR\" -Xlinker -rpath -Xlinker \"$CUDA_LIB\"\n"
+       "$NVCC $ARCH --cudart shared -o main model_kernels.o model_host.o abl_host.o -L\"$RT_DIR\" -labl_cuda -Xlinker -rpath -Xlinker \"$RT_DIR\" -Xlinker -rpath -Xlinker \"$CUDA_LIB\" -lm\n";
+  return s.str();
+}
+
+}  // namespace
+
+void CudaBackend::generate(Script &script, const BackendContext &ctx) {
+  if (!script.mainFunc) throw BackendError("cuda backend: script has no main function");
+  bool useFloat = ctx.config.getBool("use_float", false);
+
+  CudaPrinter printer(script, useFloat, ctx.config);
+  std::string host = printer.hostSource();
+  std::string kernels = printer.kernelSource();
+
+  const std::string &out = ctx.outputDir;
+  writeToFile(out + "/model_host.c", host);
+  writeToFile(out + "/model_kernels.cu", kernels);
+
+  std::string asset = ctx.assetDir + "/cuda";
+  std::string abi = asset + "/abl_cuda.h";
+  if (!fileExists(abi)) abi = ctx.assetDir + "/../include/abl_cuda.h";
+  if (!fileExists(abi)) throw std::runtime_error("abl_cuda.h not found (looked in " + asset + " and " + ctx.assetDir + "/../include)");
+  copyFile(abi, out + "/abl_cuda.h");
+  copyFile(asset + "/abl_device.cuh", out + "/abl_device.cuh");
+  copyFile(asset + "/abl_host.h", out + "/abl_host.h");
+  copyFile(asset + "/abl_host.c", out + "/abl_host.c");
+  writeToFile(out + "/build.sh", buildScript(ctx, useFloat));
+  writeToFile(out + "/run.sh", "#!/bin/sh\ncd \"$(dirname \"$0\")\"\n./main\n");
+  makeFileExecutable(out + "/build.sh");
+  makeFileExecutable(out + "/run.sh");
+}
+
+}  // namespace abl
