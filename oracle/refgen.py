@@ -71,6 +71,7 @@ def run_reference(model, params, use_float=False, keep=None):
 # name -> (model file under examples/, params, use_float)
 FIXTURES = {
     "circle_n1000_t100": ("circle.abl", {"num_agents": 1000, "num_timesteps": 100}, False),
+    "circle_n1000_t10": ("circle.abl", {"num_agents": 1000, "num_timesteps": 10}, False),
     "circle_n1000_t0": ("circle.abl", {"num_agents": 1000, "num_timesteps": 0}, False),
     "circle_n2000_t10_f32": ("circle.abl", {"num_agents": 2000, "num_timesteps": 10}, True),
     "circle3d_n2000_t10": ("circle3d.abl", {"num_agents": 2000, "num_timesteps": 10}, False),

@@ -16,7 +16,10 @@ from openabl_b200.model import Model
 from openabl_b200.state import exact_members_equal, max_rel_error
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-RUNS = [n for n, (_, p, _) in refgen.FIXTURES.items() if p["num_timesteps"] > 0]
+# 10-step runs: the bar of BASELINE.json north_star.  The 100-step circle run is order-
+# sensitive by nature (tests/test_oracle.py::test_order_sensitivity...) and is checked bit for
+# bit against the grid-ordered oracle in test_gpu_parity_oracle.py instead.
+RUNS = [n for n, (_, p, _) in refgen.FIXTURES.items() if p["num_timesteps"] == 10]
 
 
 def simulate(model, timesteps, **rt_kw):
