@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native OpenABL `cuda` backend.
+
+Metric (BASELINE.json): agent-steps/s.  A "step" is one simulation timestep of the model:
+binning of the population (cell-key counting sort + cell ranges) + every step kernel +
+commit.  Workload at N=1: boids2d.abl with 1 M agents in double precision (BASELINE
+configs[1]); `--workload` selects the other configurations.
+
+  value      device-resident throughput: population already in HBM, K timesteps timed with
+             CUDA events on the runtime's stream.
+  e2e        the same metric through the C-ABI calls the generated program makes for
+             `simulate(K)`: upload of the host AoS records, K timesteps, download back to
+             host records in id order — all inside the timed region.
+  roofline   step kernel: algorithmic bytes (S + M + S per agent) / average
+             kernel time (CUDA events), against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the plain-C oracle (restatement of the reference `c` backend, brute-force
+             O(N^2) loop, OpenMP on all host cores) on a bounded sample of the same workload.
+
+`--impl reference` times only that CPU path (there is no GPU work in it).
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {
+    # name: (model, params, use_float, S bytes/agent, M bytes/agent read per neighbour, P pos bytes)
+    "boids2d-1M-f64": ("boids2d.abl", {"num_agents": 1000000}, False, 32, 32, 16),
+    "boids2d-1M-f32": ("boids2d.abl", {"num_agents": 1000000}, True, 16, 16, 8),
+    "boids2d-4M-f64": ("boids2d.abl", {"num_agents": 4000000}, False, 32, 32, 16),
+    "boids2d-16M-f64": ("boids2d.abl", {"num_agents": 16000000}, False, 32, 32, 16),
+    "circle3d-1M-f64": ("circle3d.abl", {"num_agents": 1000000}, False, 24, 24, 24),
+    "circle3d-16M-f64": ("circle3d.abl", {"num_agents": 16000000}, False, 24, 24, 24),
+    "circle3d-16M-f32": ("circle3d.abl", {"num_agents": 16000000}, True, 12, 12, 12),
+    "game_of_life-16M-f64": ("game_of_life.abl", {"num_agents": 16777216}, False, 17, 17, 16),
+    "circle-1000-f64": ("circle.abl", {"num_agents": 1000}, False, 16, 16, 16),
+}
+DEFAULT_WORKLOAD = "boids2d-1M-f64"
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device = device
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
+                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for name, flag in zip(names, s[2:6]):
+                    if flag.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline(workload, budget_pairs=1.2e10):
+    """Times the oracle's brute-force (reference-order) step on a bounded sample of agents."""
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from oracle import BRUTE, Oracle
+    model, params, use_float, _, _, _ = WORKLOADS[workload]
+    n = params["num_agents"]
+    o = Oracle(use_float)
+    if model == "game_of_life.abl":
+        size = int(n ** 0.5)
+        n = size * size
+    state = o.init_for(model, params)
+    n = len(state)
+    sample = int(max(256, min(n, budget_pairs / n)))
+    cores = os.cpu_count() or 1
+    t0 = time.perf_counter()
+    if model == "boids2d.abl":
+        o.boids_run(state, 1, BRUTE, sample=(0, sample))
+    elif model == "circle.abl":
+        o.circle_run(2, state, 1, BRUTE, sample=(0, sample))
+    elif model == "circle3d.abl":
+        o.circle_run(3, state, 1, BRUTE, sample=(0, sample))
+    else:
+        o.gol_run(state, 1, BRUTE, num_agents=params["num_agents"], sample=(0, sample))
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "agent-steps/s", "cores": cores, "kind": "port",
+            "sample": "reference brute-force step (all %d candidates per agent) for the first %d of %d agents, "
+                      "1 timestep, OpenMP on %d threads, %.1f s" % (n, sample, n, cores, dt)}, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workload = args.workload
+    model, params, use_float, S, M, P = WORKLOADS[workload]
+    vals, last = [], None
+    total = args.warmup + args.steps
+    # each "step" is a bounded sample; keep the whole run within a few minutes
+    budget = 1.2e10 / max(1, total) * 2
+    for i in range(total):
+        base, dt = cpu_baseline(workload, budget_pairs=budget)
+        if i >= args.warmup:
+            vals.append(base["value"])
+        last = base
+    value = sum(vals) / len(vals)
+    last["value"] = value
+    line = {"impl": "reference", "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if use_float else "f64", "data": "synthetic",
+            "config": {"workload": workload, "model": model, "num_agents": params["num_agents"]},
+            "cpu_baseline": last,
+            "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--block-size", type=int, default=128)
+    ap.add_argument("--no-tile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cuda backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from openabl_b200.model import Model
+    model_file, params, use_float, S, M, P = WORKLOADS[args.workload]
+    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
+    m.populate()
+    host = [m.host_agents(t) for t in range(m.n_types)]
+    n_agents = sum(len(h) for h in host)
+    m.create_runtime(device=local_rank, block_size=args.block_size, tile=not args.no_tile)
+    rt = m.rt
+    stream = torch.cuda.ExternalStream(rt.stream(), device=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        rt.synchronize()
+
+    # ---- device-resident throughput ------------------------------------------------------
+    m.upload_host()
+    for _ in range(max(3, args.warmup)):
+        m.timestep()
+    barrier()
+    launches0 = rt.last_timing()["launches"]
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        m.timestep()
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.summary()
+    launches = rt.last_timing()["launches"] - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = n_agents * world * args.steps / (ms_max / 1e3)
+
+    # ---- per-stage device times (separate pass: timing adds a sync per step) ---------------
+    rt.enable_timing(True)
+    stage = {"bin_ms": 0.0, "kernel_ms": 0.0, "commit_ms": 0.0}
+    reps = min(args.steps, 20)
+    for _ in range(reps):
+        for s in range(m.n_steps):
+            m.run_step(s)
+            lt = rt.last_timing()
+            for k in stage:
+                stage[k] += lt[k]
+    rt.enable_timing(False)
+    for k in stage:
+        stage[k] /= reps
+    peak, peak_src = load_peaks()
+    kernel_bytes = (S + M + S) * n_agents
+    achieved = kernel_bytes / (stage["kernel_ms"] / 1e3) / 1e9 if stage["kernel_ms"] > 0 else 0.0
+    step_bytes = (P + M + 4 * S + 32) * n_agents
+    roofline = {"bound": "hbm", "kernel": "abl_kernel_%s" % m.step_names[0], "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "algorithmic_bytes_per_agent": S + M + S,
+                "kernel_ms": stage["kernel_ms"], "bin_ms": stage["bin_ms"], "commit_ms": stage["commit_ms"],
+                "whole_step_algorithmic_bytes_per_agent": P + M + 4 * S + 32,
+                "whole_step_frac": step_bytes * args.steps / (ms_max / 1e3) / 1e9 / peak}
+
+    # ---- end to end through the C ABI with host buffers -------------------------------------
+    e2e_reps = 3
+    h2d = sum(h.nbytes for h in host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_reps):
+        m.upload_host()
+        for _ in range(args.steps):
+            m.timestep()
+        out = [m.download(tt) for tt in range(m.n_types)]
+    rt.synchronize()
+    e2e_s = (time.perf_counter() - t0) / e2e_reps
+    d2h = sum(o.nbytes for o in out)
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = n_agents * world * args.steps / float(te.item())
+    m.close()
+
+    if rank == 0:
+        line = {"metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32" if use_float else "f64", "data": "synthetic",
+                "config": {"workload": args.workload, "model": model_file, "num_agents": n_agents,
+                           "agents_per_gpu": n_agents, "parallelism": "replicas" if world > 1 else "single",
+                           "block_size": args.block_size,
+                           "l2": "state (%.0f MB) is re-streamed every step; no L2 flush between steps (a "
+                                 "simulation step consumes the previous step's output)" % (n_agents * S / 1e6)},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / args.steps,
+                        "d2h_bytes_per_step": d2h / args.steps,
+                        "definition": "upload + %d timesteps + download per simulate() call" % args.steps},
+                "roofline": roofline}
+        if not args.no_cpu_baseline:
+            base, _ = cpu_baseline(args.workload)
+            line["cpu_baseline"] = base
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -825,6 +825,12 @@ std::string CudaPrinter::hostSource() {
   w << "/* statements of main() that precede `simulate` (population set-up only) */"; w.nl();
   w << "int abl_model_populate(void) {";
   w.indent();
+  w.nl();
+  w << "/* start from a clean slate so that repeated calls rebuild the same population */";
+  w.nl();
+  w << "for (int t = 0; t < abl_model_n_types; t++) abl_model_types[t].agents->len = 0;";
+  w.nl();
+  w << "abl_host_rng_reset();";
   for (const StmtP &s : mainFn->body) {
     if (s->kind == Stmt::Simulate) break;
     w.nl(); stmt(*s);
