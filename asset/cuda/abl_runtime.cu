@@ -89,6 +89,8 @@ struct Pool {
   size_t n = 0, cap = 0;
   u32 next_id = 0;
   bool binned = false;
+  bool ever_binned = false;
+  bool counted = false;   // key/local/cell_count already hold the histogram of the current positions
   bool ever_removed = false;
   // binning scratch (per pool so that pools can be binned independently)
   u32 *key = nullptr, *local = nullptr;
@@ -218,17 +220,31 @@ __global__ void k_mark_present(const u32 *ids, u32 n, u32 *present) {
 // re-launchable without any host-side memset (CUDA-graph friendly).
 enum { SCAN_INVALID = 0, SCAN_AGGREGATE = 1, SCAN_PREFIX = 2 };
 
+// Loads 16 consecutive items of thread `tid` (64 bytes of u32, 16 bytes of u8).
 template <typename T> struct ScanLoad;
 template <> struct ScanLoad<u32> {
-  static __device__ __forceinline__ void load4(const u32 *in, size_t i, u32 v[4]) {
-    uint4 q = *reinterpret_cast<const uint4 *>(in + i);
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  static __device__ __forceinline__ void load16(const u32 *in, size_t i, u32 v[16]) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(in + i);
+    uint4 q0 = p[0], q1 = p[1], q2 = p[2], q3 = p[3];  // four independent 16-byte loads
+    v[0] = q0.x; v[1] = q0.y; v[2] = q0.z; v[3] = q0.w;
+    v[4] = q1.x; v[5] = q1.y; v[6] = q1.z; v[7] = q1.w;
+    v[8] = q2.x; v[9] = q2.y; v[10] = q2.z; v[11] = q2.w;
+    v[12] = q3.x; v[13] = q3.y; v[14] = q3.z; v[15] = q3.w;
+  }
+  static __device__ __forceinline__ void zero16(u32 *in, size_t i) {
+    uint4 *p = reinterpret_cast<uint4 *>(in + i);
+    p[0] = p[1] = p[2] = p[3] = make_uint4(0, 0, 0, 0);
   }
 };
 template <> struct ScanLoad<u8> {
-  static __device__ __forceinline__ void load4(const u8 *in, size_t i, u32 v[4]) {
-    uchar4 q = *reinterpret_cast<const uchar4 *>(in + i);
-    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  static __device__ __forceinline__ void load16(const u8 *in, size_t i, u32 v[16]) {
+    uint4 q = *reinterpret_cast<const uint4 *>(in + i);
+    u32 w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int k = 0; k < 16; k++) v[k] = (w[k >> 2] >> (8 * (k & 3))) & 0xffu;
+  }
+  static __device__ __forceinline__ void zero16(u8 *in, size_t i) {
+    *reinterpret_cast<uint4 *>(in + i) = make_uint4(0, 0, 0, 0);
   }
 };
 
@@ -240,113 +256,101 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
   __shared__ u32 s_tile;
   __shared__ u32 s_warp[kScanBlock / 32];
   __shared__ u32 s_prefix;
+  __shared__ int s_first;
+  __shared__ u32 s_sum;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) s_tile = atomicAdd(&ctrl[0], 1u);
   __syncthreads();
   const u32 tile = s_tile;
   const u32 epoch = *((volatile u32 *)&ctrl[2]);
-  const size_t base = (size_t)tile * kScanTile;
+  const size_t i0 = (size_t)tile * kScanTile + (size_t)tid * kScanItems;
 
-  // local scan: 4 chunks of (256 threads x 4 items), items of a thread are consecutive
-  u32 vals[kScanItems];
-  u32 chunk_excl[4];
-  u32 running = 0;
+  // thread-local scan of 16 consecutive items (arrays are padded to a multiple of the
+  // tile, so vector accesses past n stay in bounds; values past n count as 0)
+  u32 v[kScanItems];
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    size_t i0 = base + (size_t)c * (kScanBlock * 4) + (size_t)tid * 4;
-    u32 v[4] = {0, 0, 0, 0};
-    if (i0 < n) {  // arrays are padded to a multiple of the tile, reads past n are in bounds
-      ScanLoad<T>::load4(in, i0, v);
+  for (int k = 0; k < kScanItems; k++) v[k] = 0;
+  if (i0 < n) {
+    ScanLoad<T>::load16(in, i0, v);
 #pragma unroll
-      for (int k = 0; k < 4; k++) {
-        if (MODE == 1) v[k] = v[k] ? 0u : 1u;
-        if (i0 + k >= n) v[k] = 0;
-      }
-      if (ZERO_INPUT) {
-        if (sizeof(T) == 4) *reinterpret_cast<uint4 *>(in + i0) = make_uint4(0, 0, 0, 0);
-        else *reinterpret_cast<u32 *>(in + i0) = 0;
-      }
+    for (int k = 0; k < kScanItems; k++) {
+      if (MODE == 1) v[k] = v[k] ? 0u : 1u;
+      if (i0 + k >= n) v[k] = 0;
     }
-    u32 t = v[0] + v[1] + v[2] + v[3];
-    u32 inc = t;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      u32 y = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += y;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    u32 wsum = lane < kScanBlock / 32 ? s_warp[lane] : 0;
-    u32 winc = wsum;
-#pragma unroll
-    for (int d = 1; d < kScanBlock / 32; d <<= 1) {
-      u32 y = __shfl_up_sync(0xffffffffu, winc, d);
-      if (lane >= d) winc += y;
-    }
-    u32 warp_excl = __shfl_sync(0xffffffffu, winc - wsum, warp);
-    u32 chunk_total = __shfl_sync(0xffffffffu, winc, kScanBlock / 32 - 1);
-    u32 excl = running + warp_excl + inc - t;
-    chunk_excl[c] = excl;
-    vals[c * 4 + 0] = excl;
-    vals[c * 4 + 1] = excl + v[0];
-    vals[c * 4 + 2] = excl + v[0] + v[1];
-    vals[c * 4 + 3] = excl + v[0] + v[1] + v[2];
-    running += chunk_total;
-    __syncthreads();
+    if (ZERO_INPUT) ScanLoad<T>::zero16(in, i0);
   }
-  (void)chunk_excl;
-  const u32 aggregate = running;
+  u32 t = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { u32 x = v[k]; v[k] = t; t += x; }  // v = local exclusive
+  u32 inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += y;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  u32 wsum = lane < kScanBlock / 32 ? s_warp[lane] : 0;
+  u32 winc = wsum;
+#pragma unroll
+  for (int d = 1; d < kScanBlock / 32; d <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, winc, d);
+    if (lane >= d) winc += y;
+  }
+  const u32 warp_excl = __shfl_sync(0xffffffffu, winc - wsum, warp);
+  const u32 aggregate = __shfl_sync(0xffffffffu, winc, kScanBlock / 32 - 1);
+  const u32 thread_excl = warp_excl + inc - t;
 
-  // look-back (warp 0)
-  if (warp == 0) {
-    u32 prefix = 0;
-    if (tile == 0) {
-      if (lane == 0)
-        *((volatile u64 *)&desc[0]) = ((u64)((epoch << 2) | SCAN_PREFIX) << 32) | aggregate;
-    } else {
-      if (lane == 0)
-        *((volatile u64 *)&desc[tile]) = ((u64)((epoch << 2) | SCAN_AGGREGATE) << 32) | aggregate;
-      int idx = (int)tile - 1;
-      for (;;) {
-        int my = idx - lane;
-        u32 status = SCAN_PREFIX, value = 0;  // tiles before 0 behave as prefix 0
-        if (my >= 0) {
-          for (;;) {
-            u64 d = *((volatile u64 *)&desc[my]);
-            u32 hi = (u32)(d >> 32);
-            if ((hi >> 2) == epoch && (hi & 3u) != SCAN_INVALID) {
-              status = hi & 3u;
-              value = (u32)d;
-              break;
-            }
+  // publish, then block-wide look-back: 256 predecessor descriptors per round trip
+  if (tid == 0) {
+    u32 st = tile == 0 ? SCAN_PREFIX : SCAN_AGGREGATE;
+    *((volatile u64 *)&desc[tile]) = ((u64)((epoch << 2) | st) << 32) | aggregate;
+    s_prefix = 0;
+  }
+  u32 prefix = 0;
+  if (tile > 0) {
+    int idx = (int)tile - 1;
+    for (;;) {
+      if (tid == 0) { s_first = kScanBlock; s_sum = 0; }
+      __syncthreads();
+      int my = idx - tid;
+      u32 status = SCAN_PREFIX, value = 0;  // tiles before 0 behave as prefix 0
+      if (my >= 0) {
+        for (;;) {
+          u64 d = *((volatile u64 *)&desc[my]);
+          u32 hi = (u32)(d >> 32);
+          if ((hi >> 2) == epoch && (hi & 3u) != SCAN_INVALID) {
+            status = hi & 3u;
+            value = (u32)d;
+            break;
           }
         }
-        u32 pm = __ballot_sync(0xffffffffu, status == SCAN_PREFIX);
-        int first = pm ? __ffs(pm) - 1 : 31;  // nearest predecessor with a full prefix
-        u32 contrib = lane <= first ? value : 0;
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
-        prefix += contrib;
-        if (pm) break;
-        idx -= 32;
       }
-      if (lane == 0)
-        *((volatile u64 *)&desc[tile]) =
-            ((u64)((epoch << 2) | SCAN_PREFIX) << 32) | (u32)(prefix + aggregate);
-    }
-    if (lane == 0) s_prefix = prefix;
-  }
-  __syncthreads();
-  const u32 prefix = s_prefix;
-
+      if (status == SCAN_PREFIX) atomicMin(&s_first, tid);
+      __syncthreads();
+      const int first = s_first;  // nearest predecessor holding a full prefix
+      u32 contrib = tid <= first ? value : 0;
 #pragma unroll
-  for (int c = 0; c < 4; c++) {
-    size_t i0 = base + (size_t)c * (kScanBlock * 4) + (size_t)tid * 4;
-    if (i0 < n) {
-      uint4 q = make_uint4(vals[c * 4] + prefix, vals[c * 4 + 1] + prefix,
-                           vals[c * 4 + 2] + prefix, vals[c * 4 + 3] + prefix);
-      *reinterpret_cast<uint4 *>(out + i0) = q;  // out is padded like in
+      for (int d = 16; d > 0; d >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, d);
+      if (lane == 0 && contrib) atomicAdd(&s_sum, contrib);
+      __syncthreads();
+      prefix += s_sum;
+      if (first < kScanBlock) break;
+      idx -= kScanBlock;
+      __syncthreads();
     }
+    if (tid == 0)
+      *((volatile u64 *)&desc[tile]) =
+          ((u64)((epoch << 2) | SCAN_PREFIX) << 32) | (u32)(prefix + aggregate);
+  }
+
+  if (i0 < n) {
+    const u32 b = prefix + thread_excl;
+    uint4 *o = reinterpret_cast<uint4 *>(out + i0);
+    o[0] = make_uint4(v[0] + b, v[1] + b, v[2] + b, v[3] + b);
+    o[1] = make_uint4(v[4] + b, v[5] + b, v[6] + b, v[7] + b);
+    o[2] = make_uint4(v[8] + b, v[9] + b, v[10] + b, v[11] + b);
+    o[3] = make_uint4(v[12] + b, v[13] + b, v[14] + b, v[15] + b);
   }
 
   // bookkeeping: total + self-reset by the last CTA
@@ -399,12 +403,13 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
   local[i] = atomicAdd(&cell_count[c], 1u);
 }
 
-__global__ void k_bin_scatter(const u32 *key, const u32 *local, const u32 *ids, u32 n,
-                              const u32 *cell_start, u64 *pairs) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  u32 slot = cell_start[key[i]] + local[i];
-  pairs[slot] = ((u64)ids[i] << 32) | i;
+// seg_ids[slot] = id of the agent that arrived `local`-th in its cell segment
+__global__ void k_bin_scatter(const u32 *key, const u32 *local, const u32 *ids, u32 n, u32 src_begin,
+                              const u32 *cell_start, u32 *seg_ids) {
+  u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  u32 slot = cell_start[key[t]] + local[t];
+  seg_ids[slot] = ids[src_begin + t];
 }
 
 __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src, size_t si, int elem) {
@@ -416,21 +421,22 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
   }
 }
 
-// Slot s holds one (id, src) pair of its cell segment in arrival order.  The final place of
-// that agent is segment_begin + (number of ids in the segment smaller than its id); the
-// segment is contiguous, so the rank is a short coalesced scan.  The agent's whole record is
-// then moved column by column (gather read, near-coalesced write).
-__global__ void k_bin_rank_move(ColTable t, const u64 *pairs, const u32 *key, u32 n,
-                                const u32 *cell_start) {
-  u32 s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= n) return;
-  u64 mine = pairs[s];
-  u32 src = (u32)mine;
-  u32 c = key[src];
-  u32 b = cell_start[c], e = cell_start[c + 1];
+// One thread per *source* agent.  Its final place is segment_begin + (number of ids in its
+// cell segment smaller than its own id); the segment is contiguous, so the rank is a short
+// scan of seg_ids.  All reads of the agent's record are coalesced; because agents move
+// little between two binnings the pool is already almost in cell order and the writes land
+// close to the reads (near-coalesced).
+__global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *ids, u32 n,
+                                u32 src_begin, const u32 *cell_start) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 src = src_begin + i;
+  const u32 c = key[i];
+  const u32 mine = ids[src];
+  const u32 b = cell_start[c], e = cell_start[c + 1];
   u32 rank = 0;
-  for (u32 q = b; q < e; q++) rank += (pairs[q] < mine) ? 1u : 0u;  // ids are unique
-  u32 dst = b + rank;
+  for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
+  const u32 dst = b + rank;
   for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
 }
 
@@ -834,6 +840,7 @@ extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, 
   p->n = n;
   p->next_id = (u32)n;
   p->binned = false;
+  p->counted = false;
   p->ever_removed = false;
   CU(cudaStreamSynchronize(rt->stream));  // host buffer may be reused by the caller
   return ABL_OK;
@@ -889,48 +896,60 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   return ABL_OK;
 }
 
+static int launch_bin_count(abl_runtime *rt, Pool &p) {
+  const GridParams &g = rt->grid;
+  const Member &pm = p.members[p.pos_member];
+  const u32 n = (u32)p.n;
+  const int bs = 256;
+  if (!n) return ABL_OK;
+  const void *px = p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
+  const void *py = nullptr, *pz = nullptr;
+  if (g.dim == 3) {
+    py = p.cols[pm.first_col + 1].buf[p.cols[pm.first_col + 1].cur];
+    pz = p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
+  }
+  u32 nb = blocks_for(n, bs);
+  if (rt->real_size == 8) {
+    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+  } else {
+    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+  }
+  rt->launches++;
+  CU(cudaGetLastError());
+  return ABL_OK;
+}
+
 static int bin_pool(abl_runtime *rt, Pool &p) {
   if (!rt->env_set) return fail(ABL_ERR_STATE, "binning requires an environment");
   if (p.pos_member < 0) return fail(ABL_ERR_STATE, "pool %s has no position member", p.name.c_str());
   TRY(reserve_pool(rt, p, std::max(p.n, (size_t)1)));
   TRY(ensure_grid_arrays(rt, p));
   const GridParams &g = rt->grid;
-  const Member &pm = p.members[p.pos_member];
   const u32 n = (u32)p.n;
   const int bs = 256;
-  if (n) {
-    const void *px = p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
-    const void *py = nullptr, *pz = nullptr;
-    if (g.dim == 3) {
-      py = p.cols[pm.first_col + 1].buf[p.cols[pm.first_col + 1].cur];
-      pz = p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
-    }
-    u32 nb = blocks_for(n, bs);
-    if (rt->real_size == 8) {
-      if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-      else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-    } else {
-      if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-      else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-    }
-    rt->launches++;
-    CU(cudaGetLastError());
-  }
-  // cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also clears
-  // the histogram for the next binning.
+  // 1. histogram (skipped when the step kernel that produced the positions already did it)
+  if (!p.counted) TRY(launch_bin_count(rt, p));
+  p.counted = false;
+  // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
+  //    clears the histogram for the next binning.
   TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_cells + 1, nullptr)));
   if (n) {
+    // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
+    u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
-    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, p.cell_start, p.pairs);
+    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, 0u, p.cell_start, seg_ids);
     ColTable t;
     fill_table(p, t, true);
-    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, p.pairs, p.key, n, p.cell_start);
+    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, ids, n, 0u, p.cell_start);
     rt->launches += 2;
     CU(cudaGetLastError());
     flip_all(p);
   }
   p.binned = true;
+  p.ever_binned = true;
   return ABL_OK;
 }
 
@@ -1039,7 +1058,8 @@ static int commit_removals(abl_runtime *rt, Pool &p) {
   CU(cudaGetLastError());
   flip_all(p);
   p.ever_removed = true;
-  p.binned = false;  // stable compaction keeps cell order, but cell_start is stale
+  p.binned = false;
+  p.counted = false;  // stable compaction keeps cell order, but cell_start is stale
   p.n = survivors;
   return ABL_OK;
 }
@@ -1078,6 +1098,7 @@ static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const 
   target.n += m;
   target.next_id += m;
   target.binned = false;
+  target.counted = false;
   return ABL_OK;
 }
 
@@ -1129,6 +1150,21 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       }
       a.add_flag = self.add_flag;
     }
+    // Fuse the cell histogram of the *next* binning into this kernel's epilogue when it
+    // rewrites the positions of a pool that is used for neighbour search and no commit
+    // stage reorders the pool afterwards.
+    const bool writes_pos = self.pos_member >= 0 && (s.desc.written_members >> self.pos_member & 1u);
+    bool fuse = writes_pos && rt->env_set && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
+    if (writes_pos && self.counted) {
+      // a previous fused histogram was never consumed: start over
+      CU(cudaMemsetAsync(self.cell_count, 0, ((size_t)rt->grid.n_cells + 1) * sizeof(u32), rt->stream));
+      self.counted = false;
+    }
+    if (fuse) {
+      a.bin_key = self.key;
+      a.bin_local = self.local;
+      a.bin_count = self.cell_count;
+    }
     a.seed = rt->cfg.seed;
     a.timestep = rt->timestep;
     a.step_index = (unsigned)step;
@@ -1148,6 +1184,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       for (int c = mem.first_col; c < mem.first_col + mem.ncols; c++) self.cols[c].cur ^= 1;
       if ((int)m == self.pos_member) self.binned = false;
     }
+    if (fuse) self.counted = true;
     if (added) TRY(commit_adds(rt, self, *added, staging));
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
   } else if (rt->timing) {

@@ -128,6 +128,11 @@ typedef struct {
   unsigned char *dead;                     /* [self.n] removeCurrent() flags, or NULL */
   unsigned char *add_flag;                 /* [self.n] add() flags, or NULL */
   void *add_cols[ABL_MAX_COLUMNS];         /* staging columns of the added type, [self.n] */
+  /* when non-NULL the kernel also bins the positions it writes: bin_key[i] = cell key,
+   * bin_local[i] = atomicAdd(&bin_count[key], 1) (fused histogram of the next binning) */
+  unsigned *bin_key;
+  unsigned *bin_local;
+  unsigned *bin_count;
   uint64_t seed;
   unsigned timestep;
   unsigned step_index;

@@ -93,6 +93,7 @@ private:
   // device-function context
   const FuncDecl *curFn = nullptr;
   const StepInfo *curStep = nullptr;
+  bool curStepHasLimit = false;
   std::vector<StepInfo> steps;
 
   std::string label() { return "_var" + std::to_string(anon++); }
@@ -142,6 +143,8 @@ private:
   void reachableStmt(const Stmt &s, std::set<const FuncDecl *> &seen);
 
   void stepKernel(const StepInfo &si, int index);
+  static const Expr *findNearRadius(const std::vector<StmtP> &body);
+  static bool hostEvaluable(const Expr &e);
   void loadMember(const AgentDecl &a, int m, const std::string &dst, const std::string &view,
                   const std::string &idx);
   void storeMember(const AgentDecl &a, int m, const std::string &cols, const std::string &idx,
@@ -559,34 +562,44 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   if (!selfPos) throw BackendError("cuda backend: near() needs an agent with a position");
   int dim = pos->type.vecLen();
   std::string it = label();
+  std::string sdim = std::to_string(dim);
 
   w << "{";
   w.indent(); w.nl();
-  w << "abl_near_iter " << it << ";";
+  w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
-  w << it << ".init" << dim << "(_a, "; expr(agentExpr); w << "." << selfPos->name << ", true);";
+  w << it << ".init" << sdim << "(_a, "; expr(agentExpr); w << "." << selfPos->name << ", true);";
   w.nl();
   w << "for (; " << it << ".valid(); " << it << ".next()) {";
   w.indent(); w.nl();
   w << "const unsigned " << it << "j = " << it << ".index();";
   w.nl();
   w << nbr->name << " " << s.varName << ";";
-  // position first (needed by the radius filter), then the members the body reads
-  std::set<std::string> members = curFn->nearMembers;
-  members.insert(pos->name);
+  w.nl();
+  int posIndex = nbr->memberIndex(pos->name);
+  loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+  w.nl();
+  // Radius filter: inclusive radius, self included, same operand order as the reference's
+  // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
+  // is a host-evaluable constant the launcher precomputes the equivalent bound on the
+  // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  if (curStepHasLimit) {
+    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", ";
+    expr(agentExpr);
+    w << "." << selfPos->name << ")) > _near_limit) continue;";
+  } else {
+    w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", ";
+    expr(agentExpr);
+    w << "." << selfPos->name << ") > ";
+    expr(radius);
+    w << ") continue;";
+  }
+  // members the body reads are fetched only for accepted candidates
   for (size_t m = 0; m < nbr->members.size(); m++) {
-    if (!members.count(nbr->members[m]->name)) continue;
+    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
     w.nl();
     loadMember(*nbr, (int)m, s.varName + "." + nbr->members[m]->name, "_a.nbr.in", it + "j");
   }
-  w.nl();
-  // inclusive radius, self included, same operand order as the reference's filter
-  // (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip
-  w << "if (dist_float" << dim << "(" << s.varName << "." << pos->name << ", ";
-  expr(agentExpr);
-  w << "." << selfPos->name << ") > ";
-  expr(radius);
-  w << ") continue;";
   w.nl();
   stmt(*s.body[0]);
   w.outdent(); w.nl();
@@ -936,22 +949,49 @@ void CudaPrinter::storeMember(const AgentDecl &a, int m, const std::string &cols
   else w << "abl_st<" << typeName(t) << ">(" << cols << "[" << c << "], " << idx << ", " << value << ");";
 }
 
+const Expr *CudaPrinter::findNearRadius(const std::vector<StmtP> &body) {
+  for (const StmtP &s : body) {
+    if (s->kind == Stmt::For && s->forKind == Stmt::ForNear) return s->e[0]->kids[1].get();
+    if (const Expr *r = findNearRadius(s->body)) return r;
+  }
+  return nullptr;
+}
+
+// true if `e` only involves literals, scalar global constants and arithmetic: the launcher
+// (host code in the same .cu) can then evaluate it with the arithmetic the kernel would use
+bool CudaPrinter::hostEvaluable(const Expr &e) {
+  switch (e.kind) {
+    case Expr::BoolLit: case Expr::IntLit: case Expr::FloatLit: return true;
+    case Expr::Var: return e.sym && e.sym->global && !e.type.isVec() && !e.type.isArray() && (e.type.isNum() || e.type.isBool());
+    case Expr::Unary: case Expr::Binary: case Expr::Ternary:
+      if (e.type.isVec()) return false;
+      for (const ExprP &k : e.kids) if (!hostEvaluable(*k)) return false;
+      return true;
+    case Expr::Call:
+      if (e.ckind != Expr::Ctor || e.type.isVec()) return false;
+      return hostEvaluable(*e.kids[0]);
+    default: return false;
+  }
+}
+
 void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   FuncDecl &f = *si.fn;
   AgentDecl &self = *si.self;
   const Param &p = f.params[0];
   curFn = &f;
   curStep = &si;
+  const Expr *radius = f.nearAgent ? findNearRadius(f.body) : nullptr;
+  curStepHasLimit = radius && hostEvaluable(*radius);
 
   // the user's step function
-  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const "
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
   w.nl();
   w << "}"; w.nl(); w.nl();
 
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
-    << "(const __grid_constant__ abl_step_launch _a) {";
+    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit) {";
   w.indent(); w.nl();
   w << "const unsigned _i = blockIdx.x * blockDim.x + threadIdx.x;"; w.nl();
   w << "if (_i >= _a.self.n) return;"; w.nl();
@@ -967,11 +1007,17 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << self.name << " " << p.outName << " = " << p.name << ";"; w.nl();
   w << "abl_ctx _ctx;"; w.nl();
   w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, " << (f.usesRng ? "_a.self.id[_i]" : "0u") << ");"; w.nl();
-  w << f.emitName << "(_ctx, _a, _i, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "(_ctx, _a, _i, _near_limit, " << p.name << ", " << p.outName << ");";
+  AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!si.writes.count(self.members[m]->name)) continue;
     w.nl();
     storeMember(self, (int)m, "_a.self.out", "_i", p.outName + "." + self.members[m]->name);
+  }
+  if (selfPos && si.writes.count(selfPos->name)) {
+    // fused histogram of the next binning (no-op unless the runtime asks for it)
+    w.nl();
+    w << "abl_bin_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ");";
   }
   if (f.usesRemoval) { w.nl(); w << "_a.dead[_i] = _ctx.dead ? 1 : 0;"; }
   if (f.addedAgent) { w.nl(); w << "_a.add_flag[_i] = _ctx.added ? 1 : 0;"; }
@@ -981,12 +1027,24 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *a) {"; w.nl();
   w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 128;"; w.nl();
   w << "    unsigned grid = (a->self.n + bs - 1) / bs;"; w.nl();
-  w << "    abl_kernel_" << f.emitName << "<<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a);"; w.nl();
+  if (curStepHasLimit) {
+    // host-side evaluation of the radius with the kernel's own arithmetic and constants
+    Target saved = target;
+    w << "    static abl_real limit; static bool have_limit = false;"; w.nl();
+    w << "    if (!have_limit) { const abl_real radius = ";
+    expr(*radius);
+    w << "; limit = abl_near_sq_limit(radius); have_limit = true; }"; w.nl();
+    target = saved;
+  } else {
+    w << "    const abl_real limit = 0;"; w.nl();
+  }
+  w << "    abl_kernel_" << f.emitName << "<<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
   w << "    return (int)cudaGetLastError();"; w.nl();
   w << "}"; w.nl(); w.nl();
   (void)index;
   curFn = nullptr;
   curStep = nullptr;
+  curStepHasLimit = false;
 }
 
 std::string CudaPrinter::kernelSource() {
