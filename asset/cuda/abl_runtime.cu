@@ -647,6 +647,15 @@ static void fill_table(const Pool &p, ColTable &t, bool out_is_alt) {
   }
 }
 
+// A fused histogram that will not be consumed by the next binning (the pool is about to be
+// reordered or refilled) has to be wiped, otherwise the next histogram adds on top of it.
+static int drop_fused_histogram(abl_runtime *rt, Pool &p) {
+  if (p.counted && p.cell_count)
+    CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)rt->grid.n_cells + 1) * sizeof(u32), rt->stream));
+  p.counted = false;
+  return ABL_OK;
+}
+
 static void flip_all(Pool &p) { for (Column &c : p.cols) c.cur ^= 1; }
 
 // ---------------------------------------------------------------------------------------
@@ -840,7 +849,7 @@ extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, 
   p->n = n;
   p->next_id = (u32)n;
   p->binned = false;
-  p->counted = false;
+  TRY(drop_fused_histogram(rt, *p));
   p->ever_removed = false;
   CU(cudaStreamSynchronize(rt->stream));  // host buffer may be reused by the caller
   return ABL_OK;
@@ -1059,7 +1068,7 @@ static int commit_removals(abl_runtime *rt, Pool &p) {
   flip_all(p);
   p.ever_removed = true;
   p.binned = false;
-  p.counted = false;  // stable compaction keeps cell order, but cell_start is stale
+  TRY(drop_fused_histogram(rt, p));  // stable compaction keeps cell order, but cell_start is stale
   p.n = survivors;
   return ABL_OK;
 }
@@ -1098,7 +1107,7 @@ static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const 
   target.n += m;
   target.next_id += m;
   target.binned = false;
-  target.counted = false;
+  TRY(drop_fused_histogram(rt, target));
   return ABL_OK;
 }
 
@@ -1155,11 +1164,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     // stage reorders the pool afterwards.
     const bool writes_pos = self.pos_member >= 0 && (s.desc.written_members >> self.pos_member & 1u);
     bool fuse = writes_pos && rt->env_set && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
-    if (writes_pos && self.counted) {
-      // a previous fused histogram was never consumed: start over
-      CU(cudaMemsetAsync(self.cell_count, 0, ((size_t)rt->grid.n_cells + 1) * sizeof(u32), rt->stream));
-      self.counted = false;
-    }
+    if (writes_pos) TRY(drop_fused_histogram(rt, self));  // never consumed: start over
     if (fuse) {
       a.bin_key = self.key;
       a.bin_local = self.local;

@@ -1031,9 +1031,9 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     // host-side evaluation of the radius with the kernel's own arithmetic and constants
     Target saved = target;
     w << "    static abl_real limit; static bool have_limit = false;"; w.nl();
-    w << "    if (!have_limit) { const abl_real radius = ";
+    w << "    if (!have_limit) { limit = abl_near_sq_limit((abl_real)(";
     expr(*radius);
-    w << "; limit = abl_near_sq_limit(radius); have_limit = true; }"; w.nl();
+    w << ")); have_limit = true; }"; w.nl();
     target = saved;
   } else {
     w << "    const abl_real limit = 0;"; w.nl();

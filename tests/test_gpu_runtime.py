@@ -73,3 +73,22 @@ def test_missing_device_or_library_fails_loudly(tmp_path):
             runtime.load_library(str(tmp_path / "nope.so"))
         finally:
             runtime._lib = None
+
+
+@pytest.mark.gpu
+def test_reupload_after_fused_binning_restarts_cleanly():
+    """A step kernel that rewrites positions also produces the histogram of the next binning;
+    a fresh upload must discard it (regression: stale counts corrupted cell_start)."""
+    params = {"num_agents": 100000}
+    m = Model(os.path.join(REPO, "examples", "boids2d.abl"), params)
+    m.populate()
+    m.create_runtime()
+    runs = []
+    for _ in range(2):
+        m.upload_host()
+        for _ in range(3):
+            m.timestep()
+        runs.append(m.download(0))
+    m.close()
+    for f in runs[0].dtype.names:
+        assert np.array_equal(runs[0][f], runs[1][f])
