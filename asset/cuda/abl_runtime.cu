@@ -130,6 +130,7 @@ struct GridParams {
   int n_cell[3];
   double origin[3];
   double cell;
+  double inv_cell;  // 1/cell in the precision of abl_float
   u32 n_cells;
 };
 
@@ -372,8 +373,8 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
 // kernels: binning
 // ---------------------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ int cell_coord(R p, R origin, R cell, int n) {
-  int c = (int)floor((p - origin) / cell);
+__device__ __forceinline__ int cell_coord(R p, R origin, R inv_cell, int n) {
+  int c = (int)floor((p - origin) * inv_cell);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
@@ -392,11 +393,11 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
     y = ((const R *)py)[i];
     z = ((const R *)pz)[i];
   }
-  int cx = cell_coord<R>(x, (R)g.origin[0], (R)g.cell, g.n_cell[0]);
-  int cy = cell_coord<R>(y, (R)g.origin[1], (R)g.cell, g.n_cell[1]);
+  int cx = cell_coord<R>(x, (R)g.origin[0], (R)g.inv_cell, g.n_cell[0]);
+  int cy = cell_coord<R>(y, (R)g.origin[1], (R)g.inv_cell, g.n_cell[1]);
   u32 c = (u32)cy * (u32)g.n_cell[0] + (u32)cx;
   if (DIM == 3) {
-    int cz = cell_coord<R>(z, (R)g.origin[2], (R)g.cell, g.n_cell[2]);
+    int cz = cell_coord<R>(z, (R)g.origin[2], (R)g.inv_cell, g.n_cell[2]);
     c += (u32)cz * (u32)g.n_cell[0] * (u32)g.n_cell[1];
   }
   key[i] = c;
@@ -742,6 +743,7 @@ extern "C" int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *
   GridParams &g = rt->grid;
   g.dim = dim;
   g.cell = granularity;
+  g.inv_cell = rt->real_size == 8 ? 1.0 / granularity : (double)(1.0f / (float)granularity);
   u64 cells = 1;
   for (int a = 0; a < 3; a++) {
     if (a < dim) {
@@ -1138,6 +1140,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.grid.dim = rt->grid.dim;
     for (int k = 0; k < 3; k++) { a.grid.n_cell[k] = rt->grid.n_cell[k]; a.grid.origin[k] = rt->grid.origin[k]; }
     a.grid.cell_size = rt->grid.cell;
+    a.grid.inv_cell_size = rt->grid.inv_cell;
     a.grid.n_cells = rt->grid.n_cells;
     a.reach = s.reach;
     a.dead = s.desc.uses_removal ? self.dead : nullptr;

@@ -117,6 +117,7 @@ typedef struct {
   int n_cell[3];
   double origin[3];
   double cell_size;
+  double inv_cell_size;   /* 1/cell_size rounded in the precision of abl_float */
   unsigned n_cells;
 } abl_grid_view;
 

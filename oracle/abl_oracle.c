@@ -101,20 +101,22 @@ typedef struct {
   int n_cell[3];
   abl_float origin[3];
   abl_float cell;
+  abl_float inv_cell; /* 1/cell in abl_float precision, as in the CUDA runtime */
   int n_cells;
   int *cell_start; /* [n_cells + 1] */
   int *order;      /* agent indices sorted by (cell, id) */
 } grid_t;
 
 /* same formula and precision as abl_cell_coord (asset/cuda/abl_device.cuh) */
-static inline int cell_coord(abl_float p, abl_float origin, abl_float cell, int n) {
-  int c = (int)floor((p - origin) / cell);
+static inline int cell_coord(abl_float p, abl_float origin, abl_float inv_cell, int n) {
+  int c = (int)floor((p - origin) * inv_cell);
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
 static void grid_setup(grid_t *g, int dim, const double *env_min, const double *env_max, double granularity) {
   g->dim = dim;
   g->cell = (abl_float)granularity;
+  g->inv_cell = (abl_float)1 / (abl_float)granularity;
   g->n_cells = 1;
   for (int a = 0; a < 3; a++) {
     if (a < dim) {
@@ -132,10 +134,10 @@ static void grid_setup(grid_t *g, int dim, const double *env_min, const double *
 }
 
 static inline int cell_of(const grid_t *g, const abl_float *p) {
-  int cx = cell_coord(p[0], g->origin[0], g->cell, g->n_cell[0]);
-  int cy = cell_coord(p[1], g->origin[1], g->cell, g->n_cell[1]);
+  int cx = cell_coord(p[0], g->origin[0], g->inv_cell, g->n_cell[0]);
+  int cy = cell_coord(p[1], g->origin[1], g->inv_cell, g->n_cell[1]);
   int c = cy * g->n_cell[0] + cx;
-  if (g->dim == 3) c += cell_coord(p[2], g->origin[2], g->cell, g->n_cell[2]) * g->n_cell[0] * g->n_cell[1];
+  if (g->dim == 3) c += cell_coord(p[2], g->origin[2], g->inv_cell, g->n_cell[2]) * g->n_cell[0] * g->n_cell[1];
   return c;
 }
 
@@ -165,9 +167,9 @@ static void grid_free(grid_t *g) { free(g->cell_start); free(g->order); g->cell_
   if ((mode) == MODE_BRUTE) {                                                                     \
     for (int j = 0; j < (n); j++) { BODY }                                                        \
   } else {                                                                                        \
-    int cx_ = cell_coord((self_pos)[0], (g)->origin[0], (g)->cell, (g)->n_cell[0]);               \
-    int cy_ = cell_coord((self_pos)[1], (g)->origin[1], (g)->cell, (g)->n_cell[1]);               \
-    int cz_ = (g)->dim == 3 ? cell_coord((self_pos)[2], (g)->origin[2], (g)->cell, (g)->n_cell[2]) : 0; \
+    int cx_ = cell_coord((self_pos)[0], (g)->origin[0], (g)->inv_cell, (g)->n_cell[0]);               \
+    int cy_ = cell_coord((self_pos)[1], (g)->origin[1], (g)->inv_cell, (g)->n_cell[1]);               \
+    int cz_ = (g)->dim == 3 ? cell_coord((self_pos)[2], (g)->origin[2], (g)->inv_cell, (g)->n_cell[2]) : 0; \
     int x0_ = cx_ - (reach) < 0 ? 0 : cx_ - (reach);                                              \
     int x1_ = cx_ + (reach) >= (g)->n_cell[0] ? (g)->n_cell[0] - 1 : cx_ + (reach);               \
     int y0_ = cy_ - (reach) < 0 ? 0 : cy_ - (reach);                                              \

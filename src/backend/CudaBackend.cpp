@@ -570,24 +570,31 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   w.nl();
   w << it << ".init" << sdim << "(_a, "; expr(agentExpr); w << "." << selfPos->name << ", true);";
   w.nl();
-  w << "for (; " << it << ".valid(); " << it << ".next()) {";
-  w.indent(); w.nl();
-  w << "const unsigned " << it << "j = " << it << ".index();";
-  w.nl();
-  w << nbr->name << " " << s.varName << ";";
-  w.nl();
   int posIndex = nbr->memberIndex(pos->name);
-  loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
-  w.nl();
   // Radius filter: inclusive radius, self included, same operand order as the reference's
   // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
   // is a host-evaluable constant the launcher precomputes the equivalent bound on the
-  // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  // squared distance (abl_near_sq_limit) and the iterator itself skips rejected candidates
+  // (seek), so the loop body only ever runs for neighbours inside the radius.
   if (curStepHasLimit) {
-    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", ";
-    expr(agentExpr);
-    w << "." << selfPos->name << ")) > _near_limit) continue;";
+    std::string seek = it + ".seek" + sdim + "(_a.nbr.in, " + std::to_string(columnOf(*nbr, posIndex)) + ", " +
+                       exprText(agentExpr) + "." + selfPos->name + ", _near_limit)";
+    w << "for (" << seek << "; " << it << ".valid(); " << it << ".next(), " << seek << ") {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "j = " << it << ".index();";
+    w.nl();
+    w << nbr->name << " " << s.varName << ";";
+    w.nl();
+    w << s.varName << "." << pos->name << " = " << it << ".pos" << sdim << "();";
   } else {
+    w << "for (; " << it << ".valid(); " << it << ".next()) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "j = " << it << ".index();";
+    w.nl();
+    w << nbr->name << " " << s.varName << ";";
+    w.nl();
+    loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+    w.nl();
     w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", ";
     expr(agentExpr);
     w << "." << selfPos->name << ") > ";
@@ -1006,7 +1013,8 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w.nl();
   w << self.name << " " << p.outName << " = " << p.name << ";"; w.nl();
   w << "abl_ctx _ctx;"; w.nl();
-  w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, " << (f.usesRng ? "_a.self.id[_i]" : "0u") << ");"; w.nl();
+  if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
+  else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
   w << f.emitName << "(_ctx, _a, _i, _near_limit, " << p.name << ", " << p.outName << ");";
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {

@@ -11,7 +11,7 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def cell_keys(pos, origin, cell, n_cell):
-    c = np.floor((pos - origin) / cell).astype(np.int64)
+    c = np.floor((pos - origin) * (1.0 / cell)).astype(np.int64)  # same formula as abl_cell_coord
     c = np.clip(c, 0, np.array(n_cell[: pos.shape[1]]) - 1)
     key = c[:, 1] * n_cell[0] + c[:, 0]
     if pos.shape[1] == 3:
