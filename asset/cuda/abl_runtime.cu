@@ -156,6 +156,7 @@ struct abl_runtime {
   cudaEvent_t ev_ts[2] = {nullptr, nullptr};
   bool ts_open = false;
   double last_ts_seconds = 0;
+  std::vector<std::pair<void *, size_t>> pinned_ranges;
   abl_step_timing last = {0, 0, 0, 0};
   unsigned launches = 0;
 };
@@ -711,6 +712,8 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     if (p.cell_count) cudaFree(p.cell_count);
     if (p.cell_start) cudaFree(p.cell_start);
   }
+  for (auto &pr : rt->pinned_ranges) cudaHostUnregister(pr.first);
+  rt->pinned_ranges.clear();
   if (rt->scan.desc) cudaFree(rt->scan.desc);
   if (rt->scan.ctrl) cudaFree(rt->scan.ctrl);
   if (rt->stage) cudaFree(rt->stage);
@@ -827,6 +830,37 @@ extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
   if (n) *n = p->n;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_unpin_host(abl_runtime *rt, void *ptr) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  for (size_t i = 0; i < rt->pinned_ranges.size(); i++) {
+    if (rt->pinned_ranges[i].first == ptr) {
+      CU(cudaStreamSynchronize(rt->stream));
+      cudaHostUnregister(ptr);
+      rt->pinned_ranges.erase(rt->pinned_ranges.begin() + i);
+      break;
+    }
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_pin_host(abl_runtime *rt, void *ptr, size_t bytes) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (!ptr || bytes < (1u << 16)) return ABL_OK;  // not worth it
+  for (auto &pr : rt->pinned_ranges) {
+    if (pr.first == ptr) {
+      if (pr.second >= bytes) return ABL_OK;
+      TRY(abl_cuda_unpin_host(rt, ptr));
+      break;
+    }
+  }
+  // best effort: when the pages cannot be locked the transfers simply stay pageable
+  if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess)
+    rt->pinned_ranges.push_back({ptr, bytes});
+  else
+    cudaGetLastError();
   return ABL_OK;
 }
 

@@ -254,10 +254,10 @@ def main():
         m.upload_host()
         for _ in range(args.steps):
             m.timestep()
-        out = [m.download(tt) for tt in range(m.n_types)]
+        m.download_host()
     rt.synchronize()
     e2e_s = (time.perf_counter() - t0) / e2e_reps
-    d2h = sum(o.nbytes for o in out)
+    d2h = sum(len(m.host_agents(tt)) * m.dtypes[tt].itemsize for tt in range(m.n_types))
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

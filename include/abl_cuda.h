@@ -100,6 +100,11 @@ int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n);
  * has been removed; reference save() order, asset/c/libabl.c:96-109). */
 int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity, size_t *n);
 int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
+/* Page-locks a caller-owned host buffer (the record array of an agent type) so that upload /
+ * download are direct DMA transfers.  Optional; idempotent for an unchanged (ptr, bytes).  The
+ * buffer must be unpinned before it is reallocated or freed. */
+int abl_cuda_pin_host(abl_runtime *rt, void *ptr, size_t bytes);
+int abl_cuda_unpin_host(abl_runtime *rt, void *ptr);
 
 /* ---- step functions ------------------------------------------------------------------ */
 

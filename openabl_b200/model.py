@@ -49,7 +49,7 @@ class Model:
         self.lib.abl_model_step_name.restype = C.c_char_p
         self.step_names = [self.lib.abl_model_step_name(s).decode() for s in range(self.n_steps)]
         for fn in ("abl_model_setup", "abl_model_timestep", "abl_model_parallel_steps",
-                   "abl_model_upload", "abl_model_download"):
+                   "abl_model_upload", "abl_model_download", "abl_model_unpin"):
             getattr(self.lib, fn).argtypes = [C.c_void_p]
             getattr(self.lib, fn).restype = C.c_int
         self.lib.abl_model_run_step.argtypes = [C.c_void_p, C.c_int]
@@ -90,6 +90,10 @@ class Model:
     def download(self, t):
         return self.rt.download(self.pool(t), self.dtypes[t])
 
+    def download_host(self):
+        """Device -> the model's own (page-locked) host arrays, as the generated program does."""
+        check(self.lib.abl_model_download(self.rt.handle), "abl_model_download")
+
     def timestep(self):
         check(self.lib.abl_model_timestep(self.rt.handle), "abl_model_timestep")
 
@@ -98,5 +102,6 @@ class Model:
 
     def close(self):
         if self.rt is not None:
+            self.lib.abl_model_unpin(self.rt.handle)
             self.rt.close()
             self.rt = None

@@ -47,6 +47,8 @@ ABI = {
     "abl_cuda_upload": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t]),
     "abl_cuda_download": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "abl_cuda_pool_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_pin_host": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "abl_cuda_unpin_host": (C.c_int, [_VP, _VP]),
     "abl_cuda_register_step": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
     "abl_cuda_step": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_begin_timestep": (C.c_int, [_VP]),

@@ -574,27 +574,20 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   // Radius filter: inclusive radius, self included, same operand order as the reference's
   // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
   // is a host-evaluable constant the launcher precomputes the equivalent bound on the
-  // squared distance (abl_near_sq_limit) and the iterator itself skips rejected candidates
-  // (seek), so the loop body only ever runs for neighbours inside the radius.
+  // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  w << "for (; " << it << ".valid(); " << it << ".next()) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "j = " << it << ".index();";
+  w.nl();
+  w << nbr->name << " " << s.varName << ";";
+  w.nl();
+  loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+  w.nl();
   if (curStepHasLimit) {
-    std::string seek = it + ".seek" + sdim + "(_a.nbr.in, " + std::to_string(columnOf(*nbr, posIndex)) + ", " +
-                       exprText(agentExpr) + "." + selfPos->name + ", _near_limit)";
-    w << "for (" << seek << "; " << it << ".valid(); " << it << ".next(), " << seek << ") {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "j = " << it << ".index();";
-    w.nl();
-    w << nbr->name << " " << s.varName << ";";
-    w.nl();
-    w << s.varName << "." << pos->name << " = " << it << ".pos" << sdim << "();";
+    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", ";
+    expr(agentExpr);
+    w << "." << selfPos->name << ")) > _near_limit) continue;";
   } else {
-    w << "for (; " << it << ".valid(); " << it << ".next()) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "j = " << it << ".index();";
-    w.nl();
-    w << nbr->name << " " << s.varName << ";";
-    w.nl();
-    loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
-    w.nl();
     w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", ";
     expr(agentExpr);
     w << "." << selfPos->name << ") > ";
@@ -902,19 +895,32 @@ void CudaPrinter::hostSimulate() {
   w << "    return 0;"; w.nl();
   w << "}"; w.nl(); w.nl();
 
+  w << "/* host record arrays are page-locked while the runtime uses them (direct DMA) */"; w.nl();
   w << "int abl_model_upload(abl_runtime *rt) {"; w.nl();
-  w << "    for (int t = 0; t < abl_model_n_types; t++)"; w.nl();
-  w << "        abl_host_check(abl_cuda_upload(rt, abl_model_types[t].pool, abl_model_types[t].agents->data, abl_model_types[t].agents->len), \"upload\");"; w.nl();
+  w << "    for (int t = 0; t < abl_model_n_types; t++) {"; w.nl();
+  w << "        abl_host_type *ty = &abl_model_types[t];"; w.nl();
+  w << "        abl_host_check(abl_cuda_pin_host(rt, ty->agents->data, ty->agents->cap * ty->desc.stride), \"pin\");"; w.nl();
+  w << "        abl_host_check(abl_cuda_upload(rt, ty->pool, ty->agents->data, ty->agents->len), \"upload\");"; w.nl();
+  w << "    }"; w.nl();
   w << "    return 0;"; w.nl();
   w << "}"; w.nl();
   w << "int abl_model_download(abl_runtime *rt) {"; w.nl();
   w << "    for (int t = 0; t < abl_model_n_types; t++) {"; w.nl();
+  w << "        abl_host_type *ty = &abl_model_types[t];"; w.nl();
   w << "        size_t n = 0;"; w.nl();
-  w << "        abl_host_check(abl_cuda_pool_size(rt, abl_model_types[t].pool, &n), \"pool_size\");"; w.nl();
-  w << "        abl_array_resize(abl_model_types[t].agents, abl_model_types[t].desc.stride, n);"; w.nl();
-  w << "        abl_host_check(abl_cuda_download(rt, abl_model_types[t].pool, abl_model_types[t].agents->data, n, &n), \"download\");"; w.nl();
+  w << "        abl_host_check(abl_cuda_pool_size(rt, ty->pool, &n), \"pool_size\");"; w.nl();
+  w << "        if (n > ty->agents->cap) {"; w.nl();
+  w << "            abl_host_check(abl_cuda_unpin_host(rt, ty->agents->data), \"unpin\");"; w.nl();
+  w << "            abl_array_resize(ty->agents, ty->desc.stride, n);"; w.nl();
+  w << "            abl_host_check(abl_cuda_pin_host(rt, ty->agents->data, ty->agents->cap * ty->desc.stride), \"pin\");"; w.nl();
+  w << "        }"; w.nl();
+  w << "        ty->agents->len = n;"; w.nl();
+  w << "        abl_host_check(abl_cuda_download(rt, ty->pool, ty->agents->data, n, &n), \"download\");"; w.nl();
   w << "    }"; w.nl();
   w << "    return 0;"; w.nl();
+  w << "}"; w.nl();
+  w << "void abl_model_unpin(abl_runtime *rt) {"; w.nl();
+  w << "    for (int t = 0; t < abl_model_n_types; t++) abl_cuda_unpin_host(rt, abl_model_types[t].agents->data);"; w.nl();
   w << "}"; w.nl(); w.nl();
 
   w << "/* the `simulate` statement: upload, run, download (replaces the reference's inline"; w.nl();
@@ -932,6 +938,7 @@ void CudaPrinter::hostSimulate() {
   w << "    abl_model_upload(rt);"; w.nl();
   w << "    for (int t = 0; t < timesteps; t++) abl_model_timestep(rt);"; w.nl();
   w << "    abl_model_download(rt);"; w.nl();
+  w << "    abl_model_unpin(rt);"; w.nl();
   w << "    abl_rt = NULL;"; w.nl();
   w << "    abl_host_check(abl_cuda_destroy(rt), \"destroy\");"; w.nl();
   w << "}"; w.nl(); w.nl();
