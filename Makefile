@@ -14,7 +14,7 @@ clean:
 # ---- device runtime (asset/cuda/libabl_cuda.so), cross-compiled for sm_100a ---------------
 NVCC ?= nvcc
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 --cudart shared -Xcompiler -fPIC -Iinclude
-RT_SRCS := asset/cuda/abl_runtime.cu asset/cuda/abl_exchange.cu
+RT_SRCS := asset/cuda/abl_runtime.cu
 
 runtime: asset/cuda/libabl_cuda.so
 asset/cuda/libabl_cuda.so: $(RT_SRCS) include/abl_cuda.h

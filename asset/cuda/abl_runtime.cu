@@ -19,6 +19,7 @@
 //   k_compact_move / k_append     stream compaction for remove / add
 //   k_reduce_*                    count / sum reductions
 #include <cuda_runtime.h>
+#include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <string.h>
@@ -88,6 +89,10 @@ struct Pool {
   unsigned stride = 0;
   size_t n = 0, cap = 0;
   u32 next_id = 0;
+  // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
+  // src_begin is where the live records start before the next binning compacts them
+  u32 own_begin = 0, own_end = 0, src_begin = 0;
+  bool own_valid = false;
   bool binned = false;
   bool ever_binned = false;
   bool counted = false;   // key/local/cell_count already hold the histogram of the current positions
@@ -157,6 +162,18 @@ struct abl_runtime {
   bool ts_open = false;
   double last_ts_seconds = 0;
   std::vector<std::pair<void *, size_t>> pinned_ranges;
+  // multi-GPU
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+  bool slab = false;
+  int layer_begin = 0, layer_end = 0;   // owned cell layers along the slab axis
+  int ghost_layers = 1;
+  void *xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send L, send R, recv L, recv R
+  size_t xcap[4] = {0, 0, 0, 0};
+  u32 *xflags = nullptr;  // classification scratch
+  u32 x_out[2] = {0, 0};  // outgoing counts of the last exchange_pack (to lower, to upper)
+  abl_runtime *peer_lo = nullptr, *peer_hi = nullptr;  // in-process transport (tests)
+  size_t xflags_cap = 0;
   abl_step_timing last = {0, 0, 0, 0};
   unsigned launches = 0;
 };
@@ -381,18 +398,19 @@ __device__ __forceinline__ int cell_coord(R p, R origin, R inv_cell, int n) {
 
 // POS2: position is one packed 2-vector column; otherwise three scalar columns.
 template <typename R, int DIM>
-__global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, GridParams g,
-                            u32 *key, u32 *local, u32 *cell_count) {
+__global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, u32 src_begin,
+                            GridParams g, u32 *key, u32 *local, u32 *cell_count) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  const size_t s = (size_t)src_begin + i;
   R x, y, z = 0;
   if (DIM == 2) {
-    x = ((const R *)px)[2 * (size_t)i];
-    y = ((const R *)px)[2 * (size_t)i + 1];
+    x = ((const R *)px)[2 * s];
+    y = ((const R *)px)[2 * s + 1];
   } else {
-    x = ((const R *)px)[i];
-    y = ((const R *)py)[i];
-    z = ((const R *)pz)[i];
+    x = ((const R *)px)[s];
+    y = ((const R *)py)[s];
+    z = ((const R *)pz)[s];
   }
   int cx = cell_coord<R>(x, (R)g.origin[0], (R)g.inv_cell, g.n_cell[0]);
   int cy = cell_coord<R>(y, (R)g.origin[1], (R)g.inv_cell, g.n_cell[1]);
@@ -826,9 +844,17 @@ static int get_pool(abl_runtime *rt, int pool, Pool **out) {
   return ABL_OK;
 }
 
+static int slab_bin_if_needed(abl_runtime *rt, Pool &p);
+static int bin_pool(abl_runtime *rt, Pool &p);
+
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
+  if (rt->slab && p->pos_member >= 0) {
+    TRY(slab_bin_if_needed(rt, *p));
+    if (n) *n = p->own_end - p->own_begin;
+    return ABL_OK;
+  }
   if (n) *n = p->n;
   return ABL_OK;
 }
@@ -864,7 +890,13 @@ extern "C" int abl_cuda_pin_host(abl_runtime *rt, void *ptr, size_t bytes) {
   return ABL_OK;
 }
 
-extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n) {
+__global__ void k_set_ids(u32 *dst, const u32 *src, u32 n) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+
+static int upload_impl(abl_runtime *rt, int pool, const void *host_aos, const unsigned *ids, size_t n,
+                       unsigned next_id) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
@@ -873,22 +905,48 @@ extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, 
   TRY(reserve_pool(rt, *p, std::max(n, (size_t)1)));
   size_t bytes = n * (size_t)p->stride;
   if (n) {
-    TRY(ensure_stage(rt, bytes));
+    TRY(ensure_stage(rt, round_up(bytes, 256) + (ids ? n * sizeof(u32) : 0)));
     CU(cudaMemcpyAsync(rt->stage, host_aos, bytes, cudaMemcpyHostToDevice, rt->stream));
     ColTable t;
     fill_table(*p, t, false);
     k_aos_to_soa<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->stage, p->stride,
                                                              (u32)n, 0u);
     rt->launches++;
+    if (ids) {
+      u32 *d_ids = (u32 *)((u8 *)rt->stage + round_up(bytes, 256));
+      CU(cudaMemcpyAsync(d_ids, ids, n * sizeof(u32), cudaMemcpyHostToDevice, rt->stream));
+      k_set_ids<<<blocks_for(n, 256), 256, 0, rt->stream>>>((u32 *)t.out[p->id_col], d_ids, (u32)n);
+      rt->launches++;
+    }
     CU(cudaGetLastError());
   }
   p->n = n;
-  p->next_id = (u32)n;
+  p->next_id = ids ? next_id : (u32)n;
   p->binned = false;
+  p->own_valid = false;
+  p->src_begin = 0;
+  p->own_begin = 0;
+  p->own_end = (u32)n;
   TRY(drop_fused_histogram(rt, *p));
   p->ever_removed = false;
   CU(cudaStreamSynchronize(rt->stream));  // host buffer may be reused by the caller
   return ABL_OK;
+}
+
+static int slab_crop_to_owned(abl_runtime *rt, int pool);
+
+// In slab mode every rank may upload the whole population: it keeps the agents of its own
+// slab and obtains ghosts with the first exchange.
+extern "C" int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n) {
+  TRY(upload_impl(rt, pool, host_aos, nullptr, n, 0));
+  if (rt->slab) TRY(slab_crop_to_owned(rt, pool));
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_upload_with_ids(abl_runtime *rt, int pool, const void *host_aos,
+                                        const unsigned *ids, size_t n, unsigned next_id) {
+  if (n && !ids) return fail(ABL_ERR_ARGUMENT, "null ids");
+  return upload_impl(rt, pool, host_aos, ids, n, next_id);
 }
 
 extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity,
@@ -896,22 +954,32 @@ extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size
   Pool *p;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
-  if (n_out) *n_out = p->n;
-  if (capacity < p->n) return fail(ABL_ERR_CAPACITY, "download: buffer holds %zu agents, pool has %zu", capacity, p->n);
-  if (p->n == 0) return ABL_OK;
-  size_t bytes = p->n * (size_t)p->stride;
+  // slab mode: only the owned agents are this rank's to report
+  u32 first = 0;
+  size_t count = p->n;
+  if (rt->slab && p->pos_member >= 0) {
+    if (!p->binned) TRY(bin_pool(rt, *p));
+    first = p->own_begin;
+    count = p->own_end - p->own_begin;
+  } else if (p->src_begin) {
+    first = p->src_begin;
+  }
+  if (n_out) *n_out = count;
+  if (capacity < count) return fail(ABL_ERR_CAPACITY, "download: buffer holds %zu agents, pool has %zu", capacity, count);
+  if (count == 0) return ABL_OK;
+  size_t bytes = count * (size_t)p->stride;
   size_t rank_bytes = 0;
-  const bool dense = p->next_id == p->n;  // ids are a permutation of 0..n-1
+  const bool dense = !rt->slab && p->next_id == p->n;  // ids are a permutation of 0..n-1
   if (!dense) rank_bytes = round_up((size_t)p->next_id + 1, kScanTile) * sizeof(u32) * 2;
   TRY(ensure_stage(rt, round_up(bytes, 256) + rank_bytes));
-  const u32 *ids = (const u32 *)p->cols[p->id_col].buf[p->cols[p->id_col].cur];
+  const u32 *ids = (const u32 *)p->cols[p->id_col].buf[p->cols[p->id_col].cur] + first;
   u32 *rank = nullptr;
   if (!dense) {
     u32 *present = (u32 *)((u8 *)rt->stage + round_up(bytes, 256));
     size_t padded = round_up((size_t)p->next_id + 1, kScanTile);
     rank = present + padded;
     CU(cudaMemsetAsync(present, 0, padded * sizeof(u32), rt->stream));
-    k_mark_present<<<blocks_for(p->n, 256), 256, 0, rt->stream>>>(ids, (u32)p->n, present);
+    k_mark_present<<<blocks_for(count, 256), 256, 0, rt->stream>>>(ids, (u32)count, present);
     rt->launches++;
     TRY((run_scan<u32, 0, false>(rt, present, rank, (size_t)p->next_id, nullptr)));
   }
@@ -919,11 +987,56 @@ extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size
   CU(cudaMemsetAsync(rt->stage, 0, bytes, rt->stream));
   ColTable t;
   fill_table(*p, t, false);
-  k_soa_to_aos<<<blocks_for(p->n, 256), 256, 0, rt->stream>>>(t, (u8 *)rt->stage, p->stride,
-                                                              (u32)p->n, ids, rank);
+  for (int c = 0; c < t.ncols; c++) t.in[c] = (const u8 *)t.in[c] + (size_t)first * t.elem[c];
+  k_soa_to_aos<<<blocks_for(count, 256), 256, 0, rt->stream>>>(t, (u8 *)rt->stage, p->stride,
+                                                               (u32)count, ids, rank);
   rt->launches++;
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(host_aos, rt->stage, bytes, cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  return ABL_OK;
+}
+
+__global__ void k_ids_sorted(const u32 *ids, const u32 *rank, u32 n, u32 *out) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[rank ? rank[ids[i]] : ids[i]] = ids[i];
+}
+
+// ids of the agents abl_cuda_download returns, in the same (ascending) order
+extern "C" int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids_out, size_t capacity,
+                                     size_t *n_out) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  CU(cudaSetDevice(rt->device));
+  u32 first = 0;
+  size_t count = p->n;
+  if (rt->slab && p->pos_member >= 0) {
+    if (!p->binned) TRY(bin_pool(rt, *p));
+    first = p->own_begin;
+    count = p->own_end - p->own_begin;
+  } else if (p->src_begin) {
+    first = p->src_begin;
+  }
+  if (n_out) *n_out = count;
+  if (capacity < count) return fail(ABL_ERR_CAPACITY, "download_ids: buffer too small");
+  if (!count) return ABL_OK;
+  const bool dense = !rt->slab && p->next_id == p->n;
+  size_t padded = round_up((size_t)p->next_id + 1, kScanTile);
+  TRY(ensure_stage(rt, round_up(count * sizeof(u32), 256) + padded * sizeof(u32) * 2));
+  const u32 *ids = (const u32 *)p->cols[p->id_col].buf[p->cols[p->id_col].cur] + first;
+  u32 *out = (u32 *)rt->stage;
+  u32 *rank = nullptr;
+  if (!dense) {
+    u32 *present = (u32 *)((u8 *)rt->stage + round_up(count * sizeof(u32), 256));
+    rank = present + padded;
+    CU(cudaMemsetAsync(present, 0, padded * sizeof(u32), rt->stream));
+    k_mark_present<<<blocks_for(count, 256), 256, 0, rt->stream>>>(ids, (u32)count, present);
+    TRY((run_scan<u32, 0, false>(rt, present, rank, (size_t)p->next_id, nullptr)));
+  }
+  k_ids_sorted<<<blocks_for(count, 256), 256, 0, rt->stream>>>(ids, rank, (u32)count, out);
+  rt->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaMemcpyAsync(ids_out, out, count * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaStreamSynchronize(rt->stream));
   return ABL_OK;
 }
@@ -941,6 +1054,8 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   return ABL_OK;
 }
 
+static int slab_update_owned_range(abl_runtime *rt, Pool &p);
+
 static int launch_bin_count(abl_runtime *rt, Pool &p) {
   const GridParams &g = rt->grid;
   const Member &pm = p.members[p.pos_member];
@@ -955,11 +1070,11 @@ static int launch_bin_count(abl_runtime *rt, Pool &p) {
   }
   u32 nb = blocks_for(n, bs);
   if (rt->real_size == 8) {
-    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
+    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
   } else {
-    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
-    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
+    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
   }
   rt->launches++;
   CU(cudaGetLastError());
@@ -985,16 +1100,20 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
     u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
-    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, 0u, p.cell_start, seg_ids);
+    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, p.src_begin, p.cell_start, seg_ids);
     ColTable t;
     fill_table(p, t, true);
-    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, ids, n, 0u, p.cell_start);
+    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, ids, n, p.src_begin, p.cell_start);
     rt->launches += 2;
     CU(cudaGetLastError());
     flip_all(p);
   }
+  p.src_begin = 0;
   p.binned = true;
   p.ever_binned = true;
+  if (rt->slab) TRY(slab_update_owned_range(rt, p));
+  else { p.own_begin = 0; p.own_end = (u32)p.n; }
+  p.own_valid = true;
   return ABL_OK;
 }
 
@@ -1163,6 +1282,11 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     // neighbouring cells (coalescing / L1 reuse)
     if (&self != nbr && self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self));
   }
+  if (rt->slab) {
+    if (s.desc.uses_removal || added)
+      return fail(ABL_ERR_STATE, "step %s: run-time add/remove is not supported with slab decomposition yet", s.name.c_str());
+    if (self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self));
+  }
   if (rt->timing) CU(cudaEventRecord(rt->ev[1], rt->stream));
 
   if (self.n) {
@@ -1170,6 +1294,17 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     abl_step_launch a;
     memset(&a, 0, sizeof a);
     fill_view(self, a.self, s.desc.written_members, true);
+    if (rt->slab && self.pos_member >= 0) {
+      // the step function runs over the owned range only
+      const u32 ob = self.own_begin;
+      int ncols = (int)self.cols.size() - 1;
+      for (int c = 0; c < ncols; c++) {
+        a.self.in[c] = (const u8 *)a.self.in[c] + (size_t)ob * self.cols[c].elem;
+        a.self.out[c] = (u8 *)a.self.out[c] + (size_t)ob * self.cols[c].elem;
+      }
+      a.self.id += ob;
+      a.self.n = self.own_end - ob;
+    }
     if (nbr) fill_view(*nbr, a.nbr, 0, false);
     a.grid.dim = rt->grid.dim;
     for (int k = 0; k < 3; k++) { a.grid.n_cell[k] = rt->grid.n_cell[k]; a.grid.origin[k] = rt->grid.origin[k]; }
@@ -1200,7 +1335,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     // rewrites the positions of a pool that is used for neighbour search and no commit
     // stage reorders the pool afterwards.
     const bool writes_pos = self.pos_member >= 0 && (s.desc.written_members >> self.pos_member & 1u);
-    bool fuse = writes_pos && rt->env_set && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
+    bool fuse = writes_pos && rt->env_set && !rt->slab && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
     if (writes_pos) TRY(drop_fused_histogram(rt, self));  // never consumed: start over
     if (fuse) {
       a.bin_key = self.key;
@@ -1213,7 +1348,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.block_size = rt->cfg.block_size;
     a.tile_neighbours = rt->cfg.tile_neighbours;
     a.stream = (void *)rt->stream;
-    int rc = s.desc.launch(&a);
+    int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches++;
     if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: kernel launch failed: %s", s.name.c_str(),
                              cudaGetErrorString((cudaError_t)rc));
@@ -1229,6 +1364,9 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (fuse) self.counted = true;
     if (added) TRY(commit_adds(rt, self, *added, staging));
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
+    // slab mode: ghosts of this pool are stale (and agents may have left the slab)
+    if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
+      TRY(abl_cuda_exchange(rt, s.desc.self_pool));
   } else if (rt->timing) {
     CU(cudaEventRecord(rt->ev[2], rt->stream));
   }
@@ -1386,5 +1524,347 @@ extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int com
 }
 
 // ---------------------------------------------------------------------------------------
-// multi-GPU (slab decomposition): implemented in abl_exchange.cu
+// multi-GPU: slab decomposition with halo + migration exchange over NCCL
 // ---------------------------------------------------------------------------------------
+// The grid is cut into slabs of whole cell layers along the slowest-varying axis (y in 2D,
+// z in 3D).  Rank r owns the agents whose cell layer lies in [layer_begin, layer_end) and
+// additionally holds read-only ghost copies of the `ghost_layers` adjacent layers on each
+// side.  Because the pool is kept sorted by global cell key, the array always looks like
+//     [ ghosts below | owned | ghosts above ]
+// and ownership is nothing but a key range: own_begin = cell_start[layer_begin * row],
+// own_end = cell_start[layer_end * row].  Step kernels run over the owned range only and see
+// ghosts through the ordinary neighbour search, in the same (cell key, id) order as a
+// single-GPU run, so results are bit-identical for any number of GPUs.
+//
+// After a step function has written members of a pool its ghosts are stale.  exchange():
+//   1. classify every formerly owned agent by the layer of its (new) position:
+//      layer <  layer_begin + G  -> copy goes to rank-1      (G = ghost_layers)
+//      layer >= layer_end   - G  -> copy goes to rank+1
+//      (this covers both migration and halo refresh: the receiver decides by key range
+//      whether an arrival is owned or a ghost; the sender keeps its record, which turns
+//      into a ghost by the same rule if the agent left the slab)
+//   2. pack the selected records column-wise (warp-scan compaction), swap counts, then
+//      payloads, with grouped ncclSend/ncclRecv on the runtime's stream (NVLink)
+//   3. drop the old ghosts (the owned range is contiguous), append the arrivals and let the
+//      next binning sort everything back into [ghosts | owned | ghosts].
+static int slab_bin_if_needed(abl_runtime *rt, Pool &p) {
+  if (!p.binned) TRY(bin_pool(rt, p));
+  return ABL_OK;
+}
+
+static int slab_row_cells(const abl_runtime *rt) {
+  const GridParams &g = rt->grid;
+  return g.dim == 3 ? g.n_cell[0] * g.n_cell[1] : g.n_cell[0];
+}
+static int slab_layers(const abl_runtime *rt) {
+  return rt->grid.dim == 3 ? rt->grid.n_cell[2] : rt->grid.n_cell[1];
+}
+
+static int slab_crop_to_owned(abl_runtime *rt, int pool) {
+  Pool &p = rt->pools[pool];
+  if (p.pos_member < 0) return ABL_OK;
+  TRY(bin_pool(rt, p));
+  p.src_begin = p.own_begin;
+  p.n = p.own_end - p.own_begin;
+  p.binned = false;  // the next binning compacts the owned records to the front
+  return ABL_OK;
+}
+
+static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
+  const int row = slab_row_cells(rt);
+  u32 lo_cell = (u32)rt->layer_begin * (u32)row, hi_cell = (u32)rt->layer_end * (u32)row;
+  CU(cudaMemcpyAsync(&rt->h_scalar[0], p.cell_start + lo_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaMemcpyAsync(&rt->h_scalar[1], p.cell_start + hi_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  p.own_begin = rt->h_scalar[0];
+  p.own_end = rt->h_scalar[1];
+  return ABL_OK;
+}
+
+// flags[i] bit0: send to the lower rank, bit1: send to the upper rank
+template <typename R>
+__global__ void k_slab_classify(const R *axis_col, int stride, int comp, u32 n, u32 first, R origin,
+                                R inv_cell, int n_layers, int lo_limit, int hi_limit, u8 *to_lo, u8 *to_hi) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  R v = axis_col[(size_t)(first + i) * stride + comp];
+  int layer = cell_coord<R>(v, origin, inv_cell, n_layers);
+  to_lo[i] = layer < lo_limit ? 1 : 0;
+  to_hi[i] = layer >= hi_limit ? 1 : 0;
+}
+
+// message layout: column 0 of all selected agents, column 1, ..., ids (each padded to 16 bytes)
+__global__ void k_slab_pack(ColTable t, const u8 *flag, const u32 *offsets, u32 n, u32 first, u32 count,
+                            u8 *msg) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || !flag[i]) return;
+  u32 dst = offsets[i];
+  size_t off = 0;
+  for (int k = 0; k < t.ncols; k++) {
+    copy_elem(msg + off, dst, t.in[k], first + i, t.elem[k]);
+    off += ((size_t)count * t.elem[k] + 15) / 16 * 16;
+  }
+}
+
+__global__ void k_slab_unpack(ColTable t, const u8 *msg, u32 count, u32 dst_first) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  size_t off = 0;
+  for (int k = 0; k < t.ncols; k++) {
+    copy_elem(t.out[k], dst_first + i, msg + off, i, t.elem[k]);
+    off += ((size_t)count * t.elem[k] + 15) / 16 * 16;
+  }
+}
+
+static size_t slab_msg_bytes(const Pool &p, size_t count) {
+  size_t bytes = 0;
+  for (const Column &c : p.cols) bytes += (count * (size_t)c.elem + 15) / 16 * 16;
+  return bytes;
+}
+
+static int ensure_xbuf(abl_runtime *rt, int which, size_t bytes) {
+  if (rt->xcap[which] >= bytes) return ABL_OK;
+  CU(cudaStreamSynchronize(rt->stream));
+  if (rt->xbuf[which]) CU(cudaFree(rt->xbuf[which]));
+  size_t cap = round_up(bytes + bytes / 4 + 4096, 1 << 16);
+  CU(cudaMalloc(&rt->xbuf[which], cap));
+  rt->xcap[which] = cap;
+  return ABL_OK;
+}
+
+#define NCCL(call)                                                                          \
+  do {                                                                                      \
+    ncclResult_t r_ = (call);                                                               \
+    if (r_ != ncclSuccess)                                                                  \
+      return fail(ABL_ERR_COMM, "%s failed: %s (%s:%d)", #call, ncclGetErrorString(r_),     \
+                  __FILE__, __LINE__);                                                      \
+  } while (0)
+
+extern "C" int abl_cuda_nccl_unique_id(void *id128) {
+  if (!id128) return fail(ABL_ERR_ARGUMENT, "null id buffer");
+  ncclUniqueId id;
+  NCCL(ncclGetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  memcpy(id128, &id, sizeof id);
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_comm_init_nccl(abl_runtime *rt, const void *id128, int rank, int world) {
+  if (!rt || !id128) return fail(ABL_ERR_ARGUMENT, "null argument");
+  if (world < 1 || rank < 0 || rank >= world) return fail(ABL_ERR_ARGUMENT, "bad rank/world");
+  CU(cudaSetDevice(rt->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof id);
+  NCCL(ncclCommInitRank(&rt->comm, world, id, rank));
+  rt->rank = rank;
+  rt->world = world;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers) {
+  if (!rt || !rt->env_set) return fail(ABL_ERR_STATE, "environment not set");
+  if (n_layers) *n_layers = slab_layers(rt);
+  return ABL_OK;
+}
+
+// Also usable without NCCL (world == 1 or comm == NULL): then exchange() only re-sorts, which
+// is what the single-process tests of the slab bookkeeping use.
+extern "C" int abl_cuda_set_slab(abl_runtime *rt, int layer_begin, int layer_end) {
+  if (!rt || !rt->env_set) return fail(ABL_ERR_STATE, "set_slab requires an environment");
+  const int layers = slab_layers(rt);
+  if (layer_begin < 0 || layer_end > layers || layer_begin >= layer_end)
+    return fail(ABL_ERR_ARGUMENT, "bad slab [%d, %d) of %d layers", layer_begin, layer_end, layers);
+  rt->slab = true;
+  rt->layer_begin = layer_begin;
+  rt->layer_end = layer_end;
+  int g = 1;
+  for (const Step &s : rt->steps) g = std::max(g, s.reach);
+  rt->ghost_layers = g;
+  for (Pool &p : rt->pools) p.binned = false;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  if (rt->slab && p->pos_member >= 0) {
+    if (!p->binned) TRY(bin_pool(rt, *p));
+    if (n) *n = p->own_end - p->own_begin;
+  } else if (n) {
+    *n = p->n;
+  }
+  return ABL_OK;
+}
+
+// ---- exchange, phase 1: classify + pack (per direction: message in xbuf[0/1], count in x_out) --
+static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
+  if (!p.own_valid) TRY(bin_pool(rt, p));  // fresh upload: establish the owned range
+  const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
+  const GridParams &g = rt->grid;
+  const int axis = g.dim - 1;
+  const Member &pm = p.members[p.pos_member];
+  if (rt->xflags_cap < (size_t)n_own * 2 + 64) {
+    CU(cudaStreamSynchronize(rt->stream));
+    if (rt->xflags) CU(cudaFree(rt->xflags));
+    rt->xflags_cap = round_up((size_t)n_own * 2 + 64, kScanTile) * 2;
+    CU(cudaMalloc(&rt->xflags, rt->xflags_cap));
+  }
+  u8 *to_lo = (u8 *)rt->xflags;
+  u8 *to_hi = to_lo + round_up((size_t)n_own + 16, kScanTile);
+  u32 counts[2] = {0, 0};
+  u32 *off_lo = p.offsets, *off_hi = p.local;  // scratch of at least cap entries each
+  if (n_own && (has_lo || has_hi)) {
+    int col = pm.first_col, stride = 1, comp = 0;
+    if (g.dim == 2) { stride = 2; comp = 1; } else { col += 2; }
+    const void *axis_col = p.cols[col].buf[p.cols[col].cur];
+    const int lo_limit = rt->layer_begin + rt->ghost_layers, hi_limit = rt->layer_end - rt->ghost_layers;
+    u32 nb = blocks_for(n_own, 256);
+    if (rt->real_size == 8)
+      k_slab_classify<double><<<nb, 256, 0, rt->stream>>>((const double *)axis_col, stride, comp, n_own, ob,
+          g.origin[axis], g.inv_cell, slab_layers(rt), lo_limit, hi_limit, to_lo, to_hi);
+    else
+      k_slab_classify<float><<<nb, 256, 0, rt->stream>>>((const float *)axis_col, stride, comp, n_own, ob,
+          (float)g.origin[axis], (float)g.inv_cell, slab_layers(rt), lo_limit, hi_limit, to_lo, to_hi);
+    rt->launches++;
+    CU(cudaGetLastError());
+    if (has_lo) TRY((run_scan<u8, 0, false>(rt, to_lo, off_lo, n_own, rt->d_scalar + 8)));
+    if (has_hi) TRY((run_scan<u8, 0, false>(rt, to_hi, off_hi, n_own, rt->d_scalar + 9)));
+    CU(cudaMemcpyAsync(rt->h_scalar + 8, rt->d_scalar + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaStreamSynchronize(rt->stream));
+    if (has_lo) counts[0] = rt->h_scalar[8];
+    if (has_hi) counts[1] = rt->h_scalar[9];
+  }
+  ColTable t;
+  fill_table(p, t, false);
+  TRY(ensure_xbuf(rt, 0, slab_msg_bytes(p, counts[0])));
+  TRY(ensure_xbuf(rt, 1, slab_msg_bytes(p, counts[1])));
+  if (counts[0]) {
+    k_slab_pack<<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, to_lo, off_lo, n_own, ob, counts[0], (u8 *)rt->xbuf[0]);
+    rt->launches++;
+  }
+  if (counts[1]) {
+    k_slab_pack<<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, to_hi, off_hi, n_own, ob, counts[1], (u8 *)rt->xbuf[1]);
+    rt->launches++;
+  }
+  CU(cudaGetLastError());
+  rt->x_out[0] = counts[0];
+  rt->x_out[1] = counts[1];
+  return ABL_OK;
+}
+
+// ---- exchange, phase 3: arrivals (already in xbuf[2/3]) are appended behind the owned range ----
+static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
+  const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
+  const u32 arrivals = incoming[0] + incoming[1];
+  if ((size_t)oe + arrivals > p.cap) {
+    p.n = std::max(p.n, (size_t)oe);
+    TRY(reserve_pool(rt, p, (size_t)oe + arrivals));
+  }
+  ColTable t;
+  fill_table(p, t, false);
+  for (int c = 0; c < t.ncols; c++) t.out[c] = const_cast<void *>(t.in[c]);
+  if (incoming[0]) {
+    k_slab_unpack<<<blocks_for(incoming[0], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[2], incoming[0], oe);
+    rt->launches++;
+  }
+  if (incoming[1]) {
+    k_slab_unpack<<<blocks_for(incoming[1], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[3], incoming[1], oe + incoming[0]);
+    rt->launches++;
+  }
+  CU(cudaGetLastError());
+  // old ghosts (below ob, above oe) are dead; the next binning compacts [ob, oe + arrivals)
+  p.src_begin = ob;
+  p.n = (size_t)n_own + arrivals;
+  p.binned = false;
+  TRY(drop_fused_histogram(rt, p));
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!rt->slab || p.pos_member < 0) return ABL_OK;
+  if (rt->peer_lo || rt->peer_hi)
+    return fail(ABL_ERR_STATE, "in-process peers: use abl_cuda_exchange_begin/end on all runtimes");
+  CU(cudaSetDevice(rt->device));
+  const bool has_lo = rt->comm && rt->rank > 0, has_hi = rt->comm && rt->rank < rt->world - 1;
+  TRY(exchange_pack(rt, p, has_lo, has_hi));
+  const u32 counts[2] = {rt->x_out[0], rt->x_out[1]};
+  u32 incoming[2] = {0, 0};
+  if (has_lo || has_hi) {
+    u32 *d_cnt = rt->d_scalar + 12;  // [0..1] outgoing, [2..3] incoming
+    CU(cudaMemcpyAsync(d_cnt, counts, sizeof counts, cudaMemcpyHostToDevice, rt->stream));
+    NCCL(ncclGroupStart());
+    if (has_lo) {
+      NCCL(ncclSend(d_cnt + 0, 1, ncclUint32, rt->rank - 1, rt->comm, rt->stream));
+      NCCL(ncclRecv(d_cnt + 2, 1, ncclUint32, rt->rank - 1, rt->comm, rt->stream));
+    }
+    if (has_hi) {
+      NCCL(ncclSend(d_cnt + 1, 1, ncclUint32, rt->rank + 1, rt->comm, rt->stream));
+      NCCL(ncclRecv(d_cnt + 3, 1, ncclUint32, rt->rank + 1, rt->comm, rt->stream));
+    }
+    NCCL(ncclGroupEnd());
+    CU(cudaMemcpyAsync(rt->h_scalar + 12, d_cnt + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaStreamSynchronize(rt->stream));
+    if (has_lo) incoming[0] = rt->h_scalar[12];
+    if (has_hi) incoming[1] = rt->h_scalar[13];
+    TRY(ensure_xbuf(rt, 2, slab_msg_bytes(p, incoming[0])));
+    TRY(ensure_xbuf(rt, 3, slab_msg_bytes(p, incoming[1])));
+    NCCL(ncclGroupStart());
+    if (has_lo) {
+      if (counts[0]) NCCL(ncclSend(rt->xbuf[0], slab_msg_bytes(p, counts[0]), ncclUint8, rt->rank - 1, rt->comm, rt->stream));
+      if (incoming[0]) NCCL(ncclRecv(rt->xbuf[2], slab_msg_bytes(p, incoming[0]), ncclUint8, rt->rank - 1, rt->comm, rt->stream));
+    }
+    if (has_hi) {
+      if (counts[1]) NCCL(ncclSend(rt->xbuf[1], slab_msg_bytes(p, counts[1]), ncclUint8, rt->rank + 1, rt->comm, rt->stream));
+      if (incoming[1]) NCCL(ncclRecv(rt->xbuf[3], slab_msg_bytes(p, incoming[1]), ncclUint8, rt->rank + 1, rt->comm, rt->stream));
+    }
+    NCCL(ncclGroupEnd());
+  }
+  return exchange_unpack(rt, p, incoming);
+}
+
+// ---- in-process transport: several runtimes (slabs) driven by one host thread -------------
+// Used to exercise the slab bookkeeping on a single GPU: the caller runs the step on every
+// slab, then exchange_begin on every slab, then exchange_end on every slab.
+extern "C" int abl_cuda_set_local_peers(abl_runtime *rt, abl_runtime *lower, abl_runtime *upper) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  rt->peer_lo = lower;
+  rt->peer_hi = upper;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_exchange_begin(abl_runtime *rt, int pool) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  if (!rt->slab || pp->pos_member < 0) return ABL_OK;
+  CU(cudaSetDevice(rt->device));
+  TRY(exchange_pack(rt, *pp, rt->peer_lo != nullptr, rt->peer_hi != nullptr));
+  CU(cudaStreamSynchronize(rt->stream));
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_exchange_end(abl_runtime *rt, int pool) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!rt->slab || p.pos_member < 0) return ABL_OK;
+  CU(cudaSetDevice(rt->device));
+  u32 incoming[2] = {0, 0};
+  if (rt->peer_lo) {  // what the lower slab sent upwards
+    incoming[0] = rt->peer_lo->x_out[1];
+    size_t bytes = slab_msg_bytes(p, incoming[0]);
+    TRY(ensure_xbuf(rt, 2, bytes));
+    if (bytes) CU(cudaMemcpyAsync(rt->xbuf[2], rt->peer_lo->xbuf[1], bytes, cudaMemcpyDefault, rt->stream));
+  }
+  if (rt->peer_hi) {  // what the upper slab sent downwards
+    incoming[1] = rt->peer_hi->x_out[0];
+    size_t bytes = slab_msg_bytes(p, incoming[1]);
+    TRY(ensure_xbuf(rt, 3, bytes));
+    if (bytes) CU(cudaMemcpyAsync(rt->xbuf[3], rt->peer_hi->xbuf[0], bytes, cudaMemcpyDefault, rt->stream));
+  }
+  TRY(exchange_unpack(rt, p, incoming));
+  CU(cudaStreamSynchronize(rt->stream));
+  return ABL_OK;
+}

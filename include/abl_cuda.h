@@ -96,9 +96,15 @@ int abl_cuda_add_pool(abl_runtime *rt, const abl_agent_desc *desc, int *pool);
 /* Host AoS -> device SoA.  Agent i receives id i (ids are the tie-break of the cell sort
  * and the order of every download). */
 int abl_cuda_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n);
+/* Same with caller-chosen agent ids (slab decomposition: every rank uploads its part of a
+ * globally numbered population); next_id = 1 + the largest id in the whole population. */
+int abl_cuda_upload_with_ids(abl_runtime *rt, int pool, const void *host_aos, const unsigned *ids,
+                             size_t n, unsigned next_id);
 /* Device SoA -> host AoS in ascending agent-id order (= original index order while no agent
  * has been removed; reference save() order, asset/c/libabl.c:96-109). */
 int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity, size_t *n);
+/* Ids of the agents abl_cuda_download returns, in the same (ascending) order. */
+int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids, size_t capacity, size_t *n);
 int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 /* Page-locks a caller-owned host buffer (the record array of an agent type) so that upload /
  * download are direct DMA transfers.  Optional; idempotent for an unchanged (ptr, bytes).  The
@@ -216,6 +222,13 @@ int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers);
  * arrivals, then refresh ghost layers of `pool`.  Collective over neighbouring ranks. */
 int abl_cuda_exchange(abl_runtime *rt, int pool);
 int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n);
+/* In-process transport between runtimes driven by one host thread (several slabs on one
+ * GPU; used by the single-GPU tests of the decomposition).  With local peers set the caller
+ * runs a step on every slab, then exchange_begin on every slab, then exchange_end on every
+ * slab; abl_cuda_step does not exchange by itself in this mode. */
+int abl_cuda_set_local_peers(abl_runtime *rt, abl_runtime *lower, abl_runtime *upper);
+int abl_cuda_exchange_begin(abl_runtime *rt, int pool);
+int abl_cuda_exchange_end(abl_runtime *rt, int pool);
 
 #ifdef __cplusplus
 }

@@ -45,8 +45,10 @@ ABI = {
     "abl_cuda_set_environment": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_double]),
     "abl_cuda_add_pool": (C.c_int, [_VP, C.POINTER(AgentDesc), C.POINTER(C.c_int)]),
     "abl_cuda_upload": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t]),
+    "abl_cuda_upload_with_ids": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_size_t, C.c_uint]),
     "abl_cuda_download": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "abl_cuda_pool_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_download_ids": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "abl_cuda_pin_host": (C.c_int, [_VP, _VP, C.c_size_t]),
     "abl_cuda_unpin_host": (C.c_int, [_VP, _VP]),
     "abl_cuda_register_step": (C.c_int, [_VP, _VP, C.POINTER(C.c_int)]),
@@ -72,6 +74,9 @@ ABI = {
     "abl_cuda_slab_axis_layers": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "abl_cuda_exchange": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_owned_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_set_local_peers": (C.c_int, [_VP, _VP, _VP]),
+    "abl_cuda_exchange_begin": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_exchange_end": (C.c_int, [_VP, C.c_int]),
 }
 
 _lib = None
@@ -150,6 +155,45 @@ class Runtime:
         got = C.c_size_t()
         check(self.lib.abl_cuda_download(self.handle, pool, out.ctypes.data_as(_VP), n, C.byref(got)), "download")
         return out
+
+    def download_ids(self, pool):
+        import numpy as np
+        n = self.pool_size(pool)
+        out = np.zeros(n, dtype=np.uint32)
+        got = C.c_size_t()
+        check(self.lib.abl_cuda_download_ids(self.handle, pool, out.ctypes.data_as(_VP), n, C.byref(got)), "download_ids")
+        return out
+
+    # ---- slab decomposition ------------------------------------------------------------
+    def slab_layers(self):
+        n = C.c_int()
+        check(self.lib.abl_cuda_slab_axis_layers(self.handle, C.byref(n)), "slab_axis_layers")
+        return n.value
+
+    def set_slab(self, begin, end):
+        check(self.lib.abl_cuda_set_slab(self.handle, begin, end), "set_slab")
+
+    def set_local_peers(self, lower, upper):
+        check(self.lib.abl_cuda_set_local_peers(self.handle, lower.handle if lower else None,
+                                                upper.handle if upper else None), "set_local_peers")
+
+    def exchange(self, pool):
+        check(self.lib.abl_cuda_exchange(self.handle, pool), "exchange")
+
+    def exchange_begin(self, pool):
+        check(self.lib.abl_cuda_exchange_begin(self.handle, pool), "exchange_begin")
+
+    def exchange_end(self, pool):
+        check(self.lib.abl_cuda_exchange_end(self.handle, pool), "exchange_end")
+
+    def init_nccl(self, unique_id, rank, world):
+        buf = (C.c_ubyte * 128).from_buffer_copy(bytes(unique_id))
+        check(self.lib.abl_cuda_comm_init_nccl(self.handle, buf, rank, world), "comm_init_nccl")
+
+    def nccl_unique_id(self):
+        buf = (C.c_ubyte * 128)()
+        check(self.lib.abl_cuda_nccl_unique_id(buf), "nccl_unique_id")
+        return bytes(buf)
 
     def step(self, step_id):
         check(self.lib.abl_cuda_step(self.handle, step_id), "step")

@@ -1,0 +1,128 @@
+"""Slab decomposition harness: one model, several device runtimes.
+
+  * `LocalSlabs`  — S slabs in ONE process on one GPU, exchanging through the runtime's
+    in-process transport (abl_cuda_set_local_peers / exchange_begin / exchange_end).  This is
+    how the single-GPU test tier checks that a decomposed run is bit-identical to an
+    undecomposed one.
+  * `RankSlab`    — one slab per process / GPU (torchrun), exchanging through NCCL inside
+    abl_cuda_step (abl_cuda_comm_init_nccl); used by bench.py --gpus N.
+
+The partition is by whole cell layers along the slowest grid axis, balanced by layer count
+(`split_layers`); ownership and ghosts are maintained by the runtime (abl_runtime.cu).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .runtime import Runtime, check
+
+
+def split_layers(n_layers, parts):
+    """-> [(begin, end)] contiguous, as even as possible, every part non-empty."""
+    if parts > n_layers:
+        raise ValueError("more slabs (%d) than cell layers (%d)" % (parts, n_layers))
+    bounds = [(n_layers * r) // parts for r in range(parts + 1)]
+    return [(bounds[r], bounds[r + 1]) for r in range(parts)]
+
+
+def merge_by_id(parts_ids, parts_records):
+    """Concatenates per-slab downloads and orders them by agent id."""
+    ids = np.concatenate(parts_ids)
+    rec = np.concatenate(parts_records)
+    order = np.argsort(ids, kind="stable")
+    return ids[order], rec[order]
+
+
+class LocalSlabs:
+    def __init__(self, model, n_slabs, **rt_kw):
+        self.model = model
+        self.rts = []
+        for _ in range(n_slabs):
+            rt = Runtime(use_float=model.use_float, **rt_kw)
+            check(model.lib.abl_model_setup(rt.handle), "abl_model_setup")
+            self.rts.append(rt)
+        layers = self.rts[0].slab_layers()
+        self.bounds = split_layers(layers, n_slabs)
+        for r, rt in enumerate(self.rts):
+            rt.set_slab(*self.bounds[r])
+            rt.set_local_peers(self.rts[r - 1] if r > 0 else None,
+                               self.rts[r + 1] if r + 1 < n_slabs else None)
+
+    def upload(self, host_arrays):
+        """Every slab receives the whole population and keeps its own part."""
+        m = self.model
+        for rt in self.rts:
+            for t, arr in enumerate(host_arrays):
+                rt.upload(m.pool(t), np.ascontiguousarray(arr))
+        for t in range(m.n_types):
+            self._exchange(m.pool(t))
+
+    def _exchange(self, pool):
+        for rt in self.rts:
+            rt.exchange_begin(pool)
+        for rt in self.rts:
+            rt.exchange_end(pool)
+
+    def timestep(self):
+        m = self.model
+        for s in range(m.n_steps):
+            for rt in self.rts:
+                check(m.lib.abl_model_run_step(rt.handle, s), "abl_model_run_step")
+            # the step's own pool may have changed: refresh ghosts / migrate
+            pool = self.step_pool(s)
+            self._exchange(pool)
+
+    def step_pool(self, s):
+        # pools are registered in agent declaration order; the generated library reports the
+        # pool of each step through abl_model_step_pool
+        fn = self.model.lib.abl_model_step_pool
+        fn.restype = C.c_int
+        fn.argtypes = [C.c_int]
+        return fn(s)
+
+    def download(self, t):
+        m = self.model
+        ids = [rt.download_ids(m.pool(t)) for rt in self.rts]
+        rec = [rt.download(m.pool(t), m.dtypes[t]) for rt in self.rts]
+        return merge_by_id(ids, rec)
+
+    def owned_counts(self, t):
+        return [rt.pool_size(self.model.pool(t)) for rt in self.rts]
+
+    def close(self):
+        for rt in self.rts:
+            rt.close()
+        self.rts = []
+
+
+class RankSlab:
+    """One slab per process.  `dist` is torch.distributed (already initialised)."""
+
+    def __init__(self, model, rank, world, dist=None, device=0, **rt_kw):
+        import torch
+        self.model = model
+        self.rank, self.world = rank, world
+        self.rt = model.create_runtime(device=device, **rt_kw)
+        layers = self.rt.slab_layers()
+        self.bounds = split_layers(layers, world)
+        if world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                uid = torch.tensor(list(self.rt.nccl_unique_id()), dtype=torch.uint8)
+            uid = uid.cuda(device)
+            dist.broadcast(uid, src=0)
+            self.rt.init_nccl(bytes(uid.cpu().tolist()), rank, world)
+        self.rt.set_slab(*self.bounds[rank])
+
+    def upload(self, host_arrays):
+        m = self.model
+        for t, arr in enumerate(host_arrays):
+            self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
+        for t in range(m.n_types):
+            self.rt.exchange(m.pool(t))
+
+    def timestep(self):
+        self.model.timestep()   # abl_cuda_step exchanges by itself when NCCL is attached
+
+    def owned(self, t):
+        return self.rt.pool_size(self.model.pool(t))

@@ -1111,6 +1111,13 @@ std::string CudaPrinter::kernelSource() {
   w << "    return names[s];"; w.nl();
   w << "}"; w.nl(); w.nl();
 
+  w << "extern \"C\" int abl_model_step_pool(int s) {"; w.nl();
+  w << "    static const int types[] = {";
+  for (const StepInfo &si : steps) w << " " << agentIndex(si.self) << ",";
+  w << " -1 };"; w.nl();
+  w << "    return abl_model_types[types[s]].pool;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
   w << "extern \"C\" int abl_model_setup(abl_runtime *rt) {"; w.nl();
   w << "    int rc;"; w.nl();
   if (env && env->dim > 0) {
@@ -1191,7 +1198,7 @@ std::string buildScript(const BackendContext &ctx, bool useFloat) {
        "if [ -f \"$ASSET/libabl_cuda.so\" ]; then\n"
        "  RT_DIR=\"$ASSET\"\n"
        "else\n"
-       "  $NVCC $ARCH -O3 -lineinfo -std=c++17 --cudart shared -Xcompiler -fPIC -I. -shared -o libabl_cuda.so \"$ASSET/abl_runtime.cu\" \"$ASSET/abl_exchange.cu\" -lnccl\n"
+       "  $NVCC $ARCH -O3 -lineinfo -std=c++17 --cudart shared -Xcompiler -fPIC -I. -shared -o libabl_cuda.so \"$ASSET/abl_runtime.cu\" -lnccl\n"
        "  RT_DIR=\"$(pwd)\"\n"
        "fi\n"
        "$NVCC $ARCH --cudart shared -shared -o libmodel.so model_kernels.o model_host_lib.o abl_host.o -L\"$RT_DIR\" -labl_cuda -Xlinker -rpath -Xlinker \"$RT_DIR\" -Xlinker -rpath -Xlinker \"$CUDA_LIB\"\n"
