@@ -167,6 +167,8 @@ struct abl_runtime {
   int rank = 0, world = 1;
   bool slab = false;
   int layer_begin = 0, layer_end = 0;   // owned cell layers along the slab axis
+  int n_slabs = 1, my_slab = 0;
+  int slab_bounds[ABL_MAX_SLABS + 1] = {0};
   int ghost_layers = 1;
   void *xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send L, send R, recv L, recv R
   size_t xcap[4] = {0, 0, 0, 0};
@@ -1581,16 +1583,44 @@ static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
   return ABL_OK;
 }
 
-// flags[i] bit0: send to the lower rank, bit1: send to the upper rank
+struct SlabTable {
+  int n_slabs, my;
+  int bounds[ABL_MAX_SLABS + 1];
+  int ghost;
+};
+
+// to_lo / to_hi: the record is copied to the lower / upper peer.  Peers form a ring when
+// there are more than two slabs, so that agents leaving through one end of a periodic
+// world (wraparound / teleport to the opposite bound) reach the slab at the other end.
 template <typename R>
 __global__ void k_slab_classify(const R *axis_col, int stride, int comp, u32 n, u32 first, R origin,
-                                R inv_cell, int n_layers, int lo_limit, int hi_limit, u8 *to_lo, u8 *to_hi) {
+                                R inv_cell, int n_layers, SlabTable tab, u8 *to_lo, u8 *to_hi, u32 *far) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   R v = axis_col[(size_t)(first + i) * stride + comp];
-  int layer = cell_coord<R>(v, origin, inv_cell, n_layers);
-  to_lo[i] = layer < lo_limit ? 1 : 0;
-  to_hi[i] = layer >= hi_limit ? 1 : 0;
+  const int layer = cell_coord<R>(v, origin, inv_cell, n_layers);
+  const int me = tab.my, N = tab.n_slabs;
+  const int lb = tab.bounds[me], le = tab.bounds[me + 1];
+  int owner = 0;
+  while (owner + 1 < N && layer >= tab.bounds[owner + 1]) owner++;
+  bool lo = false, hi = false;
+  if (owner == me) {
+    // still mine: neighbours need a ghost copy of my boundary layers
+    lo = me > 0 && layer < lb + tab.ghost;
+    hi = me < N - 1 && layer >= le - tab.ghost;
+  } else if (owner == me - 1) {
+    lo = true;
+  } else if (owner == me + 1) {
+    hi = true;
+  } else if (me == 0 && owner == N - 1) {
+    lo = true;   // around the ring
+  } else if (me == N - 1 && owner == 0) {
+    hi = true;
+  } else {
+    atomicAdd(far, 1u);  // moved farther than a neighbouring slab: unsupported
+  }
+  to_lo[i] = lo ? 1 : 0;
+  to_hi[i] = hi ? 1 : 0;
 }
 
 // message layout: column 0 of all selected agents, column 1, ..., ids (each padded to 16 bytes)
@@ -1669,18 +1699,25 @@ extern "C" int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers) {
 
 // Also usable without NCCL (world == 1 or comm == NULL): then exchange() only re-sorts, which
 // is what the single-process tests of the slab bookkeeping use.
-extern "C" int abl_cuda_set_slab(abl_runtime *rt, int layer_begin, int layer_end) {
+extern "C" int abl_cuda_set_slab(abl_runtime *rt, const int *layer_bounds, int n_slabs, int my_slab) {
   if (!rt || !rt->env_set) return fail(ABL_ERR_STATE, "set_slab requires an environment");
+  if (!layer_bounds || n_slabs < 1 || n_slabs > ABL_MAX_SLABS || my_slab < 0 || my_slab >= n_slabs)
+    return fail(ABL_ERR_ARGUMENT, "bad slab table");
   const int layers = slab_layers(rt);
-  if (layer_begin < 0 || layer_end > layers || layer_begin >= layer_end)
-    return fail(ABL_ERR_ARGUMENT, "bad slab [%d, %d) of %d layers", layer_begin, layer_end, layers);
+  if (layer_bounds[0] != 0 || layer_bounds[n_slabs] != layers)
+    return fail(ABL_ERR_ARGUMENT, "slab table must cover layers 0..%d", layers);
+  for (int s = 0; s < n_slabs; s++)
+    if (layer_bounds[s] >= layer_bounds[s + 1]) return fail(ABL_ERR_ARGUMENT, "empty slab %d", s);
   rt->slab = true;
-  rt->layer_begin = layer_begin;
-  rt->layer_end = layer_end;
+  rt->n_slabs = n_slabs;
+  rt->my_slab = my_slab;
+  for (int s = 0; s <= n_slabs; s++) rt->slab_bounds[s] = layer_bounds[s];
+  rt->layer_begin = layer_bounds[my_slab];
+  rt->layer_end = layer_bounds[my_slab + 1];
   int g = 1;
   for (const Step &s : rt->steps) g = std::max(g, s.reach);
   rt->ghost_layers = g;
-  for (Pool &p : rt->pools) p.binned = false;
+  for (Pool &p : rt->pools) { p.binned = false; p.own_valid = false; }
   return ABL_OK;
 }
 
@@ -1717,22 +1754,31 @@ static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
     int col = pm.first_col, stride = 1, comp = 0;
     if (g.dim == 2) { stride = 2; comp = 1; } else { col += 2; }
     const void *axis_col = p.cols[col].buf[p.cols[col].cur];
-    const int lo_limit = rt->layer_begin + rt->ghost_layers, hi_limit = rt->layer_end - rt->ghost_layers;
+    SlabTable tab;
+    tab.n_slabs = rt->n_slabs;
+    tab.my = rt->my_slab;
+    tab.ghost = rt->ghost_layers;
+    for (int s = 0; s <= rt->n_slabs; s++) tab.bounds[s] = rt->slab_bounds[s];
+    u32 *far = rt->d_scalar + 10;
+    CU(cudaMemsetAsync(far, 0, sizeof(u32), rt->stream));
     u32 nb = blocks_for(n_own, 256);
     if (rt->real_size == 8)
       k_slab_classify<double><<<nb, 256, 0, rt->stream>>>((const double *)axis_col, stride, comp, n_own, ob,
-          g.origin[axis], g.inv_cell, slab_layers(rt), lo_limit, hi_limit, to_lo, to_hi);
+          g.origin[axis], g.inv_cell, slab_layers(rt), tab, to_lo, to_hi, far);
     else
       k_slab_classify<float><<<nb, 256, 0, rt->stream>>>((const float *)axis_col, stride, comp, n_own, ob,
-          (float)g.origin[axis], (float)g.inv_cell, slab_layers(rt), lo_limit, hi_limit, to_lo, to_hi);
+          (float)g.origin[axis], (float)g.inv_cell, slab_layers(rt), tab, to_lo, to_hi, far);
     rt->launches++;
     CU(cudaGetLastError());
     if (has_lo) TRY((run_scan<u8, 0, false>(rt, to_lo, off_lo, n_own, rt->d_scalar + 8)));
     if (has_hi) TRY((run_scan<u8, 0, false>(rt, to_hi, off_hi, n_own, rt->d_scalar + 9)));
-    CU(cudaMemcpyAsync(rt->h_scalar + 8, rt->d_scalar + 8, 2 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaMemcpyAsync(rt->h_scalar + 8, rt->d_scalar + 8, 3 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
     CU(cudaStreamSynchronize(rt->stream));
     if (has_lo) counts[0] = rt->h_scalar[8];
     if (has_hi) counts[1] = rt->h_scalar[9];
+    if (rt->h_scalar[10])
+      return fail(ABL_ERR_COMM, "%u agents of pool %s moved farther than a neighbouring slab in one step "
+                  "(only neighbour and periodic wrap-around migration is supported)", rt->h_scalar[10], p.name.c_str());
   }
   ColTable t;
   fill_table(p, t, false);
@@ -1788,22 +1834,24 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
   if (rt->peer_lo || rt->peer_hi)
     return fail(ABL_ERR_STATE, "in-process peers: use abl_cuda_exchange_begin/end on all runtimes");
   CU(cudaSetDevice(rt->device));
-  const bool has_lo = rt->comm && rt->rank > 0, has_hi = rt->comm && rt->rank < rt->world - 1;
+  const int N = rt->world, me = rt->rank;
+  const bool ring = N > 2;
+  const bool has_lo = rt->comm && N > 1 && (me > 0 || ring), has_hi = rt->comm && N > 1 && (me < N - 1 || ring);
+  const int lo_peer = (me - 1 + N) % N, hi_peer = (me + 1) % N;
   TRY(exchange_pack(rt, p, has_lo, has_hi));
   const u32 counts[2] = {rt->x_out[0], rt->x_out[1]};
   u32 incoming[2] = {0, 0};
   if (has_lo || has_hi) {
-    u32 *d_cnt = rt->d_scalar + 12;  // [0..1] outgoing, [2..3] incoming
+    // Issue order per rank: (send to lower, receive from upper), (send to upper, receive from
+    // lower) — with two ranks both peers are the same process and NCCL matches operations
+    // between a pair in issue order.
+    u32 *d_cnt = rt->d_scalar + 12;  // [0..1] outgoing, [2] from lower, [3] from upper
     CU(cudaMemcpyAsync(d_cnt, counts, sizeof counts, cudaMemcpyHostToDevice, rt->stream));
     NCCL(ncclGroupStart());
-    if (has_lo) {
-      NCCL(ncclSend(d_cnt + 0, 1, ncclUint32, rt->rank - 1, rt->comm, rt->stream));
-      NCCL(ncclRecv(d_cnt + 2, 1, ncclUint32, rt->rank - 1, rt->comm, rt->stream));
-    }
-    if (has_hi) {
-      NCCL(ncclSend(d_cnt + 1, 1, ncclUint32, rt->rank + 1, rt->comm, rt->stream));
-      NCCL(ncclRecv(d_cnt + 3, 1, ncclUint32, rt->rank + 1, rt->comm, rt->stream));
-    }
+    if (has_lo) NCCL(ncclSend(d_cnt + 0, 1, ncclUint32, lo_peer, rt->comm, rt->stream));
+    if (has_hi) NCCL(ncclRecv(d_cnt + 3, 1, ncclUint32, hi_peer, rt->comm, rt->stream));
+    if (has_hi) NCCL(ncclSend(d_cnt + 1, 1, ncclUint32, hi_peer, rt->comm, rt->stream));
+    if (has_lo) NCCL(ncclRecv(d_cnt + 2, 1, ncclUint32, lo_peer, rt->comm, rt->stream));
     NCCL(ncclGroupEnd());
     CU(cudaMemcpyAsync(rt->h_scalar + 12, d_cnt + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
     CU(cudaStreamSynchronize(rt->stream));
@@ -1812,14 +1860,10 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
     TRY(ensure_xbuf(rt, 2, slab_msg_bytes(p, incoming[0])));
     TRY(ensure_xbuf(rt, 3, slab_msg_bytes(p, incoming[1])));
     NCCL(ncclGroupStart());
-    if (has_lo) {
-      if (counts[0]) NCCL(ncclSend(rt->xbuf[0], slab_msg_bytes(p, counts[0]), ncclUint8, rt->rank - 1, rt->comm, rt->stream));
-      if (incoming[0]) NCCL(ncclRecv(rt->xbuf[2], slab_msg_bytes(p, incoming[0]), ncclUint8, rt->rank - 1, rt->comm, rt->stream));
-    }
-    if (has_hi) {
-      if (counts[1]) NCCL(ncclSend(rt->xbuf[1], slab_msg_bytes(p, counts[1]), ncclUint8, rt->rank + 1, rt->comm, rt->stream));
-      if (incoming[1]) NCCL(ncclRecv(rt->xbuf[3], slab_msg_bytes(p, incoming[1]), ncclUint8, rt->rank + 1, rt->comm, rt->stream));
-    }
+    if (has_lo && counts[0]) NCCL(ncclSend(rt->xbuf[0], slab_msg_bytes(p, counts[0]), ncclUint8, lo_peer, rt->comm, rt->stream));
+    if (has_hi && incoming[1]) NCCL(ncclRecv(rt->xbuf[3], slab_msg_bytes(p, incoming[1]), ncclUint8, hi_peer, rt->comm, rt->stream));
+    if (has_hi && counts[1]) NCCL(ncclSend(rt->xbuf[1], slab_msg_bytes(p, counts[1]), ncclUint8, hi_peer, rt->comm, rt->stream));
+    if (has_lo && incoming[0]) NCCL(ncclRecv(rt->xbuf[2], slab_msg_bytes(p, incoming[0]), ncclUint8, lo_peer, rt->comm, rt->stream));
     NCCL(ncclGroupEnd());
   }
   return exchange_unpack(rt, p, incoming);

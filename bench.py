@@ -162,6 +162,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-size", type=int, default=128)
     ap.add_argument("--no-tile", action="store_true")
+    ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -181,14 +182,31 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from openabl_b200.model import Model
+    from openabl_b200.slab import RankSlab
     model_file, params, use_float, S, M, P = WORKLOADS[args.workload]
+    params = dict(params)
+    strong = args.strong or world == 1
+    if not strong:
+        # weak scaling: the per-GPU population stays fixed, the world (and the environment,
+        # which the model derives from num_agents) grows with the number of GPUs
+        params["num_agents"] = params["num_agents"] * world
     m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
     m.populate()
     host = [m.host_agents(t) for t in range(m.n_types)]
-    n_agents = sum(len(h) for h in host)
-    m.create_runtime(device=local_rank, block_size=args.block_size, tile=not args.no_tile)
+    n_agents = sum(len(h) for h in host)          # whole job, all ranks
+    slab = None
+    if world > 1:
+        slab = RankSlab(m, rank, world, dist, device=local_rank, block_size=args.block_size, tile=not args.no_tile)
+    else:
+        m.create_runtime(device=local_rank, block_size=args.block_size, tile=not args.no_tile)
     rt = m.rt
     stream = torch.cuda.ExternalStream(rt.stream(), device=torch.device("cuda", local_rank))
+
+    def upload():
+        if slab:
+            slab.upload(host)
+        else:
+            m.upload_host()
 
     def barrier():
         if world > 1:
@@ -197,7 +215,7 @@ def main():
         rt.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
-    m.upload_host()
+    upload()
     for _ in range(max(3, args.warmup)):
         m.timestep()
     barrier()
@@ -219,7 +237,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
-    value = n_agents * world * args.steps / (ms_max / 1e3)
+    value = n_agents * args.steps / (ms_max / 1e3)
 
     # ---- per-stage device times (separate pass: timing adds a sync per step) ---------------
     rt.enable_timing(True)
@@ -235,9 +253,10 @@ def main():
     for k in stage:
         stage[k] /= reps
     peak, peak_src = load_peaks()
-    kernel_bytes = (S + M + S) * n_agents
+    n_local = rt.pool_size(m.pool(0)) if world > 1 else n_agents
+    kernel_bytes = (S + M + S) * n_local
     achieved = kernel_bytes / (stage["kernel_ms"] / 1e3) / 1e9 if stage["kernel_ms"] > 0 else 0.0
-    step_bytes = (P + M + 4 * S + 32) * n_agents
+    step_bytes = (P + M + 4 * S + 32) * n_agents / world
     roofline = {"bound": "hbm", "kernel": "abl_kernel_%s" % m.step_names[0], "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": None, "algorithmic_bytes_per_agent": S + M + S,
@@ -250,27 +269,36 @@ def main():
     h2d = sum(h.nbytes for h in host)
     barrier()
     t0 = time.perf_counter()
+    d2h = 0
     for _ in range(e2e_reps):
-        m.upload_host()
+        upload()
         for _ in range(args.steps):
             m.timestep()
-        m.download_host()
+        if slab:
+            out = [m.download(tt) for tt in range(m.n_types)]   # this rank's owned agents
+            d2h = sum(o.nbytes for o in out)
+        else:
+            m.download_host()
+            d2h = sum(len(m.host_agents(tt)) * m.dtypes[tt].itemsize for tt in range(m.n_types))
     rt.synchronize()
+    if world > 1:
+        dist.barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_reps
-    d2h = sum(len(m.host_agents(tt)) * m.dtypes[tt].itemsize for tt in range(m.n_types))
     te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_agents * world * args.steps / float(te.item())
+    e2e_value = n_agents * args.steps / float(te.item())
     m.close()
 
     if rank == 0:
         line = {"metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
+                "vs_baseline": None,
                 "dtype": "f32" if use_float else "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "model": model_file, "num_agents": n_agents,
-                           "agents_per_gpu": n_agents, "parallelism": "replicas" if world > 1 else "single",
+                           "agents_per_gpu": n_agents // world,
+                           "parallelism": ("slab%d (cell layers along the slowest axis, halo + migration over NCCL send/recv)" % world) if world > 1 else "single",
                            "block_size": args.block_size,
                            "l2": "state (%.0f MB) is re-streamed every step; no L2 flush between steps (a "
                                  "simulation step consumes the previous step's output)" % (n_agents * S / 1e6)},

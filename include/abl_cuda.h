@@ -27,6 +27,7 @@ extern "C" {
 #define ABL_CUDA_ABI_VERSION 1
 #define ABL_MAX_MEMBERS 16   /* members per agent type */
 #define ABL_MAX_COLUMNS 32   /* SoA columns per agent type (a float3 member is 3 columns) */
+#define ABL_MAX_SLABS 64     /* slabs (GPUs) of one decomposed simulation */
 
 enum {
   ABL_OK = 0,
@@ -216,7 +217,10 @@ void *abl_cuda_stream(abl_runtime *rt);
  * ncclSend/ncclRecv on its own stream. */
 int abl_cuda_nccl_unique_id(void *id128);   /* 128-byte ncclUniqueId, to be broadcast by the caller */
 int abl_cuda_comm_init_nccl(abl_runtime *rt, const void *id128, int rank, int world);
-int abl_cuda_set_slab(abl_runtime *rt, int layer_begin, int layer_end);
+/* layer_bounds[0..n_slabs]: slab s owns cell layers [layer_bounds[s], layer_bounds[s+1]) along
+ * the slab axis; this runtime is slab `my_slab`.  Slabs are neighbours on a ring (periodic
+ * worlds: agents that leave through one end re-enter at the other). */
+int abl_cuda_set_slab(abl_runtime *rt, const int *layer_bounds, int n_slabs, int my_slab);
 int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers);
 /* After a step (or upload): send agents that left the slab to the neighbour ranks, receive
  * arrivals, then refresh ghost layers of `pool`.  Collective over neighbouring ranks. */

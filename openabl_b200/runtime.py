@@ -70,7 +70,7 @@ ABI = {
     "abl_cuda_stream": (_VP, [_VP]),
     "abl_cuda_nccl_unique_id": (C.c_int, [_VP]),
     "abl_cuda_comm_init_nccl": (C.c_int, [_VP, _VP, C.c_int, C.c_int]),
-    "abl_cuda_set_slab": (C.c_int, [_VP, C.c_int, C.c_int]),
+    "abl_cuda_set_slab": (C.c_int, [_VP, C.POINTER(C.c_int), C.c_int, C.c_int]),
     "abl_cuda_slab_axis_layers": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "abl_cuda_exchange": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_owned_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
@@ -170,8 +170,11 @@ class Runtime:
         check(self.lib.abl_cuda_slab_axis_layers(self.handle, C.byref(n)), "slab_axis_layers")
         return n.value
 
-    def set_slab(self, begin, end):
-        check(self.lib.abl_cuda_set_slab(self.handle, begin, end), "set_slab")
+    def set_slab(self, bounds, my_slab):
+        """bounds: [(begin, end)] per slab (contiguous)."""
+        table = [b for b, _ in bounds] + [bounds[-1][1]]
+        arr = (C.c_int * len(table))(*table)
+        check(self.lib.abl_cuda_set_slab(self.handle, arr, len(bounds), my_slab), "set_slab")
 
     def set_local_peers(self, lower, upper):
         check(self.lib.abl_cuda_set_local_peers(self.handle, lower.handle if lower else None,

@@ -43,10 +43,12 @@ class LocalSlabs:
             self.rts.append(rt)
         layers = self.rts[0].slab_layers()
         self.bounds = split_layers(layers, n_slabs)
+        ring = n_slabs > 2   # periodic worlds: the first and the last slab are neighbours too
         for r, rt in enumerate(self.rts):
-            rt.set_slab(*self.bounds[r])
-            rt.set_local_peers(self.rts[r - 1] if r > 0 else None,
-                               self.rts[r + 1] if r + 1 < n_slabs else None)
+            rt.set_slab(self.bounds, r)
+            lower = self.rts[r - 1] if r > 0 else (self.rts[-1] if ring else None)
+            upper = self.rts[r + 1] if r + 1 < n_slabs else (self.rts[0] if ring else None)
+            rt.set_local_peers(lower, upper)
 
     def upload(self, host_arrays):
         """Every slab receives the whole population and keeps its own part."""
@@ -112,7 +114,7 @@ class RankSlab:
             uid = uid.cuda(device)
             dist.broadcast(uid, src=0)
             self.rt.init_nccl(bytes(uid.cpu().tolist()), rank, world)
-        self.rt.set_slab(*self.bounds[rank])
+        self.rt.set_slab(self.bounds, rank)
 
     def upload(self, host_arrays):
         m = self.model
@@ -126,3 +128,38 @@ class RankSlab:
 
     def owned(self, t):
         return self.rt.pool_size(self.model.pool(t))
+
+
+# ---- the decomposition rules, stated once more in numpy ------------------------------------
+# (reference model of k_slab_classify / exchange in asset/cuda/abl_runtime.cu; exercised on CPU
+# by tests/test_slab_gloo.py with world_size 2 over gloo)
+def slab_layer(axis_pos, origin, cell, n_layers):
+    """Cell layer along the slab axis; same formula as abl_cell_coord."""
+    inv = axis_pos.dtype.type(1) / axis_pos.dtype.type(cell)
+    layer = np.floor((axis_pos - axis_pos.dtype.type(origin)) * inv).astype(np.int64)
+    return np.clip(layer, 0, n_layers - 1)
+
+
+def send_masks(layer, bounds, me, ghost_layers=1):
+    """Which formerly owned agents are copied to the lower / upper peer after a step.
+    Still owned and within `ghost_layers` of a boundary -> ghost copy for that neighbour;
+    now inside a neighbouring slab -> migration to it (the sender keeps its record, which
+    becomes a ghost by key range).  With more than two slabs the peers form a ring, so agents
+    teleported from one end of a periodic world to the other reach the slab over there."""
+    n = len(bounds)
+    begin, end = bounds[me]
+    starts = np.array([b for b, _ in bounds])
+    owner = np.searchsorted(starts, layer, side="right") - 1
+    mine = owner == me
+    lo = (mine & (me > 0) & (layer < begin + ghost_layers)) | (owner == me - 1)
+    hi = (mine & (me < n - 1) & (layer >= end - ghost_layers)) | (owner == me + 1)
+    if n > 2:
+        if me == 0:
+            lo = lo | (owner == n - 1)
+        if me == n - 1:
+            hi = hi | (owner == 0)
+    return lo, hi
+
+
+def owned_mask(layer, begin, end):
+    return (layer >= begin) & (layer < end)

@@ -1,0 +1,117 @@
+"""CPU test of the multi-GPU decomposition rules with world_size 2 over gloo.
+
+Each rank keeps only the agents of its slab plus ghosts, advances them with the plain-C
+oracle (grid mode, i.e. the kernels' neighbour order) and exchanges halo / migrating agents
+with its neighbour exactly by the rules the CUDA runtime implements (openabl_b200.slab:
+slab_layer, send_masks, owned_mask ⇔ k_slab_classify / exchange in abl_runtime.cu).  The
+union of the slabs must equal the undecomposed run bit for bit."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _exchange(rank, world, send_lo, send_hi, dtype):
+    """Swaps variable-length record arrays with the lower / upper neighbour."""
+    got = []
+    for peer, payload in ((rank - 1, send_lo), (rank + 1, send_hi)):
+        if peer < 0 or peer >= world:
+            continue
+        raw = torch.from_numpy(np.frombuffer(payload.tobytes(), dtype=np.uint8).copy())
+        n_out = torch.tensor([len(payload)], dtype=torch.int64)
+        n_in = torch.zeros(1, dtype=torch.int64)
+        # lower rank sends first to avoid a deadlock of blocking gloo sends
+        if rank < peer:
+            dist.send(n_out, peer); dist.recv(n_in, peer)
+        else:
+            dist.recv(n_in, peer); dist.send(n_out, peer)
+        buf = torch.zeros(int(n_in.item()) * dtype.itemsize, dtype=torch.uint8)
+        if rank < peer:
+            if len(raw): dist.send(raw, peer)
+            if len(buf): dist.recv(buf, peer)
+        else:
+            if len(buf): dist.recv(buf, peer)
+            if len(raw): dist.send(raw, peer)
+        got.append(np.frombuffer(buf.numpy().tobytes(), dtype=dtype))
+    return np.concatenate(got) if got else np.zeros(0, dtype=dtype)
+
+
+def _rank_main(rank, world, port, n, steps, out_dir):
+    import sys
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from oracle import GRID, Oracle
+    from openabl_b200.slab import owned_mask, send_masks, slab_layer, split_layers
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    o = Oracle(False)
+    full = o.boids_init(n)
+    # grid of boids2d: max_pos = sqrt(n / 500) (integer division), cell = interaction radius
+    max_pos = np.sqrt(float(n // 500))
+    cell = 0.05
+    n_layers = int(np.ceil(max_pos / cell))
+    bounds = split_layers(n_layers, world)
+    begin, end = bounds[rank]
+
+    rec_dt = np.dtype([("id", np.uint32), ("agent", full.dtype)])
+    layer = slab_layer(full["pos"][:, 1], 0.0, cell, n_layers)
+    mine = owned_mask(layer, begin, end)
+    owned = np.zeros(int(mine.sum()), dtype=rec_dt)
+    owned["id"] = np.nonzero(mine)[0]
+    owned["agent"] = full[mine]
+
+    def refresh(owned):
+        """halo + migration exchange; returns the local population (owned + ghosts + arrivals)"""
+        lay = slab_layer(owned["agent"]["pos"][:, 1], 0.0, cell, n_layers)
+        to_lo, to_hi = send_masks(lay, bounds, rank, 1)
+        arrivals = _exchange(rank, world, owned[to_lo], owned[to_hi], rec_dt)
+        local = np.concatenate([owned, arrivals])
+        return local[np.argsort(local["id"], kind="stable")]   # index order == id order
+
+    local = refresh(owned)
+    for _ in range(steps):
+        state = np.ascontiguousarray(local["agent"])
+        nxt = o.boids_run(state, 1, GRID, num_agents=n)      # all local agents; ghosts are discarded
+        lay_before = slab_layer(local["agent"]["pos"][:, 1], 0.0, cell, n_layers)
+        keep = owned_mask(lay_before, begin, end)            # results are valid for owned agents only
+        owned = np.zeros(int(keep.sum()), dtype=rec_dt)
+        owned["id"] = local["id"][keep]
+        owned["agent"] = nxt[keep]
+        local = refresh(owned)
+    lay = slab_layer(local["agent"]["pos"][:, 1], 0.0, cell, n_layers)
+    final = local[owned_mask(lay, begin, end)]
+    np.save(os.path.join(out_dir, "rank%d.npy" % rank), final)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_slabs_over_gloo_equal_undecomposed_run(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from oracle import GRID, Oracle
+    n, steps, world = 20000, 5, 2
+    port = _free_port()
+    mp.spawn(_rank_main, args=(world, port, n, steps, str(tmp_path)), nprocs=world, join=True)
+    parts = [np.load(os.path.join(str(tmp_path), "rank%d.npy" % r)) for r in range(world)]
+    merged = np.concatenate(parts)
+    merged = merged[np.argsort(merged["id"], kind="stable")]
+    assert np.array_equal(merged["id"], np.arange(n, dtype=np.uint32)), "agents lost or duplicated"
+    o = Oracle(False)
+    want = o.boids_run(o.boids_init(n), steps, GRID)
+    for f in want.dtype.names:
+        assert np.array_equal(merged["agent"][f], want[f]), "member %s differs" % f
