@@ -94,6 +94,9 @@ private:
   const FuncDecl *curFn = nullptr;
   const StepInfo *curStep = nullptr;
   bool curStepHasLimit = false;
+  // chunked near loop: `break` of the DSL body must leave two nested C++ loops
+  std::string nearBreakLabel;
+  int innerLoopDepth = 0;
   std::vector<StepInfo> steps;
 
   std::string label() { return "_var" + std::to_string(anon++); }
@@ -492,14 +495,19 @@ void CudaPrinter::stmt(const Stmt &s) {
       return;
     case Stmt::While:
       w << "while ("; expr(*s.e[0]); w << ") ";
+      innerLoopDepth++;
       stmt(*s.body[0]);
+      innerLoopDepth--;
       return;
     case Stmt::For: forStmt(s); return;
     case Stmt::Return:
       if (s.e.empty()) w << "return;";
       else { w << "return "; expr(*s.e[0]); w << ";"; }
       return;
-    case Stmt::Break: w << "break;"; return;
+    case Stmt::Break:
+      if (!nearBreakLabel.empty() && innerLoopDepth == 0) w << "goto " << nearBreakLabel << ";";
+      else w << "break;";
+      return;
     case Stmt::Continue: w << "continue;"; return;
     case Stmt::Simulate:
       if (dev()) throw BackendError("cuda backend: simulate inside device code");
@@ -509,6 +517,8 @@ void CudaPrinter::stmt(const Stmt &s) {
 }
 
 void CudaPrinter::forStmt(const Stmt &s) {
+  if (s.forKind == Stmt::ForNear) { nearLoop(s); return; }
+  struct DepthGuard { int &d; DepthGuard(int &d) : d(d) { d++; } ~DepthGuard() { d--; } } guard(innerLoopDepth);
   if (s.forKind == Stmt::ForRange) {
     std::string end = label();
     const Expr &range = *s.e[0];
@@ -518,8 +528,6 @@ void CudaPrinter::forStmt(const Stmt &s) {
     stmt(*s.body[0]);
     return;
   }
-  if (s.forKind == Stmt::ForNear) { nearLoop(s); return; }
-
   // array iteration
   const Expr &arr = *s.e[0];
   std::string idx = label();
@@ -564,17 +572,78 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   std::string it = label();
   std::string sdim = std::to_string(dim);
 
+  int posIndex = nbr->memberIndex(pos->name);
+  auto loadOthers = [&](const std::string &idx) {
+    // members the body reads are fetched only for accepted candidates
+    for (size_t m = 0; m < nbr->members.size(); m++) {
+      if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
+      w.nl();
+      loadMember(*nbr, (int)m, s.varName + "." + nbr->members[m]->name, "_a.nbr.in", idx);
+    }
+  };
+  std::string selfPosText = exprText(agentExpr) + "." + selfPos->name;
+
   w << "{";
   w.indent(); w.nl();
   w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
-  w << it << ".init" << sdim << "(_a, "; expr(agentExpr); w << "." << selfPos->name << ", true);";
+  w << it << ".init" << sdim << "(_a, " << selfPosText << ", true);";
   w.nl();
-  int posIndex = nbr->memberIndex(pos->name);
   // Radius filter: inclusive radius, self included, same operand order as the reference's
   // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
   // is a host-evaluable constant the launcher precomputes the equivalent bound on the
   // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  if (curStepHasLimit) {
+    // Dense populations (ABL_CHUNKED, chosen by the launcher from the mean cell occupancy):
+    // two phases per chunk of up to 32 candidates.  Phase 1 only evaluates the filter and
+    // records a bit per accepted candidate; phase 2 runs the loop body for the set bits, in
+    // order.  In a warp the expensive body then executes max-popcount times per chunk instead
+    // of once per candidate (with the plain loop nearly every iteration has *some* lane that
+    // accepts, so the whole warp pays for the body every time).
+    std::string done = "_near_done" + it;
+    w << "if (ABL_CHUNKED) {";
+    w.indent(); w.nl();
+    w << "while (" << it << ".valid()) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "b = " << it << ".index();"; w.nl();
+    w << "const unsigned " << it << "n = min(" << it << ".remaining(), 32u);"; w.nl();
+    w << "unsigned " << it << "m = 0;"; w.nl();
+    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "n; " << it << "k++) {";
+    w.indent(); w.nl();
+    w << typeName(pos->type) << " " << it << "q;"; w.nl();
+    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "b + " + it + "k");
+    w.nl();
+    w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
+      << ")) > _near_limit)) " << it << "m |= 1u << " << it << "k;";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "while (" << it << "m) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "j = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
+    w << it << "m &= " << it << "m - 1;"; w.nl();
+    w << nbr->name << " " << s.varName << ";"; w.nl();
+    loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+    loadOthers(it + "j");
+    w.nl();
+    {
+      std::string savedLabel = nearBreakLabel;
+      int savedDepth = innerLoopDepth;
+      nearBreakLabel = done;
+      innerLoopDepth = 0;
+      stmt(*s.body[0]);
+      nearBreakLabel = savedLabel;
+      innerLoopDepth = savedDepth;
+    }
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << it << ".skip(" << it << "n);";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << done << ": ;";
+    w.outdent(); w.nl();
+    w << "} else {";
+    w.indent(); w.nl();
+  }
   w << "for (; " << it << ".valid(); " << it << ".next()) {";
   w.indent(); w.nl();
   w << "const unsigned " << it << "j = " << it << ".index();";
@@ -584,26 +653,27 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
   w.nl();
   if (curStepHasLimit) {
-    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", ";
-    expr(agentExpr);
-    w << "." << selfPos->name << ")) > _near_limit) continue;";
+    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", "
+      << selfPosText << ")) > _near_limit) continue;";
   } else {
-    w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", ";
-    expr(agentExpr);
-    w << "." << selfPos->name << ") > ";
+    w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", " << selfPosText << ") > ";
     expr(radius);
     w << ") continue;";
   }
-  // members the body reads are fetched only for accepted candidates
-  for (size_t m = 0; m < nbr->members.size(); m++) {
-    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
-    w.nl();
-    loadMember(*nbr, (int)m, s.varName + "." + nbr->members[m]->name, "_a.nbr.in", it + "j");
-  }
+  loadOthers(it + "j");
   w.nl();
-  stmt(*s.body[0]);
+  {
+    std::string savedLabel = nearBreakLabel;
+    int savedDepth = innerLoopDepth;
+    nearBreakLabel.clear();
+    innerLoopDepth = 0;
+    stmt(*s.body[0]);
+    nearBreakLabel = savedLabel;
+    innerLoopDepth = savedDepth;
+  }
   w.outdent(); w.nl();
   w << "}";
+  if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
   w.outdent(); w.nl();
   w << "}";
 }
@@ -998,12 +1068,14 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepHasLimit = radius && hostEvaluable(*radius);
 
   // the user's step function
+  w << "template <bool ABL_CHUNKED>"; w.nl();
   w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
   w.nl();
   w << "}"; w.nl(); w.nl();
 
+  w << "template <bool ABL_CHUNKED>"; w.nl();
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit) {";
   w.indent(); w.nl();
@@ -1022,7 +1094,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "abl_ctx _ctx;"; w.nl();
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
-  w << f.emitName << "(_ctx, _a, _i, _near_limit, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "<ABL_CHUNKED>(_ctx, _a, _i, _near_limit, " << p.name << ", " << p.outName << ");";
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!si.writes.count(self.members[m]->name)) continue;
@@ -1053,7 +1125,14 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   } else {
     w << "    const abl_real limit = 0;"; w.nl();
   }
-  w << "    abl_kernel_" << f.emitName << "<<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+  if (curStepHasLimit) {
+    // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
+    w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();
+    w << "    if (chunked) abl_kernel_" << f.emitName << "<true><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+    w << "    else abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+  } else {
+    w << "    abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+  }
   w << "    return (int)cudaGetLastError();"; w.nl();
   w << "}"; w.nl(); w.nl();
   (void)index;
