@@ -470,3 +470,505 @@ void oracle_gol_step(int num_agents, const Cell *buf, Cell *dbuf, int n, int mod
 }
 
 int oracle_real_size(void) { return (int)sizeof(abl_float); }
+
+/* ===================================================================================== */
+/* predator_prey.abl — PARITY UNPINNED BY THE REFERENCE                                  */
+/* ===================================================================================== */
+/* The reference `c` backend rejects this model (run-time add/remove: BackendError,
+ * src/backend/CBackend.cpp:30-32) and no other reference backend can run in this
+ * environment, so nothing pins these semantics numerically.  What is frozen here (and
+ * implemented by the CUDA runtime) follows the Mason/FlameGPU printers where they agree:
+ *   - `out` starts as a copy of `in` for every step function (MasonPrinter.cpp:480-486);
+ *   - step functions run in the listed order, each on the committed state of the previous;
+ *   - removeCurrent(): the agent disappears when its step function commits; survivors keep
+ *     their order (MasonPrinter.cpp:358-367, FlameGPUPrinter.cpp:501-519);
+ *   - add(): at most one new agent per parent and step function; new agents are appended
+ *     after the survivors in parent order, get the next ids, and take part from the next
+ *     step function on;
+ *   - in-step random(): counter-based stream keyed by (seed, timestep, step index, agent id)
+ *     (asset/cuda/abl_device.cuh; the reference has no reproducible definition);
+ *   - the sequential step runs after all step functions (MasonPrinter.cpp:535-541):
+ *     count(T) = live agents, sum(bool member) = number of true values (:623-682).
+ * Per-step arithmetic is the reference lowering (GenericCPrinter.cpp:20-75) of the model. */
+typedef struct { float2 pos; float2 dir; float2 steer; int life; } PPAnimal;  /* Predator and Prey */
+typedef struct { float2 pos; int dead_cycles; bool avail; } PPGrass;
+
+typedef struct {
+  void *data; unsigned *ids; int n, cap; unsigned next_id; size_t stride;
+} pp_pool;
+
+typedef struct {
+  pp_pool pred, prey, grass;
+  /* constants as the generated program declares them */
+  abl_float PI, SPACE_MULT, REPRODUCE_PREY_PROB, REPRODUCE_PREDATOR_PROB;
+  int GAIN_FROM_FOOD_PREDATOR, GAIN_FROM_FOOD_PREY, GRASS_REGROW_CYCLES;
+  abl_float PRED_PREY_INTERACTION_RADIUS, PREY_GROUP_COHESION_RADIUS, SAME_SPECIES_AVOIDANCE_RADIUS,
+      GRASS_EAT_DISTANCE, PRED_KILL_DISTANCE, DELTA_TIME, PRED_SPEED_ADVANTAGE, env_size;
+  double env_exact, granularity_exact;
+  int num_agents;
+  unsigned timestep;
+  uint64_t seed;
+} pp_world;
+
+static void pp_pool_init(pp_pool *p, size_t stride) { memset(p, 0, sizeof *p); p->stride = stride; }
+static void pp_pool_reserve(pp_pool *p, int want) {
+  if (want <= p->cap) return;
+  int cap = p->cap ? p->cap : 1024;
+  while (cap < want) cap *= 2;
+  p->data = realloc(p->data, (size_t)cap * p->stride);
+  p->ids = realloc(p->ids, (size_t)cap * sizeof(unsigned));
+  p->cap = cap;
+}
+static void *pp_pool_push(pp_pool *p) {
+  pp_pool_reserve(p, p->n + 1);
+  p->ids[p->n] = p->next_id++;
+  void *slot = (char *)p->data + (size_t)p->n * p->stride;
+  memset(slot, 0, p->stride);
+  p->n++;
+  return slot;
+}
+
+static int random_int(int min, int max) { /* libabl.c:26-39 */
+  unsigned n = max - min + 1;
+  if ((n & (n - 1)) == 0) return xorshift128plus() & (n - 1);
+  unsigned r = UINT_MAX % n;
+  unsigned x;
+  do { x = xorshift128plus(); } while (x >= UINT_MAX - r);
+  return min + x % n;
+}
+
+/* counter-based in-step RNG, identical to abl_ctx_init / abl_rng_next / random_float of
+ * asset/cuda/abl_device.cuh */
+static inline uint64_t pp_mix64(uint64_t z) {
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+static inline uint64_t pp_rng_init(uint64_t seed, unsigned timestep, unsigned step, unsigned id) {
+  uint64_t k = pp_mix64(seed ^ 0x9e3779b97f4a7c15ull);
+  k = pp_mix64(k + ((uint64_t)timestep << 32 | step));
+  return pp_mix64(k + id);
+}
+static inline abl_float pp_random_float(uint64_t *state, abl_float lo, abl_float hi) {
+  *state += 0x9e3779b97f4a7c15ull;
+  uint64_t x = pp_mix64(*state);
+  return lo + (abl_float)x / ((abl_float)UINT64_MAX / (hi - lo));
+}
+
+pp_world *oracle_pp_create(int num_agents) {
+  pp_world *w = calloc(1, sizeof *w);
+  pp_pool_init(&w->pred, sizeof(PPAnimal));
+  pp_pool_init(&w->prey, sizeof(PPAnimal));
+  pp_pool_init(&w->grass, sizeof(PPGrass));
+  w->num_agents = num_agents;
+  w->seed = 0x0123456789abcdefull;
+  const double SPACE_MULT = 1.0;
+  w->PI = (abl_float)oracle_fold6(3.14159265358979323846);
+  w->SPACE_MULT = (abl_float)oracle_fold6(SPACE_MULT);
+  w->REPRODUCE_PREY_PROB = (abl_float)0.005;
+  w->REPRODUCE_PREDATOR_PROB = (abl_float)0.001;
+  w->GAIN_FROM_FOOD_PREDATOR = 35;
+  w->GAIN_FROM_FOOD_PREY = 60;
+  w->GRASS_REGROW_CYCLES = 60;
+  w->PRED_PREY_INTERACTION_RADIUS = (abl_float)oracle_fold6(0.100 * SPACE_MULT);
+  w->PREY_GROUP_COHESION_RADIUS = (abl_float)oracle_fold6(0.120 * SPACE_MULT);
+  w->SAME_SPECIES_AVOIDANCE_RADIUS = (abl_float)oracle_fold6(0.035 * SPACE_MULT);
+  w->GRASS_EAT_DISTANCE = (abl_float)oracle_fold6(0.020 * SPACE_MULT);
+  w->PRED_KILL_DISTANCE = (abl_float)oracle_fold6(0.020 * SPACE_MULT);
+  w->DELTA_TIME = (abl_float)0.0015;
+  w->PRED_SPEED_ADVANTAGE = (abl_float)2.0;
+  /* agent_density = 1600 is an integer literal: num_agents / agent_density folds as integer
+   * division (see boids_fold) */
+  w->env_exact = sqrt((double)(num_agents / 1600)) * SPACE_MULT;
+  w->env_size = (abl_float)oracle_fold6(w->env_exact);
+  w->granularity_exact = 0.120 * SPACE_MULT; /* largest for-near radius */
+
+  /* main(): sequential population set-up, reference RNG */
+  oracle_rng_reset();
+  int num_predators = (int)((abl_float)0.025 * num_agents);
+  int num_prey = (int)((abl_float)0.35 * num_agents);
+  int num_grass = num_agents - num_predators - num_prey;
+  for (int i = 0; i < num_grass; i++) {
+    abl_float y = random_float(0, w->env_size);
+    abl_float x = random_float(0, w->env_size);
+    PPGrass *g = pp_pool_push(&w->grass);
+    g->pos = float2_create(x, y);
+    g->dead_cycles = 0;
+    g->avail = true;
+  }
+  for (int k = 0; k < 2; k++) {
+    pp_pool *pool = k == 0 ? &w->prey : &w->pred;
+    int count = k == 0 ? num_prey : num_predators;
+    int gain = k == 0 ? w->GAIN_FROM_FOOD_PREY : w->GAIN_FROM_FOOD_PREDATOR;
+    for (int i = 0; i < count; i++) {
+      abl_float y = random_float(0, w->env_size);
+      abl_float x = random_float(0, w->env_size);
+      abl_float phi = random_float(0, (2.0 * w->PI));
+      int life = gain + random_int(0, 10);
+      PPAnimal *a = pp_pool_push(pool);
+      a->pos = float2_create(x, y);
+      a->dir = float2_create(sin(phi), cos(phi));
+      a->steer = float2_fill(0);
+      a->life = life;
+    }
+  }
+  return w;
+}
+
+void oracle_pp_destroy(pp_world *w) {
+  free(w->pred.data); free(w->pred.ids);
+  free(w->prey.data); free(w->prey.ids);
+  free(w->grass.data); free(w->grass.ids);
+  free(w);
+}
+
+int oracle_pp_count(pp_world *w, int type) { return type == 0 ? w->pred.n : type == 1 ? w->prey.n : w->grass.n; }
+int oracle_pp_record_size(int type) { return type == 2 ? (int)sizeof(PPGrass) : (int)sizeof(PPAnimal); }
+void oracle_pp_read(pp_world *w, int type, void *records, unsigned *ids) {
+  pp_pool *p = type == 0 ? &w->pred : type == 1 ? &w->prey : &w->grass;
+  memcpy(records, p->data, (size_t)p->n * p->stride);
+  if (ids) memcpy(ids, p->ids, (size_t)p->n * sizeof(unsigned));
+}
+int oracle_pp_sum_avail(pp_world *w) {
+  int s = 0;
+  const PPGrass *g = w->grass.data;
+  for (int i = 0; i < w->grass.n; i++) s += g[i].avail ? 1 : 0;
+  return s;
+}
+
+/* commit of one step function: new state becomes current, dead agents are compacted away
+ * (stable), new agents are appended in parent order */
+static void pp_commit(pp_pool *self, void *next, const bool *dead, pp_pool *target, const bool *added,
+                      const void *staged, size_t staged_stride) {
+  memcpy(self->data, next, (size_t)self->n * self->stride);
+  const int n_before = self->n;
+  if (target && added) {
+    for (int i = 0; i < n_before; i++) {
+      if (!added[i]) continue;
+      void *slot = pp_pool_push(target);
+      memcpy(slot, (const char *)staged + (size_t)i * staged_stride, staged_stride);
+    }
+  }
+  if (dead) {
+    int k = 0;
+    const int n_now = self->n; /* includes appended agents when target == self */
+    for (int i = 0; i < n_now; i++) {
+      if (i < n_before && dead[i]) continue;
+      if (k != i) {
+        memcpy((char *)self->data + (size_t)k * self->stride, (char *)self->data + (size_t)i * self->stride, self->stride);
+        self->ids[k] = self->ids[i];
+      }
+      k++;
+    }
+    self->n = k;
+  }
+}
+
+static inline float2 clamp_4(float2 pos, float2 max) { return clamp_1(pos, float2_fill(0), max); }
+static inline bool float2_not_equals(float2 a, float2 b) { return a.x != b.x || a.y != b.y; }
+static inline float2 normalize_float2(float2 v) { return float2_div_scalar(v, length_float2(v)); }
+
+#define PP_GRID(g, pool, type)                                                       \
+  grid_t g;                                                                          \
+  {                                                                                  \
+    double lo_[3] = {0, 0, 0}, hi_[3] = {w->env_exact, w->env_exact, 0};             \
+    grid_setup(&g, 2, lo_, hi_, w->granularity_exact);                               \
+    if (mode == MODE_GRID) grid_bin(&g, (const char *)(pool).data, sizeof(type), (pool).n); \
+  }
+
+/* One full timestep: the 13 parallel step functions in schedule order. */
+void oracle_pp_timestep(pp_world *w, int mode) {
+  const abl_float R_INT = w->PRED_PREY_INTERACTION_RADIUS, R_COH = w->PREY_GROUP_COHESION_RADIUS,
+                  R_AVOID = w->SAME_SPECIES_AVOIDANCE_RADIUS, R_EAT = w->GRASS_EAT_DISTANCE,
+                  R_KILL = w->PRED_KILL_DISTANCE;
+  const abl_float DELTA_TIME = w->DELTA_TIME, SPACE_MULT = w->SPACE_MULT,
+                  PRED_SPEED_ADVANTAGE = w->PRED_SPEED_ADVANTAGE, env_size = w->env_size;
+  const int reach = 1;
+
+#define ANIMALS(p) ((PPAnimal *)(p).data)
+#define GRASSES(p) ((PPGrass *)(p).data)
+#define NEXT_OF(pool) void *next = malloc((size_t)((pool).n ? (pool).n : 1) * (pool).stride); \
+                      memcpy(next, (pool).data, (size_t)(pool).n * (pool).stride)
+
+  { /* 0: pred_follow_prey (Predator, near Prey) */
+    NEXT_OF(w->pred);
+    PP_GRID(g, w->prey, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->prey);
+    const int n = w->prey.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->pred.n; i++) {
+      const PPAnimal *in = &ANIMALS(w->pred)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      float2 agent_position = in->pos;
+      float2 agent_steer = float2_create(0, 0);
+      float2 closest_prey_position = float2_create(0, 0);
+      abl_float closest_prey_distance = R_INT;
+      bool can_see_prey = false;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *prey = &nbrs[j];
+        if (dist_float2(prey->pos, in->pos) > R_INT) continue;
+        abl_float separation = length_float2(float2_sub(in->pos, prey->pos));
+        if ((separation < closest_prey_distance)) {
+          closest_prey_position = prey->pos;
+          closest_prey_distance = separation;
+          can_see_prey = true;
+        }
+      })
+      if (can_see_prey) agent_steer = float2_sub(closest_prey_position, agent_position);
+      out->steer = agent_steer;
+    }
+    grid_free(&g);
+    pp_commit(&w->pred, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  { /* 1: prey_avoid_pred (Prey, near Predator) */
+    NEXT_OF(w->prey);
+    PP_GRID(g, w->pred, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->pred);
+    const int n = w->pred.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->prey.n; i++) {
+      const PPAnimal *in = &ANIMALS(w->prey)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      float2 avoid_velocity = float2_fill(0.0);
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *pred = &nbrs[j];
+        if (dist_float2(pred->pos, in->pos) > R_INT) continue;
+        abl_float separation = length_float2(float2_sub(in->pos, pred->pos));
+        if ((separation < R_INT)) {
+          if ((separation > 0.0)) {
+            avoid_velocity = float2_add(avoid_velocity, float2_mul_scalar(float2_sub(in->pos, pred->pos), (R_INT / separation)));
+          }
+        }
+      })
+      out->steer = avoid_velocity;
+    }
+    grid_free(&g);
+    pp_commit(&w->prey, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  { /* 2: prey_flock (Prey, near Prey) */
+    NEXT_OF(w->prey);
+    PP_GRID(g, w->prey, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->prey);
+    const int n = w->prey.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->prey.n; i++) {
+      const PPAnimal *in = &nbrs[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      float2 group_center = float2_fill(0.0);
+      float2 group_velocity = float2_fill(0.0);
+      float2 avoid_velocity = float2_fill(0.0);
+      int group_centre_count = 0;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *prey = &nbrs[j];
+        if (dist_float2(prey->pos, in->pos) > R_COH) continue;
+        abl_float separation = length_float2(float2_sub(in->pos, prey->pos));
+        group_center = float2_add(group_center, prey->pos);
+        group_centre_count += 1;
+        if (((separation < R_AVOID) && float2_not_equals(prey->pos, in->pos))) {
+          if ((separation > 0.0)) {
+            avoid_velocity = float2_add(avoid_velocity, float2_mul_scalar(float2_sub(in->pos, prey->pos), (R_AVOID / separation)));
+          }
+        }
+      })
+      if ((group_centre_count > 0)) {
+        group_center = float2_div_scalar(group_center, group_centre_count);
+        group_velocity = float2_sub(group_center, in->pos);
+      }
+      out->steer = float2_add(float2_add(in->steer, group_velocity), avoid_velocity);
+    }
+    grid_free(&g);
+    pp_commit(&w->prey, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  { /* 3: pred_avoid (Predator, near Predator) */
+    NEXT_OF(w->pred);
+    PP_GRID(g, w->pred, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->pred);
+    const int n = w->pred.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->pred.n; i++) {
+      const PPAnimal *in = &nbrs[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      float2 avoid_velocity = float2_create(0, 0);
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *pred = &nbrs[j];
+        if (dist_float2(pred->pos, in->pos) > R_AVOID) continue;
+        abl_float separation = length_float2(float2_sub(in->pos, pred->pos));
+        if (((separation < R_AVOID) && float2_not_equals(pred->pos, in->pos))) {
+          if ((separation > 0.0))
+            avoid_velocity = float2_add(avoid_velocity, float2_mul_scalar(float2_sub(in->pos, pred->pos), (R_AVOID / separation)));
+        }
+      })
+      out->steer = float2_add(in->steer, avoid_velocity);
+    }
+    grid_free(&g);
+    pp_commit(&w->pred, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  for (int k = 0; k < 2; k++) { /* 4: prey_move, 5: pred_move */
+    pp_pool *pool = k == 0 ? &w->prey : &w->pred;
+    NEXT_OF(*pool);
+    for (int i = 0; i < pool->n; i++) {
+      const PPAnimal *in = &ANIMALS(*pool)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      float2 agent_position = in->pos;
+      float2 agent_velocity = in->dir;
+      float2 agent_steer = in->steer;
+      agent_velocity = float2_add(agent_velocity, agent_steer);
+      abl_float current_speed = length_float2(agent_velocity);
+      if ((current_speed > 1.0)) agent_velocity = normalize_float2(agent_velocity);
+      if (k == 0)
+        agent_position = float2_add(agent_position, float2_mul_scalar(float2_mul_scalar(agent_velocity, DELTA_TIME), SPACE_MULT));
+      else
+        agent_position = float2_add(agent_position, float2_mul_scalar(float2_mul_scalar(float2_mul_scalar(agent_velocity, DELTA_TIME), PRED_SPEED_ADVANTAGE), SPACE_MULT));
+      agent_position = clamp_4(agent_position, float2_create(env_size, env_size)); /* boundPosition */
+      out->pos = agent_position;
+      out->dir = agent_velocity;
+      out->life = (in->life - 1);
+    }
+    pp_commit(pool, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  { /* 6: prey_eat_or_starve (Prey, near Grass) */
+    NEXT_OF(w->prey);
+    bool *dead = calloc((size_t)(w->prey.n ? w->prey.n : 1), 1);
+    PP_GRID(g, w->grass, PPGrass);
+    const PPGrass *nbrs = GRASSES(w->grass);
+    const int n = w->grass.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->prey.n; i++) {
+      const PPAnimal *in = &ANIMALS(w->prey)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      int life = in->life;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPGrass *grass = &nbrs[j];
+        if (dist_float2(grass->pos, in->pos) > R_EAT) continue;
+        if (grass->avail) life += w->GAIN_FROM_FOOD_PREY;
+      })
+      out->life = life;
+      if ((life < 1)) dead[i] = true;
+    }
+    grid_free(&g);
+    pp_commit(&w->prey, next, dead, NULL, NULL, NULL, 0);
+    free(next); free(dead);
+  }
+  { /* 7: pred_eat_or_starve (Predator, near Prey) */
+    NEXT_OF(w->pred);
+    bool *dead = calloc((size_t)(w->pred.n ? w->pred.n : 1), 1);
+    PP_GRID(g, w->prey, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->prey);
+    const int n = w->prey.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->pred.n; i++) {
+      const PPAnimal *in = &ANIMALS(w->pred)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      int pred_life = in->life;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *prey = &nbrs[j];
+        if (dist_float2(prey->pos, in->pos) > R_KILL) continue;
+        pred_life += w->GAIN_FROM_FOOD_PREDATOR;
+      })
+      out->life = pred_life;
+      if ((pred_life < 1)) dead[i] = true;
+    }
+    grid_free(&g);
+    pp_commit(&w->pred, next, dead, NULL, NULL, NULL, 0);
+    free(next); free(dead);
+  }
+  { /* 8: grass_eaten (Grass, near Prey) */
+    NEXT_OF(w->grass);
+    PP_GRID(g, w->prey, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->prey);
+    const int n = w->prey.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->grass.n; i++) {
+      const PPGrass *in = &GRASSES(w->grass)[i];
+      PPGrass *out = &((PPGrass *)next)[i];
+      abl_float closest_prey = R_EAT;
+      bool eaten = false;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *prey = &nbrs[j];
+        if (dist_float2(prey->pos, in->pos) > R_EAT) continue;
+        abl_float distance = length_float2(float2_sub(in->pos, prey->pos));
+        if (((distance < closest_prey) && in->avail)) {
+          closest_prey = distance;
+          eaten = true;
+        }
+      })
+      if (eaten) {
+        out->dead_cycles = 0;
+        out->avail = false;
+      }
+    }
+    grid_free(&g);
+    pp_commit(&w->grass, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  { /* 9: prey_eaten (Prey, near Predator) */
+    NEXT_OF(w->prey);
+    bool *dead = calloc((size_t)(w->prey.n ? w->prey.n : 1), 1);
+    PP_GRID(g, w->pred, PPAnimal);
+    const PPAnimal *nbrs = ANIMALS(w->pred);
+    const int n = w->pred.n;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int i = 0; i < w->prey.n; i++) {
+      const PPAnimal *in = &ANIMALS(w->prey)[i];
+      bool eaten = false;
+      abl_float closest_pred = R_KILL;
+      FOR_CANDIDATES(&g, mode, n, (const abl_float *)&in->pos, reach, {
+        const PPAnimal *pred = &nbrs[j];
+        if (dist_float2(pred->pos, in->pos) > R_KILL) continue;
+        abl_float distance = length_float2(float2_sub(pred->pos, in->pos));
+        if ((distance < closest_pred)) {
+          closest_pred = distance;
+          eaten = true;
+        }
+      })
+      if (eaten) dead[i] = true;
+    }
+    grid_free(&g);
+    pp_commit(&w->prey, next, dead, NULL, NULL, NULL, 0);
+    free(next); free(dead);
+  }
+  for (int k = 0; k < 2; k++) { /* 10: pred_reproduction, 11: prey_reproduction */
+    pp_pool *pool = k == 0 ? &w->pred : &w->prey;
+    const unsigned step_index = k == 0 ? 10 : 11;
+    const abl_float prob = k == 0 ? w->REPRODUCE_PREDATOR_PROB : w->REPRODUCE_PREY_PROB;
+    NEXT_OF(*pool);
+    bool *added = calloc((size_t)(pool->n ? pool->n : 1), 1);
+    PPAnimal *staged = calloc((size_t)(pool->n ? pool->n : 1), sizeof(PPAnimal));
+    for (int i = 0; i < pool->n; i++) {
+      const PPAnimal *in = &ANIMALS(*pool)[i];
+      PPAnimal *out = &((PPAnimal *)next)[i];
+      uint64_t rng = pp_rng_init(w->seed, w->timestep, step_index, pool->ids[i]);
+      if ((pp_random_float(&rng, 0, 1.0) < prob)) {
+        added[i] = true;
+        staged[i].pos = in->pos;
+        staged[i].dir = float2_mul_scalar(in->dir, -1.0);
+        staged[i].steer = float2_mul_scalar(in->steer, -1.0);
+        staged[i].life = (in->life / 2);
+        out->life = (in->life / 2);
+      }
+    }
+    pp_commit(pool, next, NULL, pool, added, staged, sizeof(PPAnimal));
+    free(next); free(added); free(staged);
+  }
+  { /* 12: grass_growth */
+    NEXT_OF(w->grass);
+    for (int i = 0; i < w->grass.n; i++) {
+      const PPGrass *in = &GRASSES(w->grass)[i];
+      PPGrass *out = &((PPGrass *)next)[i];
+      if ((in->dead_cycles == w->GRASS_REGROW_CYCLES)) {
+        int cycle_start = 0;
+        out->dead_cycles = cycle_start;
+        out->avail = true;
+      }
+      if ((!in->avail)) out->dead_cycles = (in->dead_cycles + 1);
+    }
+    pp_commit(&w->grass, next, NULL, NULL, NULL, NULL, 0);
+    free(next);
+  }
+  w->timestep++;
+}

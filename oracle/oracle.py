@@ -131,3 +131,47 @@ class Oracle:
         if model == "game_of_life.abl":
             return self.gol_run(state, steps, mode, num_agents=params["num_agents"])
         raise KeyError(model)
+
+
+class PredatorPreyOracle:
+    """predator_prey.abl — semantics frozen by this repository (parity unpinned by the
+    reference, see abl_oracle.c).  Types: 0 Predator, 1 Prey, 2 Grass."""
+
+    def __init__(self, num_agents, use_float=False):
+        self.o = Oracle(use_float)
+        self.lib = self.o.lib
+        self.lib.oracle_pp_create.restype = C.c_void_p
+        self.lib.oracle_pp_create.argtypes = [C.c_int]
+        self.lib.oracle_pp_destroy.argtypes = [C.c_void_p]
+        self.lib.oracle_pp_timestep.argtypes = [C.c_void_p, C.c_int]
+        self.lib.oracle_pp_count.argtypes = [C.c_void_p, C.c_int]
+        self.lib.oracle_pp_read.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        self.lib.oracle_pp_sum_avail.argtypes = [C.c_void_p]
+        self.w = self.lib.oracle_pp_create(num_agents)
+        real = self.o.real
+        animal = np.dtype([("pos", real, (2,)), ("dir", real, (2,)), ("steer", real, (2,)), ("life", np.int32)], align=True)
+        grass = np.dtype([("pos", real, (2,)), ("dead_cycles", np.int32), ("avail", np.bool_)], align=True)
+        self.dtypes = [animal, animal, grass]
+        for t in range(3):
+            assert self.dtypes[t].itemsize == self.lib.oracle_pp_record_size(t)
+
+    def timestep(self, mode=GRID):
+        self.lib.oracle_pp_timestep(self.w, mode)
+
+    def count(self, t):
+        return self.lib.oracle_pp_count(self.w, t)
+
+    def sum_avail(self):
+        return self.lib.oracle_pp_sum_avail(self.w)
+
+    def read(self, t):
+        n = self.count(t)
+        rec = np.zeros(n, dtype=self.dtypes[t])
+        ids = np.zeros(n, dtype=np.uint32)
+        self.lib.oracle_pp_read(self.w, t, _ptr(rec), _ptr(ids))
+        return ids, rec
+
+    def close(self):
+        if self.w:
+            self.lib.oracle_pp_destroy(self.w)
+            self.w = None
