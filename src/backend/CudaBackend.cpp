@@ -601,24 +601,51 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     // of once per candidate (with the plain loop nearly every iteration has *some* lane that
     // accepts, so the whole warp pays for the body every time).
     std::string done = "_near_done" + it;
+    std::string rdone = "_near_round" + it;
+    std::string ptype = typeName(pos->type);
     w << "if (ABL_CHUNKED) {";
     w.indent(); w.nl();
-    w << "while (" << it << ".valid()) {";
+    w << "// phase 1 writes one acceptance bit per candidate into shared memory (32 candidates"; w.nl();
+    w << "// per word, ABL_MASK_WORDS words per thread and round); phase 2 replays the same"; w.nl();
+    w << "// chunks and runs the loop body for the set bits only, in candidate order"; w.nl();
+    w << "extern __shared__ unsigned _abl_masks[];"; w.nl();
+    w << "unsigned " << it << "nw, " << it << "w, " << it << "m, " << it << "b;"; w.nl();
+    w << "for (;;) {";
     w.indent(); w.nl();
-    w << "const unsigned " << it << "b = " << it << ".index();"; w.nl();
-    w << "const unsigned " << it << "n = min(" << it << ".remaining(), 32u);"; w.nl();
-    w << "unsigned " << it << "m = 0;"; w.nl();
-    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "n; " << it << "k++) {";
+    w << "abl_near_iter<" << sdim << "> " << it << "s = " << it << ";"; w.nl();
+    w << it << "nw = 0;"; w.nl();
+    w << "while (" << it << "s.valid() && " << it << "nw < ABL_MASK_WORDS) {";
     w.indent(); w.nl();
-    w << typeName(pos->type) << " " << it << "q;"; w.nl();
-    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "b + " + it + "k");
+    w << "const unsigned " << it << "sb = " << it << "s.index();"; w.nl();
+    w << "const unsigned " << it << "sn = min(" << it << "s.remaining(), 32u);"; w.nl();
+    w << "unsigned " << it << "sm = 0;"; w.nl();
+    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "sn; " << it << "k++) {";
+    w.indent(); w.nl();
+    w << ptype << " " << it << "q;"; w.nl();
+    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "sb + " + it + "k");
     w.nl();
     w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
-      << ")) > _near_limit)) " << it << "m |= 1u << " << it << "k;";
+      << ")) > _near_limit)) " << it << "sm |= 1u << " << it << "k;";
     w.outdent(); w.nl();
     w << "}"; w.nl();
-    w << "while (" << it << "m) {";
+    w << "_abl_masks[" << it << "nw * blockDim.x + threadIdx.x] = " << it << "sm;"; w.nl();
+    w << it << "nw++;"; w.nl();
+    w << it << "s.skip(" << it << "sn);";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "if (" << it << "nw == 0) break;"; w.nl();
+    w << it << "w = 0; " << it << "m = 0; " << it << "b = 0;"; w.nl();
+    w << "for (;;) {";
     w.indent(); w.nl();
+    w << "while (" << it << "m == 0) {";
+    w.indent(); w.nl();
+    w << "if (" << it << "w >= " << it << "nw) goto " << rdone << ";"; w.nl();
+    w << it << "b = " << it << ".index();"; w.nl();
+    w << it << "m = _abl_masks[" << it << "w * blockDim.x + threadIdx.x];"; w.nl();
+    w << it << "w++;"; w.nl();
+    w << it << ".skip(min(" << it << ".remaining(), 32u));";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
     w << "const unsigned " << it << "j = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
     w << it << "m &= " << it << "m - 1;"; w.nl();
     w << nbr->name << " " << s.varName << ";"; w.nl();
@@ -636,7 +663,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     }
     w.outdent(); w.nl();
     w << "}"; w.nl();
-    w << it << ".skip(" << it << "n);";
+    w << rdone << ": ;";
     w.outdent(); w.nl();
     w << "}"; w.nl();
     w << done << ": ;";
@@ -1128,7 +1155,9 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   if (curStepHasLimit) {
     // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
     w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();
-    w << "    if (chunked) abl_kernel_" << f.emitName << "<true><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+    w << "    static bool smem_set = false;"; w.nl();
+    w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
+    w << "    if (chunked) abl_kernel_" << f.emitName << "<true><<<grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
     w << "    else abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
   } else {
     w << "    abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
