@@ -1589,15 +1589,25 @@ struct SlabTable {
   int ghost;
 };
 
-// to_lo / to_hi: the record is copied to the lower / upper peer.  Peers form a ring when
-// there are more than two slabs, so that agents leaving through one end of a periodic
-// world (wraparound / teleport to the opposite bound) reach the slab at the other end.
+// One pass over the formerly owned agents: classify by the layer of the current position and
+// append the selected records to the outgoing messages (atomic slot allocation; the order
+// inside a message is irrelevant because the receiver's next binning sorts by (cell, id)).
+// The record is copied to the lower / upper peer.  Peers form a ring when there are more than
+// two slabs, so that agents leaving through one end of a periodic world (wraparound / teleport
+// to the opposite bound) reach the slab at the other end.
+// Message layout: u32 count (16-byte header), then packed records of `rec_words` 32-bit words:
+// the columns of one agent back to back (1-byte columns widened to a word), id last.
+static const u32 kMsgHeader = 16;
+static const u32 kMsgFirstRecords = 8192;   // records that fit the fixed-size first message
+
 template <typename R>
-__global__ void k_slab_classify(const R *axis_col, int stride, int comp, u32 n, u32 first, R origin,
-                                R inv_cell, int n_layers, SlabTable tab, u8 *to_lo, u8 *to_hi, u32 *far) {
+__global__ void k_slab_pack(ColTable t, const R *axis_col, int stride, int comp, u32 n, u32 first,
+                            R origin, R inv_cell, int n_layers, SlabTable tab, bool has_lo, bool has_hi,
+                            u8 *msg_lo, u8 *msg_hi, u32 rec_words, u32 *far) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  R v = axis_col[(size_t)(first + i) * stride + comp];
+  const size_t src = (size_t)first + i;
+  R v = axis_col[src * stride + comp];
   const int layer = cell_coord<R>(v, origin, inv_cell, n_layers);
   const int me = tab.my, N = tab.n_slabs;
   const int lb = tab.bounds[me], le = tab.bounds[me + 1];
@@ -1619,37 +1629,44 @@ __global__ void k_slab_classify(const R *axis_col, int stride, int comp, u32 n, 
   } else {
     atomicAdd(far, 1u);  // moved farther than a neighbouring slab: unsupported
   }
-  to_lo[i] = lo ? 1 : 0;
-  to_hi[i] = hi ? 1 : 0;
-}
-
-// message layout: column 0 of all selected agents, column 1, ..., ids (each padded to 16 bytes)
-__global__ void k_slab_pack(ColTable t, const u8 *flag, const u32 *offsets, u32 n, u32 first, u32 count,
-                            u8 *msg) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || !flag[i]) return;
-  u32 dst = offsets[i];
-  size_t off = 0;
-  for (int k = 0; k < t.ncols; k++) {
-    copy_elem(msg + off, dst, t.in[k], first + i, t.elem[k]);
-    off += ((size_t)count * t.elem[k] + 15) / 16 * 16;
+  lo = lo && has_lo;
+  hi = hi && has_hi;
+  for (int dir = 0; dir < 2; dir++) {
+    if (!(dir == 0 ? lo : hi)) continue;
+    u8 *msg = dir == 0 ? msg_lo : msg_hi;
+    u32 slot = atomicAdd((u32 *)msg, 1u);
+    u32 *rec = (u32 *)(msg + kMsgHeader) + (size_t)slot * rec_words;
+    u32 w = 0;
+    for (int k = 0; k < t.ncols; k++) {
+      const int e = t.elem[k];
+      if (e == 1) { rec[w++] = ((const u8 *)t.in[k])[src]; continue; }
+      const u32 *p = (const u32 *)t.in[k] + src * (e / 4);
+      for (int q = 0; q < e / 4; q++) rec[w++] = p[q];
+    }
   }
 }
 
-__global__ void k_slab_unpack(ColTable t, const u8 *msg, u32 count, u32 dst_first) {
+__global__ void k_slab_unpack(ColTable t, const u8 *msg, u32 count, u32 dst_first, u32 rec_words) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= count) return;
-  size_t off = 0;
+  const u32 *rec = (const u32 *)(msg + kMsgHeader) + (size_t)i * rec_words;
+  const size_t dst = (size_t)dst_first + i;
+  u32 w = 0;
   for (int k = 0; k < t.ncols; k++) {
-    copy_elem(t.out[k], dst_first + i, msg + off, i, t.elem[k]);
-    off += ((size_t)count * t.elem[k] + 15) / 16 * 16;
+    const int e = t.elem[k];
+    if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w++]; continue; }
+    u32 *p = (u32 *)t.out[k] + dst * (e / 4);
+    for (int q = 0; q < e / 4; q++) p[q] = rec[w++];
   }
 }
 
+static u32 slab_rec_words(const Pool &p) {
+  u32 w = 0;
+  for (const Column &c : p.cols) w += c.elem == 1 ? 1 : c.elem / 4;
+  return w;
+}
 static size_t slab_msg_bytes(const Pool &p, size_t count) {
-  size_t bytes = 0;
-  for (const Column &c : p.cols) bytes += (count * (size_t)c.elem + 15) / 16 * 16;
-  return bytes;
+  return kMsgHeader + count * (size_t)slab_rec_words(p) * 4;
 }
 
 static int ensure_xbuf(abl_runtime *rt, int which, size_t bytes) {
@@ -1733,23 +1750,21 @@ extern "C" int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n) {
   return ABL_OK;
 }
 
-// ---- exchange, phase 1: classify + pack (per direction: message in xbuf[0/1], count in x_out) --
+// ---- exchange, phase 1: classify + pack into xbuf[0] (to lower) / xbuf[1] (to upper) ----------
 static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
   if (!p.own_valid) TRY(bin_pool(rt, p));  // fresh upload: establish the owned range
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
   const GridParams &g = rt->grid;
   const int axis = g.dim - 1;
   const Member &pm = p.members[p.pos_member];
-  if (rt->xflags_cap < (size_t)n_own * 2 + 64) {
-    CU(cudaStreamSynchronize(rt->stream));
-    if (rt->xflags) CU(cudaFree(rt->xflags));
-    rt->xflags_cap = round_up((size_t)n_own * 2 + 64, kScanTile) * 2;
-    CU(cudaMalloc(&rt->xflags, rt->xflags_cap));
-  }
-  u8 *to_lo = (u8 *)rt->xflags;
-  u8 *to_hi = to_lo + round_up((size_t)n_own + 16, kScanTile);
-  u32 counts[2] = {0, 0};
-  u32 *off_lo = p.offsets, *off_hi = p.local;  // scratch of at least cap entries each
+  // worst case every owned agent is sent; the first message always has room for kMsgFirstRecords
+  const size_t cap = std::max<size_t>(n_own, kMsgFirstRecords);
+  TRY(ensure_xbuf(rt, 0, slab_msg_bytes(p, cap)));
+  TRY(ensure_xbuf(rt, 1, slab_msg_bytes(p, cap)));
+  CU(cudaMemsetAsync(rt->xbuf[0], 0, kMsgHeader, rt->stream));
+  CU(cudaMemsetAsync(rt->xbuf[1], 0, kMsgHeader, rt->stream));
+  u32 *far = rt->d_scalar + 10;
+  CU(cudaMemsetAsync(far, 0, sizeof(u32), rt->stream));
   if (n_own && (has_lo || has_hi)) {
     int col = pm.first_col, stride = 1, comp = 0;
     if (g.dim == 2) { stride = 2; comp = 1; } else { col += 2; }
@@ -1759,46 +1774,23 @@ static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
     tab.my = rt->my_slab;
     tab.ghost = rt->ghost_layers;
     for (int s = 0; s <= rt->n_slabs; s++) tab.bounds[s] = rt->slab_bounds[s];
-    u32 *far = rt->d_scalar + 10;
-    CU(cudaMemsetAsync(far, 0, sizeof(u32), rt->stream));
+    ColTable t;
+    fill_table(p, t, false);
+    const u32 rw = slab_rec_words(p);
     u32 nb = blocks_for(n_own, 256);
     if (rt->real_size == 8)
-      k_slab_classify<double><<<nb, 256, 0, rt->stream>>>((const double *)axis_col, stride, comp, n_own, ob,
-          g.origin[axis], g.inv_cell, slab_layers(rt), tab, to_lo, to_hi, far);
+      k_slab_pack<double><<<nb, 256, 0, rt->stream>>>(t, (const double *)axis_col, stride, comp, n_own, ob,
+          g.origin[axis], g.inv_cell, slab_layers(rt), tab, has_lo, has_hi, (u8 *)rt->xbuf[0], (u8 *)rt->xbuf[1], rw, far);
     else
-      k_slab_classify<float><<<nb, 256, 0, rt->stream>>>((const float *)axis_col, stride, comp, n_own, ob,
-          (float)g.origin[axis], (float)g.inv_cell, slab_layers(rt), tab, to_lo, to_hi, far);
+      k_slab_pack<float><<<nb, 256, 0, rt->stream>>>(t, (const float *)axis_col, stride, comp, n_own, ob,
+          (float)g.origin[axis], (float)g.inv_cell, slab_layers(rt), tab, has_lo, has_hi, (u8 *)rt->xbuf[0], (u8 *)rt->xbuf[1], rw, far);
     rt->launches++;
     CU(cudaGetLastError());
-    if (has_lo) TRY((run_scan<u8, 0, false>(rt, to_lo, off_lo, n_own, rt->d_scalar + 8)));
-    if (has_hi) TRY((run_scan<u8, 0, false>(rt, to_hi, off_hi, n_own, rt->d_scalar + 9)));
-    CU(cudaMemcpyAsync(rt->h_scalar + 8, rt->d_scalar + 8, 3 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-    CU(cudaStreamSynchronize(rt->stream));
-    if (has_lo) counts[0] = rt->h_scalar[8];
-    if (has_hi) counts[1] = rt->h_scalar[9];
-    if (rt->h_scalar[10])
-      return fail(ABL_ERR_COMM, "%u agents of pool %s moved farther than a neighbouring slab in one step "
-                  "(only neighbour and periodic wrap-around migration is supported)", rt->h_scalar[10], p.name.c_str());
   }
-  ColTable t;
-  fill_table(p, t, false);
-  TRY(ensure_xbuf(rt, 0, slab_msg_bytes(p, counts[0])));
-  TRY(ensure_xbuf(rt, 1, slab_msg_bytes(p, counts[1])));
-  if (counts[0]) {
-    k_slab_pack<<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, to_lo, off_lo, n_own, ob, counts[0], (u8 *)rt->xbuf[0]);
-    rt->launches++;
-  }
-  if (counts[1]) {
-    k_slab_pack<<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, to_hi, off_hi, n_own, ob, counts[1], (u8 *)rt->xbuf[1]);
-    rt->launches++;
-  }
-  CU(cudaGetLastError());
-  rt->x_out[0] = counts[0];
-  rt->x_out[1] = counts[1];
   return ABL_OK;
 }
 
-// ---- exchange, phase 3: arrivals (already in xbuf[2/3]) are appended behind the owned range ----
+// ---- exchange, phase 3: arrivals (messages in xbuf[2/3]) are appended behind the owned range --
 static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
   const u32 arrivals = incoming[0] + incoming[1];
@@ -1809,12 +1801,13 @@ static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
   ColTable t;
   fill_table(p, t, false);
   for (int c = 0; c < t.ncols; c++) t.out[c] = const_cast<void *>(t.in[c]);
+  const u32 rw = slab_rec_words(p);
   if (incoming[0]) {
-    k_slab_unpack<<<blocks_for(incoming[0], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[2], incoming[0], oe);
+    k_slab_unpack<<<blocks_for(incoming[0], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[2], incoming[0], oe, rw);
     rt->launches++;
   }
   if (incoming[1]) {
-    k_slab_unpack<<<blocks_for(incoming[1], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[3], incoming[1], oe + incoming[0]);
+    k_slab_unpack<<<blocks_for(incoming[1], 256), 256, 0, rt->stream>>>(t, (const u8 *)rt->xbuf[3], incoming[1], oe + incoming[0], rw);
     rt->launches++;
   }
   CU(cudaGetLastError());
@@ -1823,6 +1816,27 @@ static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
   p.n = (size_t)n_own + arrivals;
   p.binned = false;
   TRY(drop_fused_histogram(rt, p));
+  return ABL_OK;
+}
+
+static int exchange_check_far(abl_runtime *rt, const Pool &p, u32 far) {
+  if (far)
+    return fail(ABL_ERR_COMM, "%u agents of pool %s moved farther than a neighbouring slab in one step "
+                "(only neighbour and periodic wrap-around migration is supported)", far, p.name.c_str());
+  return ABL_OK;
+}
+
+// Grows a receive buffer while keeping the part of the message that has already arrived.
+static int grow_recv(abl_runtime *rt, int which, size_t bytes, size_t keep) {
+  if (rt->xcap[which] >= bytes) return ABL_OK;
+  void *nb = nullptr;
+  size_t cap = round_up(bytes + bytes / 4, 1 << 16);
+  CU(cudaMalloc(&nb, cap));
+  if (keep) CU(cudaMemcpyAsync(nb, rt->xbuf[which], keep, cudaMemcpyDeviceToDevice, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  if (rt->xbuf[which]) CU(cudaFree(rt->xbuf[which]));
+  rt->xbuf[which] = nb;
+  rt->xcap[which] = cap;
   return ABL_OK;
 }
 
@@ -1839,32 +1853,46 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
   const bool has_lo = rt->comm && N > 1 && (me > 0 || ring), has_hi = rt->comm && N > 1 && (me < N - 1 || ring);
   const int lo_peer = (me - 1 + N) % N, hi_peer = (me + 1) % N;
   TRY(exchange_pack(rt, p, has_lo, has_hi));
-  const u32 counts[2] = {rt->x_out[0], rt->x_out[1]};
   u32 incoming[2] = {0, 0};
   if (has_lo || has_hi) {
+    // One NCCL group moves fixed-size first messages (header + up to kMsgFirstRecords records),
+    // so neither side needs the other's count beforehand; one host synchronisation then reads
+    // all four headers.  Oversized messages (rare) send their tail in a second group.
     // Issue order per rank: (send to lower, receive from upper), (send to upper, receive from
     // lower) — with two ranks both peers are the same process and NCCL matches operations
     // between a pair in issue order.
-    u32 *d_cnt = rt->d_scalar + 12;  // [0..1] outgoing, [2] from lower, [3] from upper
-    CU(cudaMemcpyAsync(d_cnt, counts, sizeof counts, cudaMemcpyHostToDevice, rt->stream));
+    const size_t first_bytes = slab_msg_bytes(p, kMsgFirstRecords);
+    TRY(ensure_xbuf(rt, 2, first_bytes));
+    TRY(ensure_xbuf(rt, 3, first_bytes));
     NCCL(ncclGroupStart());
-    if (has_lo) NCCL(ncclSend(d_cnt + 0, 1, ncclUint32, lo_peer, rt->comm, rt->stream));
-    if (has_hi) NCCL(ncclRecv(d_cnt + 3, 1, ncclUint32, hi_peer, rt->comm, rt->stream));
-    if (has_hi) NCCL(ncclSend(d_cnt + 1, 1, ncclUint32, hi_peer, rt->comm, rt->stream));
-    if (has_lo) NCCL(ncclRecv(d_cnt + 2, 1, ncclUint32, lo_peer, rt->comm, rt->stream));
+    if (has_lo) NCCL(ncclSend(rt->xbuf[0], first_bytes, ncclUint8, lo_peer, rt->comm, rt->stream));
+    if (has_hi) NCCL(ncclRecv(rt->xbuf[3], first_bytes, ncclUint8, hi_peer, rt->comm, rt->stream));
+    if (has_hi) NCCL(ncclSend(rt->xbuf[1], first_bytes, ncclUint8, hi_peer, rt->comm, rt->stream));
+    if (has_lo) NCCL(ncclRecv(rt->xbuf[2], first_bytes, ncclUint8, lo_peer, rt->comm, rt->stream));
     NCCL(ncclGroupEnd());
-    CU(cudaMemcpyAsync(rt->h_scalar + 12, d_cnt + 2, 2 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    u32 *h = rt->h_scalar + 8;  // [0] out lo, [1] out hi, [2] in lo, [3] in hi, [4] far
+    CU(cudaMemcpyAsync(h + 0, rt->xbuf[0], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaMemcpyAsync(h + 1, rt->xbuf[1], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    if (has_lo) CU(cudaMemcpyAsync(h + 2, rt->xbuf[2], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    if (has_hi) CU(cudaMemcpyAsync(h + 3, rt->xbuf[3], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaMemcpyAsync(h + 4, rt->d_scalar + 10, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
     CU(cudaStreamSynchronize(rt->stream));
-    if (has_lo) incoming[0] = rt->h_scalar[12];
-    if (has_hi) incoming[1] = rt->h_scalar[13];
-    TRY(ensure_xbuf(rt, 2, slab_msg_bytes(p, incoming[0])));
-    TRY(ensure_xbuf(rt, 3, slab_msg_bytes(p, incoming[1])));
-    NCCL(ncclGroupStart());
-    if (has_lo && counts[0]) NCCL(ncclSend(rt->xbuf[0], slab_msg_bytes(p, counts[0]), ncclUint8, lo_peer, rt->comm, rt->stream));
-    if (has_hi && incoming[1]) NCCL(ncclRecv(rt->xbuf[3], slab_msg_bytes(p, incoming[1]), ncclUint8, hi_peer, rt->comm, rt->stream));
-    if (has_hi && counts[1]) NCCL(ncclSend(rt->xbuf[1], slab_msg_bytes(p, counts[1]), ncclUint8, hi_peer, rt->comm, rt->stream));
-    if (has_lo && incoming[0]) NCCL(ncclRecv(rt->xbuf[2], slab_msg_bytes(p, incoming[0]), ncclUint8, lo_peer, rt->comm, rt->stream));
-    NCCL(ncclGroupEnd());
+    TRY(exchange_check_far(rt, p, h[4]));
+    const u32 out_lo = has_lo ? h[0] : 0, out_hi = has_hi ? h[1] : 0;
+    incoming[0] = has_lo ? h[2] : 0;
+    incoming[1] = has_hi ? h[3] : 0;
+    const u32 K = kMsgFirstRecords;
+    if (out_lo > K || out_hi > K || incoming[0] > K || incoming[1] > K) {
+      const size_t rec = (size_t)slab_rec_words(p) * 4;
+      if (incoming[0] > K) TRY(grow_recv(rt, 2, slab_msg_bytes(p, incoming[0]), first_bytes));
+      if (incoming[1] > K) TRY(grow_recv(rt, 3, slab_msg_bytes(p, incoming[1]), first_bytes));
+      NCCL(ncclGroupStart());
+      if (out_lo > K) NCCL(ncclSend((u8 *)rt->xbuf[0] + first_bytes, (out_lo - K) * rec, ncclUint8, lo_peer, rt->comm, rt->stream));
+      if (incoming[1] > K) NCCL(ncclRecv((u8 *)rt->xbuf[3] + first_bytes, (incoming[1] - K) * rec, ncclUint8, hi_peer, rt->comm, rt->stream));
+      if (out_hi > K) NCCL(ncclSend((u8 *)rt->xbuf[1] + first_bytes, (out_hi - K) * rec, ncclUint8, hi_peer, rt->comm, rt->stream));
+      if (incoming[0] > K) NCCL(ncclRecv((u8 *)rt->xbuf[2] + first_bytes, (incoming[0] - K) * rec, ncclUint8, lo_peer, rt->comm, rt->stream));
+      NCCL(ncclGroupEnd());
+    }
   }
   return exchange_unpack(rt, p, incoming);
 }
@@ -1885,8 +1913,14 @@ extern "C" int abl_cuda_exchange_begin(abl_runtime *rt, int pool) {
   if (!rt->slab || pp->pos_member < 0) return ABL_OK;
   CU(cudaSetDevice(rt->device));
   TRY(exchange_pack(rt, *pp, rt->peer_lo != nullptr, rt->peer_hi != nullptr));
+  u32 *h = rt->h_scalar + 8;
+  CU(cudaMemcpyAsync(h + 0, rt->xbuf[0], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaMemcpyAsync(h + 1, rt->xbuf[1], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaMemcpyAsync(h + 4, rt->d_scalar + 10, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaStreamSynchronize(rt->stream));
-  return ABL_OK;
+  rt->x_out[0] = h[0];
+  rt->x_out[1] = h[1];
+  return exchange_check_far(rt, *pp, h[4]);
 }
 
 extern "C" int abl_cuda_exchange_end(abl_runtime *rt, int pool) {
@@ -1900,13 +1934,13 @@ extern "C" int abl_cuda_exchange_end(abl_runtime *rt, int pool) {
     incoming[0] = rt->peer_lo->x_out[1];
     size_t bytes = slab_msg_bytes(p, incoming[0]);
     TRY(ensure_xbuf(rt, 2, bytes));
-    if (bytes) CU(cudaMemcpyAsync(rt->xbuf[2], rt->peer_lo->xbuf[1], bytes, cudaMemcpyDefault, rt->stream));
+    CU(cudaMemcpyAsync(rt->xbuf[2], rt->peer_lo->xbuf[1], bytes, cudaMemcpyDefault, rt->stream));
   }
   if (rt->peer_hi) {  // what the upper slab sent downwards
     incoming[1] = rt->peer_hi->x_out[0];
     size_t bytes = slab_msg_bytes(p, incoming[1]);
     TRY(ensure_xbuf(rt, 3, bytes));
-    if (bytes) CU(cudaMemcpyAsync(rt->xbuf[3], rt->peer_hi->xbuf[0], bytes, cudaMemcpyDefault, rt->stream));
+    CU(cudaMemcpyAsync(rt->xbuf[3], rt->peer_hi->xbuf[0], bytes, cudaMemcpyDefault, rt->stream));
   }
   TRY(exchange_unpack(rt, p, incoming));
   CU(cudaStreamSynchronize(rt->stream));

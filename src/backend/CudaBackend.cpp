@@ -601,7 +601,6 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     // of once per candidate (with the plain loop nearly every iteration has *some* lane that
     // accepts, so the whole warp pays for the body every time).
     std::string done = "_near_done" + it;
-    std::string rdone = "_near_round" + it;
     std::string ptype = typeName(pos->type);
     w << "if (ABL_CHUNKED) {";
     w.indent(); w.nl();
@@ -637,15 +636,15 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w << it << "w = 0; " << it << "m = 0; " << it << "b = 0;"; w.nl();
     w << "for (;;) {";
     w.indent(); w.nl();
-    w << "while (" << it << "m == 0) {";
+    w << "while (" << it << "m == 0 && " << it << "w < " << it << "nw) {";
     w.indent(); w.nl();
-    w << "if (" << it << "w >= " << it << "nw) goto " << rdone << ";"; w.nl();
     w << it << "b = " << it << ".index();"; w.nl();
     w << it << "m = _abl_masks[" << it << "w * blockDim.x + threadIdx.x];"; w.nl();
     w << it << "w++;"; w.nl();
     w << it << ".skip(min(" << it << ".remaining(), 32u));";
     w.outdent(); w.nl();
     w << "}"; w.nl();
+    w << "if (" << it << "m == 0) break;"; w.nl();
     w << "const unsigned " << it << "j = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
     w << it << "m &= " << it << "m - 1;"; w.nl();
     w << nbr->name << " " << s.varName << ";"; w.nl();
@@ -662,8 +661,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
       innerLoopDepth = savedDepth;
     }
     w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << rdone << ": ;";
+    w << "}";
     w.outdent(); w.nl();
     w << "}"; w.nl();
     w << done << ": ;";
