@@ -401,7 +401,7 @@ __device__ __forceinline__ int cell_coord(R p, R origin, R inv_cell, int n) {
 // POS2: position is one packed 2-vector column; otherwise three scalar columns.
 template <typename R, int DIM>
 __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, u32 src_begin,
-                            GridParams g, u32 *key, u32 *local, u32 *cell_count) {
+                            u32 out_begin, GridParams g, u32 *key, u32 *local, u32 *cell_count) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t s = (size_t)src_begin + i;
@@ -421,8 +421,8 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
     int cz = cell_coord<R>(z, (R)g.origin[2], (R)g.inv_cell, g.n_cell[2]);
     c += (u32)cz * (u32)g.n_cell[0] * (u32)g.n_cell[1];
   }
-  key[i] = c;
-  local[i] = atomicAdd(&cell_count[c], 1u);
+  key[out_begin + i] = c;
+  local[out_begin + i] = atomicAdd(&cell_count[c], 1u);
 }
 
 // seg_ids[slot] = id of the agent that arrived `local`-th in its cell segment
@@ -1058,10 +1058,11 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
 
 static int slab_update_owned_range(abl_runtime *rt, Pool &p);
 
-static int launch_bin_count(abl_runtime *rt, Pool &p) {
+// histogram of `n` records starting at source index `src_begin`; keys/ranks go to slot
+// `out_begin + i` of the pool's key/local arrays
+static int launch_bin_count(abl_runtime *rt, Pool &p, u32 n, u32 src_begin, u32 out_begin) {
   const GridParams &g = rt->grid;
   const Member &pm = p.members[p.pos_member];
-  const u32 n = (u32)p.n;
   const int bs = 256;
   if (!n) return ABL_OK;
   const void *px = p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
@@ -1072,11 +1073,11 @@ static int launch_bin_count(abl_runtime *rt, Pool &p) {
   }
   u32 nb = blocks_for(n, bs);
   if (rt->real_size == 8) {
-    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
-    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
+    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
   } else {
-    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
-    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, p.src_begin, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
+    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
   }
   rt->launches++;
   CU(cudaGetLastError());
@@ -1092,7 +1093,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   const u32 n = (u32)p.n;
   const int bs = 256;
   // 1. histogram (skipped when the step kernel that produced the positions already did it)
-  if (!p.counted) TRY(launch_bin_count(rt, p));
+  if (!p.counted) TRY(launch_bin_count(rt, p, n, p.src_begin, 0u));
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
@@ -1337,7 +1338,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     // rewrites the positions of a pool that is used for neighbour search and no commit
     // stage reorders the pool afterwards.
     const bool writes_pos = self.pos_member >= 0 && (s.desc.written_members >> self.pos_member & 1u);
-    bool fuse = writes_pos && rt->env_set && !rt->slab && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
+    bool fuse = writes_pos && rt->env_set && !s.desc.uses_removal && added != &self && self.cell_count != nullptr && self.ever_binned;
     if (writes_pos) TRY(drop_fused_histogram(rt, self));  // never consumed: start over
     if (fuse) {
       a.bin_key = self.key;
@@ -1796,6 +1797,7 @@ static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
   const u32 arrivals = incoming[0] + incoming[1];
   if ((size_t)oe + arrivals > p.cap) {
     p.n = std::max(p.n, (size_t)oe);
+    TRY(drop_fused_histogram(rt, p));  // growing reallocates the key/rank scratch
     TRY(reserve_pool(rt, p, (size_t)oe + arrivals));
   }
   ColTable t;
@@ -1815,7 +1817,9 @@ static int exchange_unpack(abl_runtime *rt, Pool &p, const u32 incoming[2]) {
   p.src_begin = ob;
   p.n = (size_t)n_own + arrivals;
   p.binned = false;
-  TRY(drop_fused_histogram(rt, p));
+  // the step kernel already produced keys and the histogram of the owned agents (fused
+  // epilogue); only the arrivals are still missing
+  if (p.counted && arrivals) TRY(launch_bin_count(rt, p, arrivals, oe, n_own));
   return ABL_OK;
 }
 
