@@ -94,6 +94,19 @@ private:
   const FuncDecl *curFn = nullptr;
   const StepInfo *curStep = nullptr;
   bool curStepHasLimit = false;
+  // inside a for-near body: dist(in.pos, nx.pos) / length(in.pos - nx.pos) reuse the squared
+  // distance of the radius filter ((a-b)^2 == (b-a)^2 bit for bit)
+  const Symbol *nearVar = nullptr, *nearSelf = nullptr;
+  std::string nearPos, nearSelfPos, nearD2;
+  bool isNearPair(const Expr &a, const Expr &b) const;
+  void setNearContext(const Stmt &loop, const Expr &agentExpr, const std::string &pos, const std::string &selfPos,
+                      const std::string &d2) {
+    nearVar = loop.sym;
+    nearSelf = agentExpr.kind == Expr::Var ? agentExpr.sym : nullptr;
+    nearPos = pos; nearSelfPos = selfPos;
+    nearD2 = nearSelf ? d2 : std::string();
+  }
+  void clearNearContext() { nearVar = nearSelf = nullptr; nearD2.clear(); }
   // chunked near loop: `break` of the DSL body must leave two nested C++ loops
   std::string nearBreakLabel;
   int innerLoopDepth = 0;
@@ -314,6 +327,15 @@ void CudaPrinter::expr(const Expr &e) {
   }
 }
 
+bool CudaPrinter::isNearPair(const Expr &a, const Expr &b) const {
+  if (!nearVar || nearD2.empty()) return false;
+  auto is = [](const Expr &e, const Symbol *sym, const std::string &member) {
+    return e.kind == Expr::Member && e.name == member && e.kids[0]->kind == Expr::Var && e.kids[0]->sym == sym;
+  };
+  return (is(a, nearVar, nearPos) && is(b, nearSelf, nearSelfPos)) ||
+         (is(b, nearVar, nearPos) && is(a, nearSelf, nearSelfPos));
+}
+
 void CudaPrinter::callExpr(const Expr &e) {
   if (e.ckind == Expr::Ctor) {
     if (e.type.isVec()) {
@@ -329,6 +351,15 @@ void CudaPrinter::callExpr(const Expr &e) {
 
   const std::string &t = e.target;
   if (e.ckind == Expr::Builtin) {
+    if (dev() && (t == "dist_float2" || t == "dist_float3") && isNearPair(*e.kids[0], *e.kids[1])) {
+      w << "abl_sqrt_narrow(" << nearD2 << ")";
+      return;
+    }
+    if (dev() && (t == "length_float2" || t == "length_float3") && e.kids[0]->kind == Expr::Binary &&
+        e.kids[0]->op == Op::Sub && isNearPair(*e.kids[0]->kids[0], *e.kids[0]->kids[1])) {
+      w << "abl_sqrt_narrow(" << nearD2 << ")";
+      return;
+    }
     if (t == "add") {
       AgentDecl *agent = e.paramTys[0].agent;
       if (!dev()) {
@@ -649,6 +680,9 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w << it << "m &= " << it << "m - 1;"; w.nl();
     w << nbr->name << " " << s.varName << ";"; w.nl();
     loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+    w.nl();
+    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+      << pos->name << ", " << selfPosText << "));";
     loadOthers(it + "j");
     w.nl();
     {
@@ -656,7 +690,9 @@ void CudaPrinter::nearLoop(const Stmt &s) {
       int savedDepth = innerLoopDepth;
       nearBreakLabel = done;
       innerLoopDepth = 0;
+      setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
       stmt(*s.body[0]);
+      clearNearContext();
       nearBreakLabel = savedLabel;
       innerLoopDepth = savedDepth;
     }
@@ -678,8 +714,10 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
   w.nl();
   if (curStepHasLimit) {
-    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "." << pos->name << ", "
-      << selfPosText << ")) > _near_limit) continue;";
+    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+      << pos->name << ", " << selfPosText << "));";
+    w.nl();
+    w << "if (" << it << "d2 > _near_limit) continue;";
   } else {
     w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", " << selfPosText << ") > ";
     expr(radius);
@@ -692,7 +730,9 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     int savedDepth = innerLoopDepth;
     nearBreakLabel.clear();
     innerLoopDepth = 0;
+    if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
     stmt(*s.body[0]);
+    clearNearContext();
     nearBreakLabel = savedLabel;
     innerLoopDepth = savedDepth;
   }
