@@ -92,6 +92,7 @@ struct Pool {
   // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
   // src_begin is where the live records start before the next binning compacts them
   u32 own_begin = 0, own_end = 0, src_begin = 0;
+  u32 key_base_hint = 0;  // copy of grid.key_base (cell_start is handed out with a virtual origin)
   bool own_valid = false;
   bool binned = false;
   bool ever_binned = false;
@@ -137,6 +138,11 @@ struct GridParams {
   double cell;
   double inv_cell;  // 1/cell in the precision of abl_float
   u32 n_cells;
+  // window of cell layers (slowest axis) this runtime keeps cell ranges for: everything in a
+  // single-GPU run, the own slab plus ghost layers under slab decomposition.  Keys stored in
+  // the pool are relative to key_base; coordinates outside the window are clamped into it.
+  int axis_lo, axis_hi;
+  u32 key_base, n_local;
 };
 
 struct abl_runtime {
@@ -416,11 +422,14 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
   }
   int cx = cell_coord<R>(x, (R)g.origin[0], (R)g.inv_cell, g.n_cell[0]);
   int cy = cell_coord<R>(y, (R)g.origin[1], (R)g.inv_cell, g.n_cell[1]);
+  if (DIM == 2) cy = min(max(cy, g.axis_lo), g.axis_hi - 1);
   u32 c = (u32)cy * (u32)g.n_cell[0] + (u32)cx;
   if (DIM == 3) {
     int cz = cell_coord<R>(z, (R)g.origin[2], (R)g.inv_cell, g.n_cell[2]);
+    cz = min(max(cz, g.axis_lo), g.axis_hi - 1);
     c += (u32)cz * (u32)g.n_cell[0] * (u32)g.n_cell[1];
   }
+  c -= g.key_base;
   key[out_begin + i] = c;
   local[out_begin + i] = atomicAdd(&cell_count[c], 1u);
 }
@@ -673,7 +682,7 @@ static void fill_table(const Pool &p, ColTable &t, bool out_is_alt) {
 // reordered or refilled) has to be wiped, otherwise the next histogram adds on top of it.
 static int drop_fused_histogram(abl_runtime *rt, Pool &p) {
   if (p.counted && p.cell_count)
-    CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)rt->grid.n_cells + 1) * sizeof(u32), rt->stream));
+    CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)rt->grid.n_local + 1) * sizeof(u32), rt->stream));
   p.counted = false;
   return ABL_OK;
 }
@@ -785,6 +794,10 @@ extern "C" int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *
   if (cells > 0x7fffffffull)
     return fail(ABL_ERR_ARGUMENT, "grid of %llu cells exceeds 2^31; increase the granularity", cells);
   g.n_cells = (u32)cells;
+  g.axis_lo = 0;
+  g.axis_hi = dim == 3 ? g.n_cell[2] : g.n_cell[1];
+  g.key_base = 0;
+  g.n_local = g.n_cells;
   rt->env_set = true;
   for (Pool &p : rt->pools) p.binned = false;
   return ABL_OK;
@@ -1048,7 +1061,7 @@ extern "C" int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids_ou
 // ---------------------------------------------------------------------------------------
 static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   if (p.cell_count) return ABL_OK;
-  size_t padded = round_up((size_t)rt->grid.n_cells + 1, kScanTile);
+  size_t padded = round_up((size_t)rt->grid.n_local + 1, kScanTile);
   CU(cudaMalloc(&p.cell_count, padded * sizeof(u32)));
   CU(cudaMalloc(&p.cell_start, padded * sizeof(u32)));
   CU(cudaMemsetAsync(p.cell_count, 0, padded * sizeof(u32), rt->stream));
@@ -1097,7 +1110,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
-  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_cells + 1, nullptr)));
+  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 1, nullptr)));
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
@@ -1112,6 +1125,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     flip_all(p);
   }
   p.src_begin = 0;
+  p.key_base_hint = g.key_base;
   p.binned = true;
   p.ever_binned = true;
   if (rt->slab) TRY(slab_update_owned_range(rt, p));
@@ -1141,7 +1155,7 @@ extern "C" int abl_cuda_debug_binning(abl_runtime *rt, int pool, unsigned *cell_
   if (!p->binned) return fail(ABL_ERR_STATE, "pool is not binned");
   CU(cudaStreamSynchronize(rt->stream));
   if (cell_start) {
-    size_t m = std::min(n_cells_plus_1, (size_t)rt->grid.n_cells + 1);
+    size_t m = std::min(n_cells_plus_1, (size_t)rt->grid.n_local + 1);
     CU(cudaMemcpy(cell_start, p->cell_start, m * sizeof(u32), cudaMemcpyDeviceToHost));
   }
   if (ids) {
@@ -1201,7 +1215,7 @@ static void fill_view(const Pool &p, abl_pool_view &v, uint32_t written_members,
     }
   }
   v.id = (const unsigned *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
-  v.cell_start = p.binned ? p.cell_start : nullptr;
+  v.cell_start = p.binned ? p.cell_start - p.key_base_hint : nullptr;
 }
 
 static int read_scalar(abl_runtime *rt, const u32 *d, u32 *out) {
@@ -1314,6 +1328,9 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.grid.cell_size = rt->grid.cell;
     a.grid.inv_cell_size = rt->grid.inv_cell;
     a.grid.n_cells = rt->grid.n_cells;
+    a.grid.axis_lo = rt->grid.axis_lo;
+    a.grid.axis_hi = rt->grid.axis_hi;
+    a.grid.key_base = rt->grid.key_base;
     a.reach = s.reach;
     a.dead = s.desc.uses_removal ? self.dead : nullptr;
     void *staging[ABL_MAX_COLUMNS + 1];
@@ -1575,7 +1592,7 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
 
 static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
   const int row = slab_row_cells(rt);
-  u32 lo_cell = (u32)rt->layer_begin * (u32)row, hi_cell = (u32)rt->layer_end * (u32)row;
+  u32 lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base, hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
   CU(cudaMemcpyAsync(&rt->h_scalar[0], p.cell_start + lo_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaMemcpyAsync(&rt->h_scalar[1], p.cell_start + hi_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaStreamSynchronize(rt->stream));
@@ -1661,6 +1678,15 @@ __global__ void k_slab_unpack(ColTable t, const u8 *msg, u32 count, u32 dst_firs
   }
 }
 
+__global__ void k_reset_words(u32 *a, u32 *b, u32 *c) {
+  if (threadIdx.x == 0) { *a = 0; *b = 0; *c = 0; }
+}
+__global__ void k_gather_words(const u32 *a, const u32 *b, const u32 *c, const u32 *d, const u32 *e, u32 *out) {
+  if (threadIdx.x == 0) {
+    out[0] = a ? *a : 0; out[1] = b ? *b : 0; out[2] = c ? *c : 0; out[3] = d ? *d : 0; out[4] = e ? *e : 0;
+  }
+}
+
 static u32 slab_rec_words(const Pool &p) {
   u32 w = 0;
   for (const Column &c : p.cols) w += c.elem == 1 ? 1 : c.elem / 4;
@@ -1735,7 +1761,21 @@ extern "C" int abl_cuda_set_slab(abl_runtime *rt, const int *layer_bounds, int n
   int g = 1;
   for (const Step &s : rt->steps) g = std::max(g, s.reach);
   rt->ghost_layers = g;
-  for (Pool &p : rt->pools) { p.binned = false; p.own_valid = false; }
+  // cell ranges are kept for the own slab plus ghost layers only: the cost of binning does not
+  // grow with the size of the whole world
+  GridParams &gp = rt->grid;
+  gp.axis_lo = std::max(0, rt->layer_begin - g);
+  gp.axis_hi = std::min(layers, rt->layer_end + g);
+  gp.key_base = (u32)gp.axis_lo * (u32)slab_row_cells(rt);
+  gp.n_local = (u32)(gp.axis_hi - gp.axis_lo) * (u32)slab_row_cells(rt);
+  CU(cudaStreamSynchronize(rt->stream));
+  for (Pool &p : rt->pools) {
+    p.binned = false;
+    p.own_valid = false;
+    p.counted = false;
+    if (p.cell_count) { CU(cudaFree(p.cell_count)); p.cell_count = nullptr; }
+    if (p.cell_start) { CU(cudaFree(p.cell_start)); p.cell_start = nullptr; }
+  }
   return ABL_OK;
 }
 
@@ -1762,10 +1802,9 @@ static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
   const size_t cap = std::max<size_t>(n_own, kMsgFirstRecords);
   TRY(ensure_xbuf(rt, 0, slab_msg_bytes(p, cap)));
   TRY(ensure_xbuf(rt, 1, slab_msg_bytes(p, cap)));
-  CU(cudaMemsetAsync(rt->xbuf[0], 0, kMsgHeader, rt->stream));
-  CU(cudaMemsetAsync(rt->xbuf[1], 0, kMsgHeader, rt->stream));
   u32 *far = rt->d_scalar + 10;
-  CU(cudaMemsetAsync(far, 0, sizeof(u32), rt->stream));
+  k_reset_words<<<1, 32, 0, rt->stream>>>((u32 *)rt->xbuf[0], (u32 *)rt->xbuf[1], far);
+  rt->launches++;
   if (n_own && (has_lo || has_hi)) {
     int col = pm.first_col, stride = 1, comp = 0;
     if (g.dim == 2) { stride = 2; comp = 1; } else { col += 2; }
@@ -1875,11 +1914,11 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
     if (has_lo) NCCL(ncclRecv(rt->xbuf[2], first_bytes, ncclUint8, lo_peer, rt->comm, rt->stream));
     NCCL(ncclGroupEnd());
     u32 *h = rt->h_scalar + 8;  // [0] out lo, [1] out hi, [2] in lo, [3] in hi, [4] far
-    CU(cudaMemcpyAsync(h + 0, rt->xbuf[0], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-    CU(cudaMemcpyAsync(h + 1, rt->xbuf[1], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-    if (has_lo) CU(cudaMemcpyAsync(h + 2, rt->xbuf[2], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-    if (has_hi) CU(cudaMemcpyAsync(h + 3, rt->xbuf[3], sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-    CU(cudaMemcpyAsync(h + 4, rt->d_scalar + 10, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    k_gather_words<<<1, 32, 0, rt->stream>>>((const u32 *)rt->xbuf[0], (const u32 *)rt->xbuf[1],
+        has_lo ? (const u32 *)rt->xbuf[2] : nullptr, has_hi ? (const u32 *)rt->xbuf[3] : nullptr,
+        rt->d_scalar + 10, rt->d_scalar + 24);
+    rt->launches++;
+    CU(cudaMemcpyAsync(h, rt->d_scalar + 24, 5 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
     CU(cudaStreamSynchronize(rt->stream));
     TRY(exchange_check_far(rt, p, h[4]));
     const u32 out_lo = has_lo ? h[0] : 0, out_hi = has_hi ? h[1] : 0;

@@ -131,6 +131,11 @@ typedef struct {
   double cell_size;
   double inv_cell_size;   /* 1/cell_size rounded in the precision of abl_float */
   unsigned n_cells;
+  /* window of cell layers along the slowest axis held by this runtime (all layers unless the
+   * simulation is slab-decomposed) and the key of its first cell; cell_start is handed to
+   * kernels with a virtual origin so that it is indexed by global cell key */
+  int axis_lo, axis_hi;
+  unsigned key_base;
 } abl_grid_view;
 
 typedef struct {
