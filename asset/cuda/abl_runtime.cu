@@ -22,6 +22,7 @@
 #include <nccl.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -861,6 +862,7 @@ static int get_pool(abl_runtime *rt, int pool, Pool **out) {
 
 static int slab_bin_if_needed(abl_runtime *rt, Pool &p);
 static int bin_pool(abl_runtime *rt, Pool &p);
+extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
   Pool *p;
@@ -898,10 +900,14 @@ extern "C" int abl_cuda_pin_host(abl_runtime *rt, void *ptr, size_t bytes) {
     }
   }
   // best effort: when the pages cannot be locked the transfers simply stay pageable
-  if (cudaHostRegister(ptr, bytes, cudaHostRegisterPortable) == cudaSuccess)
+  cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e == cudaSuccess) {
     rt->pinned_ranges.push_back({ptr, bytes});
-  else
+  } else {
     cudaGetLastError();
+    if (getenv("ABL_CUDA_VERBOSE"))
+      fprintf(stderr, "abl_cuda: cudaHostRegister(%zu bytes) failed: %s (transfers stay pageable)\n", bytes, cudaGetErrorString(e));
+  }
   return ABL_OK;
 }
 
@@ -1449,7 +1455,23 @@ extern "C" int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t) {
 extern "C" int abl_cuda_count(abl_runtime *rt, int pool, int *result) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
-  if (result) *result = (int)p->n;
+  size_t n = 0;
+  TRY(abl_cuda_pool_size(rt, pool, &n));  // owned agents only under slab decomposition
+  if (result) *result = (int)n;
+  return ABL_OK;
+}
+
+// Range of live records a reduction runs over (rank-local under slab decomposition: the
+// caller combines the per-rank values).
+static int reduce_range(abl_runtime *rt, Pool &p, u32 *first, u32 *n) {
+  if (rt->slab && p.pos_member >= 0) {
+    if (!p.binned) TRY(bin_pool(rt, p));
+    *first = p.own_begin;
+    *n = p.own_end - p.own_begin;
+  } else {
+    *first = p.src_begin;
+    *n = (u32)p.n;
+  }
   return ABL_OK;
 }
 
@@ -1463,8 +1485,9 @@ static int get_member(abl_runtime *rt, int pool, int member, Pool **p, Member **
 static int reduce_int(abl_runtime *rt, Pool &p, Member &m, int kind, int value, int *result) {
   int *d = (int *)rt->d_scalar;
   CU(cudaMemsetAsync(d, 0, sizeof(int), rt->stream));
-  const void *col = p.cols[m.first_col].buf[p.cols[m.first_col].cur];
-  u32 n = (u32)p.n;
+  u32 first = 0, n = 0;
+  TRY(reduce_range(rt, p, &first, &n));
+  const void *col = (const u8 *)p.cols[m.first_col].buf[p.cols[m.first_col].cur] + (size_t)first * p.cols[m.first_col].elem;
   if (n) {
     u32 nb = std::min(blocks_for(n, 256), 148u * 8u);
     switch (kind) {
@@ -1504,8 +1527,9 @@ extern "C" int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member
   if (m->type != ABL_TYPE_FLOAT) return fail(ABL_ERR_ARGUMENT, "count_member_float on non-float member");
   int *d = (int *)rt->d_scalar;
   CU(cudaMemsetAsync(d, 0, sizeof(int), rt->stream));
-  const void *col = p->cols[m->first_col].buf[p->cols[m->first_col].cur];
-  u32 n = (u32)p->n;
+  u32 first = 0, n = 0;
+  TRY(reduce_range(rt, *p, &first, &n));
+  const void *col = (const u8 *)p->cols[m->first_col].buf[p->cols[m->first_col].cur] + (size_t)first * p->cols[m->first_col].elem;
   if (n) {
     u32 nb = std::min(blocks_for(n, 256), 148u * 8u);
     if (rt->real_size == 8) k_count_real<double><<<nb, 256, 0, rt->stream>>>((const double *)col, n, value, d);
@@ -1527,8 +1551,9 @@ extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int com
   else if (m->type == ABL_TYPE_FLOAT3) { col_index += component; }
   else if (m->type != ABL_TYPE_FLOAT) return fail(ABL_ERR_ARGUMENT, "sum_float on non-float member");
   if (comp < 0 || comp > 1 || component < 0 || component > 2) return fail(ABL_ERR_ARGUMENT, "bad component");
-  const void *col = p->cols[col_index].buf[p->cols[col_index].cur];
-  u32 n = (u32)p->n;
+  u32 first = 0, n = 0;
+  TRY(reduce_range(rt, *p, &first, &n));
+  const void *col = (const u8 *)p->cols[col_index].buf[p->cols[col_index].cur] + (size_t)first * p->cols[col_index].elem;
   const u32 nb = 148 * 2;
   double *partial = (double *)(rt->d_scalar + 16);  // 8-byte aligned region inside scratch
   double *d_out = (double *)(rt->d_scalar + 2);

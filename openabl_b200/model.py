@@ -70,6 +70,10 @@ class Model:
         buf = (C.c_char * (n * self.dtypes[t].itemsize)).from_address(arr.data)
         return np.frombuffer(buf, dtype=self.dtypes[t]).copy()
 
+    def host_count(self, t):
+        """Number of host records of agent type index `t` (no copy)."""
+        return self._types[t].agents.contents.len
+
     def pool(self, t):
         return self._types[t].pool
 

@@ -39,6 +39,11 @@ def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, s
     for _ in range(steps):
         ls.timestep()
     assert sum(ls.owned_counts(0)) == len(host[0]), "agents lost or duplicated by migration"
+    if model_file == "game_of_life.abl":
+        # reductions are rank-local under decomposition; their sum is the global value
+        pool = m.pool(0)
+        assert sum(rt.sum_int(pool, 1) for rt in ls.rts) == int(single["alive"].sum())
+        assert sum(rt.count(pool) for rt in ls.rts) == len(single)
     ids, rec = ls.download(0)
     ls.close()
     assert np.array_equal(ids, np.arange(len(host[0]), dtype=np.uint32))
