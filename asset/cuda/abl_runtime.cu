@@ -166,6 +166,7 @@ struct abl_runtime {
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t ev_ts[2] = {nullptr, nullptr};
+  cudaEvent_t ev_own = nullptr;  // signals that the owned-range words have reached the host
   bool ts_open = false;
   double last_ts_seconds = 0;
   std::vector<std::pair<void *, size_t>> pinned_ranges;
@@ -727,6 +728,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   CU(cudaMallocHost(&rt->h_scalar, 4096));
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&rt->ev[i]));
   for (int i = 0; i < 2; i++) CU(cudaEventCreate(&rt->ev_ts[i]));
+  CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
   *out = rt;
   return ABL_OK;
@@ -752,6 +754,7 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   if (rt->h_scalar) cudaFreeHost(rt->h_scalar);
   for (int i = 0; i < 4; i++) if (rt->ev[i]) cudaEventDestroy(rt->ev[i]);
   for (int i = 0; i < 2; i++) if (rt->ev_ts[i]) cudaEventDestroy(rt->ev_ts[i]);
+  if (rt->ev_own) cudaEventDestroy(rt->ev_own);
   cudaStreamDestroy(rt->stream);
   delete rt;
   return ABL_OK;
@@ -1076,6 +1079,7 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
 }
 
 static int slab_update_owned_range(abl_runtime *rt, Pool &p);
+static int slab_request_owned_range(abl_runtime *rt, Pool &p);
 
 // histogram of `n` records starting at source index `src_begin`; keys/ranks go to slot
 // `out_begin + i` of the pool's key/local arrays
@@ -1117,6 +1121,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
   TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 1, nullptr)));
+  if (rt->slab) TRY(slab_request_owned_range(rt, p));
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
@@ -1615,12 +1620,20 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
   return ABL_OK;
 }
 
-static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
+// The owned range is two words of cell_start.  They are copied to the host right after the
+// scan and awaited only after the remaining binning kernels have been enqueued, so the host
+// learns them while the GPU is still busy and can enqueue the step kernel without a gap.
+static int slab_request_owned_range(abl_runtime *rt, Pool &p) {
   const int row = slab_row_cells(rt);
   u32 lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base, hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
   CU(cudaMemcpyAsync(&rt->h_scalar[0], p.cell_start + lo_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaMemcpyAsync(&rt->h_scalar[1], p.cell_start + hi_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-  CU(cudaStreamSynchronize(rt->stream));
+  CU(cudaEventRecord(rt->ev_own, rt->stream));
+  return ABL_OK;
+}
+
+static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
+  CU(cudaEventSynchronize(rt->ev_own));
   p.own_begin = rt->h_scalar[0];
   p.own_end = rt->h_scalar[1];
   return ABL_OK;

@@ -213,7 +213,7 @@ def main():
 
     def upload():
         if slab:
-            slab.upload(host)
+            slab.upload()
         else:
             m.upload_host()
 

@@ -116,10 +116,15 @@ class RankSlab:
             self.rt.init_nccl(bytes(uid.cpu().tolist()), rank, world)
         self.rt.set_slab(self.bounds, rank)
 
-    def upload(self, host_arrays):
+    def upload(self, host_arrays=None):
+        """Every rank uploads the whole population from the model's own page-locked host arrays
+        (as the generated program does), keeps its slab and fetches ghosts with one exchange."""
         m = self.model
-        for t, arr in enumerate(host_arrays):
-            self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
+        if host_arrays is None:
+            m.upload_host()
+        else:
+            for t, arr in enumerate(host_arrays):
+                self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
         for t in range(m.n_types):
             self.rt.exchange(m.pool(t))
 
