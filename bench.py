@@ -22,7 +22,6 @@ import argparse
 import ctypes as C
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -63,46 +62,63 @@ def load_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
-    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
+    """Samples SM clocks and throttle reasons through NVML every few milliseconds while the
+    timed region runs (same fields as the nvidia-smi line of B200_PROFILING.md)."""
 
     def __init__(self, device):
         super().__init__(daemon=True)
         self.device = device
         self.samples = []
+        self.max_mhz = None
+        self.reasons = set()
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = int(visible.split(",")[device]) if visible else device
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
+        nv = self.nvml
+        if nv is None:
+            return
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], stdout=subprocess.PIPE,
-                                     stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.002)
 
     def summary(self):
         self.stop_flag.set()
-        self.join(timeout=6)
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
-            try:
-                sm.append(float(s[0]))
-                mx = max(mx, float(s[1]))
-                for name, flag in zip(names, s[2:6]):
-                    if flag.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.join(timeout=2)
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the
+# `ncu --set full` captures summarised under profiles/ (None where no capture exists)
+NCU_TRAFFIC = {
+    "boids2d-1M-f64": (43.04e6, "profiles/r1_final_boids_summary.txt"),
+    "circle3d-1M-f64": (24.2e6, "profiles/r1_v2_circle3d_summary.txt"),
+}
 
 
 def cpu_baseline(workload, budget_pairs=1.2e10):
@@ -268,7 +284,9 @@ def main():
     step_bytes = whole_step_bytes(args.workload) * n_agents / world
     roofline = {"bound": "hbm", "kernel": "abl_kernel_%s" % m.step_names[0], "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "algorithmic_bytes_per_agent": S + M + S,
+                "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
+                "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                "algorithmic_bytes_per_agent": S + M + S,
                 "kernel_ms": stage["kernel_ms"], "bin_ms": stage["bin_ms"], "commit_ms": stage["commit_ms"],
                 "whole_step_algorithmic_bytes_per_agent": whole_step_bytes(args.workload),
                 "whole_step_frac": step_bytes * args.steps / (ms_max / 1e3) / 1e9 / peak}
