@@ -705,13 +705,25 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w << "} else {";
     w.indent(); w.nl();
   }
-  w << "for (; " << it << ".valid(); " << it << ".next()) {";
+  // Software-pipelined candidate loop: the position of the *next* candidate is requested
+  // before the current one is tested and processed, so the load latency (L1 miss -> L2) is
+  // overlapped with the body instead of stalling every iteration.  The iterator is advanced
+  // at the top, which also makes `continue` in the body do the right thing.
+  std::string ptypeS = typeName(pos->type);
+  w << ptypeS << " " << it << "p;"; w.nl();
+  w << "if (" << it << ".valid()) ";
+  loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
+  w.nl();
+  w << "while (" << it << ".valid()) {";
   w.indent(); w.nl();
   w << "const unsigned " << it << "j = " << it << ".index();";
   w.nl();
   w << nbr->name << " " << s.varName << ";";
   w.nl();
-  loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+  w << s.varName << "." << pos->name << " = " << it << "p;"; w.nl();
+  w << it << ".next();"; w.nl();
+  w << "if (" << it << ".valid()) ";
+  loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
   w.nl();
   if (curStepHasLimit) {
     w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
