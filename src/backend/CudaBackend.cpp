@@ -709,10 +709,43 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   // before the current one is tested and processed, so the load latency (L1 miss -> L2) is
   // overlapped with the body instead of stalling every iteration.  The iterator is advanced
   // at the top, which also makes `continue` in the body do the right thing.
+  // Besides the position, up to two further neighbour members are fetched one candidate
+  // ahead as well (speculatively: a rejected candidate wastes the load, an accepted one no
+  // longer waits for a dependent L2 round trip).
+  std::vector<int> others;
+  int otherCols = 0;
+  for (size_t m = 0; m < nbr->members.size(); m++) {
+    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
+    others.push_back((int)m);
+    otherCols += nbr->members[m]->type.k == TK::Vec3 ? 3 : 1;
+  }
+  // (only floating-point members: integer/bool flags usually guard cheap bodies, where the
+  // extra load per rejected candidate costs more than the stall it hides — measured on
+  // game_of_life)
+  bool allFloat = true;
+  for (int m : others) {
+    const Ty &mt = nbr->members[m]->type;
+    allFloat = allFloat && (mt.isFloat() || mt.isVec());
+  }
+  const bool prefetchOthers = !others.empty() && otherCols <= 2 && allFloat;
   std::string ptypeS = typeName(pos->type);
+  auto prefetch = [&]() {
+    w << "if (" << it << ".valid()) {";
+    w.indent(); w.nl();
+    loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
+    if (prefetchOthers) {
+      for (int m : others) {
+        w.nl();
+        loadMember(*nbr, m, it + "m" + std::to_string(m), "_a.nbr.in", it + ".index()");
+      }
+    }
+    w.outdent(); w.nl();
+    w << "}";
+  };
   w << ptypeS << " " << it << "p;"; w.nl();
-  w << "if (" << it << ".valid()) ";
-  loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
+  if (prefetchOthers)
+    for (int m : others) { w << typeName(nbr->members[m]->type) << " " << it << "m" << m << ";"; w.nl(); }
+  prefetch();
   w.nl();
   w << "while (" << it << ".valid()) {";
   w.indent(); w.nl();
@@ -721,9 +754,10 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   w << nbr->name << " " << s.varName << ";";
   w.nl();
   w << s.varName << "." << pos->name << " = " << it << "p;"; w.nl();
+  if (prefetchOthers)
+    for (int m : others) { w << s.varName << "." << nbr->members[m]->name << " = " << it << "m" << m << ";"; w.nl(); }
   w << it << ".next();"; w.nl();
-  w << "if (" << it << ".valid()) ";
-  loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
+  prefetch();
   w.nl();
   if (curStepHasLimit) {
     w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
@@ -735,7 +769,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     expr(radius);
     w << ") continue;";
   }
-  loadOthers(it + "j");
+  if (!prefetchOthers) loadOthers(it + "j");
   w.nl();
   {
     std::string savedLabel = nearBreakLabel;
