@@ -246,15 +246,27 @@ static inline float3 clamp_2(float3 pos, float3 min, float3 max) {
 }
 
 /* One timestep of move_point for agents [i0, i1) against the whole population. */
+/* granularity <= 0: automatic (the for-near radius, AnalysisVisitor.cpp:1378-1399) */
+void oracle_circle_step_g(int dim, int num_agents, double rho_, double k_rep_, double k_att_, double r_,
+                          const abl_float *in_pos, abl_float *out_pos, int n, int mode, int i0, int i1,
+                          double granularity);
+
 void oracle_circle_step(int dim, int num_agents, double rho_, double k_rep_, double k_att_, double r_,
                         const abl_float *in_pos, abl_float *out_pos, int n, int mode, int i0, int i1) {
+  oracle_circle_step_g(dim, num_agents, rho_, k_rep_, k_att_, r_, in_pos, out_pos, n, mode, i0, i1, 0.0);
+}
+
+void oracle_circle_step_g(int dim, int num_agents, double rho_, double k_rep_, double k_att_, double r_,
+                          const abl_float *in_pos, abl_float *out_pos, int n, int mode, int i0, int i1,
+                          double granularity) {
   const circle_consts c = circle_fold(dim, num_agents, rho_, k_rep_, k_att_, r_);
+  const double cell_size = granularity > 0 ? granularity : c.radius_exact;
   const abl_float r = c.r, k_att = c.k_att, k_rep = c.k_rep, W = c.W;
   grid_t g;
   double lo[3] = {0, 0, 0}, hi[3] = {c.W_exact, c.W_exact, c.W_exact};
-  grid_setup(&g, dim, lo, hi, c.radius_exact);
+  grid_setup(&g, dim, lo, hi, cell_size);
   if (mode == MODE_GRID) grid_bin(&g, (const char *)in_pos, sizeof(abl_float) * dim, n);
-  const int reach = reach_for(c.radius_exact, c.radius_exact);
+  const int reach = reach_for(c.radius_exact, cell_size);
   if (dim == 2) {
     const Point2 *buf = (const Point2 *)in_pos;
     Point2 *dbuf = (Point2 *)out_pos;

@@ -48,15 +48,16 @@ class Oracle:
         return a
 
     def circle_run(self, dim, state, steps, mode=BRUTE, rho=0.05, k_rep=0.05, k_att=0.01, r=5.0,
-                   sample=None, num_agents=None):
+                   sample=None, num_agents=None, granularity=0.0):
         n = len(state)
         num_agents = n if num_agents is None else num_agents
         cur, nxt = state.copy(), state.copy()
         i0, i1 = sample if sample else (0, n)
         for _ in range(steps):
-            self.lib.oracle_circle_step(C.c_int(dim), C.c_int(num_agents), C.c_double(rho), C.c_double(k_rep),
-                                        C.c_double(k_att), C.c_double(r), _ptr(cur), _ptr(nxt),
-                                        C.c_int(n), C.c_int(mode), C.c_int(i0), C.c_int(i1))
+            self.lib.oracle_circle_step_g(C.c_int(dim), C.c_int(num_agents), C.c_double(rho), C.c_double(k_rep),
+                                          C.c_double(k_att), C.c_double(r), _ptr(cur), _ptr(nxt),
+                                          C.c_int(n), C.c_int(mode), C.c_int(i0), C.c_int(i1),
+                                          C.c_double(granularity))
             cur, nxt = nxt, cur
         return cur
 
