@@ -26,10 +26,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <vector>
 
 #include "abl_cuda.h"
+#include "abl_slab.cuh"
 
 typedef unsigned int u32;
 typedef unsigned long long u64;
@@ -95,6 +97,17 @@ struct Pool {
   u32 own_begin = 0, own_end = 0, src_begin = 0;
   u32 key_base_hint = 0;  // copy of grid.key_base (cell_start is handed out with a virtual origin)
   bool own_valid = false;
+  // direct halo transport (peer memory over NVLink, no NCCL, no host sync per exchange)
+  u8 *halo_recv = nullptr;                 // own receive area: [from lower | from upper] x [parity 0 | 1]
+  size_t halo_cap = 0;                     // records per block
+  size_t halo_block = 0;                   // bytes per block
+  u8 *halo_peer[2] = {nullptr, nullptr};   // receive areas of the lower / upper peer, mapped here
+  bool halo_ipc[2] = {false, false};
+  u32 *halo_ctr = nullptr;                 // [0,1] slot counters, [2,3] incoming counts, [4] timeout, [5] far, [6,7] sent
+  u32 halo_seq = 0;                        // direct exchanges performed (parity selects the block)
+  u32 halo_pad = 0;                        // host-side upper bound of arrivals (rest is sentinel padding)
+  bool halo_pending = false;               // device-side counts of the last exchange not verified yet
+  u32 halo_prev_ob = 0, halo_prev_own = 0, halo_last_arrivals = 0, halo_room = 0;
   bool binned = false;
   bool ever_binned = false;
   bool counted = false;   // key/local/cell_count already hold the histogram of the current positions
@@ -181,8 +194,19 @@ struct abl_runtime {
   void *xbuf[4] = {nullptr, nullptr, nullptr, nullptr};  // send L, send R, recv L, recv R
   size_t xcap[4] = {0, 0, 0, 0};
   u32 *xflags = nullptr;  // classification scratch
+  // optional phase trace of exchange() (ABL_CUDA_TRACE=1): device and host time per phase
+  bool trace = false;
+  cudaEvent_t xev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  double xdev[4] = {0, 0, 0, 0}, xhost[4] = {0, 0, 0, 0};
+  unsigned long xcount = 0, xskip = 0;
   u32 x_out[2] = {0, 0};  // outgoing counts of the last exchange_pack (to lower, to upper)
   abl_runtime *peer_lo = nullptr, *peer_hi = nullptr;  // in-process transport (tests)
+  // cudaFree synchronises the whole device; with the direct transport a neighbour driven by the
+  // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
+  // are released at the next explicit synchronisation point instead
+  std::vector<void *> garbage;
+  bool defer_free = false;
+  long long halo_timeout_ns = 10000000000ll;            // direct transport: wait for a neighbour at most this long
   size_t xflags_cap = 0;
   abl_step_timing last = {0, 0, 0, 0};
   unsigned launches = 0;
@@ -409,10 +433,17 @@ __device__ __forceinline__ int cell_coord(R p, R origin, R inv_cell, int n) {
 // POS2: position is one packed 2-vector column; otherwise three scalar columns.
 template <typename R, int DIM>
 __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, u32 src_begin,
-                            u32 out_begin, GridParams g, u32 *key, u32 *local, u32 *cell_count) {
+                            u32 out_begin, GridParams g, u32 *key, u32 *local, u32 *cell_count,
+                            const u32 *ids) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t s = (size_t)src_begin + i;
+  if (ids && ids[s] == ABL_SENTINEL_ID) {
+    // padding record of a halo message: parked in the trash cell behind all real cells
+    key[out_begin + i] = g.n_local;
+    local[out_begin + i] = atomicAdd(&cell_count[g.n_local], 1u);
+    return;
+  }
   R x, y, z = 0;
   if (DIM == 2) {
     x = ((const R *)px)[2 * s];
@@ -459,8 +490,8 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
 // scan of seg_ids.  All reads of the agent's record are coalesced; because agents move
 // little between two binnings the pool is already almost in cell order and the writes land
 // close to the reads (near-coalesced).
-__global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *ids, u32 n,
-                                u32 src_begin, const u32 *cell_start) {
+__global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *local,
+                                const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u32 src = src_begin + i;
@@ -468,7 +499,8 @@ __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, 
   const u32 mine = ids[src];
   const u32 b = cell_start[c], e = cell_start[c + 1];
   u32 rank = 0;
-  for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
+  if (mine == ABL_SENTINEL_ID) rank = local[i];  // padding records: any distinct slot will do
+  else for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
   const u32 dst = b + rank;
   for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
 }
@@ -617,9 +649,22 @@ static int run_scan(abl_runtime *rt, T *in, u32 *out, size_t n, u32 *total_out) 
   return ABL_OK;
 }
 
-static int free_pool_scratch(Pool &p) {
+static int release_device(abl_runtime *rt, void *q) {
+  if (!q) return ABL_OK;
+  if (rt && rt->defer_free) rt->garbage.push_back(q);
+  else CU(cudaFree(q));
+  return ABL_OK;
+}
+
+static int collect_garbage(abl_runtime *rt) {
+  for (void *q : rt->garbage) CU(cudaFree(q));
+  rt->garbage.clear();
+  return ABL_OK;
+}
+
+static int free_pool_scratch(abl_runtime *rt, Pool &p) {
   void *ptrs[] = {p.key, p.local, p.pairs, p.dead, p.add_flag, p.offsets};
-  for (void *q : ptrs) if (q) CU(cudaFree(q));
+  for (void *q : ptrs) TRY(release_device(rt, q));
   p.key = p.local = nullptr; p.pairs = nullptr; p.dead = p.add_flag = nullptr; p.offsets = nullptr;
   p.scratch_cap = 0;
   return ABL_OK;
@@ -639,7 +684,7 @@ static int reserve_pool(abl_runtime *rt, Pool &p, size_t want) {
         if (c.buf[b]) {
           if (b == c.cur && p.n)
             CU(cudaMemcpy(nb, c.buf[b], p.n * (size_t)c.elem, cudaMemcpyDeviceToDevice));
-          CU(cudaFree(c.buf[b]));
+          TRY(release_device(rt, c.buf[b]));
         }
         c.buf[b] = nb;
       }
@@ -657,7 +702,7 @@ static int reserve_pool(abl_runtime *rt, Pool &p, size_t want) {
       CU(cudaMemcpy(dead, p.dead, p.scratch_cap, cudaMemcpyDeviceToDevice));
       CU(cudaMemcpy(add_flag, p.add_flag, p.scratch_cap, cudaMemcpyDeviceToDevice));
     }
-    TRY(free_pool_scratch(p));
+    TRY(free_pool_scratch(rt, p));
     p.dead = dead;
     p.add_flag = add_flag;
     CU(cudaMalloc(&p.key, p.cap * sizeof(u32)));
@@ -684,7 +729,7 @@ static void fill_table(const Pool &p, ColTable &t, bool out_is_alt) {
 // reordered or refilled) has to be wiped, otherwise the next histogram adds on top of it.
 static int drop_fused_histogram(abl_runtime *rt, Pool &p) {
   if (p.counted && p.cell_count)
-    CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)rt->grid.n_local + 1) * sizeof(u32), rt->stream));
+    CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)rt->grid.n_local + 2) * sizeof(u32), rt->stream));
   p.counted = false;
   return ABL_OK;
 }
@@ -730,6 +775,11 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   for (int i = 0; i < 2; i++) CU(cudaEventCreate(&rt->ev_ts[i]));
   CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
+  if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
+  if (getenv("ABL_CUDA_TRACE")) {
+    rt->trace = true;
+    for (int i = 0; i < 5; i++) CU(cudaEventCreate(&rt->xev[i]));
+  }
   *out = rt;
   return ABL_OK;
 }
@@ -738,9 +788,21 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   if (!rt) return ABL_OK;
   cudaSetDevice(rt->device);
   cudaStreamSynchronize(rt->stream);
+  if (rt->trace && rt->xcount) {
+    const char *names[4] = {"pack", "nccl", "headers+sync", "unpack"};
+    char line[512];
+    int off = snprintf(line, sizeof line, "abl_cuda[rank %d] exchange trace over %lu calls (us per call):", rt->rank, rt->xcount);
+    for (int i = 0; i < 4; i++)
+      off += snprintf(line + off, sizeof line - off, " %s dev %.1f host %.1f;", names[i], 1e3 * rt->xdev[i] / rt->xcount, 1e6 * rt->xhost[i] / rt->xcount);
+    fprintf(stderr, "%s\n", line);
+  }
+  collect_garbage(rt);
   for (Pool &p : rt->pools) {
+    for (int d = 0; d < 2; d++) if (p.halo_peer[d] && p.halo_ipc[d]) cudaIpcCloseMemHandle(p.halo_peer[d]);
+    if (p.halo_recv) cudaFree(p.halo_recv);
+    if (p.halo_ctr) cudaFree(p.halo_ctr);
     for (Column &c : p.cols) for (int b = 0; b < 2; b++) if (c.buf[b]) cudaFree(c.buf[b]);
-    free_pool_scratch(p);
+    free_pool_scratch(nullptr, p);
     if (p.cell_count) cudaFree(p.cell_count);
     if (p.cell_start) cudaFree(p.cell_start);
   }
@@ -765,6 +827,7 @@ extern "C" void *abl_cuda_stream(abl_runtime *rt) { return rt ? (void *)rt->stre
 extern "C" int abl_cuda_synchronize(abl_runtime *rt) {
   if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
   CU(cudaStreamSynchronize(rt->stream));
+  TRY(collect_garbage(rt));
   return ABL_OK;
 }
 
@@ -865,6 +928,10 @@ static int get_pool(abl_runtime *rt, int pool, Pool **out) {
 
 static int slab_bin_if_needed(abl_runtime *rt, Pool &p);
 static int bin_pool(abl_runtime *rt, Pool &p);
+static bool halo_direct(const Pool &p);
+static int halo_reserve(abl_runtime *rt, Pool &p);
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v);
+static int halo_finish(abl_runtime *rt, Pool &p);
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
@@ -926,7 +993,8 @@ static int upload_impl(abl_runtime *rt, int pool, const void *host_aos, const un
   CU(cudaSetDevice(rt->device));
   if (n > 0x7fffffffu) return fail(ABL_ERR_ARGUMENT, "pool too large");
   p->n = 0;
-  TRY(reserve_pool(rt, *p, std::max(n, (size_t)1)));
+  // with the direct halo transport arrivals are appended behind the owned records: leave room
+  TRY(reserve_pool(rt, *p, std::max(n, (size_t)1) + (halo_direct(*p) ? 2 * p->halo_cap + 1024 : 0)));
   size_t bytes = n * (size_t)p->stride;
   if (n) {
     TRY(ensure_stage(rt, round_up(bytes, 256) + (ids ? n * sizeof(u32) : 0)));
@@ -1070,7 +1138,7 @@ extern "C" int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids_ou
 // ---------------------------------------------------------------------------------------
 static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   if (p.cell_count) return ABL_OK;
-  size_t padded = round_up((size_t)rt->grid.n_local + 1, kScanTile);
+  size_t padded = round_up((size_t)rt->grid.n_local + 2, kScanTile);
   CU(cudaMalloc(&p.cell_count, padded * sizeof(u32)));
   CU(cudaMalloc(&p.cell_start, padded * sizeof(u32)));
   CU(cudaMemsetAsync(p.cell_count, 0, padded * sizeof(u32), rt->stream));
@@ -1078,7 +1146,7 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   return ABL_OK;
 }
 
-static int slab_update_owned_range(abl_runtime *rt, Pool &p);
+static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo);
 static int slab_request_owned_range(abl_runtime *rt, Pool &p);
 
 // histogram of `n` records starting at source index `src_begin`; keys/ranks go to slot
@@ -1095,12 +1163,13 @@ static int launch_bin_count(abl_runtime *rt, Pool &p, u32 n, u32 src_begin, u32 
     pz = p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
   }
   u32 nb = blocks_for(n, bs);
+  const u32 *ids = rt->slab ? (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur] : nullptr;
   if (rt->real_size == 8) {
-    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
-    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<double, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count, ids);
+    else k_bin_count<double, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count, ids);
   } else {
-    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
-    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count);
+    if (g.dim == 2) k_bin_count<float, 2><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count, ids);
+    else k_bin_count<float, 3><<<nb, bs, 0, rt->stream>>>(px, py, pz, n, src_begin, out_begin, g, p.key, p.local, p.cell_count, ids);
   }
   rt->launches++;
   CU(cudaGetLastError());
@@ -1120,7 +1189,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
-  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 1, nullptr)));
+  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, nullptr)));
   if (rt->slab) TRY(slab_request_owned_range(rt, p));
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
@@ -1130,17 +1199,35 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, p.src_begin, p.cell_start, seg_ids);
     ColTable t;
     fill_table(p, t, true);
-    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, ids, n, p.src_begin, p.cell_start);
+    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, p.local, ids, n, p.src_begin, p.cell_start);
     rt->launches += 2;
     CU(cudaGetLastError());
     flip_all(p);
   }
+  const u32 src_before = p.src_begin;
   p.src_begin = 0;
   p.key_base_hint = g.key_base;
   p.binned = true;
   p.ever_binned = true;
-  if (rt->slab) TRY(slab_update_owned_range(rt, p));
-  else { p.own_begin = 0; p.own_end = (u32)p.n; }
+  if (rt->slab) {
+    bool redo = false;
+    TRY(slab_update_owned_range(rt, p, &redo));
+    if (redo) {
+      // More halo records arrived than the padding the host assumed: they were unpacked (the
+      // pool has room for two full messages) but not binned.  The source buffers of this
+      // binning are still intact in the alternate halves: bin again over the full range.
+      flip_all(p);
+      p.src_begin = src_before;
+      p.n = (size_t)p.halo_prev_own + p.halo_last_arrivals;
+      p.binned = false;
+      p.counted = false;
+      CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)g.n_local + 2) * sizeof(u32), rt->stream));
+      return bin_pool(rt, p);
+    }
+  } else {
+    p.own_begin = 0;
+    p.own_end = (u32)p.n;
+  }
   p.own_valid = true;
   return ABL_OK;
 }
@@ -1317,11 +1404,15 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   }
   if (rt->timing) CU(cudaEventRecord(rt->ev[1], rt->stream));
 
+  // slab mode with the direct transport: this step's kernel packs the halo itself
+  const bool direct = rt->slab && self.pos_member >= 0 && halo_direct(self) && s.desc.written_members;
   if (self.n) {
     TRY(reserve_pool(rt, self, self.n));
+    if (direct) TRY(halo_reserve(rt, self));  // may move the columns: before any view is taken
     abl_step_launch a;
     memset(&a, 0, sizeof a);
     fill_view(self, a.self, s.desc.written_members, true);
+    if (direct) TRY(halo_fill_view(rt, self, a.slab));
     if (rt->slab && self.pos_member >= 0) {
       // the step function runs over the owned range only
       const u32 ob = self.own_begin;
@@ -1396,10 +1487,16 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (added) TRY(commit_adds(rt, self, *added, staging));
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
-    if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
+    if (direct)
+      TRY(halo_finish(rt, self));
+    else if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
       TRY(abl_cuda_exchange(rt, s.desc.self_pool));
-  } else if (rt->timing) {
-    CU(cudaEventRecord(rt->ev[2], rt->stream));
+  } else {
+    if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
+    if (direct) {  // an empty slab still has to answer its neighbours
+      TRY(halo_reserve(rt, self));
+      TRY(halo_finish(rt, self));
+    }
   }
   if (rt->timing) {
     CU(cudaEventRecord(rt->ev[3], rt->stream));
@@ -1623,19 +1720,53 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
 // The owned range is two words of cell_start.  They are copied to the host right after the
 // scan and awaited only after the remaining binning kernels have been enqueued, so the host
 // learns them while the GPU is still busy and can enqueue the step kernel without a gap.
+__global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_cell, const u32 *halo_ctr,
+                                   u32 *out) {
+  if (threadIdx.x == 0) {
+    out[0] = cell_start[lo_cell];
+    out[1] = cell_start[hi_cell];
+    for (int k = 0; k < 6; k++) out[2 + k] = halo_ctr ? halo_ctr[2 + k] : 0;  // in lo, in hi, timeout, far, sent lo, sent hi
+  }
+}
+
 static int slab_request_owned_range(abl_runtime *rt, Pool &p) {
   const int row = slab_row_cells(rt);
   u32 lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base, hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
-  CU(cudaMemcpyAsync(&rt->h_scalar[0], p.cell_start + lo_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
-  CU(cudaMemcpyAsync(&rt->h_scalar[1], p.cell_start + hi_cell, sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, p.halo_pending ? p.halo_ctr : nullptr,
+                                               rt->d_scalar + 32);
+  rt->launches++;
+  CU(cudaMemcpyAsync(&rt->h_scalar[32], rt->d_scalar + 32, 8 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaEventRecord(rt->ev_own, rt->stream));
   return ABL_OK;
 }
 
-static int slab_update_owned_range(abl_runtime *rt, Pool &p) {
+// returns ABL_OK and sets *redo when the arrivals of the last direct exchange exceeded the
+// host's padding estimate: the pool then has to be binned again over the full live range
+static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
   CU(cudaEventSynchronize(rt->ev_own));
-  p.own_begin = rt->h_scalar[0];
-  p.own_end = rt->h_scalar[1];
+  const u32 *h = rt->h_scalar + 32;
+  p.own_begin = h[0];
+  p.own_end = h[1];
+  if (redo) *redo = false;
+  if (p.halo_pending) {
+    p.halo_pending = false;
+    const u32 in_lo = h[2], in_hi = h[3], timeout = h[4], far = h[5], sent_lo = h[6], sent_hi = h[7];
+    if (timeout) return fail(ABL_ERR_COMM, "pool %s: timed out waiting for a neighbour's halo message", p.name.c_str());
+    if (far)
+      return fail(ABL_ERR_COMM, "%u agents of pool %s moved farther than a neighbouring slab in one step "
+                  "(only neighbour and periodic wrap-around migration is supported)", far, p.name.c_str());
+    if (in_lo > p.halo_cap || in_hi > p.halo_cap || sent_lo > p.halo_cap || sent_hi > p.halo_cap)
+      return fail(ABL_ERR_COMM, "pool %s: halo message of %u records exceeds the capacity of %zu; raise the "
+                  "capacity passed to abl_cuda_halo_setup", p.name.c_str(), std::max(std::max(in_lo, in_hi), std::max(sent_lo, sent_hi)), p.halo_cap);
+    const u32 arrivals = in_lo + in_hi;
+    const u32 pad_used = p.halo_pad;
+    if (arrivals > p.halo_room)
+      return fail(ABL_ERR_COMM, "pool %s: %u halo records arrived but the pool had room for %u only", p.name.c_str(), arrivals, p.halo_room);
+    // adapt the padding to what actually arrives (25 % head room)
+    p.halo_pad = (u32)round_up((size_t)arrivals + arrivals / 4 + 256, 256);
+    if (arrivals > pad_used && redo) *redo = true;
+    p.halo_last_arrivals = arrivals;
+  }
   return ABL_OK;
 }
 
@@ -1921,11 +2052,334 @@ static int grow_recv(abl_runtime *rt, int which, size_t bytes, size_t keep) {
   return ABL_OK;
 }
 
+// ---------------------------------------------------------------------------------------
+// direct halo transport: records are written straight into the neighbour's memory
+// ---------------------------------------------------------------------------------------
+// Every rank owns a receive area of four blocks, [from lower | from upper] x [parity 0 | 1];
+// a block is a 64-byte header {seq, count} followed by packed records.  The neighbours map the
+// area (CUDA IPC across processes, plain pointers inside one process) and the *step kernel
+// itself* appends the halo / migration records of exchange number `seq` to block
+// [direction][seq & 1] over NVLink (abl_slab_epilogue).  Three small kernels follow on the
+// same stream:
+//   k_halo_publish   (1 thread)  fence, then header {count, seq} into the neighbour's block
+//   k_halo_wait      (2 threads) spins until both own headers carry `seq` (bounded by a timeout)
+//   k_halo_unpack                appends the arrivals behind the owned range and pads with
+//                                sentinel records up to the host's estimate `pad`
+// No NCCL call and no host synchronisation is involved: the host never learns the counts of
+// the current exchange.  It bins `owned + pad` records (sentinels fall into a trash cell
+// behind all real cells) and reads the true counts together with the owned range one binning
+// later (slab_update_owned_range), where capacity overruns, far migrations and time-outs are
+// reported and the padding is adapted.  Two parities suffice as flow control: a rank can only
+// start exchange seq+2 after it has consumed seq+1 from both neighbours, which they publish
+// after having consumed seq.
+struct HaloHeader {
+  u32 seq, count;
+  u32 reserved[14];
+};
+static_assert(sizeof(HaloHeader) == ABL_MSG_HEADER, "header size");
+
+static bool halo_direct(const Pool &p) { return p.halo_recv != nullptr; }
+
+static u8 *halo_block_of(u8 *area, size_t block_bytes, int from_dir, u32 seq) {
+  return area + ((size_t)from_dir * 2 + (seq & 1u)) * block_bytes;
+}
+
+__global__ void k_halo_publish(u32 *ctr, HaloHeader *to_lo, HaloHeader *to_hi, u32 seq, u32 cap) {
+  if (threadIdx.x != 0) return;
+  const u32 c0 = ctr[0], c1 = ctr[1];
+  ctr[6] = c0;
+  ctr[7] = c1;
+  ctr[0] = 0;
+  ctr[1] = 0;
+  __threadfence_system();  // the records (written by the preceding kernel) before the header
+  if (to_lo) {
+    *(volatile u32 *)&to_lo->count = min(c0, cap);
+    __threadfence_system();
+    *(volatile u32 *)&to_lo->seq = seq;
+  }
+  if (to_hi) {
+    *(volatile u32 *)&to_hi->count = min(c1, cap);
+    __threadfence_system();
+    *(volatile u32 *)&to_hi->seq = seq;
+  }
+}
+
+__global__ void k_halo_wait(u32 *ctr, const HaloHeader *from_lo, const HaloHeader *from_hi, u32 seq,
+                            long long timeout_ns) {
+  const int dir = threadIdx.x;
+  if (dir > 1) return;
+  const HaloHeader *h = dir == 0 ? from_lo : from_hi;
+  u32 count = 0;
+  if (h) {
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+      if (*(const volatile u32 *)&h->seq == seq) {
+        __threadfence_system();
+        count = *(const volatile u32 *)&h->count;
+        break;
+      }
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if ((long long)(t1 - t0) > timeout_ns) { ctr[4] = 1; break; }
+      __nanosleep(200);
+    }
+  }
+  ctr[2 + dir] = count;
+}
+
+// Arrivals go to pool slots [dst_first, dst_first + in_lo + in_hi); slots up to `pad` behind
+// them receive the sentinel id.  Grid-stride so that more arrivals than the host expected are
+// still stored (bounded by `room`); the next binning then notices and bins once more.
+__global__ void k_halo_unpack(ColTable t, const u8 *blk_lo, const u8 *blk_hi, const u32 *ctr,
+                              u32 dst_first, u32 pad, u32 room, u32 rec_words) {
+  const u32 in_lo = ctr[2], in_hi = ctr[3];
+  u32 total = in_lo + in_hi;
+  if (total < pad) total = pad;
+  if (total > room) total = room;
+  for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const size_t dst = (size_t)dst_first + i;
+    if (i >= in_lo + in_hi) {
+      ((u32 *)t.out[t.ncols - 1])[dst] = ABL_SENTINEL_ID;
+      continue;
+    }
+    const u32 *rec = i < in_lo ? (const u32 *)(blk_lo + ABL_MSG_HEADER) + (size_t)i * rec_words
+                               : (const u32 *)(blk_hi + ABL_MSG_HEADER) + (size_t)(i - in_lo) * rec_words;
+    u32 w = 0;
+    for (int k = 0; k < t.ncols; k++) {
+      const int e = t.elem[k];
+      if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w++]; continue; }
+      u32 *q = (u32 *)t.out[k] + dst * (e / 4);
+      for (int j = 0; j < e / 4; j++) q[j] = rec[w++];
+    }
+  }
+}
+
+// stand-alone classify + pack for exchanges that do not follow a step kernel (first exchange
+// after an upload): same routing and record format as abl_slab_epilogue
+template <typename R>
+__global__ void k_halo_pack(ColTable t, abl_slab_view s, u32 n, u32 first) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t src = (size_t)first + i;
+  R v;
+  if (s.dim == 2) v = ((const R *)t.in[s.pos_col])[2 * src + 1];
+  else v = ((const R *)t.in[s.pos_col + 2])[src];
+  const int layer = cell_coord<R>(v, (R)s.origin, (R)s.inv_cell, s.n_layers);
+  const unsigned route = abl_slab_route(s, layer);
+  if (route & 4u) { atomicAdd(s.far, 1u); return; }
+  for (int dir = 0; dir < 2; dir++) {
+    if (!((route >> dir) & 1u)) continue;
+    const u32 slot = atomicAdd(s.count[dir], 1u);
+    if (slot >= s.capacity || !s.msg[dir]) continue;
+    u32 *rec = (u32 *)s.msg[dir] + (size_t)slot * s.rec_words;
+    u32 w = 0;
+    for (int k = 0; k < t.ncols; k++) {
+      const int e = t.elem[k];
+      if (e == 1) { rec[w++] = ((const u8 *)t.in[k])[src]; continue; }
+      const u32 *q = (const u32 *)t.in[k] + src * (e / 4);
+      for (int j = 0; j < e / 4; j++) rec[w++] = q[j];
+    }
+  }
+}
+
+// Describes exchange number halo_seq + 1 of `p` for the kernel that packs it.
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v) {
+  memset(&v, 0, sizeof v);
+  const GridParams &g = rt->grid;
+  const int axis = g.dim - 1, N = rt->n_slabs, me = rt->my_slab;
+  const Member &pm = p.members[p.pos_member];
+  const u32 seq = p.halo_seq + 1;
+  v.active = 1;
+  v.dim = g.dim;
+  v.pos_col = pm.first_col;
+  v.n_layers = slab_layers(rt);
+  v.origin = g.origin[axis];
+  v.inv_cell = g.inv_cell;
+  v.begin = rt->layer_begin;
+  v.end = rt->layer_end;
+  v.ghost = rt->ghost_layers;
+  const bool ring = N > 2;
+  const int lo = me > 0 ? me - 1 : (ring ? N - 1 : -1), hi = me < N - 1 ? me + 1 : (ring ? 0 : -1);
+  if (lo >= 0 && p.halo_peer[0]) {
+    v.lo_begin = rt->slab_bounds[lo];
+    v.lo_end = rt->slab_bounds[lo + 1];
+    v.lo_ghost = me > 0;  // around the ring only migrants travel, ghosts are for true neighbours
+    // what I send downwards arrives "from upper" over there
+    v.msg[0] = halo_block_of(p.halo_peer[0], p.halo_block, 1, seq) + ABL_MSG_HEADER;
+  }
+  if (hi >= 0 && p.halo_peer[1]) {
+    v.hi_begin = rt->slab_bounds[hi];
+    v.hi_end = rt->slab_bounds[hi + 1];
+    v.hi_ghost = me < N - 1;
+    v.msg[1] = halo_block_of(p.halo_peer[1], p.halo_block, 0, seq) + ABL_MSG_HEADER;
+  }
+  v.count[0] = p.halo_ctr + 0;
+  v.count[1] = p.halo_ctr + 1;
+  v.far = p.halo_ctr + 5;
+  v.capacity = (unsigned)p.halo_cap;
+  v.rec_words = (unsigned)slab_rec_words(p);
+  v.n_cols = (int)p.cols.size() - 1;
+  for (int c = 0; c < v.n_cols; c++) v.elem[c] = p.cols[c].elem;
+  return ABL_OK;
+}
+
+// Room for the arrivals must exist before the packing kernel runs (growing a pool
+// synchronises and moves its columns).
+static int halo_reserve(abl_runtime *rt, Pool &p) {
+  if (p.halo_pad == 0) {
+    p.halo_pad = (u32)std::min<size_t>(2 * p.halo_cap, round_up(p.halo_cap / 2 + 256, 256));
+    if (const char *e = getenv("ABL_CUDA_HALO_PAD")) p.halo_pad = (u32)std::max(1, atoi(e));  // tests
+  }
+  const size_t want = (size_t)p.own_end + 2 * (size_t)p.halo_pad + 1024;
+  if (want > p.cap) {
+    p.n = std::max(p.n, (size_t)p.own_end);
+    TRY(drop_fused_histogram(rt, p));
+    TRY(reserve_pool(rt, p, want));
+  }
+  return ABL_OK;
+}
+
+// publish + wait + unpack of exchange number ++halo_seq; records have been packed by the
+// kernel launched just before
+static int halo_finish(abl_runtime *rt, Pool &p) {
+  const u32 seq = ++p.halo_seq;
+  const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
+  HaloHeader *to_lo = p.halo_peer[0] ? (HaloHeader *)halo_block_of(p.halo_peer[0], p.halo_block, 1, seq) : nullptr;
+  HaloHeader *to_hi = p.halo_peer[1] ? (HaloHeader *)halo_block_of(p.halo_peer[1], p.halo_block, 0, seq) : nullptr;
+  const u8 *from_lo = p.halo_peer[0] ? halo_block_of(p.halo_recv, p.halo_block, 0, seq) : nullptr;
+  const u8 *from_hi = p.halo_peer[1] ? halo_block_of(p.halo_recv, p.halo_block, 1, seq) : nullptr;
+  k_halo_publish<<<1, 32, 0, rt->stream>>>(p.halo_ctr, to_lo, to_hi, seq, (u32)p.halo_cap);
+  k_halo_wait<<<1, 32, 0, rt->stream>>>(p.halo_ctr, (const HaloHeader *)from_lo, (const HaloHeader *)from_hi, seq,
+                                        rt->halo_timeout_ns);
+  ColTable t;
+  fill_table(p, t, false);
+  const u32 pad = p.halo_pad;
+  const u32 room = (u32)std::min<size_t>(p.cap - oe, 0x7fffffffu);
+  p.halo_room = room;
+  k_halo_unpack<<<std::max(1u, blocks_for(pad, 256)), 256, 0, rt->stream>>>(t, from_lo, from_hi, p.halo_ctr, oe, pad,
+                                                                         room, (u32)slab_rec_words(p));
+  rt->launches += 3;
+  CU(cudaGetLastError());
+  p.halo_prev_ob = ob;
+  p.halo_prev_own = n_own;
+  p.halo_pending = true;
+  p.src_begin = ob;
+  p.n = (size_t)n_own + pad;
+  p.binned = false;
+  // the step kernel already produced keys and the histogram of the owned agents (fused
+  // epilogue); arrivals and padding are still missing
+  if (p.counted && pad) TRY(launch_bin_count(rt, p, pad, oe, n_own));
+  return ABL_OK;
+}
+
+static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
+  if (!p.own_valid) TRY(bin_pool(rt, p));
+  TRY(halo_reserve(rt, p));
+  abl_slab_view v;
+  TRY(halo_fill_view(rt, p, v));
+  const u32 n_own = p.own_end - p.own_begin;
+  if (n_own) {
+    ColTable t;
+    fill_table(p, t, false);
+    if (rt->real_size == 8) k_halo_pack<double><<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, v, n_own, p.own_begin);
+    else k_halo_pack<float><<<blocks_for(n_own, 256), 256, 0, rt->stream>>>(t, v, n_own, p.own_begin);
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  return halo_finish(rt, p);
+}
+
+extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_records, void *handle_out) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!rt->slab) return fail(ABL_ERR_STATE, "halo_setup requires abl_cuda_set_slab");
+  if (p.pos_member < 0) return fail(ABL_ERR_ARGUMENT, "pool %s has no position member", p.name.c_str());
+  if (p.halo_recv) return fail(ABL_ERR_STATE, "pool %s: halo transport already set up", p.name.c_str());
+  CU(cudaSetDevice(rt->device));
+  p.halo_cap = capacity_records ? capacity_records : 65536;
+  p.halo_block = round_up(ABL_MSG_HEADER + p.halo_cap * (size_t)slab_rec_words(p) * 4, 256);
+  CU(cudaMalloc(&p.halo_recv, 4 * p.halo_block));
+  CU(cudaMemset(p.halo_recv, 0, 4 * p.halo_block));
+  rt->defer_free = true;
+  CU(cudaMalloc(&p.halo_ctr, 16 * sizeof(u32)));
+  CU(cudaMemset(p.halo_ctr, 0, 16 * sizeof(u32)));
+  // CUDA loads kernels lazily and the first launch of a kernel may synchronise the context.
+  // That must not happen between k_halo_wait and the neighbours' publish when several slabs
+  // are driven by one host thread (it would wait for a spinning kernel): load them now.
+  {
+    const void *kernels[] = {(const void *)k_halo_publish, (const void *)k_halo_wait, (const void *)k_halo_unpack,
+                             (const void *)k_halo_pack<double>, (const void *)k_halo_pack<float>,
+                             (const void *)k_bin_count<double, 2>, (const void *)k_bin_count<double, 3>,
+                             (const void *)k_bin_count<float, 2>, (const void *)k_bin_count<float, 3>,
+                             (const void *)k_gather_bin_words, (const void *)k_bin_scatter,
+                             (const void *)k_bin_rank_move};
+    cudaFuncAttributes attr;
+    for (const void *k : kernels) CU(cudaFuncGetAttributes(&attr, k));
+  }
+  if (handle_out) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == ABL_IPC_HANDLE_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, p.halo_recv));
+    memcpy(handle_out, &h, sizeof h);
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_halo_connect(abl_runtime *rt, int pool, const void *lower_handle, const void *upper_handle) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!p.halo_recv) return fail(ABL_ERR_STATE, "halo_connect before halo_setup");
+  CU(cudaSetDevice(rt->device));
+  const void *hs[2] = {lower_handle, upper_handle};
+  for (int d = 0; d < 2; d++) {
+    if (!hs[d]) continue;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, hs[d], sizeof h);
+    void *ptr = nullptr;
+    CU(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p.halo_peer[d] = (u8 *)ptr;
+    p.halo_ipc[d] = true;
+  }
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_halo_connect_local(abl_runtime *rt, int pool, abl_runtime *lower, abl_runtime *upper) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!p.halo_recv) return fail(ABL_ERR_STATE, "halo_connect before halo_setup");
+  abl_runtime *peers[2] = {lower, upper};
+  for (int d = 0; d < 2; d++) {
+    if (!peers[d]) continue;
+    Pool *q;
+    TRY(get_pool(peers[d], pool, &q));
+    if (!q->halo_recv || q->halo_block != p.halo_block)
+      return fail(ABL_ERR_STATE, "halo_connect_local: the peer has no matching receive area");
+    if (peers[d]->device != rt->device) {
+      int can = 0;
+      CU(cudaDeviceCanAccessPeer(&can, rt->device, peers[d]->device));
+      if (!can) return fail(ABL_ERR_COMM, "device %d cannot access device %d", rt->device, peers[d]->device);
+      cudaError_t e = cudaDeviceEnablePeerAccess(peers[d]->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CU(e);
+      cudaGetLastError();
+    }
+    p.halo_peer[d] = q->halo_recv;
+    p.halo_ipc[d] = false;
+  }
+  return ABL_OK;
+}
+
 extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
   Pool *pp;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!rt->slab || p.pos_member < 0) return ABL_OK;
+  if (halo_direct(p)) {
+    CU(cudaSetDevice(rt->device));
+    return halo_exchange_standalone(rt, p);
+  }
   if (rt->peer_lo || rt->peer_hi)
     return fail(ABL_ERR_STATE, "in-process peers: use abl_cuda_exchange_begin/end on all runtimes");
   CU(cudaSetDevice(rt->device));
@@ -1933,7 +2387,11 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
   const bool ring = N > 2;
   const bool has_lo = rt->comm && N > 1 && (me > 0 || ring), has_hi = rt->comm && N > 1 && (me < N - 1 || ring);
   const int lo_peer = (me - 1 + N) % N, hi_peer = (me + 1) % N;
+  auto now = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double h0 = 0, h1 = 0, h2 = 0, h3 = 0;
+  if (rt->trace) { cudaEventRecord(rt->xev[0], rt->stream); h0 = now(); }
   TRY(exchange_pack(rt, p, has_lo, has_hi));
+  if (rt->trace) { cudaEventRecord(rt->xev[1], rt->stream); h1 = now(); }
   u32 incoming[2] = {0, 0};
   if (has_lo || has_hi) {
     // One NCCL group moves fixed-size first messages (header + up to kMsgFirstRecords records),
@@ -1951,13 +2409,16 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
     if (has_hi) NCCL(ncclSend(rt->xbuf[1], first_bytes, ncclUint8, hi_peer, rt->comm, rt->stream));
     if (has_lo) NCCL(ncclRecv(rt->xbuf[2], first_bytes, ncclUint8, lo_peer, rt->comm, rt->stream));
     NCCL(ncclGroupEnd());
+    if (rt->trace) { cudaEventRecord(rt->xev[2], rt->stream); h2 = now(); }
     u32 *h = rt->h_scalar + 8;  // [0] out lo, [1] out hi, [2] in lo, [3] in hi, [4] far
     k_gather_words<<<1, 32, 0, rt->stream>>>((const u32 *)rt->xbuf[0], (const u32 *)rt->xbuf[1],
         has_lo ? (const u32 *)rt->xbuf[2] : nullptr, has_hi ? (const u32 *)rt->xbuf[3] : nullptr,
         rt->d_scalar + 10, rt->d_scalar + 24);
     rt->launches++;
     CU(cudaMemcpyAsync(h, rt->d_scalar + 24, 5 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+    if (rt->trace) cudaEventRecord(rt->xev[3], rt->stream);
     CU(cudaStreamSynchronize(rt->stream));
+    if (rt->trace) h3 = now();
     TRY(exchange_check_far(rt, p, h[4]));
     const u32 out_lo = has_lo ? h[0] : 0, out_hi = has_hi ? h[1] : 0;
     incoming[0] = has_lo ? h[2] : 0;
@@ -1975,7 +2436,19 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
       NCCL(ncclGroupEnd());
     }
   }
-  return exchange_unpack(rt, p, incoming);
+  int rc = exchange_unpack(rt, p, incoming);
+  if (rt->trace && (has_lo || has_hi) && rc == ABL_OK) {
+    cudaEventRecord(rt->xev[4], rt->stream);
+    double h4 = now();
+    cudaEventSynchronize(rt->xev[4]);
+    float ms;
+    if (++rt->xskip > 64) {  // connection set-up and warm-up calls are not representative
+      for (int i = 0; i < 4; i++) { cudaEventElapsedTime(&ms, rt->xev[i], rt->xev[i + 1]); rt->xdev[i] += ms; }
+      rt->xhost[0] += h1 - h0; rt->xhost[1] += h2 - h1; rt->xhost[2] += h3 - h2; rt->xhost[3] += h4 - h3;
+      rt->xcount++;
+    }
+  }
+  return rc;
 }
 
 // ---- in-process transport: several runtimes (slabs) driven by one host thread -------------

@@ -188,6 +188,9 @@ def main():
     ap.add_argument("--block-size", type=int, default=128)
     ap.add_argument("--no-tile", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
+    ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
+                    help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
+                         "NVLink (direct) or grouped ncclSend/ncclRecv (nccl)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
@@ -221,7 +224,8 @@ def main():
     n_agents = sum(len(h) for h in host)          # whole job, all ranks
     slab = None
     if world > 1:
-        slab = RankSlab(m, rank, world, dist, device=local_rank, block_size=args.block_size, tile=not args.no_tile)
+        slab = RankSlab(m, rank, world, dist, device=local_rank, transport=args.transport,
+                        block_size=args.block_size, tile=not args.no_tile)
     else:
         m.create_runtime(device=local_rank, block_size=args.block_size, tile=not args.no_tile)
     rt = m.rt
@@ -325,7 +329,7 @@ def main():
                 "dtype": "f32" if use_float else "f64", "data": "synthetic",
                 "config": {"workload": args.workload, "model": model_file, "num_agents": n_agents,
                            "agents_per_gpu": n_agents // world,
-                           "parallelism": ("slab%d (cell layers along the slowest axis, halo + migration over NCCL send/recv)" % world) if world > 1 else "single",
+                           "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
                            "block_size": args.block_size,
                            "l2": "state (%.0f MB) is re-streamed every step; no L2 flush between steps (a "
                                  "simulation step consumes the previous step's output)" % (n_agents * S / 1e6)},

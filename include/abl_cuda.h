@@ -138,6 +138,31 @@ typedef struct {
   unsigned key_base;
 } abl_grid_view;
 
+/* Slab decomposition as seen by a step kernel: after storing its outputs the kernel itself
+ * classifies the agent by the cell layer of its (new) position and appends the record to the
+ * outgoing halo / migration messages.  The message buffers may live in the peer GPU's memory
+ * (CUDA IPC mapping, written over NVLink), which makes the step kernel and the halo send one
+ * fused kernel.  active == 0 when the simulation is not decomposed (or the runtime packs in a
+ * separate pass). */
+typedef struct {
+  int active;
+  int dim;                  /* 2 or 3: the slab axis is y or z */
+  int pos_col;              /* first column of the position member */
+  int n_layers;             /* cell layers along the slab axis */
+  double origin, inv_cell;  /* of the slab axis */
+  int begin, end, ghost;    /* owned layers [begin, end), ghost width in layers */
+  int lo_begin, lo_end;     /* layers owned by the lower peer ([0,0): none) */
+  int hi_begin, hi_end;
+  int lo_ghost, hi_ghost;   /* 1: that peer is a true neighbour and wants ghost copies */
+  unsigned char *msg[2];    /* record area of the outgoing message to the lower / upper peer */
+  unsigned *count[2];       /* slot counters (local memory) */
+  unsigned capacity;        /* records per message */
+  unsigned rec_words;       /* 32-bit words per packed record */
+  unsigned *far;            /* counts agents that moved farther than a neighbouring slab */
+  int n_cols;               /* columns of the pool (without the id) */
+  int elem[ABL_MAX_COLUMNS];
+} abl_slab_view;
+
 typedef struct {
   abl_pool_view self;                      /* pool the step function iterates */
   abl_pool_view nbr;                       /* pool of its for-near loop (n = 0 if none) */
@@ -151,6 +176,7 @@ typedef struct {
   unsigned *bin_key;
   unsigned *bin_local;
   unsigned *bin_count;
+  abl_slab_view slab;                      /* fused halo/migration pack (see above) */
   uint64_t seed;
   unsigned timestep;
   unsigned step_index;
@@ -231,6 +257,16 @@ int abl_cuda_slab_axis_layers(abl_runtime *rt, int *n_layers);
  * arrivals, then refresh ghost layers of `pool`.  Collective over neighbouring ranks. */
 int abl_cuda_exchange(abl_runtime *rt, int pool);
 int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n);
+/* Direct halo transport over peer memory.  halo_setup allocates this runtime's receive area for
+ * `pool` (capacity_records per direction, 0 = default) and returns its 64-byte CUDA IPC handle;
+ * the caller passes every rank its ring neighbours' handles (halo_connect), after which step
+ * kernels write halo and migrating records straight into the neighbour's memory over NVLink and
+ * abl_cuda_step needs neither NCCL nor a host synchronisation for the exchange.  Runtimes in one
+ * process are connected with halo_connect_local instead. */
+#define ABL_IPC_HANDLE_BYTES 64
+int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_records, void *handle_out);
+int abl_cuda_halo_connect(abl_runtime *rt, int pool, const void *lower_handle, const void *upper_handle);
+int abl_cuda_halo_connect_local(abl_runtime *rt, int pool, abl_runtime *lower, abl_runtime *upper);
 /* In-process transport between runtimes driven by one host thread (several slabs on one
  * GPU; used by the single-GPU tests of the decomposition).  With local peers set the caller
  * runs a step on every slab, then exchange_begin on every slab, then exchange_end on every

@@ -55,7 +55,7 @@ def model_key(abl_path, params, config):
     h = hashlib.sha1()
     with open(abl_path, "rb") as f:
         h.update(f.read())
-    for name in ("lib.abl", "cuda/abl_device.cuh", "cuda/abl_host.h", "cuda/abl_host.c"):
+    for name in ("lib.abl", "cuda/abl_device.cuh", "cuda/abl_slab.cuh", "cuda/abl_host.h", "cuda/abl_host.c"):
         with open(os.path.join(ASSET_DIR, name), "rb") as f:
             h.update(f.read())
     with open(os.path.join(REPO_ROOT, "include", "abl_cuda.h"), "rb") as f:

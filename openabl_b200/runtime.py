@@ -74,6 +74,9 @@ ABI = {
     "abl_cuda_slab_axis_layers": (C.c_int, [_VP, C.POINTER(C.c_int)]),
     "abl_cuda_exchange": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_owned_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_halo_setup": (C.c_int, [_VP, C.c_int, C.c_size_t, _VP]),
+    "abl_cuda_halo_connect": (C.c_int, [_VP, C.c_int, _VP, _VP]),
+    "abl_cuda_halo_connect_local": (C.c_int, [_VP, C.c_int, _VP, _VP]),
     "abl_cuda_set_local_peers": (C.c_int, [_VP, _VP, _VP]),
     "abl_cuda_exchange_begin": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_exchange_end": (C.c_int, [_VP, C.c_int]),
@@ -182,6 +185,22 @@ class Runtime:
 
     def exchange(self, pool):
         check(self.lib.abl_cuda_exchange(self.handle, pool), "exchange")
+
+    # direct halo transport (peer memory): records are written by the step kernels themselves
+    def halo_setup(self, pool, capacity_records=0):
+        """Allocates the receive area of `pool`; returns its 64-byte CUDA IPC handle."""
+        buf = (C.c_ubyte * 64)()
+        check(self.lib.abl_cuda_halo_setup(self.handle, pool, capacity_records, buf), "halo_setup")
+        return bytes(buf)
+
+    def halo_connect(self, pool, lower_handle, upper_handle):
+        lo = (C.c_ubyte * 64).from_buffer_copy(lower_handle) if lower_handle else None
+        hi = (C.c_ubyte * 64).from_buffer_copy(upper_handle) if upper_handle else None
+        check(self.lib.abl_cuda_halo_connect(self.handle, pool, lo, hi), "halo_connect")
+
+    def halo_connect_local(self, pool, lower, upper):
+        check(self.lib.abl_cuda_halo_connect_local(self.handle, pool, lower.handle if lower else None,
+                                                   upper.handle if upper else None), "halo_connect_local")
 
     def exchange_begin(self, pool):
         check(self.lib.abl_cuda_exchange_begin(self.handle, pool), "exchange_begin")

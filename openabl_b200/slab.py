@@ -1,11 +1,15 @@
 """Slab decomposition harness: one model, several device runtimes.
 
-  * `LocalSlabs`  — S slabs in ONE process on one GPU, exchanging through the runtime's
-    in-process transport (abl_cuda_set_local_peers / exchange_begin / exchange_end).  This is
-    how the single-GPU test tier checks that a decomposed run is bit-identical to an
-    undecomposed one.
-  * `RankSlab`    — one slab per process / GPU (torchrun), exchanging through NCCL inside
-    abl_cuda_step (abl_cuda_comm_init_nccl); used by bench.py --gpus N.
+  * `LocalSlabs`  — S slabs in ONE process on one GPU.  transport="staged": the runtime's
+    in-process transport (abl_cuda_set_local_peers / exchange_begin / exchange_end);
+    transport="direct": the same peer-memory transport the multi-GPU runs use
+    (abl_cuda_halo_setup / halo_connect_local) — step kernels append their halo records to the
+    neighbouring slab's receive area and nothing synchronises with the host.  This is how the
+    single-GPU test tier checks that a decomposed run is bit-identical to an undecomposed one.
+  * `RankSlab`    — one slab per process / GPU (torchrun); used by bench.py --gpus N.
+    transport="direct" (default): receive areas are exchanged as CUDA IPC handles and written
+    over NVLink by the step kernels; transport="nccl": grouped ncclSend/ncclRecv inside
+    abl_cuda_step (abl_cuda_comm_init_nccl).
 
 The partition is by whole cell layers along the slowest grid axis, balanced by layer count
 (`split_layers`); ownership and ghosts are maintained by the runtime (abl_runtime.cu).
@@ -33,9 +37,24 @@ def merge_by_id(parts_ids, parts_records):
     return ids[order], rec[order]
 
 
+def halo_capacity(total_agents, n_layers, slack=4):
+    """Records one halo message must hold: `slack` x the mean population of a cell layer."""
+    return max(16384, int(slack * total_agents / max(n_layers, 1)) + 4096)
+
+
+def ring_neighbours(rank, world):
+    """(lower, upper) slab of `rank`; slabs form a ring when there are more than two."""
+    ring = world > 2
+    lower = rank - 1 if rank > 0 else (world - 1 if ring else None)
+    upper = rank + 1 if rank + 1 < world else (0 if ring else None)
+    return lower, upper
+
+
 class LocalSlabs:
-    def __init__(self, model, n_slabs, **rt_kw):
+    def __init__(self, model, n_slabs, transport="staged", halo_records=0, **rt_kw):
         self.model = model
+        self.transport = transport
+        self.halo_records = halo_records
         self.rts = []
         for _ in range(n_slabs):
             rt = Runtime(use_float=model.use_float, **rt_kw)
@@ -43,16 +62,34 @@ class LocalSlabs:
             self.rts.append(rt)
         layers = self.rts[0].slab_layers()
         self.bounds = split_layers(layers, n_slabs)
-        ring = n_slabs > 2   # periodic worlds: the first and the last slab are neighbours too
         for r, rt in enumerate(self.rts):
             rt.set_slab(self.bounds, r)
-            lower = self.rts[r - 1] if r > 0 else (self.rts[-1] if ring else None)
-            upper = self.rts[r + 1] if r + 1 < n_slabs else (self.rts[0] if ring else None)
-            rt.set_local_peers(lower, upper)
+        self._connected = False
+        if transport == "staged":
+            for r, rt in enumerate(self.rts):
+                # periodic worlds: the first and the last slab are neighbours too
+                lo, hi = ring_neighbours(r, n_slabs)
+                rt.set_local_peers(self.rts[lo] if lo is not None else None,
+                                   self.rts[hi] if hi is not None else None)
+
+    def _connect_direct(self, total_agents):
+        m = self.model
+        layers = self.rts[0].slab_layers()
+        for t in range(m.n_types):
+            cap = self.halo_records or halo_capacity(total_agents[t], layers)
+            for rt in self.rts:
+                rt.halo_setup(m.pool(t), cap)
+            for r, rt in enumerate(self.rts):
+                lo, hi = ring_neighbours(r, len(self.rts))
+                rt.halo_connect_local(m.pool(t), self.rts[lo] if lo is not None else None,
+                                      self.rts[hi] if hi is not None else None)
+        self._connected = True
 
     def upload(self, host_arrays):
         """Every slab receives the whole population and keeps its own part."""
         m = self.model
+        if self.transport == "direct" and not self._connected:
+            self._connect_direct([len(a) for a in host_arrays])
         for rt in self.rts:
             for t, arr in enumerate(host_arrays):
                 rt.upload(m.pool(t), np.ascontiguousarray(arr))
@@ -60,6 +97,10 @@ class LocalSlabs:
             self._exchange(m.pool(t))
 
     def _exchange(self, pool):
+        if self.transport == "direct":
+            for rt in self.rts:
+                rt.exchange(pool)   # enqueues pack + publish + wait + unpack, returns at once
+            return
         for rt in self.rts:
             rt.exchange_begin(pool)
         for rt in self.rts:
@@ -70,6 +111,8 @@ class LocalSlabs:
         for s in range(m.n_steps):
             for rt in self.rts:
                 check(m.lib.abl_model_run_step(rt.handle, s), "abl_model_run_step")
+            if self.transport == "direct":
+                continue   # abl_cuda_step exchanged by itself
             # the step's own pool may have changed: refresh ghosts / migrate
             pool = self.step_pool(s)
             self._exchange(pool)
@@ -100,14 +143,18 @@ class LocalSlabs:
 class RankSlab:
     """One slab per process.  `dist` is torch.distributed (already initialised)."""
 
-    def __init__(self, model, rank, world, dist=None, device=0, **rt_kw):
+    def __init__(self, model, rank, world, dist=None, device=0, transport="direct", halo_records=0, **rt_kw):
         import torch
         self.model = model
         self.rank, self.world = rank, world
+        self.dist = dist
+        self.transport = transport if world > 1 else "none"
+        self.halo_records = halo_records
+        self._connected = False
         self.rt = model.create_runtime(device=device, **rt_kw)
         layers = self.rt.slab_layers()
         self.bounds = split_layers(layers, world)
-        if world > 1:
+        if self.transport == "nccl":
             uid = torch.zeros(128, dtype=torch.uint8)
             if rank == 0:
                 uid = torch.tensor(list(self.rt.nccl_unique_id()), dtype=torch.uint8)
@@ -120,6 +167,10 @@ class RankSlab:
         """Every rank uploads the whole population from the model's own page-locked host arrays
         (as the generated program does), keeps its slab and fetches ghosts with one exchange."""
         m = self.model
+        if self.transport == "direct" and not self._connected:
+            totals = [len(m.host_agents(t)) for t in range(m.n_types)] if host_arrays is None \
+                else [len(a) for a in host_arrays]
+            self._connect_direct(totals)
         if host_arrays is None:
             m.upload_host()
         else:
@@ -127,6 +178,27 @@ class RankSlab:
                 self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
         for t in range(m.n_types):
             self.rt.exchange(m.pool(t))
+
+    def _connect_direct(self, total_agents):
+        """Every rank allocates its receive areas and learns its ring neighbours' IPC handles."""
+        import torch
+        m = self.model
+        layers = self.rt.slab_layers()
+        lo, hi = ring_neighbours(self.rank, self.world)
+        for t in range(m.n_types):
+            cap = self.halo_records or halo_capacity(total_agents[t], layers)
+            mine = torch.tensor(list(self.rt.halo_setup(m.pool(t), cap)), dtype=torch.uint8)
+            every = [torch.zeros(64, dtype=torch.uint8) for _ in range(self.world)]
+            if self.dist.get_backend() == "nccl":
+                dev = torch.device("cuda", torch.cuda.current_device())
+                every = [e.to(dev) for e in every]
+                mine = mine.to(dev)
+            self.dist.all_gather(every, mine)
+            handles = [bytes(e.cpu().tolist()) for e in every]
+            self.rt.halo_connect(m.pool(t), handles[lo] if lo is not None else None,
+                                 handles[hi] if hi is not None else None)
+        self.dist.barrier()
+        self._connected = True
 
     def timestep(self):
         self.model.timestep()   # abl_cuda_step exchanges by itself when NCCL is attached

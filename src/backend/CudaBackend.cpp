@@ -1217,6 +1217,9 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w.nl();
     w << "abl_bin_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ");";
   }
+  // slab decomposition: route this agent's record to the neighbouring slabs (no-op otherwise)
+  w.nl();
+  w << "abl_slab_epilogue(_a, _i);";
   if (f.usesRemoval) { w.nl(); w << "_a.dead[_i] = _ctx.dead ? 1 : 0;"; }
   if (f.addedAgent) { w.nl(); w << "_a.add_flag[_i] = _ctx.added ? 1 : 0;"; }
   w.outdent(); w.nl();
@@ -1418,6 +1421,7 @@ void CudaBackend::generate(Script &script, const BackendContext &ctx) {
   if (!fileExists(abi)) throw std::runtime_error("abl_cuda.h not found (looked in " + asset + " and " + ctx.assetDir + "/../include)");
   copyFile(abi, out + "/abl_cuda.h");
   copyFile(asset + "/abl_device.cuh", out + "/abl_device.cuh");
+  copyFile(asset + "/abl_slab.cuh", out + "/abl_slab.cuh");
   copyFile(asset + "/abl_host.h", out + "/abl_host.h");
   copyFile(asset + "/abl_host.c", out + "/abl_host.c");
   writeToFile(out + "/build.sh", buildScript(ctx, useFloat));

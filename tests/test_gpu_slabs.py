@@ -1,5 +1,7 @@
 """Slab decomposition on ONE GPU: S slabs (S runtimes) exchanging halo cells and migrating
-agents through the in-process transport must reproduce the undecomposed run bit for bit."""
+agents must reproduce the undecomposed run bit for bit — through the staged in-process
+transport and through the direct peer-memory transport (step kernels write their halo records
+into the neighbouring slab's receive area; the same code path the multi-GPU runs use)."""
 import os
 
 import numpy as np
@@ -19,10 +21,21 @@ CASES = [
 ]
 
 
+def single_run(m, steps):
+    m.create_runtime()
+    m.upload_host()
+    for _ in range(steps):
+        m.timestep()
+    single = m.download(0)
+    m.close()
+    return single
+
+
 @pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["staged", "direct"])
 @pytest.mark.parametrize("model_file,params,use_float,slabs,steps", CASES,
                          ids=["%s-%dslabs-%s" % (c[0][:-4], c[3], "f32" if c[2] else "f64") for c in CASES])
-def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, steps):
+def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, steps, transport):
     m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
     m.populate()
     host = [m.host_agents(t) for t in range(m.n_types)]
@@ -33,7 +46,7 @@ def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, s
     single = m.download(0)
     m.close()
 
-    ls = LocalSlabs(m, slabs)
+    ls = LocalSlabs(m, slabs, transport=transport)
     ls.upload(host)
     assert sum(ls.owned_counts(0)) == len(host[0])
     for _ in range(steps):
@@ -49,6 +62,41 @@ def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, s
     assert np.array_equal(ids, np.arange(len(host[0]), dtype=np.uint32))
     for f in rec.dtype.names:
         assert np.array_equal(rec[f], single[f]), "member %s differs from the single-slab run" % f
+
+
+@pytest.mark.gpu
+def test_direct_transport_recovers_from_underestimated_padding(monkeypatch):
+    """The host bins `owned + pad` records without knowing how many arrive; when more arrive
+    than it assumed, the next binning notices and bins again over the true range."""
+    monkeypatch.setenv("ABL_CUDA_HALO_PAD", "256")   # far fewer than a ghost layer holds
+    m = Model(os.path.join(REPO, "examples", "circle.abl"), {"num_agents": 50000})
+    m.populate()
+    host = [m.host_agents(0)]
+    single = single_run(m, 6)
+    ls = LocalSlabs(m, 3, transport="direct")
+    ls.upload(host)
+    for _ in range(6):
+        ls.timestep()
+    ids, rec = ls.download(0)
+    ls.close()
+    assert np.array_equal(ids, np.arange(len(host[0]), dtype=np.uint32))
+    assert np.array_equal(rec["pos"], single["pos"])
+
+
+@pytest.mark.gpu
+def test_direct_transport_reports_message_overflow():
+    """A receive area too small for a ghost layer is an error, not silent loss of agents."""
+    from openabl_b200.runtime import AblError
+    m = Model(os.path.join(REPO, "examples", "circle.abl"), {"num_agents": 50000})
+    m.populate()
+    host = [m.host_agents(0)]
+    ls = LocalSlabs(m, 2, transport="direct", halo_records=64)
+    with pytest.raises(AblError, match="exceeds the capacity"):
+        ls.upload(host)
+        for _ in range(2):
+            ls.timestep()
+        ls.download(0)
+    ls.close()
 
 
 def test_split_layers():
