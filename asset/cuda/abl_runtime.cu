@@ -126,6 +126,7 @@ struct Pool {
 struct ScanState {
   u64 *desc = nullptr;   // one descriptor per tile: (epoch<<2 | status) << 32 | value
   u32 *ctrl = nullptr;   // [0] dynamic tile counter, [1] finished tiles, [2] epoch
+  u32 *tile_sum = nullptr;  // per-tile sums of the two-pass scan
   size_t max_tiles = 0;
 };
 
@@ -175,6 +176,7 @@ struct abl_runtime {
   size_t pinned_cap = 0;
   u32 *d_scalar = nullptr;     // small device scratch for totals / reductions
   u32 *h_scalar = nullptr;     // pinned mirror
+  u32 *h_scalar_dev = nullptr; // the same memory as seen from the device (mapped)
   unsigned timestep = 0;
   bool timing = false;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -204,6 +206,7 @@ struct abl_runtime {
   // cudaFree synchronises the whole device; with the direct transport a neighbour driven by the
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
+  bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
   long long halo_timeout_ns = 10000000000ll;            // direct transport: wait for a neighbour at most this long
@@ -422,6 +425,90 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Two-pass scan of the cell histogram (reduce-then-scan): k_tile_sum writes one sum per tile of
+// 4096 counters, k_tile_scan lets every CTA add up the sums of the tiles before its own (a few
+// hundred words that sit in L2) and scan its tile.  No CTA ever waits for another one, which
+// for the few hundred tiles of a cell grid beats the look-back chain of the single-pass scan
+// above (all of whose CTAs are resident at once and mostly poll).  The scan pass also clears
+// the histogram for the next binning.
+__global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u32 *tile_sum) {
+  __shared__ u32 s_warp[kScanBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)tid * kScanItems;
+  u32 t = 0;
+  if (i0 < n) {
+    u32 v[kScanItems];
+    ScanLoad<u32>::load16(in, i0, v);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) t += (i0 + k < n) ? v[k] : 0u;
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+  if (lane == 0) s_warp[warp] = t;
+  __syncthreads();
+  if (warp == 0) {
+    u32 w = lane < kScanBlock / 32 ? s_warp[lane] : 0;
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) w += __shfl_xor_sync(0xffffffffu, w, d);
+    if (lane == 0) tile_sum[blockIdx.x] = w;
+  }
+}
+
+__global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32 n, const u32 *tile_sum) {
+  __shared__ u32 s_warp[kScanBlock / 32];
+  __shared__ u32 s_pre[kScanBlock / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const u32 tile = blockIdx.x;
+  // sum of all tiles before this one
+  u32 pre = 0;
+  for (u32 q = tid; q < tile; q += kScanBlock) pre += tile_sum[q];
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) pre += __shfl_xor_sync(0xffffffffu, pre, d);
+  if (lane == 0) s_pre[warp] = pre;
+  const size_t i0 = (size_t)tile * kScanTile + (size_t)tid * kScanItems;
+  u32 v[kScanItems];
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) v[k] = 0;
+  if (i0 < n) {
+    ScanLoad<u32>::load16(in, i0, v);
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) if (i0 + k >= n) v[k] = 0;
+    ScanLoad<u32>::zero16(in, i0);
+  }
+  u32 t = 0;
+#pragma unroll
+  for (int k = 0; k < kScanItems; k++) { u32 x = v[k]; v[k] = t; t += x; }
+  u32 inc = t;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += y;
+  }
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  u32 wsum = lane < kScanBlock / 32 ? s_warp[lane] : 0;
+  u32 psum = lane < kScanBlock / 32 ? s_pre[lane] : 0;
+  u32 winc = wsum;
+#pragma unroll
+  for (int d = 1; d < kScanBlock / 32; d <<= 1) {
+    u32 y = __shfl_up_sync(0xffffffffu, winc, d);
+    if (lane >= d) winc += y;
+  }
+#pragma unroll
+  for (int d = 4; d > 0; d >>= 1) psum += __shfl_xor_sync(0xffffffffu, psum, d);
+  const u32 prefix = __shfl_sync(0xffffffffu, psum, 0);
+  const u32 warp_excl = __shfl_sync(0xffffffffu, winc - wsum, warp);
+  if (i0 < n) {
+    const u32 b = prefix + warp_excl + inc - t;
+    uint4 *o = reinterpret_cast<uint4 *>(out + i0);
+    o[0] = make_uint4(v[0] + b, v[1] + b, v[2] + b, v[3] + b);
+    o[1] = make_uint4(v[4] + b, v[5] + b, v[6] + b, v[7] + b);
+    o[2] = make_uint4(v[8] + b, v[9] + b, v[10] + b, v[11] + b);
+    o[3] = make_uint4(v[12] + b, v[13] + b, v[14] + b, v[15] + b);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // kernels: binning
 // ---------------------------------------------------------------------------------------
 template <typename R>
@@ -431,17 +518,15 @@ __device__ __forceinline__ int cell_coord(R p, R origin, R inv_cell, int n) {
 }
 
 // POS2: position is one packed 2-vector column; otherwise three scalar columns.
+// Key and arrival rank of the record at pool index `s`, stored at slot `o` of key/local.
 template <typename R, int DIM>
-__global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, u32 src_begin,
-                            u32 out_begin, GridParams g, u32 *key, u32 *local, u32 *cell_count,
-                            const u32 *ids) {
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const size_t s = (size_t)src_begin + i;
+__device__ __forceinline__ void bin_count_one(const void *px, const void *py, const void *pz, size_t s, size_t o,
+                                              const GridParams &g, u32 *key, u32 *local, u32 *cell_count,
+                                              const u32 *ids) {
   if (ids && ids[s] == ABL_SENTINEL_ID) {
     // padding record of a halo message: parked in the trash cell behind all real cells
-    key[out_begin + i] = g.n_local;
-    local[out_begin + i] = atomicAdd(&cell_count[g.n_local], 1u);
+    key[o] = g.n_local;
+    local[o] = atomicAdd(&cell_count[g.n_local], 1u);
     return;
   }
   R x, y, z = 0;
@@ -463,8 +548,17 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
     c += (u32)cz * (u32)g.n_cell[0] * (u32)g.n_cell[1];
   }
   c -= g.key_base;
-  key[out_begin + i] = c;
-  local[out_begin + i] = atomicAdd(&cell_count[c], 1u);
+  key[o] = c;
+  local[o] = atomicAdd(&cell_count[c], 1u);
+}
+
+template <typename R, int DIM>
+__global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 n, u32 src_begin,
+                            u32 out_begin, GridParams g, u32 *key, u32 *local, u32 *cell_count,
+                            const u32 *ids) {
+  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bin_count_one<R, DIM>(px, py, pz, (size_t)src_begin + i, (size_t)out_begin + i, g, key, local, cell_count, ids);
 }
 
 // seg_ids[slot] = id of the agent that arrived `local`-th in its cell segment
@@ -626,8 +720,10 @@ static int ensure_scan(abl_runtime *rt, size_t n) {
   if (rt->scan.max_tiles >= tiles) return ABL_OK;
   CU(cudaStreamSynchronize(rt->stream));
   if (rt->scan.desc) CU(cudaFree(rt->scan.desc));
+  if (rt->scan.tile_sum) CU(cudaFree(rt->scan.tile_sum));
   size_t cap = tiles * 2;
   CU(cudaMalloc(&rt->scan.desc, cap * sizeof(u64)));
+  CU(cudaMalloc(&rt->scan.tile_sum, cap * sizeof(u32)));
   CU(cudaMemsetAsync(rt->scan.desc, 0, cap * sizeof(u64), rt->stream));
   rt->scan.max_tiles = cap;
   return ABL_OK;
@@ -659,6 +755,19 @@ static int release_device(abl_runtime *rt, void *q) {
 static int collect_garbage(abl_runtime *rt) {
   for (void *q : rt->garbage) CU(cudaFree(q));
   rt->garbage.clear();
+  return ABL_OK;
+}
+
+// exclusive scan of the cell histogram into cell_start (and zeroing of the histogram)
+static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n) {
+  if (!rt->scan_two_pass) return run_scan<u32, 0, true>(rt, count, start, n, nullptr);
+  TRY(ensure_scan(rt, n));
+  const u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
+  u32 *tile_sum = rt->scan.tile_sum;
+  k_tile_sum<<<tiles, kScanBlock, 0, rt->stream>>>(count, (u32)n, tile_sum);
+  k_tile_scan<<<tiles, kScanBlock, 0, rt->stream>>>(count, start, (u32)n, tile_sum);
+  rt->launches += 2;
+  CU(cudaGetLastError());
   return ABL_OK;
 }
 
@@ -770,12 +879,14 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   CU(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
   CU(cudaMalloc(&rt->d_scalar, 4096));
   CU(cudaMemset(rt->d_scalar, 0, 4096));
-  CU(cudaMallocHost(&rt->h_scalar, 4096));
+  CU(cudaHostAlloc(&rt->h_scalar, 4096, cudaHostAllocMapped));
+  CU(cudaHostGetDevicePointer(&rt->h_scalar_dev, rt->h_scalar, 0));
   for (int i = 0; i < 4; i++) CU(cudaEventCreate(&rt->ev[i]));
   for (int i = 0; i < 2; i++) CU(cudaEventCreate(&rt->ev_ts[i]));
   CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
   if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
+  if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
   if (getenv("ABL_CUDA_TRACE")) {
     rt->trace = true;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&rt->xev[i]));
@@ -809,6 +920,7 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   for (auto &pr : rt->pinned_ranges) cudaHostUnregister(pr.first);
   rt->pinned_ranges.clear();
   if (rt->scan.desc) cudaFree(rt->scan.desc);
+  if (rt->scan.tile_sum) cudaFree(rt->scan.tile_sum);
   if (rt->scan.ctrl) cudaFree(rt->scan.ctrl);
   if (rt->stage) cudaFree(rt->stage);
   if (rt->pinned) cudaFreeHost(rt->pinned);
@@ -1189,7 +1301,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
-  TRY((run_scan<u32, 0, true>(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, nullptr)));
+  TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2));
   if (rt->slab) TRY(slab_request_owned_range(rt, p));
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
@@ -1722,10 +1834,13 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
 // learns them while the GPU is still busy and can enqueue the step kernel without a gap.
 __global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_cell, const u32 *halo_ctr,
                                    u32 *out) {
+  // `out` is page-locked host memory mapped into the device address space: the words reach the
+  // host without a copy-engine operation between two kernels of the stream
   if (threadIdx.x == 0) {
     out[0] = cell_start[lo_cell];
     out[1] = cell_start[hi_cell];
     for (int k = 0; k < 6; k++) out[2 + k] = halo_ctr ? halo_ctr[2 + k] : 0;  // in lo, in hi, timeout, far, sent lo, sent hi
+    __threadfence_system();
   }
 }
 
@@ -1733,9 +1848,8 @@ static int slab_request_owned_range(abl_runtime *rt, Pool &p) {
   const int row = slab_row_cells(rt);
   u32 lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base, hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
   k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, p.halo_pending ? p.halo_ctr : nullptr,
-                                               rt->d_scalar + 32);
+                                               rt->h_scalar_dev + 32);
   rt->launches++;
-  CU(cudaMemcpyAsync(&rt->h_scalar[32], rt->d_scalar + 32, 8 * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaEventRecord(rt->ev_own, rt->stream));
   return ABL_OK;
 }
@@ -2059,12 +2173,11 @@ static int grow_recv(abl_runtime *rt, int which, size_t bytes, size_t keep) {
 // a block is a 64-byte header {seq, count} followed by packed records.  The neighbours map the
 // area (CUDA IPC across processes, plain pointers inside one process) and the *step kernel
 // itself* appends the halo / migration records of exchange number `seq` to block
-// [direction][seq & 1] over NVLink (abl_slab_epilogue).  Three small kernels follow on the
-// same stream:
-//   k_halo_publish   (1 thread)  fence, then header {count, seq} into the neighbour's block
-//   k_halo_wait      (2 threads) spins until both own headers carry `seq` (bounded by a timeout)
-//   k_halo_unpack                appends the arrivals behind the owned range and pads with
-//                                sentinel records up to the host's estimate `pad`
+// [direction][seq & 1] over NVLink (abl_slab_epilogue).  One small kernel follows on the same
+// stream (k_halo_exchange): block 0 fences and writes the header {count, seq} into the
+// neighbours' blocks; every block spins until both own headers carry `seq` (bounded by a
+// time-out); then the arrivals are appended behind the owned range, padded with sentinel
+// records up to the host's estimate `pad`, and entered into the cell histogram.
 // No NCCL call and no host synchronisation is involved: the host never learns the counts of
 // the current exchange.  It bins `owned + pad` records (sentinels fall into a trash cell
 // behind all real cells) and reads the true counts together with the owned range one binning
@@ -2084,73 +2197,94 @@ static u8 *halo_block_of(u8 *area, size_t block_bytes, int from_dir, u32 seq) {
   return area + ((size_t)from_dir * 2 + (seq & 1u)) * block_bytes;
 }
 
-__global__ void k_halo_publish(u32 *ctr, HaloHeader *to_lo, HaloHeader *to_hi, u32 seq, u32 cap) {
-  if (threadIdx.x != 0) return;
-  const u32 c0 = ctr[0], c1 = ctr[1];
-  ctr[6] = c0;
-  ctr[7] = c1;
-  ctr[0] = 0;
-  ctr[1] = 0;
-  __threadfence_system();  // the records (written by the preceding kernel) before the header
-  if (to_lo) {
-    *(volatile u32 *)&to_lo->count = min(c0, cap);
-    __threadfence_system();
-    *(volatile u32 *)&to_lo->seq = seq;
-  }
-  if (to_hi) {
-    *(volatile u32 *)&to_hi->count = min(c1, cap);
-    __threadfence_system();
-    *(volatile u32 *)&to_hi->seq = seq;
-  }
-}
+// One kernel per exchange: block 0 publishes this rank's counts, every block waits for both
+// neighbours' headers, then all blocks unpack (grid-stride) and — when the step kernel has
+// already produced the histogram of the owned agents — add keys and arrival ranks of the
+// arrivals and of the padding, so that the next binning starts with the scan.
+// Arrivals go to pool slots [dst_first, dst_first + in_lo + in_hi); slots up to `pad` behind
+// them receive the sentinel id.  More arrivals than the host expected are still stored (bounded
+// by `room`); the next binning then notices and bins once more.
+struct HaloExchangeArgs {
+  u32 *ctr;
+  HaloHeader *to_lo, *to_hi;
+  const u8 *from_lo, *from_hi;
+  u32 seq, cap;
+  long long timeout_ns;
+  u32 dst_first, pad, room, rec_words;
+  // fused histogram of the arrivals (count != 0)
+  int count;
+  const void *px, *py, *pz;
+  u32 key_first;   // slot of the first arrival in key/local
+  u32 *key, *local, *cell_count;
+};
 
-__global__ void k_halo_wait(u32 *ctr, const HaloHeader *from_lo, const HaloHeader *from_hi, u32 seq,
-                            long long timeout_ns) {
-  const int dir = threadIdx.x;
-  if (dir > 1) return;
-  const HaloHeader *h = dir == 0 ? from_lo : from_hi;
-  u32 count = 0;
-  if (h) {
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    for (;;) {
-      if (*(const volatile u32 *)&h->seq == seq) {
-        __threadfence_system();
-        count = *(const volatile u32 *)&h->count;
-        break;
-      }
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if ((long long)(t1 - t0) > timeout_ns) { ctr[4] = 1; break; }
-      __nanosleep(200);
+template <typename R, int DIM>
+__global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeArgs a, GridParams g) {
+  __shared__ u32 s_in[2];
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const u32 c0 = a.ctr[0], c1 = a.ctr[1];
+    a.ctr[6] = c0;
+    a.ctr[7] = c1;
+    a.ctr[0] = 0;
+    a.ctr[1] = 0;
+    __threadfence_system();  // the records (written by the preceding kernel) before the header
+    if (a.to_lo) {
+      *(volatile u32 *)&a.to_lo->count = min(c0, a.cap);
+      __threadfence_system();
+      *(volatile u32 *)&a.to_lo->seq = a.seq;
+    }
+    if (a.to_hi) {
+      *(volatile u32 *)&a.to_hi->count = min(c1, a.cap);
+      __threadfence_system();
+      *(volatile u32 *)&a.to_hi->seq = a.seq;
     }
   }
-  ctr[2 + dir] = count;
-}
-
-// Arrivals go to pool slots [dst_first, dst_first + in_lo + in_hi); slots up to `pad` behind
-// them receive the sentinel id.  Grid-stride so that more arrivals than the host expected are
-// still stored (bounded by `room`); the next binning then notices and bins once more.
-__global__ void k_halo_unpack(ColTable t, const u8 *blk_lo, const u8 *blk_hi, const u32 *ctr,
-                              u32 dst_first, u32 pad, u32 room, u32 rec_words) {
-  const u32 in_lo = ctr[2], in_hi = ctr[3];
+  if (threadIdx.x < 2) {
+    const int dir = threadIdx.x;
+    const HaloHeader *h = (const HaloHeader *)(dir == 0 ? a.from_lo : a.from_hi);
+    u32 count = 0;
+    if (h) {
+      unsigned long long t0, t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      for (;;) {
+        if (*(const volatile u32 *)&h->seq == a.seq) {
+          __threadfence_system();
+          count = *(const volatile u32 *)&h->count;
+          break;
+        }
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if ((long long)(t1 - t0) > a.timeout_ns) { a.ctr[4] = 1; break; }
+        __nanosleep(100);
+      }
+    }
+    s_in[dir] = count;
+    if (blockIdx.x == 0) a.ctr[2 + dir] = count;
+  }
+  __syncthreads();
+  const u32 in_lo = s_in[0], in_hi = s_in[1];
   u32 total = in_lo + in_hi;
-  if (total < pad) total = pad;
-  if (total > room) total = room;
+  if (total < a.pad) total = a.pad;
+  if (total > a.room) total = a.room;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const size_t dst = (size_t)dst_first + i;
+    const size_t dst = (size_t)a.dst_first + i;
     if (i >= in_lo + in_hi) {
       ((u32 *)t.out[t.ncols - 1])[dst] = ABL_SENTINEL_ID;
-      continue;
+    } else {
+      const u32 *rec = i < in_lo ? (const u32 *)(a.from_lo + ABL_MSG_HEADER) + (size_t)i * a.rec_words
+                                 : (const u32 *)(a.from_hi + ABL_MSG_HEADER) + (size_t)(i - in_lo) * a.rec_words;
+      u32 w = 0;
+      for (int k = 0; k < t.ncols; k++) {
+        const int e = t.elem[k];
+        if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w++]; continue; }
+        u32 *q = (u32 *)t.out[k] + dst * (e / 4);
+        for (int j = 0; j < e / 4; j++) q[j] = rec[w++];
+      }
     }
-    const u32 *rec = i < in_lo ? (const u32 *)(blk_lo + ABL_MSG_HEADER) + (size_t)i * rec_words
-                               : (const u32 *)(blk_hi + ABL_MSG_HEADER) + (size_t)(i - in_lo) * rec_words;
-    u32 w = 0;
-    for (int k = 0; k < t.ncols; k++) {
-      const int e = t.elem[k];
-      if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w++]; continue; }
-      u32 *q = (u32 *)t.out[k] + dst * (e / 4);
-      for (int j = 0; j < e / 4; j++) q[j] = rec[w++];
-    }
+    // only the part the host will bin (`pad` records) enters the histogram; a surplus makes
+    // the next binning start over anyway
+    if (a.count && i < a.pad)
+      bin_count_one<R, DIM>(a.px, a.py, a.pz, dst, (size_t)a.key_first + i, g, a.key, a.local, a.cell_count,
+                            (const u32 *)t.out[t.ncols - 1]);
   }
 }
 
@@ -2248,17 +2382,43 @@ static int halo_finish(abl_runtime *rt, Pool &p) {
   HaloHeader *to_hi = p.halo_peer[1] ? (HaloHeader *)halo_block_of(p.halo_peer[1], p.halo_block, 0, seq) : nullptr;
   const u8 *from_lo = p.halo_peer[0] ? halo_block_of(p.halo_recv, p.halo_block, 0, seq) : nullptr;
   const u8 *from_hi = p.halo_peer[1] ? halo_block_of(p.halo_recv, p.halo_block, 1, seq) : nullptr;
-  k_halo_publish<<<1, 32, 0, rt->stream>>>(p.halo_ctr, to_lo, to_hi, seq, (u32)p.halo_cap);
-  k_halo_wait<<<1, 32, 0, rt->stream>>>(p.halo_ctr, (const HaloHeader *)from_lo, (const HaloHeader *)from_hi, seq,
-                                        rt->halo_timeout_ns);
   ColTable t;
   fill_table(p, t, false);
   const u32 pad = p.halo_pad;
   const u32 room = (u32)std::min<size_t>(p.cap - oe, 0x7fffffffu);
   p.halo_room = room;
-  k_halo_unpack<<<std::max(1u, blocks_for(pad, 256)), 256, 0, rt->stream>>>(t, from_lo, from_hi, p.halo_ctr, oe, pad,
-                                                                         room, (u32)slab_rec_words(p));
-  rt->launches += 3;
+  HaloExchangeArgs a;
+  memset(&a, 0, sizeof a);
+  a.ctr = p.halo_ctr;
+  a.to_lo = to_lo; a.to_hi = to_hi;
+  a.from_lo = from_lo; a.from_hi = from_hi;
+  a.seq = seq; a.cap = (u32)p.halo_cap;
+  a.timeout_ns = rt->halo_timeout_ns;
+  a.dst_first = oe; a.pad = pad; a.room = room; a.rec_words = (u32)slab_rec_words(p);
+  const GridParams &g = rt->grid;
+  // the step kernel already produced keys and the histogram of the owned agents (fused
+  // epilogue); arrivals and padding are added by the exchange kernel
+  a.count = p.counted ? 1 : 0;
+  if (a.count) {
+    const Member &pm = p.members[p.pos_member];
+    a.px = p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
+    if (g.dim == 3) {
+      a.py = p.cols[pm.first_col + 1].buf[p.cols[pm.first_col + 1].cur];
+      a.pz = p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
+    }
+    a.key_first = n_own;
+    a.key = p.key; a.local = p.local; a.cell_count = p.cell_count;
+  }
+  // few blocks: every block polls the headers, and several slabs may share one GPU (tests)
+  const u32 nb = std::max(1u, std::min(blocks_for(pad, 256), 32u));
+  if (rt->real_size == 8) {
+    if (g.dim == 2) k_halo_exchange<double, 2><<<nb, 256, 0, rt->stream>>>(t, a, g);
+    else k_halo_exchange<double, 3><<<nb, 256, 0, rt->stream>>>(t, a, g);
+  } else {
+    if (g.dim == 2) k_halo_exchange<float, 2><<<nb, 256, 0, rt->stream>>>(t, a, g);
+    else k_halo_exchange<float, 3><<<nb, 256, 0, rt->stream>>>(t, a, g);
+  }
+  rt->launches++;
   CU(cudaGetLastError());
   p.halo_prev_ob = ob;
   p.halo_prev_own = n_own;
@@ -2266,9 +2426,6 @@ static int halo_finish(abl_runtime *rt, Pool &p) {
   p.src_begin = ob;
   p.n = (size_t)n_own + pad;
   p.binned = false;
-  // the step kernel already produced keys and the histogram of the owned agents (fused
-  // epilogue); arrivals and padding are still missing
-  if (p.counted && pad) TRY(launch_bin_count(rt, p, pad, oe, n_own));
   return ABL_OK;
 }
 
@@ -2308,7 +2465,8 @@ extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_re
   // That must not happen between k_halo_wait and the neighbours' publish when several slabs
   // are driven by one host thread (it would wait for a spinning kernel): load them now.
   {
-    const void *kernels[] = {(const void *)k_halo_publish, (const void *)k_halo_wait, (const void *)k_halo_unpack,
+    const void *kernels[] = {(const void *)k_halo_exchange<double, 2>, (const void *)k_halo_exchange<double, 3>,
+                             (const void *)k_halo_exchange<float, 2>, (const void *)k_halo_exchange<float, 3>,
                              (const void *)k_halo_pack<double>, (const void *)k_halo_pack<float>,
                              (const void *)k_bin_count<double, 2>, (const void *)k_bin_count<double, 3>,
                              (const void *)k_bin_count<float, 2>, (const void *)k_bin_count<float, 3>,

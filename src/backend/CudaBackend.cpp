@@ -94,6 +94,23 @@ private:
   const FuncDecl *curFn = nullptr;
   const StepInfo *curStep = nullptr;
   bool curStepHasLimit = false;
+  bool curStepTile = false;     // the step's for-near loop can run from a shared-memory tile
+  // one neighbour column staged in shared memory by a tiled kernel
+  struct TileCol {
+    int member;          // member of the neighbour agent
+    int comp;            // component of a float3 member (its columns are scalar), else 0
+    int column;          // SoA column index in the pool
+    std::string ctype;   // element type in shared memory
+    std::string bytes;   // sizeof expression of one element
+  };
+  std::vector<TileCol> tileColumns(const FuncDecl &f, const AgentDecl &nbr) const;
+  // byte offset (per tile entry) of staged column q; and of the whole entry for q == size
+  static std::string tileOffset(const std::vector<TileCol> &cols, size_t q) {
+    std::string r = "(0";
+    for (size_t i = 0; i < q && i < cols.size(); i++) r += " + " + cols[i].bytes;
+    return r + ")";
+  }
+  const Stmt *findNearStmt(const std::vector<StmtP> &body) const;
   // inside a for-near body: dist(in.pos, nx.pos) / length(in.pos - nx.pos) reuse the squared
   // distance of the radius filter ((a-b)^2 == (b-a)^2 bit for bit)
   const Symbol *nearVar = nullptr, *nearSelf = nullptr;
@@ -616,6 +633,112 @@ void CudaPrinter::nearLoop(const Stmt &s) {
 
   w << "{";
   w.indent(); w.nl();
+  const bool tile = curStepTile;
+  if (tile) {
+    // ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
+    // (abl_device.cuh: abl_tile_plan); same visiting order as abl_near_iter
+    std::vector<TileCol> cols = tileColumns(*curFn, *nbr);
+    const std::string rows = dim == 2 ? "3" : "9";
+    std::string done = "_near_done" + it + "t";
+    w << "if (ABL_MODE == 2 && _tile_ok) {";
+    w.indent(); w.nl();
+    w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
+    w << "const uint2 *" << it << "seg = reinterpret_cast<const uint2 *>(_abl_smem + ABL_TILE_HDR_BYTES) + threadIdx.x;"; w.nl();
+    w << "const unsigned char *const " << it << "cols = _abl_smem + ABL_TILE_HDR_BYTES + " << rows << " * blockDim.x * sizeof(uint2);"; w.nl();
+    // Two phases per row and chunk of up to 32 candidates: phase 1 only evaluates the radius
+    // filter and collects one acceptance bit per candidate in a register; phase 2 runs the
+    // loop body for the set bits, in candidate order.  A warp then pays for the body
+    // max-popcount times per chunk instead of once per candidate (in the single-phase loop
+    // nearly every iteration has some lane that accepts).
+    w << "for (int " << it << "k = 0; " << it << "k < " << rows << "; " << it << "k++) {";
+    w.indent(); w.nl();
+    w << "const uint2 " << it << "sg = " << it << "seg[" << it << "k * blockDim.x];"; w.nl();
+    w << "for (unsigned " << it << "b = " << it << "sg.x, " << it << "e = " << it << "sg.x + " << it << "sg.y; "
+      << it << "b < " << it << "e; " << it << "b += 32) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "n = min(32u, " << it << "e - " << it << "b);"; w.nl();
+    w << "unsigned " << it << "m = 0;"; w.nl();
+    std::string posSrc = "reinterpret_cast<const " + cols[0].ctype + " *>(" + it + "cols)";
+    auto tilePos = [&](const std::string &dst, const std::string &idx) {
+      // position columns come first in the tile (offsets 0, 1, 2 scalar columns for float3)
+      if (dim == 2) {
+        w << dst << " = reinterpret_cast<const abl_float2 *>(" << it << "cols)[" << idx << "];";
+      } else {
+        for (int c = 0; c < 3; c++) {
+          if (c) w.nl();
+          w << dst << "." << "xyz"[c] << " = reinterpret_cast<const abl_real *>(" << it << "cols + (size_t)_tile_cap * "
+            << tileOffset(cols, (size_t)c) << ")[" << idx << "];";
+        }
+      }
+    };
+    (void)posSrc;
+    std::string ptypeT = typeName(pos->type);
+    w << "for (unsigned " << it << "c = 0; " << it << "c < " << it << "n; " << it << "c++) {";
+    w.indent(); w.nl();
+    w << ptypeT << " " << it << "q;"; w.nl();
+    tilePos(it + "q", it + "b + " + it + "c");
+    w.nl();
+    if (curStepHasLimit) {
+      w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
+        << ")) > _near_limit)) " << it << "m |= 1u << " << it << "c;";
+    } else {
+      w << "if (!(dist_float" << sdim << "(" << it << "q, " << selfPosText << ") > ";
+      expr(radius);
+      w << ")) " << it << "m |= 1u << " << it << "c;";
+    }
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "while (" << it << "m) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "s = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
+    w << it << "m &= " << it << "m - 1;"; w.nl();
+    w << nbr->name << " " << s.varName << ";";
+    auto tileLoad = [&](int member) {
+      const Ty &mt = nbr->members[member]->type;
+      std::string dst = s.varName + "." + nbr->members[member]->name;
+      for (size_t q = 0; q < cols.size(); q++) {
+        if (cols[q].member != member) continue;
+        w.nl();
+        std::string src = "reinterpret_cast<const " + cols[q].ctype + " *>(" + it + "cols + (size_t)_tile_cap * " +
+                          tileOffset(cols, q) + ")[" + it + "s]";
+        if (mt.k == TK::Vec3) w << dst << "." << "xyz"[cols[q].comp] << " = " << src << ";";
+        else if (mt.k == TK::Bool) w << dst << " = " << src << " != 0;";
+        else w << dst << " = " << src << ";";
+      }
+    };
+    tileLoad(posIndex);
+    if (curStepHasLimit) {
+      w.nl();
+      w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+        << pos->name << ", " << selfPosText << "));";
+    }
+    for (size_t m = 0; m < nbr->members.size(); m++) {
+      if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
+      tileLoad((int)m);
+    }
+    w.nl();
+    {
+      std::string savedLabel = nearBreakLabel;
+      int savedDepth = innerLoopDepth;
+      nearBreakLabel = done;
+      innerLoopDepth = 0;
+      if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+      stmt(*s.body[0]);
+      clearNearContext();
+      nearBreakLabel = savedLabel;
+      innerLoopDepth = savedDepth;
+    }
+    w.outdent(); w.nl();
+    w << "}";
+    w.outdent(); w.nl();
+    w << "}";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << done << ": ;";
+    w.outdent(); w.nl();
+    w << "} else {";
+    w.indent(); w.nl();
+  }
   w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
   w << it << ".init" << sdim << "(_a, " << selfPosText << ", true);";
@@ -625,7 +748,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   // is a host-evaluable constant the launcher precomputes the equivalent bound on the
   // squared distance (abl_near_sq_limit) and the kernel skips the square root.
   if (curStepHasLimit) {
-    // Dense populations (ABL_CHUNKED, chosen by the launcher from the mean cell occupancy):
+    // Dense populations (ABL_MODE 1, chosen by the launcher from the mean cell occupancy):
     // two phases per chunk of up to 32 candidates.  Phase 1 only evaluates the filter and
     // records a bit per accepted candidate; phase 2 runs the loop body for the set bits, in
     // order.  In a warp the expensive body then executes max-popcount times per chunk instead
@@ -633,7 +756,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     // accepts, so the whole warp pays for the body every time).
     std::string done = "_near_done" + it;
     std::string ptype = typeName(pos->type);
-    w << "if (ABL_CHUNKED) {";
+    w << "if (ABL_MODE == 1) {";
     w.indent(); w.nl();
     w << "// phase 1 writes one acceptance bit per candidate into shared memory (32 candidates"; w.nl();
     w << "// per word, ABL_MASK_WORDS words per thread and round); phase 2 replays the same"; w.nl();
@@ -785,8 +908,43 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   w.outdent(); w.nl();
   w << "}";
   if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
+  if (tile) { w.outdent(); w.nl(); w << "}"; }
   w.outdent(); w.nl();
   w << "}";
+}
+
+std::vector<CudaPrinter::TileCol> CudaPrinter::tileColumns(const FuncDecl &f, const AgentDecl &nbr) const {
+  std::vector<TileCol> cols;
+  AgentMember *pos = nbr.position();
+  auto add = [&](int m) {
+    const Ty &t = nbr.members[m]->type;
+    int c = columnOf(nbr, m);
+    switch (t.k) {
+      case TK::Vec2: cols.push_back({m, 0, c, "abl_float2", "sizeof(abl_float2)"}); break;
+      case TK::Vec3:
+        for (int k = 0; k < 3; k++) cols.push_back({m, k, c + k, "abl_real", "sizeof(abl_real)"});
+        break;
+      case TK::Float: cols.push_back({m, 0, c, "abl_real", "sizeof(abl_real)"}); break;
+      case TK::Int: cols.push_back({m, 0, c, "int", "sizeof(int)"}); break;
+      case TK::Bool: cols.push_back({m, 0, c, "unsigned char", "1"}); break;
+      default: throw BackendError("cuda backend: member type " + t.str() + " cannot be staged");
+    }
+  };
+  int posIndex = nbr.memberIndex(pos->name);
+  add(posIndex);
+  for (size_t m = 0; m < nbr.members.size(); m++) {
+    if ((int)m == posIndex || !f.nearMembers.count(nbr.members[m]->name)) continue;
+    add((int)m);
+  }
+  return cols;
+}
+
+const Stmt *CudaPrinter::findNearStmt(const std::vector<StmtP> &body) const {
+  for (const StmtP &s : body) {
+    if (s->kind == Stmt::For && s->forKind == Stmt::ForNear) return s.get();
+    if (const Stmt *r = findNearStmt(s->body)) return r;
+  }
+  return nullptr;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1177,35 +1335,94 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStep = &si;
   const Expr *radius = f.nearAgent ? findNearRadius(f.body) : nullptr;
   curStepHasLimit = radius && hostEvaluable(*radius);
+  // Shared-memory tiling needs the loop to range over the neighbourhood of the stepped agent
+  // itself (`near(in, r)`): the kernel prologue plans the tile from in.pos of every thread.
+  const Stmt *nearStmt = f.nearAgent ? findNearStmt(f.body) : nullptr;
+  AgentMember *selfPosM = self.position();
+  curStepTile = false;
+  std::vector<TileCol> tcols;
+  int tdim = 0;
+  if (nearStmt && selfPosM && nearStmt->declTy.agent && nearStmt->declTy.agent->position()) {
+    const Expr &ae = *nearStmt->e[0]->kids[0];
+    curStepTile = ae.kind == Expr::Var && ae.sym && ae.sym == p.sym;
+    if (curStepTile) {
+      tcols = tileColumns(f, *nearStmt->declTy.agent);
+      tdim = nearStmt->declTy.agent->position()->type.vecLen();
+    }
+  }
+  const std::string trows = tdim == 2 ? "3" : "9";
 
   // the user's step function
-  w << "template <bool ABL_CHUNKED>"; w.nl();
-  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const "
+  w << "template <int ABL_MODE>"; w.nl();
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const unsigned _tile_cap, const bool _tile_ok, const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
   w.nl();
   w << "}"; w.nl(); w.nl();
 
-  w << "template <bool ABL_CHUNKED>"; w.nl();
+  w << "template <int ABL_MODE>"; w.nl();
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
-    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit) {";
+    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const unsigned _tile_cap) {";
   w.indent(); w.nl();
   w << "const unsigned _i = blockIdx.x * blockDim.x + threadIdx.x;"; w.nl();
-  w << "if (_i >= _a.self.n) return;"; w.nl();
-  w << self.name << " " << p.name << ";";
   std::set<std::string> loads = si.reads;
   for (const std::string &m : si.writes) loads.insert(m);
+  // the slab epilogue routes by the agent's position: always have it in registers
+  if (selfPosM) loads.insert(selfPosM->name);
+  if (curStepTile) {
+    // tiled kernels keep surplus threads of the last block alive for the cooperative staging
+    w << "const bool _active = _i < _a.self.n;"; w.nl();
+    w << "if (ABL_MODE != 2 && !_active) return;"; w.nl();
+    w << self.name << " " << p.name << " = {};"; w.nl();
+    w << "if (_active) {";
+    w.indent();
+  } else {
+    w << "if (_i >= _a.self.n) return;"; w.nl();
+    w << self.name << " " << p.name << ";";
+  }
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!loads.count(self.members[m]->name)) continue;
     w.nl();
     loadMember(self, (int)m, p.name + "." + self.members[m]->name, "_a.self.in", "_i");
   }
   w.nl();
+  if (curStepTile) {
+    w.outdent(); w << "}"; w.nl();
+    w << "bool _tile_ok = false;"; w.nl();
+    w << "if (ABL_MODE == 2) {";
+    w.indent(); w.nl();
+    w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
+    w << "abl_near_iter<" << tdim << "> _rows;"; w.nl();
+    w << "_rows.rows" << tdim << "(_a, " << p.name << "." << selfPosM->name << ", _active);"; w.nl();
+    w << "_tile_ok = abl_tile_plan<" << tdim << ">(_rows, _tile_cap, _abl_smem);"; w.nl();
+    w << "if (_tile_ok) {";
+    w.indent(); w.nl();
+    w << "unsigned char *const _cols = _abl_smem + ABL_TILE_HDR_BYTES + " << trows << " * blockDim.x * sizeof(uint2);"; w.nl();
+    w << "const unsigned _total = reinterpret_cast<const abl_tile_hdr *>(_abl_smem)->total;"; w.nl();
+    w << "for (unsigned _e = threadIdx.x; _e < _total; _e += blockDim.x) {";
+    w.indent(); w.nl();
+    w << "const unsigned _g = abl_tile_src<" << tdim << ">(_abl_smem, _e);";
+    for (size_t q = 0; q < tcols.size(); q++) {
+      w.nl();
+      w << "reinterpret_cast<" << tcols[q].ctype << " *>(_cols + (size_t)_tile_cap * " << tileOffset(tcols, q) << ")[_e] = "
+        << "abl_ld<" << tcols[q].ctype << ">(_a.nbr.in[" << tcols[q].column << "], _g);";
+    }
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "__syncthreads();";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "if (!_active) return;";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+  } else {
+    w << "const bool _tile_ok = false;"; w.nl();
+  }
   w << self.name << " " << p.outName << " = " << p.name << ";"; w.nl();
   w << "abl_ctx _ctx;"; w.nl();
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
-  w << f.emitName << "<ABL_CHUNKED>(_ctx, _a, _i, _near_limit, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, _tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!si.writes.count(self.members[m]->name)) continue;
@@ -1219,7 +1436,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   }
   // slab decomposition: route this agent's record to the neighbouring slabs (no-op otherwise)
   w.nl();
-  w << "abl_slab_epilogue(_a, _i);";
+  if (selfPos) w << "abl_slab_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ");";
   if (f.usesRemoval) { w.nl(); w << "_a.dead[_i] = _ctx.dead ? 1 : 0;"; }
   if (f.addedAgent) { w.nl(); w << "_a.add_flag[_i] = _ctx.added ? 1 : 0;"; }
   w.outdent(); w.nl();
@@ -1242,12 +1459,28 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   if (curStepHasLimit) {
     // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
     w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();
-    w << "    static bool smem_set = false;"; w.nl();
-    w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
-    w << "    if (chunked) abl_kernel_" << f.emitName << "<true><<<grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
-    w << "    else abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
   } else {
-    w << "    abl_kernel_" << f.emitName << "<false><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit);"; w.nl();
+    w << "    const bool chunked = false;"; w.nl();
+  }
+  if (curStepTile) {
+    // sparse neighbourhoods: stage the block's candidate rows in shared memory (ABL_MODE 2)
+    w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
+    w << "    const unsigned tile_cap = (a->tile_neighbours && !chunked && bs % 32 == 0) ? abl_tile_capacity(a, " << trows << ", bs, tile_entry, 64u * 1024u) : 0u;"; w.nl();
+    w << "    if (tile_cap) {"; w.nl();
+    w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
+    w << "        static bool tile_set = false;"; w.nl();
+    w << "        if (!tile_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
+    w << "        abl_kernel_" << f.emitName << "<2><<<grid, bs, smem, (cudaStream_t)a->stream>>>(*a, limit, tile_cap);"; w.nl();
+    w << "        return (int)cudaGetLastError();"; w.nl();
+    w << "    }"; w.nl();
+  }
+  if (curStepHasLimit) {
+    w << "    static bool smem_set = false;"; w.nl();
+    w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
+    w << "    if (chunked) abl_kernel_" << f.emitName << "<1><<<grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
+    w << "    else abl_kernel_" << f.emitName << "<0><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
+  } else {
+    w << "    abl_kernel_" << f.emitName << "<0><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
   }
   w << "    return (int)cudaGetLastError();"; w.nl();
   w << "}"; w.nl(); w.nl();
@@ -1255,6 +1488,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curFn = nullptr;
   curStep = nullptr;
   curStepHasLimit = false;
+  curStepTile = false;
 }
 
 std::string CudaPrinter::kernelSource() {
