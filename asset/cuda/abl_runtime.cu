@@ -859,7 +859,7 @@ extern "C" void abl_cuda_default_config(abl_config *cfg) {
   cfg->seed = 0x0123456789abcdefull;
   cfg->deterministic = 1;
   cfg->tile_neighbours = 1;
-  cfg->block_size = 128;
+  cfg->block_size = 0;
 }
 
 extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
@@ -873,7 +873,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (c.device >= 0) CU(cudaSetDevice(c.device));
   abl_runtime *rt = new abl_runtime;
   rt->cfg = c;
-  if (rt->cfg.block_size <= 0) rt->cfg.block_size = 128;
+  if (rt->cfg.block_size < 0) rt->cfg.block_size = 0;
   CU(cudaGetDevice(&rt->device));
   rt->real_size = c.use_float ? 4 : 8;
   CU(cudaStreamCreateWithFlags(&rt->stream, cudaStreamNonBlocking));
@@ -2409,8 +2409,11 @@ static int halo_finish(abl_runtime *rt, Pool &p) {
     a.key_first = n_own;
     a.key = p.key; a.local = p.local; a.cell_count = p.cell_count;
   }
-  // few blocks: every block polls the headers, and several slabs may share one GPU (tests)
-  const u32 nb = std::max(1u, std::min(blocks_for(pad, 256), 32u));
+  // Every block polls the headers before it unpacks.  When several slabs share one GPU (local
+  // peers, single host thread) the spinning blocks of one slab must leave room for the kernels
+  // of the others, so the grid stays small there; across GPUs it covers the device.
+  const bool local_peers = (p.halo_peer[0] && !p.halo_ipc[0]) || (p.halo_peer[1] && !p.halo_ipc[1]);
+  const u32 nb = std::max(1u, std::min(blocks_for(pad, 256), local_peers ? 32u : 4u * 148u));
   if (rt->real_size == 8) {
     if (g.dim == 2) k_halo_exchange<double, 2><<<nb, 256, 0, rt->stream>>>(t, a, g);
     else k_halo_exchange<double, 3><<<nb, 256, 0, rt->stream>>>(t, a, g);

@@ -185,7 +185,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--block-size", type=int, default=128)
+    ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
     ap.add_argument("--no-tile", action="store_true")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
     ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],

@@ -76,7 +76,7 @@ typedef struct {
   uint64_t seed;         /* seed of the in-step counter-based RNG */
   int deterministic;     /* reserved, must be 1: neighbour order = (cell, agent id) */
   int tile_neighbours;   /* 1: step kernels stage neighbour cell ranges in shared memory */
-  int block_size;        /* threads per CTA for step kernels (0 = default 128) */
+  int block_size;        /* threads per CTA for step kernels (0 = automatic: 128, or 256 for dense neighbourhoods) */
 } abl_config;
 
 /* ---- life cycle -------------------------------------------------------------------- */

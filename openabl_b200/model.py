@@ -31,6 +31,8 @@ class Model:
         if use_float:
             cfg["use_float"] = True
         self.dir = _build.build_model(abl_path, self.params, cfg)
+        # A/B experiments: load a hand-modified build of the same model instead
+        self.dir = os.environ.get("ABL_MODEL_DIR", self.dir)
         load_library()
         lib_path = os.path.join(self.dir, "libmodel.so")
         if not os.path.exists(lib_path):

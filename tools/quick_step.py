@@ -12,7 +12,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("workload")
 ap.add_argument("--no-tile", action="store_true")
 ap.add_argument("--steps", type=int, default=100)
-ap.add_argument("--bs", type=int, default=128)
+ap.add_argument("--bs", type=int, default=0)
 args = ap.parse_args()
 model_file, params, use_float, S, M, P = bench.WORKLOADS[args.workload]
 m = Model(os.path.join(REPO, "examples", model_file), dict(params), use_float=use_float)
