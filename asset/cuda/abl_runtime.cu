@@ -206,6 +206,7 @@ struct abl_runtime {
   // cudaFree synchronises the whole device; with the direct transport a neighbour driven by the
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
+  bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
@@ -214,6 +215,26 @@ struct abl_runtime {
   abl_step_timing last = {0, 0, 0, 0};
   unsigned launches = 0;
 };
+
+// Programmatic dependent launch: the kernel may be set up on the SMs while its predecessor in
+// the stream is still draining; it calls cudaGridDependencySynchronize() before it touches
+// memory.  Hides the launch latency between the short kernels of the binning chain.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 static const int kScanBlock = 256;
 static const int kScanItems = 16;                      // per thread
@@ -433,6 +454,7 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
 // the histogram for the next binning.
 __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u32 *tile_sum) {
   __shared__ u32 s_warp[kScanBlock / 32];
+  cudaGridDependencySynchronize();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)tid * kScanItems;
   u32 t = 0;
@@ -457,6 +479,7 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u
 __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32 n, const u32 *tile_sum) {
   __shared__ u32 s_warp[kScanBlock / 32];
   __shared__ u32 s_pre[kScanBlock / 32];
+  cudaGridDependencySynchronize();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 tile = blockIdx.x;
   // sum of all tiles before this one
@@ -564,6 +587,7 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
 // seg_ids[slot] = id of the agent that arrived `local`-th in its cell segment
 __global__ void k_bin_scatter(const u32 *key, const u32 *local, const u32 *ids, u32 n, u32 src_begin,
                               const u32 *cell_start, u32 *seg_ids) {
+  cudaGridDependencySynchronize();
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
   u32 slot = cell_start[key[t]] + local[t];
@@ -586,6 +610,7 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
 // close to the reads (near-coalesced).
 __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *local,
                                 const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start) {
+  cudaGridDependencySynchronize();
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u32 src = src_begin + i;
@@ -764,8 +789,8 @@ static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n) {
   TRY(ensure_scan(rt, n));
   const u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
   u32 *tile_sum = rt->scan.tile_sum;
-  k_tile_sum<<<tiles, kScanBlock, 0, rt->stream>>>(count, (u32)n, tile_sum);
-  k_tile_scan<<<tiles, kScanBlock, 0, rt->stream>>>(count, start, (u32)n, tile_sum);
+  CU(launch_pdl(rt->pdl, k_tile_sum, dim3(tiles), dim3(kScanBlock), 0, rt->stream, (const u32 *)count, (u32)n, tile_sum));
+  CU(launch_pdl(rt->pdl, k_tile_scan, dim3(tiles), dim3(kScanBlock), 0, rt->stream, count, start, (u32)n, (const u32 *)tile_sum));
   rt->launches += 2;
   CU(cudaGetLastError());
   return ABL_OK;
@@ -858,7 +883,7 @@ extern "C" void abl_cuda_default_config(abl_config *cfg) {
   cfg->use_float = 0;
   cfg->seed = 0x0123456789abcdefull;
   cfg->deterministic = 1;
-  cfg->tile_neighbours = 1;
+  cfg->tile_neighbours = 0;
   cfg->block_size = 0;
 }
 
@@ -886,6 +911,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
   if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
+  if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
   if (getenv("ABL_CUDA_TRACE")) {
     rt->trace = true;
@@ -1308,10 +1334,12 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
     u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
-    k_bin_scatter<<<nb, bs, 0, rt->stream>>>(p.key, p.local, ids, n, p.src_begin, p.cell_start, seg_ids);
+    CU(launch_pdl(rt->pdl, k_bin_scatter, dim3(nb), dim3(bs), 0, rt->stream, (const u32 *)p.key, (const u32 *)p.local, ids, n,
+                  p.src_begin, (const u32 *)p.cell_start, seg_ids));
     ColTable t;
     fill_table(p, t, true);
-    k_bin_rank_move<<<nb, bs, 0, rt->stream>>>(t, seg_ids, p.key, p.local, ids, n, p.src_begin, p.cell_start);
+    CU(launch_pdl(rt->pdl, k_bin_rank_move, dim3(nb), dim3(bs), 0, rt->stream, t, (const u32 *)seg_ids, (const u32 *)p.key,
+                  (const u32 *)p.local, ids, n, p.src_begin, (const u32 *)p.cell_start));
     rt->launches += 2;
     CU(cudaGetLastError());
     flip_all(p);
@@ -1581,6 +1609,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.step_index = (unsigned)step;
     a.block_size = rt->cfg.block_size;
     a.tile_neighbours = rt->cfg.tile_neighbours;
+    a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
     int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches++;

@@ -186,7 +186,7 @@ def main():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
-    ap.add_argument("--no-tile", action="store_true")
+    ap.add_argument("--tile", action="store_true", help="stage neighbour rows in shared memory (ABL_MODE 2 kernels)")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
     ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
                     help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
@@ -225,9 +225,9 @@ def main():
     slab = None
     if world > 1:
         slab = RankSlab(m, rank, world, dist, device=local_rank, transport=args.transport,
-                        block_size=args.block_size, tile=not args.no_tile)
+                        block_size=args.block_size, tile=args.tile)
     else:
-        m.create_runtime(device=local_rank, block_size=args.block_size, tile=not args.no_tile)
+        m.create_runtime(device=local_rank, block_size=args.block_size, tile=args.tile)
     rt = m.rt
     stream = torch.cuda.ExternalStream(rt.stream(), device=torch.device("cuda", local_rank))
 

@@ -75,7 +75,8 @@ typedef struct {
   int use_float;         /* 1: abl_float is float (reference -DLIBABL_USE_FLOAT=1), 0: double */
   uint64_t seed;         /* seed of the in-step counter-based RNG */
   int deterministic;     /* reserved, must be 1: neighbour order = (cell, agent id) */
-  int tile_neighbours;   /* 1: step kernels stage neighbour cell ranges in shared memory */
+  int tile_neighbours;   /* 1: step kernels stage neighbour cell ranges in shared memory (default 0: measured
+                            neutral to slightly slower than the L1-cached global loop on B200) */
   int block_size;        /* threads per CTA for step kernels (0 = automatic: 128, or 256 for dense neighbourhoods) */
 } abl_config;
 
@@ -182,6 +183,7 @@ typedef struct {
   unsigned step_index;
   int block_size;
   int tile_neighbours;
+  int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
 } abl_step_launch;
 

@@ -111,7 +111,7 @@ def check(rc, what=""):
 class Runtime:
     """One device runtime (one GPU)."""
 
-    def __init__(self, use_float=False, device=-1, block_size=0, tile=True, seed=None):
+    def __init__(self, use_float=False, device=-1, block_size=0, tile=False, seed=None):
         self.lib = load_library()
         cfg = Config()
         self.lib.abl_cuda_default_config(C.byref(cfg))

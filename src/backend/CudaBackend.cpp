@@ -1269,7 +1269,7 @@ void CudaPrinter::hostSimulate() {
   w << "    abl_cuda_default_config(&cfg);"; w.nl();
   w << "    cfg.use_float = abl_model_use_float;"; w.nl();
   w << "    cfg.block_size = " << config.getInt("cuda.block_size", 0) << ";"; w.nl();
-  w << "    cfg.tile_neighbours = " << (config.getBool("cuda.tile", true) ? 1 : 0) << ";"; w.nl();
+  w << "    cfg.tile_neighbours = " << (config.getBool("cuda.tile", false) ? 1 : 0) << ";"; w.nl();
   w << "    if (getenv(\"ABL_CUDA_DEVICE\")) cfg.device = atoi(getenv(\"ABL_CUDA_DEVICE\"));"; w.nl();
   w << "    abl_runtime *rt = NULL;"; w.nl();
   w << "    abl_host_check(abl_cuda_create(&rt, &cfg), \"create\");"; w.nl();
@@ -1364,6 +1364,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const unsigned _tile_cap) {";
   w.indent(); w.nl();
+  w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
   w << "const unsigned _i = blockIdx.x * blockDim.x + threadIdx.x;"; w.nl();
   std::set<std::string> loads = si.reads;
   for (const std::string &m : si.writes) loads.insert(m);
@@ -1473,19 +1474,17 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
     w << "        static bool tile_set = false;"; w.nl();
     w << "        if (!tile_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
-    w << "        abl_kernel_" << f.emitName << "<2><<<grid, bs, smem, (cudaStream_t)a->stream>>>(*a, limit, tile_cap);"; w.nl();
-    w << "        return (int)cudaGetLastError();"; w.nl();
+    w << "        return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<2>, grid, bs, smem, *a, limit, tile_cap);"; w.nl();
     w << "    }"; w.nl();
   }
   if (curStepHasLimit) {
     w << "    static bool smem_set = false;"; w.nl();
     w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
-    w << "    if (chunked) abl_kernel_" << f.emitName << "<1><<<grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
-    w << "    else abl_kernel_" << f.emitName << "<0><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
+    w << "    if (chunked) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, limit, 0u);"; w.nl();
+    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, limit, 0u);"; w.nl();
   } else {
-    w << "    abl_kernel_" << f.emitName << "<0><<<grid, bs, 0, (cudaStream_t)a->stream>>>(*a, limit, 0u);"; w.nl();
+    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, limit, 0u);"; w.nl();
   }
-  w << "    return (int)cudaGetLastError();"; w.nl();
   w << "}"; w.nl(); w.nl();
   (void)index;
   curFn = nullptr;

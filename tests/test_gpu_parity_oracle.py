@@ -29,11 +29,11 @@ CASES = [
 ]
 
 
-def gpu_run(model_file, params, use_float, steps):
+def gpu_run(model_file, params, use_float, steps, **rt_kw):
     m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
     m.populate()
     init = m.host_agents(0)
-    m.create_runtime()
+    m.create_runtime(**rt_kw)
     m.upload_host()
     for _ in range(steps):
         m.timestep()
@@ -43,10 +43,13 @@ def gpu_run(model_file, params, use_float, steps):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("tile", [False, True], ids=["global", "smem-tile"])
 @pytest.mark.parametrize("model_file,params,use_float,steps", CASES,
                          ids=["%s-%d-%s" % (c[0][:-4], c[1]["num_agents"], "f32" if c[2] else "f64") for c in CASES])
-def test_gpu_equals_grid_oracle(model_file, params, use_float, steps):
-    init, got = gpu_run(model_file, params, use_float, steps)
+def test_gpu_equals_grid_oracle(model_file, params, use_float, steps, tile):
+    """Both neighbour-loop variants: the L1-cached global-memory loop (default) and the
+    shared-memory tile path (cuda.tile=true)."""
+    init, got = gpu_run(model_file, params, use_float, steps, tile=tile)
     o = Oracle(use_float)
     state = o.init_for(model_file, params)
     # the generated host program and the oracle build the same initial population

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Quick device-side timing of one workload: ms per timestep and per-stage times.
-usage: quick_step.py WORKLOAD [--no-tile] [--steps K] [--bs B]"""
+usage: quick_step.py WORKLOAD [--tile] [--steps K] [--bs B]"""
 import argparse, os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -10,14 +10,14 @@ from openabl_b200.model import Model  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("workload")
-ap.add_argument("--no-tile", action="store_true")
+ap.add_argument("--tile", action="store_true")
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--bs", type=int, default=0)
 args = ap.parse_args()
 model_file, params, use_float, S, M, P = bench.WORKLOADS[args.workload]
 m = Model(os.path.join(REPO, "examples", model_file), dict(params), use_float=use_float)
 m.populate()
-m.create_runtime(device=0, block_size=args.bs, tile=not args.no_tile)
+m.create_runtime(device=0, block_size=args.bs, tile=args.tile)
 m.upload_host()
 stream = torch.cuda.ExternalStream(m.rt.stream())
 for _ in range(10):
@@ -40,4 +40,4 @@ for _ in range(20):
             st[k] += lt[k] / 20
 n = sum(m.host_count(t) for t in range(m.n_types))
 print("%s tile=%s bs=%d: %.4f ms/step, %.2f G agent-steps/s; stages %s" % (
-    args.workload, not args.no_tile, args.bs, ms, n / ms / 1e6, {k: round(v, 4) for k, v in st.items()}))
+    args.workload, args.tile, args.bs, ms, n / ms / 1e6, {k: round(v, 4) for k, v in st.items()}))
