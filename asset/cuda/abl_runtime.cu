@@ -95,6 +95,7 @@ struct Pool {
   // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
   // src_begin is where the live records start before the next binning compacts them
   u32 own_begin = 0, own_end = 0, src_begin = 0;
+  u32 bnd_lo_end = 0, bnd_hi_begin = 0;   // pool indices delimiting the boundary parts of the owned range
   u32 key_base_hint = 0;  // copy of grid.key_base (cell_start is handed out with a virtual origin)
   bool own_valid = false;
   // direct halo transport (peer memory over NVLink, no NCCL, no host sync per exchange)
@@ -201,11 +202,14 @@ struct abl_runtime {
   cudaEvent_t xev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double xdev[4] = {0, 0, 0, 0}, xhost[4] = {0, 0, 0, 0};
   unsigned long xcount = 0, xskip = 0;
+  double own_wait_s = 0;
+  unsigned long own_waits = 0;
   u32 x_out[2] = {0, 0};  // outgoing counts of the last exchange_pack (to lower, to upper)
   abl_runtime *peer_lo = nullptr, *peer_hi = nullptr;  // in-process transport (tests)
   // cudaFree synchronises the whole device; with the direct transport a neighbour driven by the
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
+  bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
@@ -476,7 +480,19 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u
   }
 }
 
-__global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32 n, const u32 *tile_sum) {
+// Slab decomposition: the two words of cell_start that delimit the owned range (and the
+// counters of the last halo exchange) are written to page-locked host memory by the very
+// threads that produce them (`report.host` mapped into the device address space), so the host
+// learns them without a further kernel or copy.
+struct ScanReport {
+  u32 *host;            // nullptr: nothing to report
+  u32 lo_cell, hi_cell;
+  u32 lo2_cell, hi2_cell;  // end of the lower / begin of the upper boundary part (boundary-first scheduling)
+  const u32 *halo_ctr;  // may be nullptr
+};
+
+__global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32 n, const u32 *tile_sum,
+                                                          ScanReport report) {
   __shared__ u32 s_warp[kScanBlock / 32];
   __shared__ u32 s_pre[kScanBlock / 32];
   cudaGridDependencySynchronize();
@@ -528,6 +544,21 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
     o[1] = make_uint4(v[4] + b, v[5] + b, v[6] + b, v[7] + b);
     o[2] = make_uint4(v[8] + b, v[9] + b, v[10] + b, v[11] + b);
     o[3] = make_uint4(v[12] + b, v[13] + b, v[14] + b, v[15] + b);
+    if (report.host) {
+#pragma unroll
+      for (int k = 0; k < kScanItems; k++) {
+        if (i0 + k == report.lo_cell) { report.host[0] = v[k] + b; __threadfence_system(); }
+        if (i0 + k == report.hi_cell) { report.host[1] = v[k] + b; __threadfence_system(); }
+        if (i0 + k == report.lo2_cell) { report.host[8] = v[k] + b; __threadfence_system(); }
+        if (i0 + k == report.hi2_cell) { report.host[9] = v[k] + b; __threadfence_system(); }
+      }
+    }
+  }
+  if (report.host && tile == 0 && tid == 0) {
+    // in lo, in hi, timeout, far, sent lo, sent hi of the last halo exchange
+    for (int k = 0; k < 6; k++) report.host[2 + k] = report.halo_ctr ? report.halo_ctr[2 + k] : 0;
+    report.host[10] = report.halo_ctr ? report.halo_ctr[12] : 0;  // late
+    __threadfence_system();
   }
 }
 
@@ -784,13 +815,19 @@ static int collect_garbage(abl_runtime *rt) {
 }
 
 // exclusive scan of the cell histogram into cell_start (and zeroing of the histogram)
-static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n) {
+// `report` (optional): see ScanReport; *reported tells the caller whether the scan took care of it
+static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n, const ScanReport *report = nullptr,
+                         bool *reported = nullptr) {
+  if (reported) *reported = false;
   if (!rt->scan_two_pass) return run_scan<u32, 0, true>(rt, count, start, n, nullptr);
   TRY(ensure_scan(rt, n));
   const u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
   u32 *tile_sum = rt->scan.tile_sum;
   CU(launch_pdl(rt->pdl, k_tile_sum, dim3(tiles), dim3(kScanBlock), 0, rt->stream, (const u32 *)count, (u32)n, tile_sum));
-  CU(launch_pdl(rt->pdl, k_tile_scan, dim3(tiles), dim3(kScanBlock), 0, rt->stream, count, start, (u32)n, (const u32 *)tile_sum));
+  ScanReport rep;
+  memset(&rep, 0, sizeof rep);
+  if (report) { rep = *report; if (reported) *reported = true; }
+  CU(launch_pdl(rt->pdl, k_tile_scan, dim3(tiles), dim3(kScanBlock), 0, rt->stream, count, start, (u32)n, (const u32 *)tile_sum, rep));
   rt->launches += 2;
   CU(cudaGetLastError());
   return ABL_OK;
@@ -911,6 +948,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
   if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
+  if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
   if (getenv("ABL_CUDA_TRACE")) {
@@ -934,6 +972,20 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     fprintf(stderr, "%s\n", line);
   }
   collect_garbage(rt);
+  if (rt->trace && rt->own_waits)
+    fprintf(stderr, "abl_cuda[slab %d] host blocked %.2f us per binning waiting for the owned range (%lu binnings)\n",
+            rt->my_slab, 1e6 * rt->own_wait_s / rt->own_waits, rt->own_waits);
+  if (rt->trace) {
+    for (Pool &p : rt->pools) {
+      if (!p.halo_ctr) continue;
+      u32 w[16];
+      if (cudaMemcpy(w, p.halo_ctr, sizeof w, cudaMemcpyDeviceToHost) != cudaSuccess || !w[10]) continue;
+      unsigned long long ns;
+      memcpy(&ns, w + 8, sizeof ns);
+      fprintf(stderr, "abl_cuda[slab %d] pool %s: %u direct exchanges, publish + wait for neighbours %.2f us per exchange\n",
+              rt->my_slab, p.name.c_str(), w[10], 1e-3 * (double)ns / w[10]);
+    }
+  }
   for (Pool &p : rt->pools) {
     for (int d = 0; d < 2; d++) if (p.halo_peer[d] && p.halo_ipc[d]) cudaIpcCloseMemHandle(p.halo_peer[d]);
     if (p.halo_recv) cudaFree(p.halo_recv);
@@ -1068,8 +1120,8 @@ static int slab_bin_if_needed(abl_runtime *rt, Pool &p);
 static int bin_pool(abl_runtime *rt, Pool &p);
 static bool halo_direct(const Pool &p);
 static int halo_reserve(abl_runtime *rt, Pool &p);
-static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v);
-static int halo_finish(abl_runtime *rt, Pool &p);
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel);
+static int halo_finish(abl_runtime *rt, Pool &p, bool published);
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
@@ -1285,7 +1337,9 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
 }
 
 static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo);
-static int slab_request_owned_range(abl_runtime *rt, Pool &p);
+static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported);
+static void slab_owned_cells(const abl_runtime *rt, u32 *lo_cell, u32 *hi_cell);
+static void slab_boundary_cells(const abl_runtime *rt, u32 *lo2_cell, u32 *hi2_cell);
 
 // histogram of `n` records starting at source index `src_begin`; keys/ranks go to slot
 // `out_begin + i` of the pool's key/local arrays
@@ -1327,8 +1381,18 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
-  TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2));
-  if (rt->slab) TRY(slab_request_owned_range(rt, p));
+  if (rt->slab) {
+    ScanReport rep;
+    bool reported = false;
+    slab_owned_cells(rt, &rep.lo_cell, &rep.hi_cell);
+    slab_boundary_cells(rt, &rep.lo2_cell, &rep.hi2_cell);
+    rep.host = rt->h_scalar_dev + 32;
+    rep.halo_ctr = p.halo_pending ? p.halo_ctr : nullptr;
+    TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, &rep, &reported));
+    TRY(slab_request_owned_range(rt, p, reported));
+  } else {
+    TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2));
+  }
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
@@ -1552,7 +1616,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     abl_step_launch a;
     memset(&a, 0, sizeof a);
     fill_view(self, a.self, s.desc.written_members, true);
-    if (direct) TRY(halo_fill_view(rt, self, a.slab));
+    if (direct) TRY(halo_fill_view(rt, self, a.slab, true));
     if (rt->slab && self.pos_member >= 0) {
       // the step function runs over the owned range only
       const u32 ob = self.own_begin;
@@ -1629,14 +1693,14 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
     if (direct)
-      TRY(halo_finish(rt, self));
+      TRY(halo_finish(rt, self, a.slab.boundary_first && a.self.n));
     else if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
       TRY(abl_cuda_exchange(rt, s.desc.self_pool));
   } else {
     if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
     if (direct) {  // an empty slab still has to answer its neighbours
       TRY(halo_reserve(rt, self));
-      TRY(halo_finish(rt, self));
+      TRY(halo_finish(rt, self, false));
     }
   }
   if (rt->timing) {
@@ -1861,24 +1925,50 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
 // The owned range is two words of cell_start.  They are copied to the host right after the
 // scan and awaited only after the remaining binning kernels have been enqueued, so the host
 // learns them while the GPU is still busy and can enqueue the step kernel without a gap.
-__global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_cell, const u32 *halo_ctr,
-                                   u32 *out) {
+__global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_cell, u32 lo2_cell, u32 hi2_cell,
+                                   const u32 *halo_ctr, u32 *out) {
   // `out` is page-locked host memory mapped into the device address space: the words reach the
   // host without a copy-engine operation between two kernels of the stream
   if (threadIdx.x == 0) {
     out[0] = cell_start[lo_cell];
     out[1] = cell_start[hi_cell];
     for (int k = 0; k < 6; k++) out[2 + k] = halo_ctr ? halo_ctr[2 + k] : 0;  // in lo, in hi, timeout, far, sent lo, sent hi
+    out[8] = cell_start[lo2_cell];
+    out[9] = cell_start[hi2_cell];
+    out[10] = halo_ctr ? halo_ctr[12] : 0;  // late
     __threadfence_system();
   }
 }
 
-static int slab_request_owned_range(abl_runtime *rt, Pool &p) {
+static void slab_owned_cells(const abl_runtime *rt, u32 *lo_cell, u32 *hi_cell) {
   const int row = slab_row_cells(rt);
-  u32 lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base, hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
-  k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, p.halo_pending ? p.halo_ctr : nullptr,
-                                               rt->h_scalar_dev + 32);
-  rt->launches++;
+  *lo_cell = (u32)rt->layer_begin * (u32)row - rt->grid.key_base;
+  *hi_cell = (u32)rt->layer_end * (u32)row - rt->grid.key_base;
+}
+// Boundary parts for boundary-first scheduling: the 2 * ghost outermost owned layers on each
+// side (an agent further inside cannot reach the halo zone by moving less than `ghost` layers).
+// Slabs too thin for an interior are all boundary.
+static void slab_boundary_cells(const abl_runtime *rt, u32 *lo2_cell, u32 *hi2_cell) {
+  const int row = slab_row_cells(rt);
+  const int w = 2 * rt->ghost_layers;
+  int lo2 = rt->layer_begin + w, hi2 = rt->layer_end - w;
+  if (lo2 >= hi2) lo2 = hi2 = rt->layer_end;   // everything belongs to the lower boundary part
+  *lo2_cell = (u32)lo2 * (u32)row - rt->grid.key_base;
+  *hi2_cell = (u32)hi2 * (u32)row - rt->grid.key_base;
+}
+
+// `reported`: the scan kernel has already written the words (two-pass scan); otherwise a
+// one-thread kernel gathers them
+static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported) {
+  if (!reported) {
+    u32 lo_cell, hi_cell;
+    slab_owned_cells(rt, &lo_cell, &hi_cell);
+    u32 lo2_cell, hi2_cell;
+    slab_boundary_cells(rt, &lo2_cell, &hi2_cell);
+    k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, lo2_cell, hi2_cell,
+                                                 p.halo_pending ? p.halo_ctr : nullptr, rt->h_scalar_dev + 32);
+    rt->launches++;
+  }
   CU(cudaEventRecord(rt->ev_own, rt->stream));
   return ABL_OK;
 }
@@ -1886,15 +1976,29 @@ static int slab_request_owned_range(abl_runtime *rt, Pool &p) {
 // returns ABL_OK and sets *redo when the arrivals of the last direct exchange exceeded the
 // host's padding estimate: the pool then has to be binned again over the full live range
 static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
-  CU(cudaEventSynchronize(rt->ev_own));
+  if (rt->trace) {
+    // how long the host blocks here tells who is ahead: ~0 means the GPU is waiting for the host
+    auto t0 = std::chrono::steady_clock::now();
+    CU(cudaEventSynchronize(rt->ev_own));
+    rt->own_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    rt->own_waits++;
+  } else {
+    CU(cudaEventSynchronize(rt->ev_own));
+  }
   const u32 *h = rt->h_scalar + 32;
   p.own_begin = h[0];
   p.own_end = h[1];
+  p.bnd_lo_end = h[8];
+  p.bnd_hi_begin = h[9];
   if (redo) *redo = false;
   if (p.halo_pending) {
     p.halo_pending = false;
     const u32 in_lo = h[2], in_hi = h[3], timeout = h[4], far = h[5], sent_lo = h[6], sent_hi = h[7];
     if (timeout) return fail(ABL_ERR_COMM, "pool %s: timed out waiting for a neighbour's halo message", p.name.c_str());
+    if (h[10])
+      return fail(ABL_ERR_COMM, "%u agents of pool %s crossed more than %d cell layers in one step and reached the halo "
+                  "zone after the messages had been published; set ABL_CUDA_HALO_OVERLAP=0", h[10], p.name.c_str(),
+                  rt->ghost_layers);
     if (far)
       return fail(ABL_ERR_COMM, "%u agents of pool %s moved farther than a neighbouring slab in one step "
                   "(only neighbour and periodic wrap-around migration is supported)", far, p.name.c_str());
@@ -2240,6 +2344,8 @@ struct HaloExchangeArgs {
   u32 seq, cap;
   long long timeout_ns;
   u32 dst_first, pad, room, rec_words;
+  int publish;     // 0: the step kernel has published already (boundary-first scheduling)
+  int trace;       // accumulate the wait time of block 0 in ctr[8..9] (ns) and calls in ctr[10]
   // fused histogram of the arrivals (count != 0)
   int count;
   const void *px, *py, *pz;
@@ -2250,7 +2356,9 @@ struct HaloExchangeArgs {
 template <typename R, int DIM>
 __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeArgs a, GridParams g) {
   __shared__ u32 s_in[2];
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
+  unsigned long long trace_t0 = 0;
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
+  if (a.publish && blockIdx.x == 0 && threadIdx.x == 0) {
     const u32 c0 = a.ctr[0], c1 = a.ctr[1];
     a.ctr[6] = c0;
     a.ctr[7] = c1;
@@ -2290,6 +2398,13 @@ __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeA
     if (blockIdx.x == 0) a.ctr[2 + dir] = count;
   }
   __syncthreads();
+  if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) {
+    // ABL_CUDA_TRACE: time block 0 spent publishing and waiting for the neighbours, and calls
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicAdd((unsigned long long *)(a.ctr + 8), t1 - trace_t0);
+    atomicAdd(a.ctr + 10, 1u);
+  }
   const u32 in_lo = s_in[0], in_hi = s_in[1];
   u32 total = in_lo + in_hi;
   if (total < a.pad) total = a.pad;
@@ -2346,7 +2461,7 @@ __global__ void k_halo_pack(ColTable t, abl_slab_view s, u32 n, u32 first) {
 }
 
 // Describes exchange number halo_seq + 1 of `p` for the kernel that packs it.
-static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v) {
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel) {
   memset(&v, 0, sizeof v);
   const GridParams &g = rt->grid;
   const int axis = g.dim - 1, N = rt->n_slabs, me = rt->my_slab;
@@ -2383,6 +2498,21 @@ static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v) {
   v.rec_words = (unsigned)slab_rec_words(p);
   v.n_cols = (int)p.cols.size() - 1;
   for (int c = 0; c < v.n_cols; c++) v.elem[c] = p.cols[c].elem;
+  // boundary-first scheduling with the publish inside the step kernel
+  const u32 n_own = p.own_end - p.own_begin;
+  const u32 lo_end = std::min(std::max(p.bnd_lo_end, p.own_begin), p.own_end) - p.own_begin;
+  const u32 hi_begin = std::min(std::max(p.bnd_hi_begin, p.own_begin + lo_end), p.own_end) - p.own_begin;
+  if (step_kernel && rt->halo_overlap && n_own && (lo_end > 0 || hi_begin < n_own)) {
+    v.boundary_first = 1;
+    v.idx_lo_end = lo_end;
+    v.idx_hi_begin = hi_begin;
+    v.done = p.halo_ctr + 11;
+    v.late = p.halo_ctr + 12;
+    v.sent = p.halo_ctr + 6;
+    v.hdr[0] = v.msg[0] ? (unsigned *)(v.msg[0] - ABL_MSG_HEADER) : nullptr;
+    v.hdr[1] = v.msg[1] ? (unsigned *)(v.msg[1] - ABL_MSG_HEADER) : nullptr;
+    v.seq = seq;
+  }
   return ABL_OK;
 }
 
@@ -2404,7 +2534,7 @@ static int halo_reserve(abl_runtime *rt, Pool &p) {
 
 // publish + wait + unpack of exchange number ++halo_seq; records have been packed by the
 // kernel launched just before
-static int halo_finish(abl_runtime *rt, Pool &p) {
+static int halo_finish(abl_runtime *rt, Pool &p, bool published) {
   const u32 seq = ++p.halo_seq;
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
   HaloHeader *to_lo = p.halo_peer[0] ? (HaloHeader *)halo_block_of(p.halo_peer[0], p.halo_block, 1, seq) : nullptr;
@@ -2423,6 +2553,8 @@ static int halo_finish(abl_runtime *rt, Pool &p) {
   a.from_lo = from_lo; a.from_hi = from_hi;
   a.seq = seq; a.cap = (u32)p.halo_cap;
   a.timeout_ns = rt->halo_timeout_ns;
+  a.trace = rt->trace ? 1 : 0;
+  a.publish = published ? 0 : 1;
   a.dst_first = oe; a.pad = pad; a.room = room; a.rec_words = (u32)slab_rec_words(p);
   const GridParams &g = rt->grid;
   // the step kernel already produced keys and the histogram of the owned agents (fused
@@ -2465,7 +2597,7 @@ static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
   if (!p.own_valid) TRY(bin_pool(rt, p));
   TRY(halo_reserve(rt, p));
   abl_slab_view v;
-  TRY(halo_fill_view(rt, p, v));
+  TRY(halo_fill_view(rt, p, v, false));
   const u32 n_own = p.own_end - p.own_begin;
   if (n_own) {
     ColTable t;
@@ -2475,7 +2607,7 @@ static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
     rt->launches++;
     CU(cudaGetLastError());
   }
-  return halo_finish(rt, p);
+  return halo_finish(rt, p, false);
 }
 
 extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_records, void *handle_out) {

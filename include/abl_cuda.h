@@ -162,6 +162,21 @@ typedef struct {
   unsigned *far;            /* counts agents that moved farther than a neighbouring slab */
   int n_cols;               /* columns of the pool (without the id) */
   int elem[ABL_MAX_COLUMNS];
+  /* Boundary-first scheduling (boundary_first != 0): the kernel's first nb_lo + nb_hi thread
+   * blocks step the agents of the outermost cell layers of the slab — indices [0, idx_lo_end)
+   * and [idx_hi_begin, n) of the launched range — and the last of them to finish publishes the
+   * messages (counts + sequence number into the neighbours' headers) while the remaining
+   * blocks are still stepping the interior [idx_lo_end, idx_hi_begin).  Interior agents are at
+   * least two layers away from the halo zone; one that still needs routing is counted in
+   * `late` (reported as an error by the runtime). */
+  int boundary_first;
+  unsigned idx_lo_end, idx_hi_begin;
+  unsigned nb_lo, nb_hi;
+  unsigned *done;           /* finished boundary blocks (reset by the publishing block) */
+  unsigned *late;
+  unsigned *sent;           /* [2] copies of the final counts, for the host's bookkeeping */
+  unsigned *hdr[2];         /* headers {seq, count} of the neighbours' receive blocks (NULL: no such neighbour) */
+  unsigned seq;
 } abl_slab_view;
 
 typedef struct {

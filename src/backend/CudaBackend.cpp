@@ -1365,7 +1365,8 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const unsigned _tile_cap) {";
   w.indent(); w.nl();
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
-  w << "const unsigned _i = blockIdx.x * blockDim.x + threadIdx.x;"; w.nl();
+  w << "bool _boundary;"; w.nl();
+  w << "const unsigned _i = abl_agent_index(_a, _boundary);"; w.nl();
   std::set<std::string> loads = si.reads;
   for (const std::string &m : si.writes) loads.insert(m);
   // the slab epilogue routes by the agent's position: always have it in registers
@@ -1437,13 +1438,16 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   }
   // slab decomposition: route this agent's record to the neighbouring slabs (no-op otherwise)
   w.nl();
-  if (selfPos) w << "abl_slab_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ");";
+  if (selfPos) w << "abl_slab_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ", _boundary);";
   if (f.usesRemoval) { w.nl(); w << "_a.dead[_i] = _ctx.dead ? 1 : 0;"; }
   if (f.addedAgent) { w.nl(); w << "_a.add_flag[_i] = _ctx.added ? 1 : 0;"; }
+  if (selfPos) { w.nl(); w << "abl_slab_block_done(_a, _boundary);"; }
   w.outdent(); w.nl();
   w << "}"; w.nl(); w.nl();
 
-  w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *a) {"; w.nl();
+  w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *_args) {"; w.nl();
+  w << "    abl_step_launch _copy = *_args;   // block counts of the boundary parts are filled in below"; w.nl();
+  w << "    abl_step_launch *a = &_copy;"; w.nl();
   w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 0;"; w.nl();
   if (curStepHasLimit) {
     // host-side evaluation of the radius with the kernel's own arithmetic and constants
@@ -1465,7 +1469,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   // block size 0 = automatic: 128 threads for sparse neighbourhoods, 256 for dense ones
   // (measured on circle3d 1 M: 3.9 ms against 4.5 ms per step)
   w << "    if (bs == 0) bs = chunked ? 256 : 128;"; w.nl();
-  w << "    unsigned grid = (a->self.n + bs - 1) / bs;"; w.nl();
+  w << "    unsigned grid = abl_grid_blocks(a, bs);"; w.nl();
   if (curStepTile) {
     // sparse neighbourhoods: stage the block's candidate rows in shared memory (ABL_MODE 2)
     w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
