@@ -2414,14 +2414,15 @@ __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeA
     if (i >= in_lo + in_hi) {
       ((u32 *)t.out[t.ncols - 1])[dst] = ABL_SENTINEL_ID;
     } else {
-      const u32 *rec = i < in_lo ? (const u32 *)(a.from_lo + ABL_MSG_HEADER) + (size_t)i * a.rec_words
-                                 : (const u32 *)(a.from_hi + ABL_MSG_HEADER) + (size_t)(i - in_lo) * a.rec_words;
-      u32 w = 0;
+      // word-major message: word w of record r at w * cap + r (see abl_slab_send)
+      const u32 *rec = i < in_lo ? (const u32 *)(a.from_lo + ABL_MSG_HEADER) + i
+                                 : (const u32 *)(a.from_hi + ABL_MSG_HEADER) + (i - in_lo);
+      size_t w = 0;
       for (int k = 0; k < t.ncols; k++) {
         const int e = t.elem[k];
-        if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w++]; continue; }
+        if (e == 1) { ((u8 *)t.out[k])[dst] = (u8)rec[w]; w += a.cap; continue; }
         u32 *q = (u32 *)t.out[k] + dst * (e / 4);
-        for (int j = 0; j < e / 4; j++) q[j] = rec[w++];
+        for (int j = 0; j < e / 4; j++) { q[j] = rec[w]; w += a.cap; }
       }
     }
     // only the part the host will bin (`pad` records) enters the histogram; a surplus makes
@@ -2449,13 +2450,13 @@ __global__ void k_halo_pack(ColTable t, abl_slab_view s, u32 n, u32 first) {
     if (!((route >> dir) & 1u)) continue;
     const u32 slot = atomicAdd(s.count[dir], 1u);
     if (slot >= s.capacity || !s.msg[dir]) continue;
-    u32 *rec = (u32 *)s.msg[dir] + (size_t)slot * s.rec_words;
-    u32 w = 0;
+    u32 *rec = (u32 *)s.msg[dir] + slot;   // word-major, see abl_slab_send
+    size_t w = 0;
     for (int k = 0; k < t.ncols; k++) {
       const int e = t.elem[k];
-      if (e == 1) { rec[w++] = ((const u8 *)t.in[k])[src]; continue; }
+      if (e == 1) { rec[w] = ((const u8 *)t.in[k])[src]; w += s.capacity; continue; }
       const u32 *q = (const u32 *)t.in[k] + src * (e / 4);
-      for (int j = 0; j < e / 4; j++) rec[w++] = q[j];
+      for (int j = 0; j < e / 4; j++) { rec[w] = q[j]; w += s.capacity; }
     }
   }
 }
@@ -2618,7 +2619,7 @@ extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_re
   if (p.pos_member < 0) return fail(ABL_ERR_ARGUMENT, "pool %s has no position member", p.name.c_str());
   if (p.halo_recv) return fail(ABL_ERR_STATE, "pool %s: halo transport already set up", p.name.c_str());
   CU(cudaSetDevice(rt->device));
-  p.halo_cap = capacity_records ? capacity_records : 65536;
+  p.halo_cap = round_up(capacity_records ? capacity_records : 65536, 32);   // rows of the word-major message stay 128-byte aligned
   p.halo_block = round_up(ABL_MSG_HEADER + p.halo_cap * (size_t)slab_rec_words(p) * 4, 256);
   CU(cudaMalloc(&p.halo_recv, 4 * p.halo_block));
   CU(cudaMemset(p.halo_recv, 0, 4 * p.halo_block));

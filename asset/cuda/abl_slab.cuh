@@ -7,8 +7,10 @@
 
 #define ABL_SLAB_HD __host__ __device__ __forceinline__
 
-// Message: 64-byte header, then packed records of `rec_words` 32-bit words each: the columns
-// of one agent back to back (1-byte columns widened to a word), the agent id last.
+// Message: 64-byte header, then `rec_words` rows of `capacity` 32-bit words (word-major): row w
+// holds word w of every record — the columns of an agent in pool order (1-byte columns widened
+// to a word), the agent id last.  Lanes of a warp write consecutive slots, so every store
+// instruction of the packing code is one contiguous 128-byte write into the peer's memory.
 #define ABL_MSG_HEADER 64u
 #define ABL_SENTINEL_ID 0xffffffffu   // padding record: sorted into the trash cell by binning
 

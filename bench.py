@@ -43,6 +43,9 @@ WORKLOADS = {
     "circle3d-16M-f32": ("circle3d.abl", {"num_agents": 16000000}, True, 12, 12, 12),
     "game_of_life-16M-f64": ("game_of_life.abl", {"num_agents": 16777216}, False, 17, 17, 16),
     "circle-1000-f64": ("circle.abl", {"num_agents": 1000}, False, 16, 16, 16),
+    # BASELINE configs[3]: three agent types, run-time add/remove; S/M/P of the Prey type (the
+    # roofline object is only indicative for this workload)
+    "predator_prey-4M-f64": ("predator_prey.abl", {"num_agents": 4000000}, False, 52, 16, 16),
 }
 BINNING_HOISTED = {"game_of_life-16M-f64"}
 
@@ -126,6 +129,9 @@ def cpu_baseline(workload, budget_pairs=1.2e10):
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     from oracle import BRUTE, Oracle
     model, params, use_float, _, _, _ = WORKLOADS[workload]
+    if model not in ("boids2d.abl", "circle.abl", "circle3d.abl", "game_of_life.abl"):
+        raise SystemExit("no CPU baseline for %s: the reference `c` backend rejects run-time add/remove "
+                         "(use --no-cpu-baseline)" % model)
     n = params["num_agents"]
     o = Oracle(use_float)
     if model == "game_of_life.abl":
