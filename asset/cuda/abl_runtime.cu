@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <string>
 #include <vector>
@@ -202,6 +203,7 @@ struct abl_runtime {
   cudaEvent_t xev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   double xdev[4] = {0, 0, 0, 0}, xhost[4] = {0, 0, 0, 0};
   unsigned long xcount = 0, xskip = 0;
+  unsigned long long *trace_state = nullptr;   // device: [0] last stamp, [1..8] ns per bucket, [9..16] counts
   double own_wait_s = 0;
   unsigned long own_waits = 0;
   u32 x_out[2] = {0, 0};  // outgoing counts of the last exchange_pack (to lower, to upper)
@@ -209,6 +211,7 @@ struct abl_runtime {
   // cudaFree synchronises the whole device; with the direct transport a neighbour driven by the
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
+  u32 bin_stamp = 0;           // number of the last slab-mode binning (stamps of the owned-range report)
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
@@ -484,7 +487,14 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u
 // counters of the last halo exchange) are written to page-locked host memory by the very
 // threads that produce them (`report.host` mapped into the device address space), so the host
 // learns them without a further kernel or copy.
+// Every value is followed (after a system-scope fence) by a stamp word carrying the number of
+// this binning, and the host simply polls the stamps in its own memory: no event, no driver
+// call and no copy engine between two kernels of the stream.
+// host words: [0] own begin, [1] own end, [2..7] halo counters, [8] lower boundary end,
+// [9] upper boundary begin, [10] late; stamps at [16] own begin, [17] own end, [18], [19]
+// boundaries, [20] counters.
 struct ScanReport {
+  u32 stamp;
   u32 *host;            // nullptr: nothing to report
   u32 lo_cell, hi_cell;
   u32 lo2_cell, hi2_cell;  // end of the lower / begin of the upper boundary part (boundary-first scheduling)
@@ -547,10 +557,11 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
     if (report.host) {
 #pragma unroll
       for (int k = 0; k < kScanItems; k++) {
-        if (i0 + k == report.lo_cell) { report.host[0] = v[k] + b; __threadfence_system(); }
-        if (i0 + k == report.hi_cell) { report.host[1] = v[k] + b; __threadfence_system(); }
-        if (i0 + k == report.lo2_cell) { report.host[8] = v[k] + b; __threadfence_system(); }
-        if (i0 + k == report.hi2_cell) { report.host[9] = v[k] + b; __threadfence_system(); }
+        volatile u32 *hw = report.host;
+        if (i0 + k == report.lo_cell) { hw[0] = v[k] + b; __threadfence_system(); hw[16] = report.stamp; }
+        if (i0 + k == report.hi_cell) { hw[1] = v[k] + b; __threadfence_system(); hw[17] = report.stamp; }
+        if (i0 + k == report.lo2_cell) { hw[8] = v[k] + b; __threadfence_system(); hw[18] = report.stamp; }
+        if (i0 + k == report.hi2_cell) { hw[9] = v[k] + b; __threadfence_system(); hw[19] = report.stamp; }
       }
     }
   }
@@ -559,6 +570,7 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
     for (int k = 0; k < 6; k++) report.host[2 + k] = report.halo_ctr ? report.halo_ctr[2 + k] : 0;
     report.host[10] = report.halo_ctr ? report.halo_ctr[12] : 0;  // late
     __threadfence_system();
+    *(volatile u32 *)(report.host + 20) = report.stamp;
   }
 }
 
@@ -814,6 +826,21 @@ static int collect_garbage(abl_runtime *rt) {
   return ABL_OK;
 }
 
+// ABL_CUDA_TRACE: device-side timeline.  A one-thread kernel between two stages adds the time
+// since the previous stamp (globaltimer, so idle gaps count as well) to the bucket of the stage
+// that has just ended.
+__global__ void k_trace_stamp(unsigned long long *state, int bucket) {
+  unsigned long long now;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+  if (state[0]) { state[1 + bucket] += now - state[0]; state[9 + bucket] += 1; }
+  state[0] = now;
+}
+enum { TR_SCAN = 0, TR_MOVE = 1, TR_STEP = 2, TR_EXCHANGE = 3, TR_OTHER = 4 };
+static void trace_stamp(abl_runtime *rt, int bucket) {
+  if (!rt->trace || !rt->trace_state) return;
+  k_trace_stamp<<<1, 1, 0, rt->stream>>>(rt->trace_state, bucket);
+}
+
 // exclusive scan of the cell histogram into cell_start (and zeroing of the histogram)
 // `report` (optional): see ScanReport; *reported tells the caller whether the scan took care of it
 static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n, const ScanReport *report = nullptr,
@@ -954,6 +981,8 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (getenv("ABL_CUDA_TRACE")) {
     rt->trace = true;
     for (int i = 0; i < 5; i++) CU(cudaEventCreate(&rt->xev[i]));
+    CU(cudaMalloc(&rt->trace_state, 17 * sizeof(unsigned long long)));
+    CU(cudaMemset(rt->trace_state, 0, 17 * sizeof(unsigned long long)));
   }
   *out = rt;
   return ABL_OK;
@@ -972,6 +1001,18 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     fprintf(stderr, "%s\n", line);
   }
   collect_garbage(rt);
+  if (rt->trace && rt->trace_state) {
+    unsigned long long st[17];
+    if (cudaMemcpy(st, rt->trace_state, sizeof st, cudaMemcpyDeviceToHost) == cudaSuccess && st[9 + TR_STEP]) {
+      const char *names[5] = {"histogram+scan", "scatter+rank/move", "step kernel", "exchange", "other"};
+      char line[512];
+      int off = snprintf(line, sizeof line, "abl_cuda[slab %d] device timeline, us per occurrence (idle gaps included):", rt->my_slab);
+      for (int b = 0; b < 5; b++)
+        if (st[9 + b]) off += snprintf(line + off, sizeof line - off, " %s %.1f;", names[b], 1e-3 * (double)st[1 + b] / (double)st[9 + b]);
+      fprintf(stderr, "%s\n", line);
+    }
+    cudaFree(rt->trace_state);
+  }
   if (rt->trace && rt->own_waits)
     fprintf(stderr, "abl_cuda[slab %d] host blocked %.2f us per binning waiting for the owned range (%lu binnings)\n",
             rt->my_slab, 1e6 * rt->own_wait_s / rt->own_waits, rt->own_waits);
@@ -1376,6 +1417,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   const GridParams &g = rt->grid;
   const u32 n = (u32)p.n;
   const int bs = 256;
+  trace_stamp(rt, TR_OTHER);
   // 1. histogram (skipped when the step kernel that produced the positions already did it)
   if (!p.counted) TRY(launch_bin_count(rt, p, n, p.src_begin, 0u));
   p.counted = false;
@@ -1387,12 +1429,14 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     slab_owned_cells(rt, &rep.lo_cell, &rep.hi_cell);
     slab_boundary_cells(rt, &rep.lo2_cell, &rep.hi2_cell);
     rep.host = rt->h_scalar_dev + 32;
+    rep.stamp = ++rt->bin_stamp;
     rep.halo_ctr = p.halo_pending ? p.halo_ctr : nullptr;
     TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, &rep, &reported));
     TRY(slab_request_owned_range(rt, p, reported));
   } else {
     TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2));
   }
+  trace_stamp(rt, TR_SCAN);
   if (n) {
     // 3. ids into their cell segments, 4. rank by id inside the segment + move the records
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
@@ -1408,6 +1452,7 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     CU(cudaGetLastError());
     flip_all(p);
   }
+  trace_stamp(rt, TR_MOVE);
   const u32 src_before = p.src_begin;
   p.src_begin = 0;
   p.key_base_hint = g.key_base;
@@ -1675,8 +1720,10 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.tile_neighbours = rt->cfg.tile_neighbours;
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
+    trace_stamp(rt, TR_OTHER);
     int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches++;
+    trace_stamp(rt, TR_STEP);
     if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: kernel launch failed: %s", s.name.c_str(),
                              cudaGetErrorString((cudaError_t)rc));
     if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
@@ -1692,8 +1739,10 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (added) TRY(commit_adds(rt, self, *added, staging));
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
-    if (direct)
+    if (direct) {
       TRY(halo_finish(rt, self, a.slab.boundary_first && a.self.n));
+      trace_stamp(rt, TR_EXCHANGE);
+    }
     else if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
       TRY(abl_cuda_exchange(rt, s.desc.self_pool));
   } else {
@@ -1926,7 +1975,7 @@ static int slab_crop_to_owned(abl_runtime *rt, int pool) {
 // scan and awaited only after the remaining binning kernels have been enqueued, so the host
 // learns them while the GPU is still busy and can enqueue the step kernel without a gap.
 __global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_cell, u32 lo2_cell, u32 hi2_cell,
-                                   const u32 *halo_ctr, u32 *out) {
+                                   const u32 *halo_ctr, u32 *out, u32 stamp) {
   // `out` is page-locked host memory mapped into the device address space: the words reach the
   // host without a copy-engine operation between two kernels of the stream
   if (threadIdx.x == 0) {
@@ -1937,6 +1986,7 @@ __global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_ce
     out[9] = cell_start[hi2_cell];
     out[10] = halo_ctr ? halo_ctr[12] : 0;  // late
     __threadfence_system();
+    for (int k = 16; k <= 20; k++) *(volatile u32 *)(out + k) = stamp;
   }
 }
 
@@ -1966,24 +2016,39 @@ static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported) {
     u32 lo2_cell, hi2_cell;
     slab_boundary_cells(rt, &lo2_cell, &hi2_cell);
     k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, lo2_cell, hi2_cell,
-                                                 p.halo_pending ? p.halo_ctr : nullptr, rt->h_scalar_dev + 32);
+                                                 p.halo_pending ? p.halo_ctr : nullptr, rt->h_scalar_dev + 32, rt->bin_stamp);
     rt->launches++;
   }
-  CU(cudaEventRecord(rt->ev_own, rt->stream));
   return ABL_OK;
 }
 
 // returns ABL_OK and sets *redo when the arrivals of the last direct exchange exceeded the
 // host's padding estimate: the pool then has to be binned again over the full live range
 static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
-  if (rt->trace) {
-    // how long the host blocks here tells who is ahead: ~0 means the GPU is waiting for the host
+  {
+    // poll the stamps the scan kernel writes into this (mapped, page-locked) memory
+    const volatile u32 *hv = rt->h_scalar + 32;
+    const u32 stamp = rt->bin_stamp;
     auto t0 = std::chrono::steady_clock::now();
-    CU(cudaEventSynchronize(rt->ev_own));
-    rt->own_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    rt->own_waits++;
-  } else {
-    CU(cudaEventSynchronize(rt->ev_own));
+    unsigned long spins = 0;
+    for (;;) {
+      if (hv[16] == stamp && hv[17] == stamp && hv[18] == stamp && hv[19] == stamp && hv[20] == stamp) break;
+      if ((++spins & 0xfffu) == 0) {
+        // a failed kernel never writes its stamps: surface the error instead of spinning
+        cudaError_t e = cudaStreamQuery(rt->stream);
+        if (e != cudaSuccess && e != cudaErrorNotReady) CU(e);
+        if (e == cudaSuccess && !(hv[16] == stamp && hv[17] == stamp && hv[18] == stamp && hv[19] == stamp && hv[20] == stamp))
+          return fail(ABL_ERR_STATE, "pool %s: the binning finished without reporting the owned range", p.name.c_str());
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 120.0)
+          return fail(ABL_ERR_COMM, "pool %s: no owned-range report from the device after 120 s", p.name.c_str());
+      }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (rt->trace) {
+      // how long the host waits here tells who is ahead: ~0 means the GPU is waiting for the host
+      rt->own_wait_s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      rt->own_waits++;
+    }
   }
   const u32 *h = rt->h_scalar + 32;
   p.own_begin = h[0];

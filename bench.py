@@ -124,7 +124,7 @@ NCU_TRAFFIC = {
 }
 
 
-def cpu_baseline(workload, budget_pairs=1.2e10):
+def cpu_baseline(workload, budget_pairs=1.5e11):
     """Times the oracle's brute-force (reference-order) step on a bounded sample of agents."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     from oracle import BRUTE, Oracle
@@ -164,8 +164,9 @@ def run_reference_arm(args):
     model, params, use_float, S, M, P = WORKLOADS[workload]
     vals, last = [], None
     total = args.warmup + args.steps
-    # each "step" is a bounded sample; keep the whole run within a few minutes
-    budget = 1.2e10 / max(1, total) * 2
+    # each "step" is a bounded sample; the whole run stays within about half a minute of CPU work
+    # at ~1e10 candidate tests per second (16 threads)
+    budget = max(2e9, 3e11 / max(1, total))
     for i in range(total):
         base, dt = cpu_baseline(workload, budget_pairs=budget)
         if i >= args.warmup:
