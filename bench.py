@@ -119,8 +119,8 @@ class ClockSampler(threading.Thread):
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the
 # `ncu --set full` captures summarised under profiles/ (None where no capture exists)
 NCU_TRAFFIC = {
-    "boids2d-1M-f64": (43.04e6, "profiles/r1_final_boids_summary.txt"),
-    "circle3d-1M-f64": (24.2e6, "profiles/r1_v2_circle3d_summary.txt"),
+    "boids2d-1M-f64": (44.68e6, "profiles/r1c_boids_summary.txt"),
+    "circle3d-1M-f64": (25.39e6, "profiles/r1c_circle3d_summary.txt"),
 }
 
 
