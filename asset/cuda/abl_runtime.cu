@@ -96,7 +96,17 @@ struct Pool {
   // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
   // src_begin is where the live records start before the next binning compacts them
   u32 own_begin = 0, own_end = 0, src_begin = 0;
-  u32 bnd_lo_end = 0, bnd_hi_begin = 0;   // pool indices delimiting the boundary parts of the owned range
+  u32 bnd_lo_end = 0, bnd_hi_begin = 0;
+  // The report of the last slab-mode binning (owned range, boundary parts, counters of the
+  // preceding halo exchange) lands in a per-pool slice of mapped host memory.  With device-side
+  // ranges the host consumes it lazily: at the latest when the next binning needs the pool size.
+  int index = 0;                  // position in rt->pools
+  bool report_pending = false;
+  u32 report_stamp = 0;
+  bool exch_deferred = false;     // a direct exchange was queued without the host knowing the owned range
+  u32 exch_pad = 0;               // padding of that exchange
+  u32 pad_used[2] = {0, 0};       // padding of the exchanges in flight, by parity of their sequence number
+  bool halo_sync_check = false;   // verify the counts of the last exchange synchronously at the next binning (stand-alone exchanges)   // pool indices delimiting the boundary parts of the owned range
   u32 key_base_hint = 0;  // copy of grid.key_base (cell_start is handed out with a virtual origin)
   bool own_valid = false;
   // direct halo transport (peer memory over NVLink, no NCCL, no host sync per exchange)
@@ -212,6 +222,7 @@ struct abl_runtime {
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
   u32 bin_stamp = 0;           // number of the last slab-mode binning (stamps of the owned-range report)
+  bool device_range = true;    // ABL_CUDA_DEVICE_RANGE=0: the host waits for the owned range before it queues a step kernel
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
@@ -248,6 +259,12 @@ static const int kScanItems = 16;                      // per thread
 static const int kScanTile = kScanBlock * kScanItems;  // 4096
 
 static inline size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+// per-pool slice of the mapped host buffer the binning reports into (32 words each, after the
+// first 64 words that other transfers use)
+static u32 *report_host(abl_runtime *rt, const Pool &p) { return rt->h_scalar + 64 + 32 * (p.index % 28); }
+static u32 *report_dev(abl_runtime *rt, const Pool &p) { return rt->h_scalar_dev + 64 + 32 * (p.index % 28); }
+
 
 // ---------------------------------------------------------------------------------------
 // kernels: transpose between host records and columns
@@ -491,8 +508,9 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u
 // this binning, and the host simply polls the stamps in its own memory: no event, no driver
 // call and no copy engine between two kernels of the stream.
 // host words: [0] own begin, [1] own end, [2..7] halo counters, [8] lower boundary end,
-// [9] upper boundary begin, [10] late; stamps at [16] own begin, [17] own end, [18], [19]
-// boundaries, [20] counters.
+// [9] upper boundary begin, [10] late, [11] sequence number of the exchange the counters belong
+// to, [12] counters present; stamps at [16] own begin, [17] own end, [18], [19] boundaries,
+// [20] counters.
 struct ScanReport {
   u32 stamp;
   u32 *host;            // nullptr: nothing to report
@@ -569,6 +587,8 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
     // in lo, in hi, timeout, far, sent lo, sent hi of the last halo exchange
     for (int k = 0; k < 6; k++) report.host[2 + k] = report.halo_ctr ? report.halo_ctr[2 + k] : 0;
     report.host[10] = report.halo_ctr ? report.halo_ctr[12] : 0;  // late
+    report.host[11] = report.halo_ctr ? report.halo_ctr[14] : 0;  // sequence number of that exchange
+    report.host[12] = report.halo_ctr ? 1u : 0u;
     __threadfence_system();
     *(volatile u32 *)(report.host + 20) = report.stamp;
   }
@@ -975,6 +995,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   CU(cudaEventCreateWithFlags(&rt->ev_own, cudaEventDisableTiming));
   memset(&rt->grid, 0, sizeof rt->grid);
   if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
+  if (const char *dr = getenv("ABL_CUDA_DEVICE_RANGE")) rt->device_range = atoi(dr) != 0;
   if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
@@ -1145,6 +1166,7 @@ extern "C" int abl_cuda_add_pool(abl_runtime *rt, const abl_agent_desc *desc, in
   idc.comp = 4; idc.ncomp = 1; idc.elem = 4; idc.host_off = -1;
   p.id_col = (int)p.cols.size();
   p.cols.push_back(idc);
+  p.index = (int)rt->pools.size();
   rt->pools.push_back(p);
   if (pool) *pool = (int)rt->pools.size() - 1;
   return ABL_OK;
@@ -1158,11 +1180,12 @@ static int get_pool(abl_runtime *rt, int pool, Pool **out) {
 }
 
 static int slab_bin_if_needed(abl_runtime *rt, Pool &p);
-static int bin_pool(abl_runtime *rt, Pool &p);
+static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report = false);
+static int slab_settle(abl_runtime *rt, Pool &p);
 static bool halo_direct(const Pool &p);
 static int halo_reserve(abl_runtime *rt, Pool &p);
-static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel);
-static int halo_finish(abl_runtime *rt, Pool &p, bool published);
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel, bool dev_range);
+static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range);
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
@@ -1247,6 +1270,10 @@ static int upload_impl(abl_runtime *rt, int pool, const void *host_aos, const un
   p->next_id = ids ? next_id : (u32)n;
   p->binned = false;
   p->own_valid = false;
+  p->report_pending = false;
+  p->exch_deferred = false;
+  p->halo_pending = false;
+  p->halo_sync_check = false;
   p->src_begin = 0;
   p->own_begin = 0;
   p->own_end = (u32)n;
@@ -1281,7 +1308,7 @@ extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size
   u32 first = 0;
   size_t count = p->n;
   if (rt->slab && p->pos_member >= 0) {
-    if (!p->binned) TRY(bin_pool(rt, *p));
+    TRY(slab_settle(rt, *p));
     first = p->own_begin;
     count = p->own_end - p->own_begin;
   } else if (p->src_begin) {
@@ -1334,7 +1361,7 @@ extern "C" int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids_ou
   u32 first = 0;
   size_t count = p->n;
   if (rt->slab && p->pos_member >= 0) {
-    if (!p->binned) TRY(bin_pool(rt, *p));
+    TRY(slab_settle(rt, *p));
     first = p->own_begin;
     count = p->own_end - p->own_begin;
   } else if (p->src_begin) {
@@ -1377,8 +1404,10 @@ static int ensure_grid_arrays(abl_runtime *rt, Pool &p) {
   return ABL_OK;
 }
 
-static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo);
-static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported);
+static int slab_consume_report(abl_runtime *rt, Pool &p, bool *redo);
+static int slab_settle(abl_runtime *rt, Pool &p);
+struct ScanReport;
+static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported, const ScanReport &rep);
 static void slab_owned_cells(const abl_runtime *rt, u32 *lo_cell, u32 *hi_cell);
 static void slab_boundary_cells(const abl_runtime *rt, u32 *lo2_cell, u32 *hi2_cell);
 
@@ -1409,9 +1438,13 @@ static int launch_bin_count(abl_runtime *rt, Pool &p, u32 n, u32 src_begin, u32 
   return ABL_OK;
 }
 
-static int bin_pool(abl_runtime *rt, Pool &p) {
+// defer_report (slab mode): do not wait for the owned range; the caller queues kernels that
+// read it on the device and the host catches up later (slab_consume_report)
+static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
   if (!rt->env_set) return fail(ABL_ERR_STATE, "binning requires an environment");
   if (p.pos_member < 0) return fail(ABL_ERR_STATE, "pool %s has no position member", p.name.c_str());
+  // the extent of this binning may still be on its way from the device
+  if (rt->slab) TRY(slab_consume_report(rt, p, nullptr));
   TRY(reserve_pool(rt, p, std::max(p.n, (size_t)1)));
   TRY(ensure_grid_arrays(rt, p));
   const GridParams &g = rt->grid;
@@ -1428,11 +1461,14 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
     bool reported = false;
     slab_owned_cells(rt, &rep.lo_cell, &rep.hi_cell);
     slab_boundary_cells(rt, &rep.lo2_cell, &rep.hi2_cell);
-    rep.host = rt->h_scalar_dev + 32;
-    rep.stamp = ++rt->bin_stamp;
+    rep.host = report_dev(rt, p);
+    rep.stamp = p.report_stamp = ++rt->bin_stamp;
     rep.halo_ctr = p.halo_pending ? p.halo_ctr : nullptr;
+    p.halo_pending = false;
     TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, &rep, &reported));
-    TRY(slab_request_owned_range(rt, p, reported));
+    TRY(slab_request_owned_range(rt, p, reported, rep));
+    p.report_pending = true;
+    p.own_valid = false;
   } else {
     TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2));
   }
@@ -1459,8 +1495,10 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
   p.binned = true;
   p.ever_binned = true;
   if (rt->slab) {
+    if (defer_report && !p.halo_sync_check) return ABL_OK;
     bool redo = false;
-    TRY(slab_update_owned_range(rt, p, &redo));
+    TRY(slab_consume_report(rt, p, &redo));
+    p.halo_sync_check = false;
     if (redo) {
       // More halo records arrived than the padding the host assumed: they were unpacked (the
       // pool has room for two full messages) but not binned.  The source buffers of this
@@ -1471,13 +1509,13 @@ static int bin_pool(abl_runtime *rt, Pool &p) {
       p.binned = false;
       p.counted = false;
       CU(cudaMemsetAsync(p.cell_count, 0, ((size_t)g.n_local + 2) * sizeof(u32), rt->stream));
-      return bin_pool(rt, p);
+      return bin_pool(rt, p, defer_report);
     }
   } else {
     p.own_begin = 0;
     p.own_end = (u32)p.n;
+    p.own_valid = true;
   }
-  p.own_valid = true;
   return ABL_OK;
 }
 
@@ -1640,29 +1678,37 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   Pool *added = s.desc.added_pool >= 0 ? &rt->pools[s.desc.added_pool] : nullptr;
 
   if (rt->timing) CU(cudaEventRecord(rt->ev[0], rt->stream));
+  // slab mode with the direct transport: this step's kernel packs the halo itself, and (device
+  // range) reads the owned range of its pool from cell_start, so that it can be queued without
+  // the host waiting for the binning
+  const bool direct = rt->slab && self.pos_member >= 0 && halo_direct(self) && s.desc.written_members;
+  const bool dev_range = direct && rt->device_range && !rt->timing;
   if (nbr) {
-    if (!nbr->binned) TRY(bin_pool(rt, *nbr));
+    if (!nbr->binned) TRY(bin_pool(rt, *nbr, dev_range && nbr == &self));
     // keep the iterating pool in cell order too: neighbouring threads then walk
     // neighbouring cells (coalescing / L1 reuse)
-    if (&self != nbr && self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self));
+    if (&self != nbr && self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self, dev_range));
   }
   if (rt->slab) {
     if (s.desc.uses_removal || added)
       return fail(ABL_ERR_STATE, "step %s: run-time add/remove is not supported with slab decomposition yet", s.name.c_str());
-    if (self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self));
+    if (self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self, dev_range));
+    // a pool whose range the host has to know (no device range for this launch)
+    if (self.pos_member >= 0 && !dev_range && self.report_pending) TRY(slab_consume_report(rt, self, nullptr));
   }
+  // the device range can only be used while the host's view is behind (report pending); once it
+  // has caught up (first step after an upload, timing mode) the classic host-side range is used
+  const bool use_dev_range = dev_range && self.report_pending;
   if (rt->timing) CU(cudaEventRecord(rt->ev[1], rt->stream));
 
-  // slab mode with the direct transport: this step's kernel packs the halo itself
-  const bool direct = rt->slab && self.pos_member >= 0 && halo_direct(self) && s.desc.written_members;
   if (self.n) {
     TRY(reserve_pool(rt, self, self.n));
     if (direct) TRY(halo_reserve(rt, self));  // may move the columns: before any view is taken
     abl_step_launch a;
     memset(&a, 0, sizeof a);
     fill_view(self, a.self, s.desc.written_members, true);
-    if (direct) TRY(halo_fill_view(rt, self, a.slab, true));
-    if (rt->slab && self.pos_member >= 0) {
+    if (direct) TRY(halo_fill_view(rt, self, a.slab, true, use_dev_range));
+    if (rt->slab && self.pos_member >= 0 && !use_dev_range) {
       // the step function runs over the owned range only
       const u32 ob = self.own_begin;
       int ncols = (int)self.cols.size() - 1;
@@ -1740,7 +1786,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (s.desc.uses_removal) TRY(commit_removals(rt, self));
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
     if (direct) {
-      TRY(halo_finish(rt, self, a.slab.boundary_first && a.self.n));
+      TRY(halo_finish(rt, self, !use_dev_range && a.slab.boundary_first && a.self.n, use_dev_range));
       trace_stamp(rt, TR_EXCHANGE);
     }
     else if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
@@ -1749,7 +1795,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
     if (direct) {  // an empty slab still has to answer its neighbours
       TRY(halo_reserve(rt, self));
-      TRY(halo_finish(rt, self, false));
+      TRY(halo_finish(rt, self, false, use_dev_range));
     }
   }
   if (rt->timing) {
@@ -1821,7 +1867,7 @@ extern "C" int abl_cuda_count(abl_runtime *rt, int pool, int *result) {
 // caller combines the per-rank values).
 static int reduce_range(abl_runtime *rt, Pool &p, u32 *first, u32 *n) {
   if (rt->slab && p.pos_member >= 0) {
-    if (!p.binned) TRY(bin_pool(rt, p));
+    TRY(slab_settle(rt, p));
     *first = p.own_begin;
     *n = p.own_end - p.own_begin;
   } else {
@@ -1949,7 +1995,7 @@ extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int com
 //   3. drop the old ghosts (the owned range is contiguous), append the arrivals and let the
 //      next binning sort everything back into [ghosts | owned | ghosts].
 static int slab_bin_if_needed(abl_runtime *rt, Pool &p) {
-  if (!p.binned) TRY(bin_pool(rt, p));
+  TRY(slab_settle(rt, p));
   return ABL_OK;
 }
 
@@ -1985,6 +2031,8 @@ __global__ void k_gather_bin_words(const u32 *cell_start, u32 lo_cell, u32 hi_ce
     out[8] = cell_start[lo2_cell];
     out[9] = cell_start[hi2_cell];
     out[10] = halo_ctr ? halo_ctr[12] : 0;  // late
+    out[11] = halo_ctr ? halo_ctr[14] : 0;
+    out[12] = halo_ctr ? 1u : 0u;
     __threadfence_system();
     for (int k = 16; k <= 20; k++) *(volatile u32 *)(out + k) = stamp;
   }
@@ -2009,26 +2057,29 @@ static void slab_boundary_cells(const abl_runtime *rt, u32 *lo2_cell, u32 *hi2_c
 
 // `reported`: the scan kernel has already written the words (two-pass scan); otherwise a
 // one-thread kernel gathers them
-static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported) {
+static int slab_request_owned_range(abl_runtime *rt, Pool &p, bool reported, const ScanReport &rep) {
   if (!reported) {
-    u32 lo_cell, hi_cell;
-    slab_owned_cells(rt, &lo_cell, &hi_cell);
-    u32 lo2_cell, hi2_cell;
-    slab_boundary_cells(rt, &lo2_cell, &hi2_cell);
-    k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, lo_cell, hi_cell, lo2_cell, hi2_cell,
-                                                 p.halo_pending ? p.halo_ctr : nullptr, rt->h_scalar_dev + 32, rt->bin_stamp);
+    k_gather_bin_words<<<1, 32, 0, rt->stream>>>(p.cell_start, rep.lo_cell, rep.hi_cell, rep.lo2_cell, rep.hi2_cell,
+                                                 rep.halo_ctr, rep.host, rep.stamp);
     rt->launches++;
   }
   return ABL_OK;
 }
 
-// returns ABL_OK and sets *redo when the arrivals of the last direct exchange exceeded the
-// host's padding estimate: the pool then has to be binned again over the full live range
-static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
+// Waits for the report of the pool's last binning (normally long there) and brings the host's
+// view up to date: owned range, boundary parts, and — if a direct exchange was queued with a
+// device-side range — the extent the next binning has to cover.  The counters of the halo
+// exchange that preceded the reported binning are checked here.  `redo` (synchronous callers
+// only): set when more records arrived than the padding covered, so that the caller can bin
+// again; without it that condition is an error.
+static int slab_consume_report(abl_runtime *rt, Pool &p, bool *redo) {
+  if (redo) *redo = false;
+  if (!p.report_pending) return ABL_OK;
+  p.report_pending = false;
   {
     // poll the stamps the scan kernel writes into this (mapped, page-locked) memory
-    const volatile u32 *hv = rt->h_scalar + 32;
-    const u32 stamp = rt->bin_stamp;
+    const volatile u32 *hv = report_host(rt, p);
+    const u32 stamp = p.report_stamp;
     auto t0 = std::chrono::steady_clock::now();
     unsigned long spins = 0;
     for (;;) {
@@ -2050,16 +2101,17 @@ static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
       rt->own_waits++;
     }
   }
-  const u32 *h = rt->h_scalar + 32;
+  const u32 *h = report_host(rt, p);
   p.own_begin = h[0];
   p.own_end = h[1];
   p.bnd_lo_end = h[8];
   p.bnd_hi_begin = h[9];
-  if (redo) *redo = false;
-  if (p.halo_pending) {
-    p.halo_pending = false;
-    const u32 in_lo = h[2], in_hi = h[3], timeout = h[4], far = h[5], sent_lo = h[6], sent_hi = h[7];
-    if (timeout) return fail(ABL_ERR_COMM, "pool %s: timed out waiting for a neighbour's halo message", p.name.c_str());
+  p.own_valid = true;
+  if (h[12]) {
+    // the report carries the counters of halo exchange number h[11]
+    const u32 seq = h[11];
+    const u32 in_lo = h[2], in_hi = h[3], flags = h[4], far = h[5], sent_lo = h[6], sent_hi = h[7];
+    if (flags & 1u) return fail(ABL_ERR_COMM, "pool %s: timed out waiting for a neighbour's halo message", p.name.c_str());
     if (h[10])
       return fail(ABL_ERR_COMM, "%u agents of pool %s crossed more than %d cell layers in one step and reached the halo "
                   "zone after the messages had been published; set ABL_CUDA_HALO_OVERLAP=0", h[10], p.name.c_str(),
@@ -2071,14 +2123,37 @@ static int slab_update_owned_range(abl_runtime *rt, Pool &p, bool *redo) {
       return fail(ABL_ERR_COMM, "pool %s: halo message of %u records exceeds the capacity of %zu; raise the "
                   "capacity passed to abl_cuda_halo_setup", p.name.c_str(), std::max(std::max(in_lo, in_hi), std::max(sent_lo, sent_hi)), p.halo_cap);
     const u32 arrivals = in_lo + in_hi;
-    const u32 pad_used = p.halo_pad;
-    if (arrivals > p.halo_room)
-      return fail(ABL_ERR_COMM, "pool %s: %u halo records arrived but the pool had room for %u only", p.name.c_str(), arrivals, p.halo_room);
-    // adapt the padding to what actually arrives (25 % head room)
-    p.halo_pad = (u32)round_up((size_t)arrivals + arrivals / 4 + 256, 256);
-    if (arrivals > pad_used && redo) *redo = true;
+    if (flags & 2u)
+      return fail(ABL_ERR_COMM, "pool %s: %u halo records arrived but the pool had no room for them", p.name.c_str(), arrivals);
+    const u32 pad_used = p.pad_used[seq & 1u];
+    // adapt the padding to what actually arrives: the counts of an exchange are verified one
+    // binning later, so the head room has to absorb the growth of two steps
+    p.halo_pad = (u32)round_up(2 * (size_t)arrivals + 1024, 256);
     p.halo_last_arrivals = arrivals;
+    if (arrivals > pad_used) {
+      if (redo) *redo = true;
+      else
+        return fail(ABL_ERR_COMM, "pool %s: %u halo records arrived in exchange %u but the binning was sized for %u "
+                    "(arrivals more than doubled within two steps)", p.name.c_str(), arrivals, seq, pad_used);
+    }
   }
+  if (p.exch_deferred) {
+    // a direct exchange was queued behind the reported binning: old ghosts are dead, arrivals and
+    // padding sit behind the owned range
+    p.exch_deferred = false;
+    p.halo_prev_ob = p.own_begin;
+    p.halo_prev_own = p.own_end - p.own_begin;
+    p.src_begin = p.own_begin;
+    p.n = (size_t)(p.own_end - p.own_begin) + p.exch_pad;
+  }
+  return ABL_OK;
+}
+
+// the host needs the owned range of a pool (downloads, reductions, staged / NCCL exchange)
+static int slab_settle(abl_runtime *rt, Pool &p) {
+  if (!rt->slab || p.pos_member < 0) return ABL_OK;
+  if (p.report_pending && !p.exch_deferred) TRY(slab_consume_report(rt, p, nullptr));
+  if (!p.binned) TRY(bin_pool(rt, p));
   return ABL_OK;
 }
 
@@ -2253,6 +2328,8 @@ extern "C" int abl_cuda_set_slab(abl_runtime *rt, const int *layer_bounds, int n
   for (Pool &p : rt->pools) {
     p.binned = false;
     p.own_valid = false;
+    p.report_pending = false;
+    p.exch_deferred = false;
     p.counted = false;
     if (p.cell_count) { CU(cudaFree(p.cell_count)); p.cell_count = nullptr; }
     if (p.cell_start) { CU(cudaFree(p.cell_start)); p.cell_start = nullptr; }
@@ -2264,7 +2341,7 @@ extern "C" int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
   if (rt->slab && p->pos_member >= 0) {
-    if (!p->binned) TRY(bin_pool(rt, *p));
+    TRY(slab_settle(rt, *p));
     if (n) *n = p->own_end - p->own_begin;
   } else if (n) {
     *n = p->n;
@@ -2274,6 +2351,8 @@ extern "C" int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n) {
 
 // ---- exchange, phase 1: classify + pack into xbuf[0] (to lower) / xbuf[1] (to upper) ----------
 static int exchange_pack(abl_runtime *rt, Pool &p, bool has_lo, bool has_hi) {
+  // (the owned range of the binning the step ran on — not a fresh binning of the new positions)
+  if (p.report_pending && !p.exch_deferred) TRY(slab_consume_report(rt, p, nullptr));
   if (!p.own_valid) TRY(bin_pool(rt, p));  // fresh upload: establish the owned range
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
   const GridParams &g = rt->grid;
@@ -2409,6 +2488,11 @@ struct HaloExchangeArgs {
   u32 seq, cap;
   long long timeout_ns;
   u32 dst_first, pad, room, rec_words;
+  // device-side range (dev_range != 0): dst_first / room / key_first are derived from the pool's
+  // cell_start (owned range = [cs[lo_cell], cs[hi_cell])) instead of being passed by the host
+  int dev_range;
+  const u32 *cs;
+  u32 lo_cell, hi_cell, pool_cap;
   int publish;     // 0: the step kernel has published already (boundary-first scheduling)
   int trace;       // accumulate the wait time of block 0 in ctr[8..9] (ns) and calls in ctr[10]
   // fused histogram of the arrivals (count != 0)
@@ -2421,9 +2505,17 @@ struct HaloExchangeArgs {
 template <typename R, int DIM>
 __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeArgs a, GridParams g) {
   __shared__ u32 s_in[2];
+  if (a.dev_range) {
+    const u32 ob = a.cs[a.lo_cell], oe = a.cs[a.hi_cell];
+    a.dst_first = oe;
+    a.key_first = oe - ob;
+    a.room = a.pool_cap - oe;
+  }
   unsigned long long trace_t0 = 0;
   if (a.trace && blockIdx.x == 0 && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(trace_t0));
-  if (a.publish && blockIdx.x == 0 && threadIdx.x == 0) {
+  // (publish == 2: the step kernel publishes unless it had no boundary block to do it)
+  if (blockIdx.x == 0 && threadIdx.x == 0) a.ctr[14] = a.seq;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && (a.publish == 1 || (a.publish == 2 && a.ctr[13] != a.seq))) {
     const u32 c0 = a.ctr[0], c1 = a.ctr[1];
     a.ctr[6] = c0;
     a.ctr[7] = c1;
@@ -2455,7 +2547,7 @@ __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeA
           break;
         }
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if ((long long)(t1 - t0) > a.timeout_ns) { a.ctr[4] = 1; break; }
+        if ((long long)(t1 - t0) > a.timeout_ns) { atomicOr(a.ctr + 4, 1u); break; }
         __nanosleep(100);
       }
     }
@@ -2472,6 +2564,7 @@ __global__ void __launch_bounds__(256) k_halo_exchange(ColTable t, HaloExchangeA
   }
   const u32 in_lo = s_in[0], in_hi = s_in[1];
   u32 total = in_lo + in_hi;
+  if (total > a.room && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.ctr + 4, 2u);   // no room: reported by the host
   if (total < a.pad) total = a.pad;
   if (total > a.room) total = a.room;
   for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -2527,7 +2620,7 @@ __global__ void k_halo_pack(ColTable t, abl_slab_view s, u32 n, u32 first) {
 }
 
 // Describes exchange number halo_seq + 1 of `p` for the kernel that packs it.
-static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel) {
+static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel, bool dev_range) {
   memset(&v, 0, sizeof v);
   const GridParams &g = rt->grid;
   const int axis = g.dim - 1, N = rt->n_slabs, me = rt->my_slab;
@@ -2568,10 +2661,25 @@ static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_
   const u32 n_own = p.own_end - p.own_begin;
   const u32 lo_end = std::min(std::max(p.bnd_lo_end, p.own_begin), p.own_end) - p.own_begin;
   const u32 hi_begin = std::min(std::max(p.bnd_hi_begin, p.own_begin + lo_end), p.own_end) - p.own_begin;
-  if (step_kernel && rt->halo_overlap && n_own && (lo_end > 0 || hi_begin < n_own)) {
+  if (dev_range) {
+    // the kernel reads the ranges from cell_start itself (global cell keys; the view's
+    // cell_start pointer has a virtual origin)
+    u32 lo, hi, lo2, hi2;
+    slab_owned_cells(rt, &lo, &hi);
+    slab_boundary_cells(rt, &lo2, &hi2);
+    v.device_range = 1;
+    v.lo_key = lo + rt->grid.key_base;
+    v.hi_key = hi + rt->grid.key_base;
+    v.lo2_key = lo2 + rt->grid.key_base;
+    v.hi2_key = hi2 + rt->grid.key_base;
+    v.boundary_first = rt->halo_overlap ? 1 : 0;
+  } else if (step_kernel && rt->halo_overlap && n_own && (lo_end > 0 || hi_begin < n_own)) {
     v.boundary_first = 1;
     v.idx_lo_end = lo_end;
     v.idx_hi_begin = hi_begin;
+  }
+  v.published = p.halo_ctr + 13;
+  if (v.boundary_first) {
     v.done = p.halo_ctr + 11;
     v.late = p.halo_ctr + 12;
     v.sent = p.halo_ctr + 6;
@@ -2589,9 +2697,11 @@ static int halo_reserve(abl_runtime *rt, Pool &p) {
     p.halo_pad = (u32)std::min<size_t>(2 * p.halo_cap, round_up(p.halo_cap / 2 + 256, 256));
     if (const char *e = getenv("ABL_CUDA_HALO_PAD")) p.halo_pad = (u32)std::max(1, atoi(e));  // tests
   }
-  const size_t want = (size_t)p.own_end + 2 * (size_t)p.halo_pad + 1024;
+  // (with a device-side range the host only knows an upper bound of the owned range: the pool size)
+  const size_t own_end = p.report_pending ? p.n : (size_t)p.own_end;
+  const size_t want = own_end + 2 * (size_t)p.halo_pad + 1024;
   if (want > p.cap) {
-    p.n = std::max(p.n, (size_t)p.own_end);
+    p.n = std::max(p.n, own_end);
     TRY(drop_fused_histogram(rt, p));
     TRY(reserve_pool(rt, p, want));
   }
@@ -2600,8 +2710,9 @@ static int halo_reserve(abl_runtime *rt, Pool &p) {
 
 // publish + wait + unpack of exchange number ++halo_seq; records have been packed by the
 // kernel launched just before
-static int halo_finish(abl_runtime *rt, Pool &p, bool published) {
+static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range) {
   const u32 seq = ++p.halo_seq;
+  // (dev_range: the host's owned range is stale; the kernel reads it from cell_start)
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
   HaloHeader *to_lo = p.halo_peer[0] ? (HaloHeader *)halo_block_of(p.halo_peer[0], p.halo_block, 1, seq) : nullptr;
   HaloHeader *to_hi = p.halo_peer[1] ? (HaloHeader *)halo_block_of(p.halo_peer[1], p.halo_block, 0, seq) : nullptr;
@@ -2610,8 +2721,7 @@ static int halo_finish(abl_runtime *rt, Pool &p, bool published) {
   ColTable t;
   fill_table(p, t, false);
   const u32 pad = p.halo_pad;
-  const u32 room = (u32)std::min<size_t>(p.cap - oe, 0x7fffffffu);
-  p.halo_room = room;
+  p.pad_used[seq & 1u] = pad;
   HaloExchangeArgs a;
   memset(&a, 0, sizeof a);
   a.ctr = p.halo_ctr;
@@ -2620,8 +2730,18 @@ static int halo_finish(abl_runtime *rt, Pool &p, bool published) {
   a.seq = seq; a.cap = (u32)p.halo_cap;
   a.timeout_ns = rt->halo_timeout_ns;
   a.trace = rt->trace ? 1 : 0;
-  a.publish = published ? 0 : 1;
-  a.dst_first = oe; a.pad = pad; a.room = room; a.rec_words = (u32)slab_rec_words(p);
+  a.pad = pad; a.rec_words = (u32)slab_rec_words(p);
+  if (dev_range) {
+    a.dev_range = 1;
+    a.cs = p.cell_start;
+    slab_owned_cells(rt, &a.lo_cell, &a.hi_cell);
+    a.pool_cap = (u32)std::min<size_t>(p.cap, 0x7fffffffu);
+    a.publish = 2;
+  } else {
+    a.publish = published ? 0 : 1;
+    a.dst_first = oe;
+    a.room = (u32)std::min<size_t>(p.cap - oe, 0x7fffffffu);
+  }
   const GridParams &g = rt->grid;
   // the step kernel already produced keys and the histogram of the owned agents (fused
   // epilogue); arrivals and padding are added by the exchange kernel
@@ -2650,20 +2770,28 @@ static int halo_finish(abl_runtime *rt, Pool &p, bool published) {
   }
   rt->launches++;
   CU(cudaGetLastError());
-  p.halo_prev_ob = ob;
-  p.halo_prev_own = n_own;
   p.halo_pending = true;
-  p.src_begin = ob;
-  p.n = (size_t)n_own + pad;
   p.binned = false;
+  if (dev_range) {
+    // src_begin and the extent of the next binning follow from the report still in flight
+    p.exch_deferred = true;
+    p.exch_pad = pad;
+  } else {
+    p.halo_prev_ob = ob;
+    p.halo_prev_own = n_own;
+    p.src_begin = ob;
+    p.n = (size_t)n_own + pad;
+  }
   return ABL_OK;
 }
 
 static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
+  // (the owned range of the binning the step ran on — not a fresh binning of the new positions)
+  if (p.report_pending && !p.exch_deferred) TRY(slab_consume_report(rt, p, nullptr));
   if (!p.own_valid) TRY(bin_pool(rt, p));
   TRY(halo_reserve(rt, p));
   abl_slab_view v;
-  TRY(halo_fill_view(rt, p, v, false));
+  TRY(halo_fill_view(rt, p, v, false, false));
   const u32 n_own = p.own_end - p.own_begin;
   if (n_own) {
     ColTable t;
@@ -2673,7 +2801,10 @@ static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
     rt->launches++;
     CU(cudaGetLastError());
   }
-  return halo_finish(rt, p, false);
+  // the host sized this exchange blindly: let the next binning verify the counts synchronously
+  // (it can still bin again if more arrived than the padding covered)
+  p.halo_sync_check = true;
+  return halo_finish(rt, p, false, false);
 }
 
 extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_records, void *handle_out) {

@@ -172,6 +172,14 @@ typedef struct {
   int boundary_first;
   unsigned idx_lo_end, idx_hi_begin;
   unsigned nb_lo, nb_hi;
+  /* device_range != 0: the launch covers the whole pool (self.n is an upper bound, pointers are
+   * not offset) and the kernel reads its range from the pool's own cell_start: owned agents are
+   * [cell_start[lo_key], cell_start[hi_key]), the boundary parts end / begin at
+   * cell_start[lo2_key] / cell_start[hi2_key] (global cell keys).  The host does not have to
+   * know the range when it queues the kernel. */
+  int device_range;
+  unsigned lo_key, hi_key, lo2_key, hi2_key;
+  unsigned *published;      /* sequence number of the last exchange the step kernel published itself */
   unsigned *done;           /* finished boundary blocks (reset by the publishing block) */
   unsigned *late;
   unsigned *sent;           /* [2] copies of the final counts, for the host's bookkeeping */

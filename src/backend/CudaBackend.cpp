@@ -1365,21 +1365,24 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const unsigned _tile_cap) {";
   w.indent(); w.nl();
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
+  // _r: index inside the launched (owned) range, _i: index in the pool's columns
   w << "bool _boundary;"; w.nl();
-  w << "const unsigned _i = abl_agent_index(_a, _boundary);"; w.nl();
+  w << "unsigned _ob;"; w.nl();
+  w << "const unsigned _r = abl_agent_index(_a, _boundary, _ob);"; w.nl();
+  w << "const unsigned _i = _r + _ob;"; w.nl();
   std::set<std::string> loads = si.reads;
   for (const std::string &m : si.writes) loads.insert(m);
   // the slab epilogue routes by the agent's position: always have it in registers
   if (selfPosM) loads.insert(selfPosM->name);
   if (curStepTile) {
     // tiled kernels keep surplus threads of the last block alive for the cooperative staging
-    w << "const bool _active = _i < _a.self.n;"; w.nl();
+    w << "const bool _active = _r != 0xffffffffu;"; w.nl();
     w << "if (ABL_MODE != 2 && !_active) return;"; w.nl();
     w << self.name << " " << p.name << " = {};"; w.nl();
     w << "if (_active) {";
     w.indent();
   } else {
-    w << "if (_i >= _a.self.n) return;"; w.nl();
+    w << "if (_r == 0xffffffffu) return;"; w.nl();
     w << self.name << " " << p.name << ";";
   }
   for (size_t m = 0; m < self.members.size(); m++) {
@@ -1434,7 +1437,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   if (selfPos && si.writes.count(selfPos->name)) {
     // fused histogram of the next binning (no-op unless the runtime asks for it)
     w.nl();
-    w << "abl_bin_epilogue" << selfPos->type.vecLen() << "(_a, _i, " << p.outName << "." << selfPos->name << ");";
+    w << "abl_bin_epilogue" << selfPos->type.vecLen() << "(_a, _r, " << p.outName << "." << selfPos->name << ");";
   }
   // slab decomposition: route this agent's record to the neighbouring slabs (no-op otherwise)
   w.nl();
