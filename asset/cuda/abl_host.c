@@ -87,6 +87,52 @@ int abl_host_save_json(const abl_host_type *types, int n_types, const char *path
   return 0;
 }
 
+static void xml_member(FILE *f, const char *rec, const abl_member_desc *m, int for_gpu) {
+  const char *p = rec + m->offset;
+  const char *name = m->name;
+  if (for_gpu && m->is_pos) {
+    const abl_real *v = (const abl_real *)p;
+    if (m->type == ABL_TYPE_FLOAT2) fprintf(f, "<x>%f</x>\n<y>%f</y>\n<z>0.0</z>\n", (double)v[0], (double)v[1]);
+    else if (m->type == ABL_TYPE_FLOAT3) fprintf(f, "<x>%f</x>\n<y>%f</y>\n<z>%f</z>\n", (double)v[0], (double)v[1], (double)v[2]);
+    return;
+  }
+  switch (m->type) {
+    case ABL_TYPE_BOOL: fprintf(f, "<%s>%d</%s>\n", name, *(const bool *)p ? 1 : 0, name); break;
+    case ABL_TYPE_INT: fprintf(f, "<%s>%d</%s>\n", name, *(const int *)p, name); break;
+    case ABL_TYPE_FLOAT: fprintf(f, "<%s>%f</%s>\n", name, (double)*(const abl_real *)p, name); break;
+    case ABL_TYPE_FLOAT2: {
+      const abl_real *v = (const abl_real *)p;
+      fprintf(f, "<%s_x>%f</%s_x>\n<%s_y>%f</%s_y>\n", name, (double)v[0], name, name, (double)v[1], name);
+      break;
+    }
+    case ABL_TYPE_FLOAT3: {
+      const abl_real *v = (const abl_real *)p;
+      fprintf(f, "<%s_x>%f</%s_x>\n<%s_y>%f</%s_y>\n<%s_z>%f</%s_z>\n", name, (double)v[0], name, name,
+              (double)v[1], name, name, (double)v[2], name);
+      break;
+    }
+    default: break;
+  }
+}
+
+int abl_host_save_flame_xml(const abl_host_type *types, int n_types, const char *path, int for_gpu) {
+  FILE *f = fopen(path, "w");
+  if (!f) { fprintf(stderr, "save: cannot open %s\n", path); return 1; }
+  fputs("<states>\n<itno>0</itno>\n", f);
+  for (int t = 0; t < n_types; t++) {
+    const abl_host_type *ty = &types[t];
+    const char *rec = (const char *)ty->agents->data;
+    for (size_t i = 0; i < ty->agents->len; i++, rec += ty->desc.stride) {
+      fprintf(f, "<xagent>\n<name>%s</name>\n", ty->desc.name);
+      for (int m = 0; m < ty->desc.n_members; m++) xml_member(f, rec, &ty->desc.members[m], for_gpu);
+      fputs("</xagent>\n", f);
+    }
+  }
+  fputs("</states>\n", f);
+  fclose(f);
+  return 0;
+}
+
 int abl_host_save_raw(const abl_host_type *types, int n_types, const char *path) {
   FILE *f = fopen(path, "wb");
   if (!f) return 1;

@@ -222,7 +222,11 @@ struct abl_runtime {
   // same host thread may be spinning in k_halo_wait, so buffers replaced while growing a pool
   // are released at the next explicit synchronisation point instead
   u32 bin_stamp = 0;           // number of the last slab-mode binning (stamps of the owned-range report)
-  bool device_range = true;    // ABL_CUDA_DEVICE_RANGE=0: the host waits for the owned range before it queues a step kernel
+  // ABL_CUDA_DEVICE_RANGE=1: step and exchange kernels read the owned range from cell_start on
+  // the device, so the host can queue them without waiting for the binning report.  Off by
+  // default: measured slightly slower on 2 x B200 (boids2d 1 M agents per GPU, 0.1511 against
+  // 0.1467 ms per step, profiles/scaling/r1d_weak2_device_range_*.json)
+  bool device_range = false;
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
@@ -232,6 +236,15 @@ struct abl_runtime {
   size_t xflags_cap = 0;
   abl_step_timing last = {0, 0, 0, 0};
   unsigned launches = 0;
+  // slab decomposition + run-time add(): ids of new agents are global, so a step function that
+  // adds agents stays open until the caller has supplied the ranks of its parents among the
+  // parents of all slabs (abl_cuda_pending_adds / abl_cuda_resolve_adds)
+  int open_step = -1;
+  std::vector<u64> open_list;               // (parent id << 32 | slot relative to the owned range), ascending
+  void *open_staging[ABL_MAX_COLUMNS + 1];
+  // combines rank-local reduction results across slabs (installed by the harness)
+  abl_reduce_hook reduce_hook = nullptr;
+  void *reduce_user = nullptr;
 };
 
 // Programmatic dependent launch: the kernel may be set up on the SMs while its predecessor in
@@ -690,11 +703,14 @@ __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, 
 // ---------------------------------------------------------------------------------------
 // kernels: compaction (remove) and append (add)
 // ---------------------------------------------------------------------------------------
-__global__ void k_compact_move(ColTable t, const u8 *dead, const u32 *offsets, u32 n) {
+// (`first`: pool index of the record flag 0 belongs to — the first owned record under slab
+// decomposition, where the flags are relative to the owned range and survivors move to the
+// front of the alternate buffers)
+__global__ void k_compact_move(ColTable t, const u8 *dead, const u32 *offsets, u32 n, u32 first) {
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || dead[i]) return;
   u32 dst = offsets[i];
-  for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], i, t.elem[k]);
+  for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], (size_t)first + i, t.elem[k]);
 }
 
 // list[rank] = (parent id << 32 | parent slot) for every flagged parent
@@ -717,6 +733,19 @@ __global__ void k_append(ColTable t, const u64 *list, u32 m, u32 base, u32 first
   u32 dst = base + rank;
   for (int k = 0; k < t.ncols; k++) {
     if (t.host_off[k] < 0) ((u32 *)t.out[k])[dst] = first_id + rank;  // id column
+    else copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
+  }
+}
+
+// Slab decomposition: the list arrives sorted by parent id from the host, together with the
+// rank of every parent among the parents of ALL slabs (ids of new agents are global).
+__global__ void k_append_ranked(ColTable t, const u64 *list, const u32 *global_rank, u32 m, u32 base, u32 first_id) {
+  u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  const u32 src = (u32)list[a];
+  const u32 dst = base + a;
+  for (int k = 0; k < t.ncols; k++) {
+    if (t.host_off[k] < 0) ((u32 *)t.out[k])[dst] = first_id + global_rank[a];  // id column
     else copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
   }
 }
@@ -1610,8 +1639,11 @@ static int read_scalar(abl_runtime *rt, const u32 *d, u32 *out) {
   return ABL_OK;
 }
 
-static int commit_removals(abl_runtime *rt, Pool &p) {
-  const u32 n = (u32)p.n;
+// Stream compaction of the records [first, first + n) by the flags dead[0..n).  Under slab
+// decomposition that range is the owned part of the pool (ghosts are stale after a mutating step
+// and are replaced by the exchange that follows): survivors move to the front of the alternate
+// buffers and become the new owned range.
+static int commit_removals(abl_runtime *rt, Pool &p, u32 first, u32 n, bool slab) {
   if (!n) return ABL_OK;
   TRY((run_scan<u8, 1, false>(rt, p.dead, p.offsets, n, rt->d_scalar)));
   u32 survivors = 0;
@@ -1619,7 +1651,7 @@ static int commit_removals(abl_runtime *rt, Pool &p) {
   if (survivors == n) return ABL_OK;  // nobody died: nothing to move
   ColTable t;
   fill_table(p, t, true);
-  k_compact_move<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, p.dead, p.offsets, n);
+  k_compact_move<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, p.dead, p.offsets, n, first);
   rt->launches++;
   CU(cudaGetLastError());
   flip_all(p);
@@ -1627,6 +1659,12 @@ static int commit_removals(abl_runtime *rt, Pool &p) {
   p.binned = false;
   TRY(drop_fused_histogram(rt, p));  // stable compaction keeps cell order, but cell_start is stale
   p.n = survivors;
+  if (slab) {
+    p.own_begin = 0;
+    p.own_end = survivors;
+    p.src_begin = 0;
+    p.own_valid = true;
+  }
   return ABL_OK;
 }
 
@@ -1668,6 +1706,88 @@ static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const 
   return ABL_OK;
 }
 
+// ---- run-time add() under slab decomposition -------------------------------------------------
+// New agents get ids next_id + (rank of their parent's id among the parents of ALL slabs), the
+// numbering an undecomposed run produces (k_append).  The step function therefore stays open
+// after its kernel: the parents' ids are brought to the host in ascending order, the caller
+// exchanges them between the slabs and hands back global ranks and the global total.
+static int slab_open_adds(abl_runtime *rt, int step, Pool &parent, u32 first, u32 n, void *const *staging) {
+  rt->open_list.clear();
+  u32 m = 0;
+  if (n) {
+    TRY((run_scan<u8, 0, false>(rt, parent.add_flag, parent.offsets, n, rt->d_scalar)));
+    TRY(read_scalar(rt, rt->d_scalar, &m));
+  }
+  if (m) {
+    const u32 *pids = (const u32 *)parent.cols[parent.id_col].buf[parent.cols[parent.id_col].cur] + first;
+    k_collect_adds<<<blocks_for(n, 256), 256, 0, rt->stream>>>(parent.add_flag, parent.offsets, pids, n, parent.pairs);
+    rt->launches++;
+    CU(cudaGetLastError());
+    rt->open_list.resize(m);
+    CU(cudaMemcpyAsync(rt->open_list.data(), parent.pairs, (size_t)m * sizeof(u64), cudaMemcpyDeviceToHost, rt->stream));
+    CU(cudaStreamSynchronize(rt->stream));
+    std::sort(rt->open_list.begin(), rt->open_list.end());
+  }
+  memcpy(rt->open_staging, staging, sizeof rt->open_staging);
+  rt->open_step = step;
+  return ABL_OK;
+}
+
+static int slab_after_mutation(abl_runtime *rt, int pool_index);
+
+extern "C" int abl_cuda_pending_adds(abl_runtime *rt, int *open, unsigned *count) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (open) *open = rt->open_step >= 0 ? 1 : 0;
+  if (count) *count = rt->open_step >= 0 ? (unsigned)rt->open_list.size() : 0u;
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_pending_add_parents(abl_runtime *rt, unsigned *parent_ids, size_t capacity) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (rt->open_step < 0) return fail(ABL_ERR_STATE, "no step function is waiting for abl_cuda_resolve_adds");
+  if (capacity < rt->open_list.size()) return fail(ABL_ERR_CAPACITY, "parent id buffer too small");
+  for (size_t i = 0; i < rt->open_list.size(); i++) parent_ids[i] = (unsigned)(rt->open_list[i] >> 32);
+  return ABL_OK;
+}
+
+extern "C" int abl_cuda_resolve_adds(abl_runtime *rt, const unsigned *global_rank, unsigned global_total) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (rt->open_step < 0) return fail(ABL_ERR_STATE, "no step function is waiting for abl_cuda_resolve_adds");
+  CU(cudaSetDevice(rt->device));
+  Step &s = rt->steps[rt->open_step];
+  Pool &p = rt->pools[s.desc.self_pool];   // (added pool == stepped pool: checked by abl_cuda_step)
+  const u32 m = (u32)rt->open_list.size();
+  if (m && !global_rank) return fail(ABL_ERR_ARGUMENT, "null rank array");
+  for (u32 i = 0; i < m; i++)
+    if (global_rank[i] >= global_total) return fail(ABL_ERR_ARGUMENT, "global rank %u out of range (total %u)", global_rank[i], global_total);
+  rt->open_step = -1;
+  if (s.desc.uses_removal) TRY(commit_removals(rt, p, p.own_begin, p.own_end - p.own_begin, true));
+  if (m) {
+    const size_t want = (size_t)p.own_end + m;
+    if (want > p.cap) {
+      p.n = std::max(p.n, (size_t)p.own_end);
+      TRY(drop_fused_histogram(rt, p));
+      TRY(reserve_pool(rt, p, want));
+    }
+    // (pairs / offsets are free between binnings)
+    CU(cudaMemcpyAsync(p.pairs, rt->open_list.data(), (size_t)m * sizeof(u64), cudaMemcpyHostToDevice, rt->stream));
+    CU(cudaMemcpyAsync(p.offsets, global_rank, (size_t)m * sizeof(u32), cudaMemcpyHostToDevice, rt->stream));
+    ColTable t;
+    fill_table(p, t, false);
+    for (int c = 0; c < t.ncols; c++) t.in[c] = t.host_off[c] < 0 ? nullptr : rt->open_staging[c];
+    k_append_ranked<<<blocks_for(m, 128), 128, 0, rt->stream>>>(t, p.pairs, p.offsets, m, p.own_end, p.next_id);
+    rt->launches++;
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(rt->stream));   // the host arrays may go away
+    p.own_end += m;
+    p.n = std::max(p.n, (size_t)p.own_end);
+    p.binned = false;
+    TRY(drop_fused_histogram(rt, p));
+  }
+  p.next_id += global_total;
+  return slab_after_mutation(rt, s.desc.self_pool);
+}
+
 extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
   if (step < 0 || step >= (int)rt->steps.size()) return fail(ABL_ERR_ARGUMENT, "bad step index %d", step);
@@ -1676,12 +1796,24 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   Pool &self = rt->pools[s.desc.self_pool];
   Pool *nbr = s.desc.nbr_pool >= 0 ? &rt->pools[s.desc.nbr_pool] : nullptr;
   Pool *added = s.desc.added_pool >= 0 ? &rt->pools[s.desc.added_pool] : nullptr;
+  if (rt->open_step >= 0)
+    return fail(ABL_ERR_STATE, "step %s added agents under slab decomposition: call abl_cuda_resolve_adds before the next step",
+                rt->steps[rt->open_step].name.c_str());
+  // a step that removes or adds agents: under slab decomposition the runtime commits over the
+  // owned range and exchanges in a separate pass afterwards (no fused send, no device range)
+  const bool mutating = s.desc.uses_removal || added;
+  const bool slab_pool = rt->slab && self.pos_member >= 0;
+  if (rt->slab && mutating) {
+    if (!slab_pool) return fail(ABL_ERR_STATE, "step %s: run-time add/remove of agents without a position is not supported with slab decomposition", s.name.c_str());
+    if (added && added != &self)
+      return fail(ABL_ERR_STATE, "step %s: adding agents of another type is not supported with slab decomposition", s.name.c_str());
+  }
 
   if (rt->timing) CU(cudaEventRecord(rt->ev[0], rt->stream));
   // slab mode with the direct transport: this step's kernel packs the halo itself, and (device
   // range) reads the owned range of its pool from cell_start, so that it can be queued without
   // the host waiting for the binning
-  const bool direct = rt->slab && self.pos_member >= 0 && halo_direct(self) && s.desc.written_members;
+  const bool direct = rt->slab && self.pos_member >= 0 && halo_direct(self) && s.desc.written_members && !mutating;
   const bool dev_range = direct && rt->device_range && !rt->timing;
   if (nbr) {
     if (!nbr->binned) TRY(bin_pool(rt, *nbr, dev_range && nbr == &self));
@@ -1690,8 +1822,6 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     if (&self != nbr && self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self, dev_range));
   }
   if (rt->slab) {
-    if (s.desc.uses_removal || added)
-      return fail(ABL_ERR_STATE, "step %s: run-time add/remove is not supported with slab decomposition yet", s.name.c_str());
     if (self.pos_member >= 0 && !self.binned) TRY(bin_pool(rt, self, dev_range));
     // a pool whose range the host has to know (no device range for this launch)
     if (self.pos_member >= 0 && !dev_range && self.report_pending) TRY(slab_consume_report(rt, self, nullptr));
@@ -1782,8 +1912,15 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       if ((int)m == self.pos_member) self.binned = false;
     }
     if (fuse) self.counted = true;
+    if (slab_pool && mutating) {
+      const u32 n_own = self.own_end - self.own_begin;
+      // (the caller resolves the global ids, then abl_cuda_resolve_adds removes, appends and exchanges)
+      if (added) return slab_open_adds(rt, step, self, self.own_begin, n_own, staging);
+      TRY(commit_removals(rt, self, self.own_begin, n_own, true));
+      return slab_after_mutation(rt, s.desc.self_pool);
+    }
     if (added) TRY(commit_adds(rt, self, *added, staging));
-    if (s.desc.uses_removal) TRY(commit_removals(rt, self));
+    if (s.desc.uses_removal) TRY(commit_removals(rt, self, 0, (u32)self.n, false));
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
     if (direct) {
       TRY(halo_finish(rt, self, !use_dev_range && a.slab.boundary_first && a.self.n, use_dev_range));
@@ -1793,6 +1930,12 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       TRY(abl_cuda_exchange(rt, s.desc.self_pool));
   } else {
     if (rt->timing) CU(cudaEventRecord(rt->ev[2], rt->stream));
+    if (slab_pool && mutating) {  // an empty slab still takes part in the id resolution and the exchange
+      void *none[ABL_MAX_COLUMNS + 1];
+      memset(none, 0, sizeof none);
+      if (added) return slab_open_adds(rt, step, self, 0, 0, none);
+      return slab_after_mutation(rt, s.desc.self_pool);
+    }
     if (direct) {  // an empty slab still has to answer its neighbours
       TRY(halo_reserve(rt, self));
       TRY(halo_finish(rt, self, false, use_dev_range));
@@ -1854,12 +1997,36 @@ extern "C" int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t) {
 // ---------------------------------------------------------------------------------------
 // reductions
 // ---------------------------------------------------------------------------------------
+extern "C" int abl_cuda_set_reduce_hook(abl_runtime *rt, abl_reduce_hook hook, void *user) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  rt->reduce_hook = hook;
+  rt->reduce_user = user;
+  return ABL_OK;
+}
+
+// Under slab decomposition a reduction covers the owned agents of this runtime; the hook (if
+// the harness installed one) turns the rank-local value into the global one.
+static int combine_int(abl_runtime *rt, int *v) {
+  if (!rt->slab || !rt->reduce_hook || !v) return ABL_OK;
+  long long x = *v;
+  if (rt->reduce_hook(rt->reduce_user, &x, 1, nullptr, 0) != 0) return fail(ABL_ERR_COMM, "reduction hook failed");
+  *v = (int)x;
+  return ABL_OK;
+}
+static int combine_real(abl_runtime *rt, double *v) {
+  if (!rt->slab || !rt->reduce_hook || !v) return ABL_OK;
+  if (rt->reduce_hook(rt->reduce_user, nullptr, 0, v, 1) != 0) return fail(ABL_ERR_COMM, "reduction hook failed");
+  return ABL_OK;
+}
+
 extern "C" int abl_cuda_count(abl_runtime *rt, int pool, int *result) {
   Pool *p;
   TRY(get_pool(rt, pool, &p));
   size_t n = 0;
   TRY(abl_cuda_pool_size(rt, pool, &n));  // owned agents only under slab decomposition
-  if (result) *result = (int)n;
+  int r = (int)n;
+  TRY(combine_int(rt, &r));
+  if (result) *result = r;
   return ABL_OK;
 }
 
@@ -1903,7 +2070,9 @@ static int reduce_int(abl_runtime *rt, Pool &p, Member &m, int kind, int value, 
   }
   u32 out = 0;
   TRY(read_scalar(rt, rt->d_scalar, &out));
-  if (result) *result = (int)out;
+  int r = (int)out;
+  TRY(combine_int(rt, &r));
+  if (result) *result = r;
   return ABL_OK;
 }
 
@@ -1941,7 +2110,9 @@ extern "C" int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member
   }
   u32 out = 0;
   TRY(read_scalar(rt, rt->d_scalar, &out));
-  if (result) *result = (int)out;
+  int r = (int)out;
+  TRY(combine_int(rt, &r));
+  if (result) *result = r;
   return ABL_OK;
 }
 
@@ -1966,7 +2137,10 @@ extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int com
   CU(cudaGetLastError());
   CU(cudaMemcpyAsync(rt->h_scalar, d_out, sizeof(double), cudaMemcpyDeviceToHost, rt->stream));
   CU(cudaStreamSynchronize(rt->stream));
-  if (result) memcpy(result, rt->h_scalar, sizeof(double));
+  double r;
+  memcpy(&r, rt->h_scalar, sizeof(double));
+  TRY(combine_real(rt, &r));
+  if (result) *result = r;
   return ABL_OK;
 }
 
@@ -2968,6 +3142,16 @@ extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
     }
   }
   return rc;
+}
+
+// After a step function removed or added agents: the owned range changed under the neighbours'
+// feet, so ghosts are refreshed even when no member was written.  With in-process peers the
+// caller exchanges (exchange_begin / exchange_end on every runtime).
+static int slab_after_mutation(abl_runtime *rt, int pool_index) {
+  Pool &p = rt->pools[pool_index];
+  if (halo_direct(p)) return halo_exchange_standalone(rt, p);
+  if (rt->peer_lo || rt->peer_hi) return ABL_OK;
+  return abl_cuda_exchange(rt, pool_index);
 }
 
 // ---- in-process transport: several runtimes (slabs) driven by one host thread -------------

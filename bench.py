@@ -194,6 +194,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
     ap.add_argument("--tile", action="store_true", help="stage neighbour rows in shared memory (ABL_MODE 2 kernels)")
+    ap.add_argument("--unroll", action="store_true", help="-C cuda.unroll=true: for-near candidate loop unrolled by two")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
     ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
                     help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
@@ -225,7 +226,8 @@ def main():
         # weak scaling: the per-GPU population stays fixed, the world (and the environment,
         # which the model derives from num_agents) grows with the number of GPUs
         params["num_agents"] = params["num_agents"] * world
-    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
+    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float,
+              config={"cuda.unroll": True} if args.unroll else None)
     m.populate()
     host = [m.host_agents(t) for t in range(m.n_types)]
     n_agents = sum(len(h) for h in host)          # whole job, all ranks
@@ -244,6 +246,11 @@ def main():
         else:
             m.upload_host()
 
+    # (models with run-time add() are driven step by step under decomposition: the ids of new
+    # agents are resolved across the ranks, see RankSlab.timestep)
+    timestep = slab.timestep if slab else m.timestep
+    mutating_slabs = bool(slab and slab._mutating)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -253,7 +260,7 @@ def main():
     # ---- device-resident throughput ------------------------------------------------------
     upload()
     for _ in range(max(3, args.warmup)):
-        m.timestep()
+        timestep()
     barrier()
     launches0 = rt.last_timing()["launches"]
     sampler = ClockSampler(local_rank)
@@ -263,7 +270,7 @@ def main():
     barrier()
     ev0.record(stream)
     for _ in range(args.steps):
-        m.timestep()
+        timestep()
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -279,7 +286,7 @@ def main():
     rt.enable_timing(True)
     stage = {"bin_ms": 0.0, "kernel_ms": 0.0, "commit_ms": 0.0}
     reps = min(args.steps, 20)
-    for _ in range(reps):
+    for _ in range(reps if not mutating_slabs else 0):
         for s in range(m.n_steps):
             m.run_step(s)
             lt = rt.last_timing()
@@ -311,7 +318,7 @@ def main():
     for _ in range(e2e_reps):
         upload()
         for _ in range(args.steps):
-            m.timestep()
+            timestep()
         if slab:
             out = [m.download(tt) for tt in range(m.n_types)]   # this rank's owned agents
             d2h = sum(o.nbytes for o in out)

@@ -300,6 +300,32 @@ int abl_cuda_set_local_peers(abl_runtime *rt, abl_runtime *lower, abl_runtime *u
 int abl_cuda_exchange_begin(abl_runtime *rt, int pool);
 int abl_cuda_exchange_end(abl_runtime *rt, int pool);
 
+
+/* ---- run-time add() / removeCurrent() under slab decomposition ---------------------------
+ * (semantics of add/remove: reference src/backend/MasonPrinter.cpp:159-178, 358-367; they are
+ * absent from the `c` backend, CBackend.cpp:30-32.)  Removal is local to the owning slab:
+ * abl_cuda_step compacts the owned range and refreshes the neighbours' ghosts.  New agents get
+ * the ids an undecomposed run gives them: next_id + rank of the parent's id among the parents
+ * of ALL slabs.  A step function that adds agents is therefore left open by abl_cuda_step; the
+ * caller fetches the local parents' ids (ascending), combines them across the slabs and hands
+ * back, for every local parent, its rank among all parents plus the global number of adds:
+ *     abl_cuda_step(rt, s);                              on every slab
+ *     abl_cuda_pending_adds(rt, &open, &m);              open == 1 after an adding step
+ *     abl_cuda_pending_add_parents(rt, ids, m);
+ *     ... all-gather of ids, rank of each local id in the sorted union ...
+ *     abl_cuda_resolve_adds(rt, ranks, total);           appends, removes, exchanges
+ * Any other abl_cuda_step while a step is open fails with ABL_ERR_STATE. */
+int abl_cuda_pending_adds(abl_runtime *rt, int *open, unsigned *count);
+int abl_cuda_pending_add_parents(abl_runtime *rt, unsigned *parent_ids, size_t capacity);
+int abl_cuda_resolve_adds(abl_runtime *rt, const unsigned *global_rank, unsigned global_total);
+
+/* Reductions (count / sum / count_member) cover the owned agents of one runtime under slab
+ * decomposition.  A hook installed here is called with the rank-local values and replaces them
+ * by the sums over all slabs (e.g. an all-reduce of the calling harness); it returns 0 on
+ * success.  Without a hook the caller combines the per-rank results itself. */
+typedef int (*abl_reduce_hook)(void *user, long long *ints, int n_ints, double *reals, int n_reals);
+int abl_cuda_set_reduce_hook(abl_runtime *rt, abl_reduce_hook hook, void *user);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,6 +55,10 @@ class Model:
             getattr(self.lib, fn).argtypes = [C.c_void_p]
             getattr(self.lib, fn).restype = C.c_int
         self.lib.abl_model_run_step.argtypes = [C.c_void_p, C.c_int]
+        self.lib.abl_model_step_flags.argtypes = [C.c_int]
+        self.lib.abl_model_step_flags.restype = C.c_int
+        self.lib.abl_model_sequential_step.argtypes = [C.c_void_p]
+        self.lib.abl_model_sequential_step.restype = C.c_int
         self.lib.abl_model_set_runtime.argtypes = [C.c_void_p]
         self.rt = None
 
@@ -105,6 +109,13 @@ class Model:
 
     def run_step(self, s):
         check(self.lib.abl_model_run_step(self.rt.handle, s), "abl_model_run_step")
+
+    def step_flags(self, s):
+        """bit 0: step function `s` removes agents, bit 1: it adds agents at run time."""
+        return self.lib.abl_model_step_flags(s)
+
+    def sequential_step(self):
+        check(self.lib.abl_model_sequential_step(self.rt.handle), "abl_model_sequential_step")
 
     def close(self):
         if self.rt is not None:

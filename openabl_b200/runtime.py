@@ -80,7 +80,14 @@ ABI = {
     "abl_cuda_set_local_peers": (C.c_int, [_VP, _VP, _VP]),
     "abl_cuda_exchange_begin": (C.c_int, [_VP, C.c_int]),
     "abl_cuda_exchange_end": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_pending_adds": (C.c_int, [_VP, C.POINTER(C.c_int), C.POINTER(C.c_uint)]),
+    "abl_cuda_pending_add_parents": (C.c_int, [_VP, _VP, C.c_size_t]),
+    "abl_cuda_resolve_adds": (C.c_int, [_VP, _VP, C.c_uint]),
+    "abl_cuda_set_reduce_hook": (C.c_int, [_VP, _VP, _VP]),
 }
+
+# int (*abl_reduce_hook)(void *user, long long *ints, int n_ints, double *reals, int n_reals)
+REDUCE_HOOK = C.CFUNCTYPE(C.c_int, _VP, C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_double), C.c_int)
 
 _lib = None
 
@@ -219,6 +226,53 @@ class Runtime:
 
     def step(self, step_id):
         check(self.lib.abl_cuda_step(self.handle, step_id), "step")
+
+    def begin_timestep(self):
+        check(self.lib.abl_cuda_begin_timestep(self.handle), "begin_timestep")
+
+    def end_timestep(self):
+        check(self.lib.abl_cuda_end_timestep(self.handle), "end_timestep")
+
+    # run-time add() under slab decomposition: ids of new agents are resolved across slabs
+    def pending_add_parents(self):
+        """-> ascending ids of the local parents of the open adding step, or None if no step is open."""
+        import numpy as np
+        is_open, m = C.c_int(), C.c_uint()
+        check(self.lib.abl_cuda_pending_adds(self.handle, C.byref(is_open), C.byref(m)), "pending_adds")
+        if not is_open.value:
+            return None
+        ids = np.zeros(m.value, dtype=np.uint32)
+        check(self.lib.abl_cuda_pending_add_parents(self.handle, ids.ctypes.data_as(_VP), len(ids)), "pending_add_parents")
+        return ids
+
+    def resolve_adds(self, global_rank, global_total):
+        import numpy as np
+        r = np.ascontiguousarray(global_rank, dtype=np.uint32)
+        check(self.lib.abl_cuda_resolve_adds(self.handle, r.ctypes.data_as(_VP), int(global_total)), "resolve_adds")
+
+    def set_reduce_hook(self, fn):
+        """fn(ints: list[int], reals: list[float]) -> (ints, reals) summed over all slabs; None removes the hook."""
+        if fn is None:
+            self._hook = None
+            check(self.lib.abl_cuda_set_reduce_hook(self.handle, None, None), "set_reduce_hook")
+            return
+
+        def trampoline(_user, ints, n_ints, reals, n_reals):
+            try:
+                i_in = [ints[k] for k in range(n_ints)]
+                r_in = [reals[k] for k in range(n_reals)]
+                i_out, r_out = fn(i_in, r_in)
+                for k in range(n_ints):
+                    ints[k] = int(i_out[k])
+                for k in range(n_reals):
+                    reals[k] = float(r_out[k])
+                return 0
+            except Exception:   # must not propagate through the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        self._hook = REDUCE_HOOK(trampoline)   # keep the thunk alive
+        check(self.lib.abl_cuda_set_reduce_hook(self.handle, C.cast(self._hook, _VP), None), "set_reduce_hook")
 
     def bin(self, pool):
         check(self.lib.abl_cuda_bin(self.handle, pool), "bin")

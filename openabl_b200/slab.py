@@ -42,6 +42,37 @@ def halo_capacity(total_agents, n_layers, slack=4):
     return max(16384, int(slack * total_agents / max(n_layers, 1)) + 4096)
 
 
+def global_add_ranks(parts):
+    """parts: ascending parent-id arrays of the slabs (one adding step).  -> (per-slab ranks of
+    the parents in the sorted union, total).  New agents are numbered next_id + rank, exactly
+    as an undecomposed run numbers them (parent-id order)."""
+    parts = [np.asarray(p, dtype=np.uint32) for p in parts]
+    every = np.sort(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.uint32)
+    return [np.searchsorted(every, p).astype(np.uint32) for p in parts], int(len(every))
+
+
+def all_gather_ids(dist, world, mine):
+    """Variable-length all-gather of uint32 id arrays over torch.distributed (counts first, then
+    padded payloads).  -> list of arrays, one per rank."""
+    import torch
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    n = torch.tensor([len(mine)], dtype=torch.int64, device=dev)
+    counts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    buf = torch.zeros(width, dtype=torch.int64, device=dev)
+    if len(mine):
+        buf[:len(mine)] = torch.from_numpy(np.asarray(mine).astype(np.int64)).to(dev)
+    every = [torch.zeros(width, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(every, buf)
+    return [e[:c].cpu().numpy().astype(np.uint32) for e, c in zip(every, counts)]
+
+
+ADDS = 2      # abl_model_step_flags bits
+REMOVES = 1
+
+
 def ring_neighbours(rank, world):
     """(lower, upper) slab of `rank`; slabs form a ring when there are more than two."""
     ring = world > 2
@@ -108,14 +139,23 @@ class LocalSlabs:
 
     def timestep(self):
         m = self.model
+        for rt in self.rts:
+            rt.begin_timestep()
         for s in range(m.n_steps):
             for rt in self.rts:
                 check(m.lib.abl_model_run_step(rt.handle, s), "abl_model_run_step")
+            if m.step_flags(s) & ADDS:
+                # ids of new agents are global: rank of every parent among the parents of all slabs
+                ranks, total = global_add_ranks([rt.pending_add_parents() for rt in self.rts])
+                for rt, r in zip(self.rts, ranks):
+                    rt.resolve_adds(r, total)
             if self.transport == "direct":
-                continue   # abl_cuda_step exchanged by itself
+                continue   # abl_cuda_step / resolve_adds exchanged by themselves
             # the step's own pool may have changed: refresh ghosts / migrate
             pool = self.step_pool(s)
             self._exchange(pool)
+        for rt in self.rts:
+            rt.end_timestep()   # advances the counter the in-step RNG is keyed by
 
     def step_pool(self, s):
         # pools are registered in agent declaration order; the generated library reports the
@@ -162,6 +202,9 @@ class RankSlab:
             dist.broadcast(uid, src=0)
             self.rt.init_nccl(bytes(uid.cpu().tolist()), rank, world)
         self.rt.set_slab(self.bounds, rank)
+        self._mutating = any(model.step_flags(s) for s in range(model.n_steps))
+        if world > 1 and dist is not None:
+            self._install_reduce_hook()
 
     def upload(self, host_arrays=None):
         """Every rank uploads the whole population from the model's own page-locked host arrays
@@ -201,7 +244,41 @@ class RankSlab:
         self._connected = True
 
     def timestep(self):
-        self.model.timestep()   # abl_cuda_step exchanges by itself when NCCL is attached
+        m = self.model
+        if not self._mutating or self.world == 1:
+            m.timestep()   # abl_cuda_step exchanges by itself (peer memory or NCCL)
+            return
+        # run-time add(): the step stays open until the parents' ids have been combined across ranks
+        self.rt.begin_timestep()
+        for s in range(m.n_steps):
+            m.run_step(s)
+            if m.step_flags(s) & ADDS:
+                mine = self.rt.pending_add_parents()
+                ranks, total = global_add_ranks(self._all_gather_ids(mine))
+                self.rt.resolve_adds(ranks[self.rank], total)
+        m.sequential_step()
+        self.rt.end_timestep()
+
+    def _all_gather_ids(self, mine):
+        return all_gather_ids(self.dist, self.world, mine)
+
+    def _install_reduce_hook(self):
+        """count()/sum() of the sequential step become sums over all ranks."""
+        import torch
+        dist = self.dist
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+        def hook(ints, reals):
+            if ints:
+                t = torch.tensor(ints, dtype=torch.int64, device=dev)
+                dist.all_reduce(t)
+                ints = t.cpu().tolist()
+            if reals:
+                t = torch.tensor(reals, dtype=torch.float64, device=dev)
+                dist.all_reduce(t)
+                reals = t.cpu().tolist()
+            return ints, reals
+        self.rt.set_reduce_hook(hook)
 
     def owned(self, t):
         return self.rt.pool_size(self.model.pool(t))

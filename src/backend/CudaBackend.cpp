@@ -126,6 +126,7 @@ private:
   void clearNearContext() { nearVar = nearSelf = nullptr; nearD2.clear(); }
   // chunked near loop: `break` of the DSL body must leave two nested C++ loops
   std::string nearBreakLabel;
+  std::string nearContinueLabel;   // non-empty: `continue` of the for-near body jumps there (unrolled loop)
   int innerLoopDepth = 0;
   std::vector<StepInfo> steps;
 
@@ -556,7 +557,10 @@ void CudaPrinter::stmt(const Stmt &s) {
       if (!nearBreakLabel.empty() && innerLoopDepth == 0) w << "goto " << nearBreakLabel << ";";
       else w << "break;";
       return;
-    case Stmt::Continue: w << "continue;"; return;
+    case Stmt::Continue:
+      if (!nearContinueLabel.empty() && innerLoopDepth == 0) w << "goto " << nearContinueLabel << ";";
+      else w << "continue;";
+      return;
     case Stmt::Simulate:
       if (dev()) throw BackendError("cuda backend: simulate inside device code");
       w << "abl_model_simulate("; expr(*s.e[0]); w << ");";
@@ -852,61 +856,91 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   }
   const bool prefetchOthers = !others.empty() && otherCols <= 2 && allFloat;
   std::string ptypeS = typeName(pos->type);
-  auto prefetch = [&]() {
+  // `-C cuda.unroll=true`: the loop is unrolled by two with alternating prefetch registers, so
+  // that handing the prefetched candidate to the body costs no register copies (8 moves per
+  // iteration for a double-precision float2 position + float2 member)
+  const bool unroll = config.getBool("cuda.unroll", false);
+  auto setName = [&](int set, const std::string &base) { return unroll ? base + (set ? "B" : "A") : base; };
+  auto prefetch = [&](int set) {
     w << "if (" << it << ".valid()) {";
     w.indent(); w.nl();
-    loadMember(*nbr, posIndex, it + "p", "_a.nbr.in", it + ".index()");
+    loadMember(*nbr, posIndex, setName(set, it + "p"), "_a.nbr.in", it + ".index()");
     if (prefetchOthers) {
       for (int m : others) {
         w.nl();
-        loadMember(*nbr, m, it + "m" + std::to_string(m), "_a.nbr.in", it + ".index()");
+        loadMember(*nbr, m, setName(set, it + "m" + std::to_string(m)), "_a.nbr.in", it + ".index()");
       }
     }
     w.outdent(); w.nl();
     w << "}";
   };
-  w << ptypeS << " " << it << "p;"; w.nl();
-  if (prefetchOthers)
-    for (int m : others) { w << typeName(nbr->members[m]->type) << " " << it << "m" << m << ";"; w.nl(); }
-  prefetch();
+  for (int set = 0; set < (unroll ? 2 : 1); set++) {
+    w << ptypeS << " " << setName(set, it + "p") << ";"; w.nl();
+    if (prefetchOthers)
+      for (int m : others) { w << typeName(nbr->members[m]->type) << " " << setName(set, it + "m" + std::to_string(m)) << ";"; w.nl(); }
+  }
+  prefetch(0);
   w.nl();
-  w << "while (" << it << ".valid()) {";
-  w.indent(); w.nl();
-  w << "const unsigned " << it << "j = " << it << ".index();";
-  w.nl();
-  w << nbr->name << " " << s.varName << ";";
-  w.nl();
-  w << s.varName << "." << pos->name << " = " << it << "p;"; w.nl();
-  if (prefetchOthers)
-    for (int m : others) { w << s.varName << "." << nbr->members[m]->name << " = " << it << "m" << m << ";"; w.nl(); }
-  w << it << ".next();"; w.nl();
-  prefetch();
-  w.nl();
-  if (curStepHasLimit) {
-    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
-      << pos->name << ", " << selfPosText << "));";
+  // one candidate: take it from register set `set`, request the next one into the other set
+  auto half = [&](int set, const std::string &skip) {
+    w << "const unsigned " << it << "j = " << it << ".index();";
     w.nl();
-    w << "if (" << it << "d2 > _near_limit) continue;";
+    w << nbr->name << " " << s.varName << ";";
+    w.nl();
+    w << s.varName << "." << pos->name << " = " << setName(set, it + "p") << ";"; w.nl();
+    if (prefetchOthers)
+      for (int m : others) { w << s.varName << "." << nbr->members[m]->name << " = " << setName(set, it + "m" + std::to_string(m)) << ";"; w.nl(); }
+    w << it << ".next();"; w.nl();
+    prefetch(unroll ? 1 - set : 0);
+    w.nl();
+    if (curStepHasLimit) {
+      w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+        << pos->name << ", " << selfPosText << "));";
+      w.nl();
+      w << "if (" << it << "d2 > _near_limit) " << skip;
+    } else {
+      w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", " << selfPosText << ") > ";
+      expr(radius);
+      w << ") " << skip;
+    }
+    if (!prefetchOthers) loadOthers(it + "j");
+    w.nl();
+    {
+      std::string savedLabel = nearBreakLabel;
+      int savedDepth = innerLoopDepth;
+      nearBreakLabel.clear();
+      innerLoopDepth = 0;
+      if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+      stmt(*s.body[0]);
+      clearNearContext();
+      nearBreakLabel = savedLabel;
+      innerLoopDepth = savedDepth;
+    }
+  };
+  if (!unroll) {
+    w << "while (" << it << ".valid()) {";
+    w.indent(); w.nl();
+    half(0, "continue;");
+    w.outdent(); w.nl();
+    w << "}";
   } else {
-    w << "if (dist_float" << sdim << "(" << s.varName << "." << pos->name << ", " << selfPosText << ") > ";
-    expr(radius);
-    w << ") continue;";
+    const std::string second = "_near_second" + it;
+    w << "while (" << it << ".valid()) {";
+    w.indent(); w.nl();
+    w << "{";
+    w.indent(); w.nl();
+    std::string savedContinue = nearContinueLabel;
+    nearContinueLabel = second;
+    half(0, "goto " + second + ";");
+    nearContinueLabel = savedContinue;
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << second << ": ;"; w.nl();
+    w << "if (!" << it << ".valid()) break;"; w.nl();
+    half(1, "continue;");
+    w.outdent(); w.nl();
+    w << "}";
   }
-  if (!prefetchOthers) loadOthers(it + "j");
-  w.nl();
-  {
-    std::string savedLabel = nearBreakLabel;
-    int savedDepth = innerLoopDepth;
-    nearBreakLabel.clear();
-    innerLoopDepth = 0;
-    if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-    stmt(*s.body[0]);
-    clearNearContext();
-    nearBreakLabel = savedLabel;
-    innerLoopDepth = savedDepth;
-  }
-  w.outdent(); w.nl();
-  w << "}";
   if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
   if (tile) { w.outdent(); w.nl(); w << "}"; }
   w.outdent(); w.nl();
@@ -1216,7 +1250,17 @@ void CudaPrinter::hostSeqSupport() {
   w << "static ABL_UNUSED abl_float3 abl_model_sum_float3(int t, int m) { double v[3] = {0, 0, 0}; for (int k = 0; k < 3; k++) abl_host_check(abl_cuda_sum_float(abl_rt, abl_model_types[t].pool, m, k, &v[k]), \"sum\"); return float3_create((abl_real)v[0], (abl_real)v[1], (abl_real)v[2]); }"; w.nl();
   w << "static ABL_UNUSED abl_real abl_model_last_exec_time(void) { double s = 0; abl_host_check(abl_cuda_last_exec_time(abl_rt, &s), \"getLastExecTime\"); return (abl_real)s; }"; w.nl();
   w << "static ABL_UNUSED void abl_model_save(const char *path) {"; w.nl();
-  w << "    abl_host_save_json(abl_model_types, abl_model_n_types, path);"; w.nl();
+  {
+    // save() format: the reference runtime knows three (asset/c/libabl.h:211-215); its `c` backend
+    // always passes SAVE_JSON (CPrinter.cpp:74-77), the FLAME backends write their initial states
+    // as XML.  Selected at compile time with -C cuda.save_format=json|flame_xml|flamegpu_xml.
+    std::string fmt = config.getString("cuda.save_format", "json");
+    if (fmt == "json") { w << "    abl_host_save_json(abl_model_types, abl_model_n_types, path);"; }
+    else if (fmt == "flame_xml") { w << "    abl_host_save_flame_xml(abl_model_types, abl_model_n_types, path, 0);"; }
+    else if (fmt == "flamegpu_xml") { w << "    abl_host_save_flame_xml(abl_model_types, abl_model_n_types, path, 1);"; }
+    else throw BackendError("cuda backend: unknown cuda.save_format \"" + fmt + "\" (json, flame_xml, flamegpu_xml)");
+    w.nl();
+  }
   w << "    if (getenv(\"ABL_DUMP_STATE\")) { char raw[4096]; snprintf(raw, sizeof raw, \"%s.bin\", path); abl_host_save_raw(abl_model_types, abl_model_n_types, raw); }"; w.nl();
   w << "}"; w.nl();
   w.nl();
@@ -1231,6 +1275,13 @@ void CudaPrinter::hostSimulate() {
   w << "    abl_host_check(abl_model_parallel_steps(rt), \"step\");"; w.nl();
   if (seq) { w << "    " << seq->emitName << "();"; w.nl(); }
   w << "    abl_host_check(abl_cuda_end_timestep(rt), \"end_timestep\");"; w.nl();
+  w << "    return 0;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "/* the sequential step alone (harnesses that drive the parallel step functions one by one) */"; w.nl();
+  w << "int abl_model_sequential_step(abl_runtime *rt) {"; w.nl();
+  w << "    abl_rt = rt;"; w.nl();
+  if (seq) { w << "    " << seq->emitName << "();"; w.nl(); }
   w << "    return 0;"; w.nl();
   w << "}"; w.nl(); w.nl();
 
@@ -1554,6 +1605,14 @@ std::string CudaPrinter::kernelSource() {
   for (const StepInfo &si : steps) w << " " << agentIndex(si.self) << ",";
   w << " -1 };"; w.nl();
   w << "    return abl_model_types[types[s]].pool;"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "/* bit 0: the step function calls removeCurrent(), bit 1: it adds agents at run time */"; w.nl();
+  w << "extern \"C\" int abl_model_step_flags(int s) {"; w.nl();
+  w << "    static const int flags[] = {";
+  for (const StepInfo &si : steps) w << " " << ((si.fn->usesRemoval ? 1 : 0) | (si.fn->addedAgent ? 2 : 0)) << ",";
+  w << " 0 };"; w.nl();
+  w << "    return flags[s];"; w.nl();
   w << "}"; w.nl(); w.nl();
 
   w << "extern \"C\" int abl_model_setup(abl_runtime *rt) {"; w.nl();

@@ -93,8 +93,10 @@ static void printHelp() {
                "\n"
                "Available configuration options:\n"
                " * bool use_float       (default: false) single precision agent state\n"
-               " * int  cuda.block_size (default: 128)   threads per CTA of step kernels\n"
-               " * bool cuda.tile       (default: true)  stage neighbour cells in shared memory\n"
+               " * int  cuda.block_size (default: 0)     threads per CTA of step kernels (0 = automatic)\n"
+               " * bool cuda.tile       (default: false) stage neighbour cells in shared memory\n"
+               " * bool cuda.unroll     (default: false) unroll the for-near candidate loop by two\n"
+               " * str  cuda.save_format (default: json) save() output: json, flame_xml or flamegpu_xml\n"
                " * int  cuda.dump_state (default: 0)     also write raw binary state on save()\n"
             << std::flush;
 }

@@ -29,8 +29,8 @@ CASES = [
 ]
 
 
-def gpu_run(model_file, params, use_float, steps, **rt_kw):
-    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
+def gpu_run(model_file, params, use_float, steps, config=None, **rt_kw):
+    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float, config=config)
     m.populate()
     init = m.host_agents(0)
     m.create_runtime(**rt_kw)
@@ -64,3 +64,25 @@ def test_gpu_equals_grid_oracle(model_file, params, use_float, steps, tile):
         for f in got.dtype.names:
             assert np.array_equal(got[f], want[f]), "member %s is not bit-equal (max rel err %.3e)" % (
                 f, max_rel_error(got, want))
+
+
+UNROLL_CASES = [CASES[1], CASES[2], CASES[3], CASES[4], CASES[5]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_file,params,use_float,steps", UNROLL_CASES,
+                         ids=["%s-%d-%s" % (c[0][:-4], c[1]["num_agents"], "f32" if c[2] else "f64") for c in UNROLL_CASES])
+def test_unrolled_candidate_loop_equals_grid_oracle(model_file, params, use_float, steps):
+    """-C cuda.unroll=true: the for-near loop unrolled by two with alternating prefetch
+    registers visits the same candidates in the same order."""
+    init, got = gpu_run(model_file, params, use_float, steps, config={"cuda.unroll": True})
+    o = Oracle(use_float)
+    state = o.init_for(model_file, params)
+    want = o.run_for(model_file, params, state, steps, GRID)
+    assert len(got) == len(want)
+    assert exact_members_equal(got, want), "integer/bool state differs"
+    if use_float:
+        assert max_rel_error(got, want) <= 1e-4
+    else:
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[f]), "member %s is not bit-equal" % f

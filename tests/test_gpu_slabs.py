@@ -99,6 +99,57 @@ def test_direct_transport_reports_message_overflow():
     ls.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("transport", ["staged", "direct"])
+@pytest.mark.parametrize("slabs", [2, 3])
+def test_predator_prey_decomposed_add_remove_is_bit_identical(slabs, transport):
+    """Run-time add()/removeCurrent() under slab decomposition (three agent types reading each
+    other): removal compacts the owned range of the owning slab, new agents get the ids of the
+    undecomposed run (rank of the parent among the parents of all slabs), and every member of
+    every survivor equals the single-slab run bit for bit."""
+    steps = 12
+    m = Model(os.path.join(REPO, "examples", "predator_prey.abl"), {"num_agents": 32000})
+    m.populate()
+    host = [m.host_agents(t) for t in range(m.n_types)]
+    m.create_runtime()
+    m.upload_host()
+    counts_single = []
+    for _ in range(steps):
+        m.timestep()
+        counts_single.append([m.rt.count(m.pool(t)) for t in range(m.n_types)])
+    single_ids = [m.rt.download_ids(m.pool(t)) for t in range(m.n_types)]
+    single = [m.download(t) for t in range(m.n_types)]
+    m.close()
+    assert any(len(single[t]) != len(host[t]) for t in range(m.n_types)), "population never changed"
+    assert any(len(single_ids[t]) and single_ids[t].max() >= len(host[t]) for t in range(m.n_types)), "nothing was added"
+
+    ls = LocalSlabs(m, slabs, transport=transport)
+    ls.upload(host)
+    for k in range(steps):
+        ls.timestep()
+        got = [sum(ls.owned_counts(t)) for t in range(m.n_types)]
+        assert got == counts_single[k], "agent counts differ from the single-slab run after timestep %d" % k
+    # rank-local reductions add up to the global value
+    grass = m.pool(2)
+    assert sum(rt.sum_int(grass, 2) for rt in ls.rts) == int(single[2]["avail"].sum())
+    for t in range(m.n_types):
+        ids, rec = ls.download(t)
+        assert np.array_equal(ids, single_ids[t]), "%s: ids differ from the single-slab run" % m.names[t]
+        for f in rec.dtype.names:
+            assert np.array_equal(rec[f], single[t][f]), "%s.%s differs from the single-slab run" % (m.names[t], f)
+    ls.close()
+
+
+def test_global_add_ranks():
+    from openabl_b200.slab import global_add_ranks
+    ranks, total = global_add_ranks([np.array([3, 10, 42], dtype=np.uint32), np.zeros(0, dtype=np.uint32),
+                                     np.array([1, 11], dtype=np.uint32)])
+    assert total == 5
+    assert [r.tolist() for r in ranks] == [[1, 2, 4], [], [0, 3]]
+    ranks, total = global_add_ranks([np.zeros(0, dtype=np.uint32)] * 2)
+    assert total == 0 and all(len(r) == 0 for r in ranks)
+
+
 def test_split_layers():
     assert split_layers(69, 8) == [(0, 8), (8, 17), (17, 25), (25, 34), (34, 43), (43, 51), (51, 60), (60, 69)]
     assert split_layers(4, 4) == [(0, 1), (1, 2), (2, 3), (3, 4)]

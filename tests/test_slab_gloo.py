@@ -115,3 +115,35 @@ def test_two_slabs_over_gloo_equal_undecomposed_run(tmp_path):
     want = o.boids_run(o.boids_init(n), steps, GRID)
     for f in want.dtype.names:
         assert np.array_equal(merged["agent"][f], want[f]), "member %s differs" % f
+
+
+def _ids_main(rank, world, port, out_dir):
+    import sys
+    sys.path.insert(0, REPO)
+    from openabl_b200.slab import all_gather_ids, global_add_ranks
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    # parents of one adding step: rank 0 owns ids 5, 9, 40; rank 1 owns 7 only; then an empty round
+    rounds = [([5, 9, 40], [7]), ([], []), ([], [3, 4])]
+    next_id = 100
+    log = []
+    for parts in rounds:
+        mine = np.array(parts[rank], dtype=np.uint32)
+        ranks, total = global_add_ranks(all_gather_ids(dist, world, mine))
+        log.append(((next_id + ranks[rank]).tolist(), total))
+        next_id += total
+    np.save(os.path.join(out_dir, "ids%d.npy" % rank), np.array(log, dtype=object), allow_pickle=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_new_agent_ids_are_resolved_across_ranks(tmp_path):
+    """Run-time add() under slab decomposition: every rank numbers its new agents
+    next_id + (rank of the parent among the parents of all ranks) and all ranks advance next_id
+    by the global total — the numbering of an undecomposed run (k_append: parent-id order)."""
+    world = 2
+    port = _free_port()
+    mp.spawn(_ids_main, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    got = [np.load(os.path.join(str(tmp_path), "ids%d.npy" % r), allow_pickle=True).tolist() for r in range(world)]
+    assert got[0] == [[[100, 102, 103], 4], [[], 0], [[], 2]]
+    assert got[1] == [[[101], 4], [[], 0], [[104, 105], 2]]
