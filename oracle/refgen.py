@@ -84,6 +84,26 @@ FIXTURES = {
 }
 
 
+# Feature-test models (tests/models/): constructs of the reference's other examples — 3-D
+# flocking, two agent types reading each other over several step functions, constant tables /
+# while / float modulo.  Golden vectors come from the real reference as above; there is no
+# plain-C restatement of these models (tests/test_oracle.py covers FIXTURES only), the GPU is
+# compared with the reference's output directly (tests/test_gpu_parity_reference.py).
+EXTRA_FIXTURES = {
+    "flock3d_n2000_t10": ("tests/models/flock3d.abl", {"num_agents": 2000, "num_timesteps": 10}, False),
+    "flock3d_n2000_t10_f32": ("tests/models/flock3d.abl", {"num_agents": 2000, "num_timesteps": 10}, True),
+    "two_species_n3000_t10": ("tests/models/two_species.abl", {"num_agents": 3000, "num_timesteps": 10}, False),
+    "two_species_n3000_t0": ("tests/models/two_species.abl", {"num_agents": 3000, "num_timesteps": 0}, False),
+    "table_cells_n2500_t10": ("tests/models/table_cells.abl", {"num_agents": 2500, "num_timesteps": 10}, False),
+    "table_cells_n2500_t10_f32": ("tests/models/table_cells.abl", {"num_agents": 2500, "num_timesteps": 10}, True),
+}
+
+
+def model_path(model):
+    """Fixture model names are relative to examples/ unless they carry a directory."""
+    return os.path.join(REPO, model) if os.sep in model or "/" in model else os.path.join(REPO, "examples", model)
+
+
 def fixture_paths(name):
     return os.path.join(GOLDEN, name + ".npz"), os.path.join(GOLDEN, name + ".json")
 
@@ -100,8 +120,11 @@ def main():
     if not reference_available():
         sys.exit("reference not available: build oracle/_ref first (make -C oracle ref)")
     os.makedirs(GOLDEN, exist_ok=True)
-    for name, (model, params, use_float) in FIXTURES.items():
-        path = os.path.join(REPO, "examples", model)
+    only = set(sys.argv[1:])
+    for name, (model, params, use_float) in list(FIXTURES.items()) + list(EXTRA_FIXTURES.items()):
+        if only and name not in only:
+            continue
+        path = model_path(model)
         state, text = run_reference(path, params, use_float)
         npz, meta = fixture_paths(name)
         np.savez_compressed(npz, **{"type%d" % i: s for i, s in enumerate(state)})

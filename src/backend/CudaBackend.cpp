@@ -125,6 +125,7 @@ private:
   }
   void clearNearContext() { nearVar = nearSelf = nullptr; nearD2.clear(); }
   // chunked near loop: `break` of the DSL body must leave two nested C++ loops
+  std::string arrayElemName(const Ty &base) const;
   std::string nearBreakLabel;
   std::string nearContinueLabel;   // non-empty: `continue` of the for-near body jumps there (unrolled loop)
   int innerLoopDepth = 0;
@@ -984,12 +985,21 @@ const Stmt *CudaPrinter::findNearStmt(const std::vector<StmtP> &body) const {
 // ---------------------------------------------------------------------------------------
 // declarations
 // ---------------------------------------------------------------------------------------
+// Element type of a global constant array.  The reference prints the DSL's base type name for
+// arrays (CPrinter::printType, CPrinter.cpp:20-24: `float FORCE[] = {...}`), so a table of
+// `float` is stored in SINGLE precision even when abl_float is double; elements widen when they
+// are read.  Kept, because it defines the values the reference `c` backend computes with.
+std::string CudaPrinter::arrayElemName(const Ty &base) const {
+  if (base.isFloat()) return "float";
+  return typeName(base);
+}
+
 void CudaPrinter::constDecl(const ConstDecl &c) {
   const Ty &t = c.type;
   if (!dev()) {
     // same text as the reference: `double W = 141.421;`, vectors as brace initialisers
     Ty base = c.isArray ? t.elem() : t;
-    w << typeName(base) << " " << c.name << (c.isArray ? "[]" : "") << " = ";
+    w << (c.isArray ? arrayElemName(base) : typeName(base)) << " " << c.name << (c.isArray ? "[]" : "") << " = ";
     if (base.isVec() && !c.isArray) {
       w << "{";
       args(*c.init);
@@ -1002,7 +1012,7 @@ void CudaPrinter::constDecl(const ConstDecl &c) {
   }
   if (c.isArray) {
     Ty base = t.elem();
-    w << "__device__ const " << typeName(base) << " " << c.name << "[] = ";
+    w << "__device__ const " << arrayElemName(base) << " " << c.name << "[] = ";
     if (base.isVec()) throw BackendError("cuda backend: vector constant arrays are not supported");
     expr(*c.init);
     w << ";";

@@ -11,6 +11,7 @@ from openabl_b200 import build
 from openabl_b200.paths import ASSET_DIR, COMPILER, REPO_ROOT
 
 REF = "/root/reference"
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_BIN = os.path.join(REPO_ROOT, "oracle", "_ref", "OpenABL_ref")
 needs_ref = pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree not present")
 
@@ -97,3 +98,35 @@ def test_reference_c_backend_rejects_add_remove(tmp_path):
                            os.path.join(REF, "examples", "predator_prey.abl"), "-b", "c", "-o", str(tmp_path / "o")],
                           stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     assert proc.returncode == 2
+
+
+ARRAY_RE = re.compile(r"^(\w+)\s+(\w+)\[\]\s*=\s*\{([^}]*)\};", re.M)
+
+
+@needs_ref
+@pytest.mark.skipif(not os.path.exists(REF_BIN), reason="oracle/_ref not built")
+@pytest.mark.parametrize("model", ["tests/models/table_cells.abl", "tests/models/flock3d.abl",
+                                   "tests/models/two_species.abl", os.path.join(REF, "examples", "keratinocyte.abl")])
+def test_constants_and_tables_of_feature_models_match_reference(model, tmp_path):
+    """Scalars fold to the reference's 6-digit text, and constant TABLES keep the reference's
+    element type: the reference prints the DSL base type for arrays (CPrinter.cpp:20-24), so a
+    `float` table is single precision even in a double-precision build."""
+    build.build_compiler()
+    model = model if os.path.isabs(model) else os.path.join(REPO, model)
+    mine, theirs = tmp_path / "mine", tmp_path / "theirs"
+    subprocess.run([COMPILER, "-A", ASSET_DIR, "-i", model, "-b", "cuda", "-o", str(mine)], check=True)
+    proc = subprocess.run([REF_BIN, "-A", os.path.join(REF, "asset"), "-i", model, "-b", "c", "-o", str(theirs)],
+                          stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode == 2:
+        pytest.skip("the reference c backend rejects this model (run-time add/remove)")
+    assert proc.returncode == 0, proc.stdout
+    host, ref = (mine / "model_host.c").read_text(), (theirs / "main.c").read_text()
+    dev = (mine / "model_kernels.cu").read_text()
+    mine_consts, ref_consts = dict(CONST_RE.findall(host)), dict(CONST_RE.findall(ref))
+    for name, value in ref_consts.items():
+        assert mine_consts.get(name, "").strip() == value.strip(), "constant %s" % name
+    norm = lambda t: re.sub(r"\s+", "", t)
+    mine_tabs = {n: (ty, norm(v)) for ty, n, v in ARRAY_RE.findall(host)}
+    for ty, name, values in ARRAY_RE.findall(ref):
+        assert mine_tabs.get(name) == (ty, norm(values)), "table %s: %r vs reference %r" % (name, mine_tabs.get(name), (ty, norm(values)))
+        assert re.search(r"__device__ const %s %s\[\]" % (ty, name), dev), "device copy of %s has another element type" % name

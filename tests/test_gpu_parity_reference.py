@@ -20,6 +20,9 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # sensitive by nature (tests/test_oracle.py::test_order_sensitivity...) and is checked bit for
 # bit against the grid-ordered oracle in test_gpu_parity_oracle.py instead.
 RUNS = [n for n, (_, p, _) in refgen.FIXTURES.items() if p["num_timesteps"] == 10]
+# feature-test models (tests/models/): 3-D flocking, two agent types reading each other over
+# three step functions, constant tables / while / float modulo
+EXTRA_RUNS = [n for n, (_, p, _) in refgen.EXTRA_FIXTURES.items() if p["num_timesteps"] == 10]
 
 
 def simulate(model, timesteps, **rt_kw):
@@ -34,12 +37,12 @@ def simulate(model, timesteps, **rt_kw):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", RUNS)
+@pytest.mark.parametrize("name", RUNS + EXTRA_RUNS)
 def test_matches_reference_c_backend(name):
     info, gold = refgen.load_fixture(name)
     params = dict(info["params"])
     steps = params["num_timesteps"]
-    m = Model(os.path.join(REPO, "examples", info["model"]), params, use_float=info["use_float"])
+    m = Model(refgen.model_path(info["model"]), params, use_float=info["use_float"])
     got = simulate(m, steps)
     tol = 1e-4 if info["use_float"] else 1e-9
     for g, ref in zip(got, gold):
@@ -53,7 +56,7 @@ def test_matches_reference_c_backend(name):
 def test_initial_state_roundtrip_is_bit_exact():
     """upload -> (bin) -> download returns the records in original order, bit for bit."""
     info, gold = refgen.load_fixture("boids2d_n4000_t0")
-    m = Model(os.path.join(REPO, "examples", info["model"]), dict(info["params"]))
+    m = Model(refgen.model_path(info["model"]), dict(info["params"]))
     m.populate()
     m.create_runtime()
     m.upload_host()
@@ -62,3 +65,19 @@ def test_initial_state_roundtrip_is_bit_exact():
     m.close()
     for f in back.dtype.names:
         assert np.array_equal(back[f], gold[0][f])
+
+
+@pytest.mark.parametrize("name", ["two_species_n3000_t0", "boids2d_n4000_t0", "circle3d_n2000_t0", "game_of_life_n4096_t0"])
+def test_generated_host_program_builds_the_reference_population(name):
+    """CPU: the initialisation code of the generated host program (gcc-compiled C, the same
+    xorshift128+ stream and argument evaluation order as the reference's main.c) produces the
+    reference's initial population bit for bit — every agent type, every member."""
+    info, gold = refgen.load_fixture(name)
+    m = Model(refgen.model_path(info["model"]), dict(info["params"]), use_float=info["use_float"])
+    m.populate()
+    assert m.n_types == len(gold)
+    for t, ref in enumerate(gold):
+        host = m.host_agents(t)
+        assert len(host) == len(ref)
+        for f in host.dtype.names:
+            assert np.array_equal(host[f], ref[f]), "%s.%s differs" % (m.names[t], f)
