@@ -96,7 +96,7 @@ struct Pool {
   // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
   // src_begin is where the live records start before the next binning compacts them
   u32 own_begin = 0, own_end = 0, src_begin = 0;
-  u32 bnd_lo_end = 0, bnd_hi_begin = 0;
+  u32 bnd_lo_end = 0, bnd_hi_begin = 0;   // pool indices delimiting the boundary parts of the owned range
   // The report of the last slab-mode binning (owned range, boundary parts, counters of the
   // preceding halo exchange) lands in a per-pool slice of mapped host memory.  With device-side
   // ranges the host consumes it lazily: at the latest when the next binning needs the pool size.
@@ -106,7 +106,7 @@ struct Pool {
   bool exch_deferred = false;     // a direct exchange was queued without the host knowing the owned range
   u32 exch_pad = 0;               // padding of that exchange
   u32 pad_used[2] = {0, 0};       // padding of the exchanges in flight, by parity of their sequence number
-  bool halo_sync_check = false;   // verify the counts of the last exchange synchronously at the next binning (stand-alone exchanges)   // pool indices delimiting the boundary parts of the owned range
+  bool halo_sync_check = false;   // verify the counts of the last exchange synchronously at the next binning (stand-alone exchanges)
   u32 key_base_hint = 0;  // copy of grid.key_base (cell_start is handed out with a virtual origin)
   bool own_valid = false;
   // direct halo transport (peer memory over NVLink, no NCCL, no host sync per exchange)
@@ -242,6 +242,10 @@ struct abl_runtime {
   int open_step = -1;
   std::vector<u64> open_list;               // (parent id << 32 | slot relative to the owned range), ascending
   void *open_staging[ABL_MAX_COLUMNS + 1];
+  // timing mode: the four events of every abl_cuda_step are queued here and evaluated when the
+  // caller asks (abl_cuda_last_timing) — no host synchronisation between the timed steps, so the
+  // GPU is never idle between them and the stages are timed as they run in a real simulation
+  std::vector<cudaEvent_t> timing_log;
   // combines rank-local reduction results across slabs (installed by the harness)
   abl_reduce_hook reduce_hook = nullptr;
   void *reduce_user = nullptr;
@@ -1096,6 +1100,8 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   if (rt->d_scalar) cudaFree(rt->d_scalar);
   if (rt->h_scalar) cudaFreeHost(rt->h_scalar);
   for (int i = 0; i < 4; i++) if (rt->ev[i]) cudaEventDestroy(rt->ev[i]);
+  for (cudaEvent_t e : rt->timing_log) cudaEventDestroy(e);
+  rt->timing_log.clear();
   for (int i = 0; i < 2; i++) if (rt->ev_ts[i]) cudaEventDestroy(rt->ev_ts[i]);
   if (rt->ev_own) cudaEventDestroy(rt->ev_own);
   cudaStreamDestroy(rt->stream);
@@ -1788,6 +1794,29 @@ extern "C" int abl_cuda_resolve_adds(abl_runtime *rt, const unsigned *global_ran
   return slab_after_mutation(rt, s.desc.self_pool);
 }
 
+// Evaluates the queued step timings: rt->last becomes the MEAN per abl_cuda_step call over the
+// steps since the last evaluation (a caller that asks after every step gets that step's times).
+static int drain_timing(abl_runtime *rt) {
+  const size_t quads = rt->timing_log.size() / 4;
+  if (!quads) return ABL_OK;
+  CU(cudaEventSynchronize(rt->timing_log.back()));
+  double bin = 0, kernel = 0, commit = 0;
+  for (size_t q = 0; q < quads; q++) {
+    cudaEvent_t *e = &rt->timing_log[4 * q];
+    float a = 0, b = 0, c = 0;
+    CU(cudaEventElapsedTime(&a, e[0], e[1]));
+    CU(cudaEventElapsedTime(&b, e[1], e[2]));
+    CU(cudaEventElapsedTime(&c, e[2], e[3]));
+    bin += a; kernel += b; commit += c;
+  }
+  for (cudaEvent_t e : rt->timing_log) cudaEventDestroy(e);
+  rt->timing_log.clear();
+  rt->last.bin_ms = (float)(bin / quads);
+  rt->last.kernel_ms = (float)(kernel / quads);
+  rt->last.commit_ms = (float)(commit / quads);
+  return ABL_OK;
+}
+
 extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
   if (step < 0 || step >= (int)rt->steps.size()) return fail(ABL_ERR_ARGUMENT, "bad step index %d", step);
@@ -1943,10 +1972,11 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
   }
   if (rt->timing) {
     CU(cudaEventRecord(rt->ev[3], rt->stream));
-    CU(cudaEventSynchronize(rt->ev[3]));
-    CU(cudaEventElapsedTime(&rt->last.bin_ms, rt->ev[0], rt->ev[1]));
-    CU(cudaEventElapsedTime(&rt->last.kernel_ms, rt->ev[1], rt->ev[2]));
-    CU(cudaEventElapsedTime(&rt->last.commit_ms, rt->ev[2], rt->ev[3]));
+    for (int i = 0; i < 4; i++) {
+      rt->timing_log.push_back(rt->ev[i]);
+      CU(cudaEventCreate(&rt->ev[i]));
+    }
+    if (rt->timing_log.size() >= 4 * 2048) TRY(drain_timing(rt));   // bounded number of live events
   }
   return ABL_OK;
 }
@@ -1983,12 +2013,14 @@ extern "C" int abl_cuda_last_exec_time(abl_runtime *rt, double *seconds) {
 
 extern "C" int abl_cuda_enable_timing(abl_runtime *rt, int on) {
   if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  TRY(drain_timing(rt));
   rt->timing = on != 0;
   return ABL_OK;
 }
 
 extern "C" int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t) {
   if (!rt || !t) return fail(ABL_ERR_ARGUMENT, "null argument");
+  TRY(drain_timing(rt));
   *t = rt->last;
   t->launches = rt->launches;
   return ABL_OK;
