@@ -1,0 +1,98 @@
+// tests/emu/emu_kernels.cpp — TEST INFRASTRUCTURE (see cuda_runtime.h in this directory).
+//
+// Compiles the generated device program of one model for the host and exposes its step
+// launchers to Python: the three runtime calls abl_model_setup() makes are redirected to
+// recorders below, so the harness learns the environment, the pools and — through the
+// abl_step_desc the generated code registers — the launcher of every step function, exactly
+// as the device runtime does (asset/cuda/abl_runtime.cu: abl_cuda_register_step).
+#include "cuda_runtime.h"
+
+emu_idx threadIdx, blockIdx, blockDim, gridDim;
+unsigned long long emu_threads_run = 0;
+
+#define abl_cuda_set_environment emu_set_environment
+#define abl_cuda_add_pool emu_add_pool
+#define abl_cuda_register_step emu_register_step
+#define abl_cuda_step emu_step_unused
+
+#include "model_kernels.cu"
+
+// the dynamic shared memory of the generated kernels (ABL_MODE 1 acceptance masks; the tile
+// kernels' buffer is declared but never used here)
+unsigned _abl_masks[ABL_MASK_WORDS * 1024];
+__attribute__((aligned(16))) unsigned char _abl_smem[64 * 1024];
+
+namespace {
+struct Env { int dim; double lo[3], hi[3], cell; bool set; } g_env;
+struct StepRec { abl_step_desc desc; };
+StepRec g_steps[64];
+int g_n_steps = 0;
+int g_n_pools = 0;
+}
+
+extern "C" int emu_set_environment(abl_runtime *, int dim, const double *env_min, const double *env_max, double granularity) {
+  g_env.dim = dim;
+  for (int a = 0; a < 3; a++) { g_env.lo[a] = a < dim ? env_min[a] : 0; g_env.hi[a] = a < dim ? env_max[a] : 0; }
+  g_env.cell = granularity;
+  g_env.set = true;
+  return 0;
+}
+extern "C" int emu_add_pool(abl_runtime *, const abl_agent_desc *, int *pool) { *pool = g_n_pools++; return 0; }
+extern "C" int emu_register_step(abl_runtime *, const abl_step_desc *desc, int *step) {
+  g_steps[g_n_steps].desc = *desc;
+  *step = g_n_steps++;
+  return 0;
+}
+extern "C" int emu_step_unused(abl_runtime *, int) { return -1; }
+
+extern "C" {
+
+int emu_setup(void) {
+  g_n_steps = 0; g_n_pools = 0; g_env.set = false;
+  return abl_model_setup(nullptr);
+}
+
+// environment as registered by the model: dim, min[3], max[3], granularity (0 if none)
+int emu_environment(int *dim, double *lo, double *hi, double *cell) {
+  if (!g_env.set) return 1;
+  *dim = g_env.dim;
+  for (int a = 0; a < 3; a++) { lo[a] = g_env.lo[a]; hi[a] = g_env.hi[a]; }
+  *cell = g_env.cell;
+  return 0;
+}
+
+int emu_step_info(int s, int *self_pool, int *nbr_pool, double *radius, unsigned *written, int *uses_removal, int *added_pool) {
+  if (s < 0 || s >= g_n_steps) return 1;
+  const abl_step_desc &d = g_steps[s].desc;
+  *self_pool = d.self_pool; *nbr_pool = d.nbr_pool; *radius = d.radius; *written = d.written_members;
+  *uses_removal = d.uses_removal; *added_pool = d.added_pool;
+  return 0;
+}
+
+int emu_real_size(void) { return (int)sizeof(abl_real); }
+unsigned long long emu_thread_count(void) { return emu_threads_run; }
+
+// Runs step function `s` over the given (already binned) pools: the launcher the generated code
+// registered picks the kernel variant and the block size like on the device.
+int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, const abl_grid_view *grid, int reach,
+                 unsigned char *dead, unsigned *bin_key, unsigned *bin_local, unsigned *bin_count,
+                 unsigned long long seed, unsigned timestep, int block_size) {
+  if (s < 0 || s >= g_n_steps) return 1;
+  abl_step_launch a;
+  memset(&a, 0, sizeof a);
+  a.self = *self;
+  if (nbr) a.nbr = *nbr;
+  a.grid = *grid;
+  a.reach = reach;
+  a.dead = dead;
+  a.bin_key = bin_key; a.bin_local = bin_local; a.bin_count = bin_count;
+  a.seed = seed;
+  a.timestep = timestep;
+  a.step_index = (unsigned)s;
+  a.block_size = block_size;
+  a.tile_neighbours = 0;   // block-cooperative kernels cannot be emulated sequentially
+  a.pdl = 0;
+  return a.self.n ? g_steps[s].desc.launch(&a) : 0;
+}
+
+}
