@@ -229,6 +229,7 @@ struct abl_runtime {
   bool device_range = false;
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
+  int flat_loop = -1;          // ABL_CUDA_FLAT=0/1 pins the candidate loop of sparse 2-D step kernels (default: timed at run time)
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
@@ -1031,6 +1032,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *dr = getenv("ABL_CUDA_DEVICE_RANGE")) rt->device_range = atoi(dr) != 0;
   if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
+  if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
   if (getenv("ABL_CUDA_TRACE")) {
     rt->trace = true;
@@ -1923,6 +1925,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.step_index = (unsigned)step;
     a.block_size = rt->cfg.block_size;
     a.tile_neighbours = rt->cfg.tile_neighbours;
+    a.flat_loop = rt->flat_loop;
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
     trace_stamp(rt, TR_OTHER);

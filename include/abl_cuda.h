@@ -206,6 +206,8 @@ typedef struct {
   unsigned step_index;
   int block_size;
   int tile_neighbours;
+  int flat_loop;                           /* flat candidate loop of sparse 2-D for-near loops (ABL_MODE 3 kernels): 1 always, 0 never,
+                                              -1 the launcher times both bit-identical variants over its first launches and keeps the faster */
   int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
 } abl_step_launch;

@@ -17,6 +17,7 @@
 
 #include <cmath>
 #include <functional>
+#include <map>
 #include <sstream>
 
 #include "../FileUtil.hpp"
@@ -95,6 +96,7 @@ private:
   const StepInfo *curStep = nullptr;
   bool curStepHasLimit = false;
   bool curStepTile = false;     // the step's for-near loop can run from a shared-memory tile
+  bool curStepFlat = false;     // `-C cuda.flat=true` and a 2-D for-near loop: ABL_MODE 3 is printed
   // one neighbour column staged in shared memory by a tiled kernel
   struct TileCol {
     int member;          // member of the neighbour agent
@@ -122,8 +124,23 @@ private:
     nearSelf = agentExpr.kind == Expr::Var ? agentExpr.sym : nullptr;
     nearPos = pos; nearSelfPos = selfPos;
     nearD2 = nearSelf ? d2 : std::string();
+    nearBody = loop.body.empty() ? nullptr : loop.body[0].get();
+    sqAlias.clear();
   }
-  void clearNearContext() { nearVar = nearSelf = nullptr; nearD2.clear(); }
+  void clearNearContext() { nearVar = nearSelf = nullptr; nearD2.clear(); nearBody = nullptr; sqAlias.clear(); }
+  // `-C cuda.sqcmp=true`: comparisons of the near pair's distance with a constant become
+  // comparisons of the squared distance with a host-computed bound (abl_sq_cmp_limit).
+  // sqAlias: local float variables of the loop body that hold dist(in.pos, nx.pos) and are never
+  // assigned again -> name of the squared-distance variable; sqLimits: the bounds of the step
+  // kernel being printed, (operator, constant text), deduplicated across the loop variants.
+  const Stmt *nearBody = nullptr;
+  std::map<const Symbol *, std::string> sqAlias;
+  std::vector<std::pair<int, std::string>> sqLimits;
+  bool sqcmpOn() const { return config.getBool("cuda.sqcmp", true); }
+  const std::string *nearDistSquare(const Expr &e) const;
+  bool isNearDistCall(const Expr &e) const;
+  bool sqCompare(const Expr &e);
+  static bool assignsTo(const Stmt &s, const Symbol *sym);
   // chunked near loop: `break` of the DSL body must leave two nested C++ loops
   std::string arrayElemName(const Ty &base) const;
   std::string nearBreakLabel;
@@ -279,6 +296,7 @@ void CudaPrinter::expr(const Expr &e) {
     case Expr::Binary: {
       const Expr &l = *e.kids[0], &r = *e.kids[1];
       if (l.type.isVec() || r.type.isVec()) { vecBinary(e.op, l, r); return; }
+      if (sqCompare(e)) return;
       if (e.op == Op::Mod && !(l.type.isInt() && r.type.isInt())) {
         w << (dev() ? "abl_fmod(" : "fmod(");
         expr(l); w << ", "; expr(r); w << ")";
@@ -353,6 +371,71 @@ bool CudaPrinter::isNearPair(const Expr &a, const Expr &b) const {
   };
   return (is(a, nearVar, nearPos) && is(b, nearSelf, nearSelfPos)) ||
          (is(b, nearVar, nearPos) && is(a, nearSelf, nearSelfPos));
+}
+
+// dist(in.pos, nx.pos) / dist(nx.pos, in.pos) / length(in.pos - nx.pos) of the current near pair
+bool CudaPrinter::isNearDistCall(const Expr &e) const {
+  if (e.kind != Expr::Call || e.ckind != Expr::Builtin) return false;
+  const std::string &t = e.target;
+  if ((t == "dist_float2" || t == "dist_float3") && isNearPair(*e.kids[0], *e.kids[1])) return true;
+  return (t == "length_float2" || t == "length_float3") && e.kids[0]->kind == Expr::Binary &&
+         e.kids[0]->op == Op::Sub && isNearPair(*e.kids[0]->kids[0], *e.kids[0]->kids[1]);
+}
+
+// name of the squared-distance variable if `e` is the near pair's distance (the call itself or a
+// local variable known to hold it)
+const std::string *CudaPrinter::nearDistSquare(const Expr &e) const {
+  if (!dev() || !nearVar || nearD2.empty()) return nullptr;
+  if (isNearDistCall(e)) return &nearD2;
+  if (e.kind == Expr::Var && e.sym) {
+    auto it = sqAlias.find(e.sym);
+    if (it != sqAlias.end()) return &it->second;
+  }
+  return nullptr;
+}
+
+bool CudaPrinter::assignsTo(const Stmt &s, const Symbol *sym) {
+  if (s.kind == Stmt::Assign || s.kind == Stmt::AssignOp) {
+    const Expr *root = s.e[0].get();
+    while (root->kind == Expr::Member || root->kind == Expr::Index) root = root->kids[0].get();
+    if (root->kind == Expr::Var && root->sym == sym) return true;
+  }
+  for (const StmtP &b : s.body) if (assignsTo(*b, sym)) return true;
+  return false;
+}
+
+// `<distance> < C`, `C >= <distance>`, ... with a host-evaluable C -> comparison of the squared
+// distance with kernel parameter _sql.v[k]
+bool CudaPrinter::sqCompare(const Expr &e) {
+  if (!dev() || !sqcmpOn() || !curStepHasLimit) return false;
+  int op;
+  switch (e.op) {
+    case Op::Lt: op = 0; break;
+    case Op::Le: op = 1; break;
+    case Op::Gt: op = 2; break;
+    case Op::Ge: op = 3; break;
+    default: return false;
+  }
+  const Expr *d = e.kids[0].get(), *c = e.kids[1].get();
+  const std::string *sq = nearDistSquare(*d);
+  if (!sq) {
+    // constant on the left: C < d  is  d > C
+    std::swap(d, c);
+    sq = nearDistSquare(*d);
+    if (!sq) return false;
+    static const int mirrored[4] = {2, 3, 0, 1};
+    op = mirrored[op];
+  }
+  if (!hostEvaluable(*c) || !(c->type.isNum())) return false;
+  std::string text = exprText(*c);
+  size_t k = 0;
+  for (; k < sqLimits.size(); k++) if (sqLimits[k].first == op && sqLimits[k].second == text) break;
+  if (k == sqLimits.size()) {
+    if (k >= 8) return false;   // ABL_SQ_LIMITS
+    sqLimits.push_back({op, text});
+  }
+  w << "(" << *sq << (op <= 1 ? " <= " : " >= ") << "_sql.v[" << k << "])";
+  return true;
 }
 
 void CudaPrinter::callExpr(const Expr &e) {
@@ -514,6 +597,9 @@ void CudaPrinter::stmt(const Stmt &s) {
       w << typeName(t) << " " << s.varName;
       if (!s.e.empty()) { w << " = "; expr(*s.e[0]); }
       w << ";";
+      if (dev() && sqcmpOn() && curStepHasLimit && !s.e.empty() && t.isFloat() && s.sym && nearBody &&
+          innerLoopDepth == 0 && isNearDistCall(*s.e[0]) && !assignsTo(*nearBody, s.sym))
+        sqAlias[s.sym] = nearD2;
       return;
     }
     case Stmt::Assign:
@@ -746,6 +832,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   }
   w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
+  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true); else ";
   w << it << ".init" << sdim << "(_a, " << selfPosText << ", true);";
   w.nl();
   // Radius filter: inclusive radius, self included, same operand order as the reference's
@@ -875,6 +962,81 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w.outdent(); w.nl();
     w << "}";
   };
+  // `-C cuda.flat=true` (ABL_MODE 3, 2-D grids, reach 1): ONE flat candidate counter over the
+  // three row ranges instead of a cursor that switches rows.  The pool index of candidate k is
+  // k plus a per-row offset picked with two compares and two selects, so no lane ever leaves the
+  // loop body to open its next row — in the cursor loop nearly every iteration has *some* lane
+  // doing that, and the whole warp pays for the divergent path.  Two candidates are handled per
+  // iteration: both positions (and prefetched members) are requested up front and both filters
+  // evaluated back to back (independent dependency chains), then the bodies run in candidate
+  // order.  Same candidates, same order as abl_near_iter: bit-identical results.
+  if (curStepFlat) {
+    w << "if (ABL_MODE == 3) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "T1 = " << it << ".re[0] - " << it << ".rb[0];"; w.nl();
+    w << "const unsigned " << it << "T2 = " << it << "T1 + (" << it << ".re[1] - " << it << ".rb[1]);"; w.nl();
+    w << "const unsigned " << it << "N = " << it << "T2 + (" << it << ".re[2] - " << it << ".rb[2]);"; w.nl();
+    w << "const unsigned " << it << "O0 = " << it << ".rb[0], " << it << "O1 = " << it << ".rb[1] - " << it << "T1, "
+      << it << "O2 = " << it << ".rb[2] - " << it << "T2;"; w.nl();
+    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "N; " << it << "k += 2) {";
+    w.indent(); w.nl();
+    w << "const bool " << it << "hB = " << it << "k + 1u < " << it << "N;"; w.nl();
+    w << "const unsigned " << it << "kB = " << it << "hB ? " << it << "k + 1u : " << it << "k;"; w.nl();
+    w << "const unsigned " << it << "jA = " << it << "k + (" << it << "k < " << it << "T1 ? " << it << "O0 : (" << it << "k < "
+      << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
+    w << "const unsigned " << it << "jB = " << it << "kB + (" << it << "kB < " << it << "T1 ? " << it << "O0 : (" << it << "kB < "
+      << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
+    for (int h = 0; h < 2; h++) {
+      const std::string H = h ? "B" : "A";
+      w << ptypeS << " " << it << "p" << H << ";"; w.nl();
+      loadMember(*nbr, posIndex, it + "p" + H, "_a.nbr.in", it + "j" + H); w.nl();
+      if (prefetchOthers)
+        for (int m : others) {
+          w << typeName(nbr->members[m]->type) << " " << it << "m" << m << H << ";"; w.nl();
+          loadMember(*nbr, m, it + "m" + std::to_string(m) + H, "_a.nbr.in", it + "j" + H); w.nl();
+        }
+    }
+    for (int h = 0; h < 2; h++) {
+      const std::string H = h ? "B" : "A";
+      w << "const abl_real " << it << "d2" << H << " = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "p" << H
+        << ", " << selfPosText << "));"; w.nl();
+    }
+    const std::string second = "_near_flatB" + it;
+    for (int h = 0; h < 2; h++) {
+      const std::string H = h ? "B" : "A";
+      w << "if (" << (h ? it + "hB && " : std::string()) << "!(" << it << "d2" << H << " > _near_limit)) {";
+      w.indent(); w.nl();
+      w << nbr->name << " " << s.varName << ";"; w.nl();
+      w << s.varName << "." << pos->name << " = " << it << "p" << H << ";";
+      if (prefetchOthers) {
+        for (int m : others) { w.nl(); w << s.varName << "." << nbr->members[m]->name << " = " << it << "m" << m << H << ";"; }
+      } else {
+        loadOthers(it + "j" + H);
+      }
+      w.nl();
+      {
+        std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
+        int savedDepth = innerLoopDepth;
+        nearBreakLabel.clear();
+        nearContinueLabel = h ? std::string() : second;
+        innerLoopDepth = 0;
+        setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2" + H);
+        stmt(*s.body[0]);
+        clearNearContext();
+        nearBreakLabel = savedLabel;
+        nearContinueLabel = savedContinue;
+        innerLoopDepth = savedDepth;
+      }
+      w.outdent(); w.nl();
+      w << "}"; w.nl();
+      if (h == 0) { w << second << ": ;"; w.nl(); }
+    }
+    w.outdent(); w.nl();
+    w << "}";
+    w.outdent(); w.nl();
+    w << "} else {";
+    w.indent(); w.nl();
+  }
   for (int set = 0; set < (unroll ? 2 : 1); set++) {
     w << ptypeS << " " << setName(set, it + "p") << ";"; w.nl();
     if (prefetchOthers)
@@ -942,6 +1104,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w.outdent(); w.nl();
     w << "}";
   }
+  if (curStepFlat) { w.outdent(); w.nl(); w << "}"; }
   if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
   if (tile) { w.outdent(); w.nl(); w << "}"; }
   w.outdent(); w.nl();
@@ -1412,10 +1575,15 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     }
   }
   const std::string trows = tdim == 2 ? "3" : "9";
+  curStepFlat = config.getBool("cuda.flat", true) && curStepHasLimit && nearStmt && nearStmt->declTy.agent &&
+                nearStmt->declTy.agent->position() && nearStmt->declTy.agent->position()->type.vecLen() == 2;
 
   // the user's step function
   w << "template <int ABL_MODE>"; w.nl();
-  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const unsigned _tile_cap, const bool _tile_ok, const "
+  sqLimits.clear();
+  const bool sql = sqcmpOn() && curStepHasLimit;   // comparison bounds on the squared distance travel as a kernel parameter
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, "
+    << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok, const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
   w.nl();
@@ -1423,7 +1591,8 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
 
   w << "template <int ABL_MODE>"; w.nl();
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
-    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const unsigned _tile_cap) {";
+    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, "
+    << (sql ? "const abl_sq_limits _sql, " : "") << "const unsigned _tile_cap) {";
   w.indent(); w.nl();
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
   // _r: index inside the launched (owned) range, _i: index in the pool's columns
@@ -1488,7 +1657,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "abl_ctx _ctx;"; w.nl();
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
-  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, _tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!si.writes.count(self.members[m]->name)) continue;
@@ -1524,6 +1693,17 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   } else {
     w << "    const abl_real limit = 0;"; w.nl();
   }
+  if (sql) {
+    w << "    static abl_sq_limits sql; static bool have_sql = false;"; w.nl();
+    w << "    if (!have_sql) {"; w.nl();
+    w << "        memset(&sql, 0, sizeof sql);"; w.nl();
+    for (size_t k = 0; k < sqLimits.size(); k++) {
+      w << "        sql.v[" << k << "] = abl_sq_cmp_limit(" << sqLimits[k].first << ", (abl_real)(" << sqLimits[k].second << "));"; w.nl();
+    }
+    w << "        have_sql = true;"; w.nl();
+    w << "    }"; w.nl();
+  }
+  const std::string lim = sql ? "limit, sql" : "limit";
   if (curStepHasLimit) {
     // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
     w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();
@@ -1542,16 +1722,28 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
     w << "        static bool tile_set = false;"; w.nl();
     w << "        if (!tile_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
-    w << "        return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<2>, grid, bs, smem, *a, limit, tile_cap);"; w.nl();
+    w << "        return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<2>, grid, bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
+    w << "    }"; w.nl();
+  }
+  if (curStepFlat) {
+    // sparse 2-D neighbourhoods with one cell of reach: the flat candidate loop (ABL_MODE 3)
+    // (a->flat_loop < 0: the first launches time both variants, abl_device.cuh: abl_tuner)
+    w << "    static abl_tuner tune[ABL_TUNE_DEVICES];"; w.nl();
+    w << "    if (!chunked && a->reach == 1" << (curStepTile ? " && !tile_cap" : "") << ") {"; w.nl();
+    w << "        const int flat = abl_tune_begin(tune, a->flat_loop, \"" << f.emitName << ": flat candidate loop\", a->stream);"; w.nl();
+    w << "        const int rc = flat ? (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<3>, grid, bs, 0, *a, " << lim << ", 0u)"; w.nl();
+    w << "                            : (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+    w << "        abl_tune_end(tune, a->flat_loop, a->stream);"; w.nl();
+    w << "        return rc;"; w.nl();
     w << "    }"; w.nl();
   }
   if (curStepHasLimit) {
     w << "    static bool smem_set = false;"; w.nl();
     w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
-    w << "    if (chunked) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, limit, 0u);"; w.nl();
-    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, limit, 0u);"; w.nl();
+    w << "    if (chunked) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, " << lim << ", 0u);"; w.nl();
+    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
   } else {
-    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, limit, 0u);"; w.nl();
+    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
   }
   w << "}"; w.nl(); w.nl();
   (void)index;
@@ -1559,6 +1751,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStep = nullptr;
   curStepHasLimit = false;
   curStepTile = false;
+  curStepFlat = false;
 }
 
 std::string CudaPrinter::kernelSource() {

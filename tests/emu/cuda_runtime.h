@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
 
 #define __device__
 #define __host__
@@ -63,6 +64,19 @@ static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
 struct emu_idx { unsigned x, y, z; };
 extern emu_idx threadIdx, blockIdx, blockDim, gridDim;
 extern unsigned long long emu_threads_run;
+extern char emu_last_kernel[256];   // mangled name of the kernel launched last (shows the ABL_MODE instance)
+
+// events read a simulated clock that every launch advances by emu_cost_ms[ABL_MODE of the kernel]
+// (set from Python), so the launchers' run-time tuner can be driven either way
+struct emu_event { float t; };
+typedef emu_event *cudaEvent_t;
+extern float emu_clock_ms, emu_cost_ms[8];
+static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0.f}; return cudaSuccess; }
+static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+static inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t) { e->t = emu_clock_ms; return cudaSuccess; }
+static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = b->t - a->t; return cudaSuccess; }
 
 static inline void cudaGridDependencySynchronize() {}
 static inline void __threadfence() {}
@@ -100,6 +114,16 @@ static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void
   blockDim.x = cfg->blockDim.x; blockDim.y = blockDim.z = 1;
   gridDim.x = cfg->gridDim.x; gridDim.y = gridDim.z = 1;
   threadIdx.y = threadIdx.z = blockIdx.y = blockIdx.z = 0;
+  Dl_info info;
+  emu_last_kernel[0] = 0;
+  if (dladdr(reinterpret_cast<void *>(kernel), &info) && info.dli_sname) {
+    strncpy(emu_last_kernel, info.dli_sname, sizeof emu_last_kernel - 1);
+    emu_last_kernel[sizeof emu_last_kernel - 1] = 0;
+  }
+  if (const char *m = strstr(emu_last_kernel, "ILi")) {
+    const int mode = atoi(m + 3);
+    emu_clock_ms += emu_cost_ms[mode >= 0 && mode < 8 ? mode : 0];
+  }
   for (unsigned b = 0; b < cfg->gridDim.x; b++) {
     blockIdx.x = b;
     for (unsigned t = 0; t < cfg->blockDim.x; t++) {

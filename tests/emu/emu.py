@@ -51,7 +51,7 @@ def _build_emu(model_dir):
     cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-fPIC", "-w", "-I", HERE, "-I", model_dir, "-shared",
            "-o", lib, "-x", "c++", os.path.join(HERE, "emu_kernels.cpp"), "-x", "none",
            os.path.join(model_dir, "model_host_lib.o"), os.path.join(model_dir, "abl_host.o"),
-           "-L", rt_dir, "-labl_cuda", "-Wl,-rpath," + rt_dir]
+           "-L", rt_dir, "-labl_cuda", "-ldl", "-Wl,-rpath," + rt_dir]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + proc.stdout)
@@ -116,8 +116,14 @@ class _Pool:
         self.ids = np.ascontiguousarray(self.ids[order])
 
 
+def modes(kernels):
+    """ABL_MODE template arguments of a set of mangled kernel names."""
+    import re
+    return sorted({int(m.group(1)) for k in kernels for m in [re.search(r"ILi(\d+)E", k)] if m})
+
+
 class EmuModel:
-    def __init__(self, abl_path, params=None, use_float=False, config=None):
+    def __init__(self, abl_path, params=None, use_float=False, config=None, lib_path=None):
         cfg = dict(config or {})
         if use_float:
             cfg["use_float"] = True
@@ -125,7 +131,7 @@ class EmuModel:
         self.real = np.float32 if use_float else np.float64
         self.dir = _build.build_model(abl_path, dict(params or {}), cfg)
         load_library()   # the host part of the model resolves against libabl_cuda.so (never called here)
-        self.lib = C.CDLL(_build_emu(self.dir), mode=C.RTLD_LOCAL)
+        self.lib = C.CDLL(lib_path or _build_emu(self.dir), mode=C.RTLD_LOCAL)
         with open(abl_path) as f:
             self.agents = parse_agents(f.read())
         self.dtypes = [agent_dtype(m, self.use_float) for _, m in self.agents]
@@ -136,7 +142,8 @@ class EmuModel:
         self.n_steps = C.c_int.in_dll(self.lib, "abl_model_n_steps").value
         self.lib.emu_run_step.argtypes = [C.c_int, C.POINTER(PoolView), C.POINTER(PoolView), C.POINTER(GridView),
                                           C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                          C.c_ulonglong, C.c_uint, C.c_int]
+                                          C.c_ulonglong, C.c_uint, C.c_int, C.c_int]
+        self.lib.emu_set_cost.argtypes = [C.c_int, C.c_float]
         self.steps = []
         for s in range(self.n_steps):
             sp, nb, ap, ur = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -152,8 +159,11 @@ class EmuModel:
         self.pools = [_Pool(m, dt, self.real) for (_, m), dt in zip(self.agents, self.dtypes)]
         self.timestep_no = 0
         self.block_size = 0
+        self.flat_loop = 0         # abl_step_launch.flat_loop: 0 cursor loop, 1 flat loop, -1 timed by the launcher
         self.check_fused_histogram = True
         self.fused_checked = 0
+        self.lib.emu_last_kernel_name.restype = C.c_char_p
+        self.kernels = set()     # mangled names of the kernels launched (…ILi<ABL_MODE>EE…)
 
     # abl_cuda_set_environment (asset/cuda/abl_runtime.cu)
     def _grid(self, dim, lo, hi, cell):
@@ -250,8 +260,10 @@ class EmuModel:
         rc = self.lib.emu_run_step(s, C.byref(sv), C.byref(nv) if nv is not None else None, C.byref(grid), reach,
                                    dead.ctypes.data if dead is not None else None,
                                    bk.ctypes.data if fuse else None, bl.ctypes.data if fuse else None,
-                                   bc.ctypes.data if fuse else None, 0, self.timestep_no, self.block_size)
+                                   bc.ctypes.data if fuse else None, 0, self.timestep_no, self.block_size, self.flat_loop)
         assert rc == 0, "emulated launch of step %d failed (%d)" % (s, rc)
+        if n:
+            self.kernels.add(self.lib.emu_last_kernel_name().decode())
         me.cols = out
         me.cell_start = None
         if fuse:

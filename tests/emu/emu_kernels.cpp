@@ -9,6 +9,8 @@
 
 emu_idx threadIdx, blockIdx, blockDim, gridDim;
 unsigned long long emu_threads_run = 0;
+char emu_last_kernel[256];
+float emu_clock_ms = 0.f, emu_cost_ms[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
 
 #define abl_cuda_set_environment emu_set_environment
 #define abl_cuda_add_pool emu_add_pool
@@ -71,12 +73,14 @@ int emu_step_info(int s, int *self_pool, int *nbr_pool, double *radius, unsigned
 
 int emu_real_size(void) { return (int)sizeof(abl_real); }
 unsigned long long emu_thread_count(void) { return emu_threads_run; }
+const char *emu_last_kernel_name(void) { return emu_last_kernel; }
+void emu_set_cost(int mode, float ms) { if (mode >= 0 && mode < 8) emu_cost_ms[mode] = ms; }
 
 // Runs step function `s` over the given (already binned) pools: the launcher the generated code
 // registered picks the kernel variant and the block size like on the device.
 int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, const abl_grid_view *grid, int reach,
                  unsigned char *dead, unsigned *bin_key, unsigned *bin_local, unsigned *bin_count,
-                 unsigned long long seed, unsigned timestep, int block_size) {
+                 unsigned long long seed, unsigned timestep, int block_size, int flat_loop) {
   if (s < 0 || s >= g_n_steps) return 1;
   abl_step_launch a;
   memset(&a, 0, sizeof a);
@@ -91,6 +95,7 @@ int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, con
   a.step_index = (unsigned)s;
   a.block_size = block_size;
   a.tile_neighbours = 0;   // block-cooperative kernels cannot be emulated sequentially
+  a.flat_loop = flat_loop;
   a.pdl = 0;
   return a.self.n ? g_steps[s].desc.launch(&a) : 0;
 }

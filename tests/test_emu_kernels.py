@@ -30,14 +30,20 @@ CASES = [
     ("game_of_life.abl", {"num_agents": 65536}, True, 5),
 ]
 IDS = ["%s-%d-%s" % (c[0][:-4], c[1]["num_agents"], "f32" if c[2] else "f64") for c in CASES]
-VARIANTS = [None, {"cuda.unroll": True}, {"cuda.flat": True}, {"cuda.sqcmp": True},
-            {"cuda.flat": True, "cuda.sqcmp": True}]
-VARIANT_IDS = ["default", "unroll", "flat", "sqcmp", "flat+sqcmp"]
+# (-C options, abl_step_launch.flat_loop).  Defaults of the code generator: cuda.sqcmp=true (distance
+# comparisons on the squared distance) and cuda.flat=true (the flat loop is generated; whether a
+# launch uses it is the runtime's flat_loop setting: 0 cursor loop, 1 flat loop, -1 timed).
+VARIANTS = [(None, 0), (None, 1), ({"cuda.unroll": True}, 0), ({"cuda.sqcmp": False}, 0), ({"cuda.sqcmp": False}, 1),
+            ({"cuda.flat": False, "cuda.sqcmp": False}, 1)]
+VARIANT_IDS = ["cursor", "flat", "unroll", "cursor-sqrt", "flat-sqrt", "plain"]
 
 
-def emulate(model_path, params, use_float, steps, config=None, block_size=0):
+def emulate(model_path, params, use_float, steps, config=None, block_size=0, flat_loop=0, costs=None):
     m = EmuModel(model_path, params, use_float=use_float, config=config)
     m.block_size = block_size
+    m.flat_loop = flat_loop
+    for mode in range(8):
+        m.lib.emu_set_cost(mode, (costs or {}).get(mode, 1.0))
     m.populate()
     init = [m.host_agents(t) for t in range(m.n_types)]
     for _ in range(steps):
@@ -45,10 +51,11 @@ def emulate(model_path, params, use_float, steps, config=None, block_size=0):
     return m, init, [m.host_agents(t) for t in range(m.n_types)]
 
 
-@pytest.mark.parametrize("config", VARIANTS, ids=VARIANT_IDS)
+@pytest.mark.parametrize("config,flat_loop", VARIANTS, ids=VARIANT_IDS)
 @pytest.mark.parametrize("model_file,params,use_float,steps", CASES, ids=IDS)
-def test_generated_kernels_equal_grid_oracle(model_file, params, use_float, steps, config):
-    m, init, got = emulate(os.path.join(REPO, "examples", model_file), params, use_float, steps, config)
+def test_generated_kernels_equal_grid_oracle(model_file, params, use_float, steps, config, flat_loop):
+    m, init, got = emulate(os.path.join(REPO, "examples", model_file), params, use_float, steps, config,
+                           flat_loop=flat_loop)
     o = Oracle(use_float)
     state = o.init_for(model_file, params)
     for f in state.dtype.names:
@@ -73,14 +80,15 @@ RUNS = [n for n, (_, p, _) in refgen.FIXTURES.items() if p["num_timesteps"] == 1
 EXTRA_RUNS = [n for n, (_, p, _) in refgen.EXTRA_FIXTURES.items() if p["num_timesteps"] == 10]
 
 
-@pytest.mark.parametrize("config", [None, {"cuda.flat": True, "cuda.sqcmp": True}], ids=["default", "flat+sqcmp"])
+@pytest.mark.parametrize("flat_loop", [0, 1, -1], ids=["cursor", "flat", "timed"])
 @pytest.mark.parametrize("name", RUNS + EXTRA_RUNS)
-def test_generated_kernels_match_reference_c_backend(name, config):
+def test_generated_kernels_match_reference_c_backend(name, flat_loop):
     """Golden vectors of the unmodified reference compiler + libabl (oracle/refgen.py), 10 steps:
     counts and integer/bool state exact, positions within 1e-9 (double) / 1e-4 (use_float)."""
     info, gold = refgen.load_fixture(name)
     params = dict(info["params"])
-    m, _, got = emulate(refgen.model_path(info["model"]), params, info["use_float"], params["num_timesteps"], config)
+    m, _, got = emulate(refgen.model_path(info["model"]), params, info["use_float"], params["num_timesteps"],
+                        flat_loop=flat_loop)
     tol = 1e-4 if info["use_float"] else 1e-9
     for g, ref in zip(got, gold):
         assert len(g) == len(ref), "agent count differs"
@@ -97,3 +105,69 @@ def test_block_size_does_not_change_results(block_size):
     _, _, b = emulate(path, params, False, 2, block_size=block_size)
     for f in a[0].dtype.names:
         assert np.array_equal(a[0][f], b[0][f])
+
+
+def test_launchers_pick_the_expected_kernel_variant():
+    """The emulated launch goes through the generated launcher: sparse 2-D neighbourhoods run the
+    cursor loop (ABL_MODE 0) or the flat loop (3) as the runtime asks; dense ones the chunked
+    two-phase loop (1); 3-D models never the flat loop."""
+    from emu.emu import modes
+    b = os.path.join(REPO, "examples", "boids2d.abl")
+    c3 = os.path.join(REPO, "examples", "circle3d.abl")
+    assert modes(emulate(b, {"num_agents": 100000}, False, 1)[0].kernels) == [0]
+    assert modes(emulate(b, {"num_agents": 100000}, False, 1, flat_loop=1)[0].kernels) == [3]
+    assert modes(emulate(b, {"num_agents": 100000}, False, 1, {"cuda.flat": False}, flat_loop=1)[0].kernels) == [0]
+    assert modes(emulate(c3, {"num_agents": 20000}, False, 1)[0].kernels) == [1]
+    assert modes(emulate(c3, {"num_agents": 20000}, False, 1, flat_loop=1)[0].kernels) == [1]
+
+
+@pytest.mark.parametrize("faster", [0, 3])
+def test_run_time_tuner_times_both_variants_and_keeps_the_faster(faster):
+    """flat_loop = -1: the first eight launches alternate between the cursor loop and the flat loop
+    (events on the launch stream; here a simulated clock), afterwards every launch uses the variant
+    with the smaller time.  Results are those of any fixed choice, bit for bit."""
+    import ctypes as C
+    from emu.emu import modes
+    params = {"num_agents": 4000, "num_timesteps": 10}
+    path = os.path.join(REPO, "examples", "boids2d.abl")
+    # (the tuner is static in the launcher: a private copy of the library gives this test its own)
+    m = EmuModel(path, params)
+    import shutil, tempfile
+    with tempfile.TemporaryDirectory() as tmp:
+        private = os.path.join(tmp, "libmodel_emu_%d.so" % faster)
+        shutil.copy(os.path.join(m.dir, "libmodel_emu.so"), private)
+        m = EmuModel(path, params, lib_path=private)
+        for mode in range(8):
+            m.lib.emu_set_cost(mode, 1.0 if mode == faster else 2.0)
+        m.flat_loop = -1
+        m.populate()
+        seen = []
+        for _ in range(12):
+            m.kernels = set()
+            m.timestep()
+            seen += modes(m.kernels)
+        assert seen[:8] == [0, 3, 0, 3, 0, 3, 0, 3]
+        assert seen[8:] == [faster] * 4
+        _, _, want = emulate(path, params, False, 12)
+        got = m.host_agents(0)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[0][f])
+
+
+@pytest.mark.parametrize("use_float", [False, True], ids=["f64", "f32"])
+def test_squared_distance_bounds_decide_like_the_square_root(use_float, tmp_path):
+    """abl_near_sq_limit / abl_sq_cmp_limit (host code of the generated launchers): the bound found
+    by bisection decides `s <= limit` / `s >= limit` exactly like `(abl_real)sqrtf((float)s) <op> C`
+    for every representable s within 64 ulps of the bound, for special values (0, inf, NaN,
+    denormals) and for 13 M random s, over 16 constants and the four operators."""
+    import subprocess
+    here = os.path.join(REPO, "tests", "emu")
+    exe = str(tmp_path / "sq_limit_check")
+    cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-w", "-I", here, "-I", os.path.join(REPO, "include"),
+           "-I", os.path.join(REPO, "asset", "cuda"), os.path.join(here, "sq_limit_check.cpp"), "-o", exe, "-ldl"]
+    if use_float:
+        cmd.insert(1, "-DABL_USE_FLOAT")
+    subprocess.run(cmd, check=True)
+    out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
+    assert out.returncode == 0, out.stdout
+    assert " 0 failures" in out.stdout
