@@ -1951,8 +1951,13 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       TRY(commit_removals(rt, self, self.own_begin, n_own, true));
       return slab_after_mutation(rt, s.desc.self_pool);
     }
+    const size_t n_stepped = self.n;
     if (added) TRY(commit_adds(rt, self, *added, staging));
-    if (s.desc.uses_removal) TRY(commit_removals(rt, self, 0, (u32)self.n, false));
+    if (s.desc.uses_removal) {
+      // agents the step appended to its own pool carry no removal flag of their own
+      if (self.n > n_stepped) CU(cudaMemsetAsync(self.dead + n_stepped, 0, self.n - n_stepped, rt->stream));
+      TRY(commit_removals(rt, self, 0, (u32)self.n, false));
+    }
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
     if (direct) {
       TRY(halo_finish(rt, self, !use_dev_range && a.slab.boundary_first && a.self.n, use_dev_range));

@@ -259,8 +259,11 @@ def main():
         rt.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
+    # (at least 10 warm-up timesteps: the launchers' run-time tuner times its two candidate-loop
+    # variants over the first 8 launches of a step function, asset/cuda/abl_device.cuh)
+    n_warmup = max(10, args.warmup)
     upload()
-    for _ in range(max(3, args.warmup)):
+    for _ in range(n_warmup):
         timestep()
     barrier()
     launches0 = rt.last_timing()["launches"]
@@ -364,7 +367,7 @@ def main():
 
     if rank == 0:
         line = {"metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps,
+                "steps": args.steps, "warmup": n_warmup, "ms_per_step": ms_max / args.steps,
                 "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
                 "vs_baseline": None,
                 "dtype": "f32" if use_float else "f64", "data": "synthetic",
@@ -372,6 +375,8 @@ def main():
                            "agents_per_gpu": n_agents // world,
                            "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
                            "block_size": args.block_size,
+                           "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
+                               os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor loop against flat loop, the faster is kept"),
                            "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))
                                  if args.no_l2_flush else
                                  ("flushed: a %d MB write before every timed timestep (state: %.0f MB per GPU, L2: 126 MB); "

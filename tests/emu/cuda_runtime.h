@@ -59,6 +59,7 @@ struct cudaLaunchConfig_t {
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 template <typename F> static inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 static inline const char *cudaGetErrorString(cudaError_t) { return "emulated"; }
+static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 
 // ---- the one simulated thread --------------------------------------------------------------
 struct emu_idx { unsigned x, y, z; };

@@ -86,6 +86,7 @@ class _Pool:
             else:
                 self.cols.append(np.ascontiguousarray(v))
         self.ids = np.arange(len(records), dtype=np.uint32) if ids is None else ids.astype(np.uint32)
+        self.next_id = int(self.ids.max()) + 1 if len(self.ids) else 0
         self.cell_start = None
 
     def records(self):
@@ -141,7 +142,8 @@ class EmuModel:
         assert self.lib.emu_setup() == 0
         self.n_steps = C.c_int.in_dll(self.lib, "abl_model_n_steps").value
         self.lib.emu_run_step.argtypes = [C.c_int, C.POINTER(PoolView), C.POINTER(PoolView), C.POINTER(GridView),
-                                          C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p * ABL_MAX_COLUMNS),
+                                          C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_ulonglong, C.c_uint, C.c_int, C.c_int]
         self.lib.emu_set_cost.argtypes = [C.c_int, C.c_float]
         self.steps = []
@@ -158,6 +160,7 @@ class EmuModel:
             self.grid = self._grid(dim.value, list(lo), list(hi), cell.value)
         self.pools = [_Pool(m, dt, self.real) for (_, m), dt in zip(self.agents, self.dtypes)]
         self.timestep_no = 0
+        self.seed = 0x0123456789abcdef     # abl_cuda_default_config
         self.block_size = 0
         self.flat_loop = 0         # abl_step_launch.flat_loop: 0 cursor loop, 1 flat loop, -1 timed by the launcher
         self.check_fused_histogram = True
@@ -223,6 +226,22 @@ class EmuModel:
         p.cell_start[1:self.grid.n_cells + 1] = np.cumsum(counts)
         p.cell_start[self.grid.n_cells + 1] = p.cell_start[self.grid.n_cells]
 
+    def _column_protos(self, p):
+        """Empty arrays with the dtype / trailing shape of each column of pool `p`."""
+        protos = []
+        for _, ty, _ in p.members:
+            if ty == "bool":
+                protos.append(np.zeros(0, np.uint8))
+            elif ty == "int":
+                protos.append(np.zeros(0, np.int32))
+            elif ty == "float":
+                protos.append(np.zeros(0, self.real))
+            elif ty == "float2":
+                protos.append(np.zeros((0, 2), self.real))
+            else:
+                protos += [np.zeros(0, self.real)] * 3
+        return protos
+
     def _view(self, p, out_cols):
         v = PoolView()
         v.n = len(p.ids)
@@ -235,8 +254,6 @@ class EmuModel:
 
     def run_step(self, s):
         st = self.steps[s]
-        if st["added"] >= 0:
-            raise NotImplementedError("run-time add() is not emulated")
         me = self.pools[st["self"]]
         nb = self.pools[st["nbr"]] if st["nbr"] >= 0 else None
         if nb is not None:
@@ -244,6 +261,15 @@ class EmuModel:
         n = len(me.ids)
         out = [c.copy() for c in me.cols]
         dead = np.zeros(n, dtype=np.uint8) if st["removal"] else None
+        # run-time add(): one staging slot per parent in the column layout of the added type
+        target = self.pools[st["added"]] if st["added"] >= 0 else None
+        add_flag, staging, staging_ptrs = None, None, None
+        if target is not None:
+            add_flag = np.zeros(n, dtype=np.uint8)
+            staging = [np.zeros((n,) + c.shape[1:], dtype=c.dtype) for c in self._column_protos(target)]
+            staging_ptrs = (C.c_void_p * ABL_MAX_COLUMNS)()
+            for c, col in enumerate(staging):
+                staging_ptrs[c] = col.ctypes.data
         writes_pos = me.pos_member >= 0 and (st["written"] >> me.pos_member) & 1
         fuse = bool(writes_pos and self.grid is not None and not st["removal"] and self.check_fused_histogram)
         bk = bl = bc = None
@@ -259,8 +285,10 @@ class EmuModel:
         grid = self.grid if self.grid is not None else GridView()
         rc = self.lib.emu_run_step(s, C.byref(sv), C.byref(nv) if nv is not None else None, C.byref(grid), reach,
                                    dead.ctypes.data if dead is not None else None,
+                                   add_flag.ctypes.data if add_flag is not None else None,
+                                   C.byref(staging_ptrs) if staging_ptrs is not None else None,
                                    bk.ctypes.data if fuse else None, bl.ctypes.data if fuse else None,
-                                   bc.ctypes.data if fuse else None, 0, self.timestep_no, self.block_size, self.flat_loop)
+                                   bc.ctypes.data if fuse else None, self.seed, self.timestep_no, self.block_size, self.flat_loop)
         assert rc == 0, "emulated launch of step %d failed (%d)" % (s, rc)
         if n:
             self.kernels.add(self.lib.emu_last_kernel_name().decode())
@@ -277,6 +305,18 @@ class EmuModel:
             starts = np.repeat(np.cumsum(counts) - counts, counts)
             assert np.array_equal(ranks, np.arange(n) - starts), "fused arrival ranks are not a permutation per cell"
             self.fused_checked += 1
+        # commit (asset/cuda/abl_runtime.cu: commit_adds, then commit_removals): new agents are
+        # appended in ascending parent-id order with ids next_id + rank; removal is a stable compaction
+        if target is not None and add_flag.any():
+            parents = np.nonzero(add_flag)[0]
+            parents = parents[np.argsort(me.ids[parents], kind="stable")]
+            m = len(parents)
+            target.cols = [np.ascontiguousarray(np.concatenate([tc, sc[parents]])) for tc, sc in zip(target.cols, staging)]
+            target.ids = np.concatenate([target.ids, (target.next_id + np.arange(m)).astype(np.uint32)])
+            target.next_id += m
+            target.cell_start = None
+            if target is me and dead is not None:
+                dead = np.concatenate([dead, np.zeros(m, dtype=np.uint8)])
         if dead is not None and dead.any():
             keep = dead == 0
             me.cols = [np.ascontiguousarray(c[keep]) for c in me.cols]

@@ -79,7 +79,8 @@ void emu_set_cost(int mode, float ms) { if (mode >= 0 && mode < 8) emu_cost_ms[m
 // Runs step function `s` over the given (already binned) pools: the launcher the generated code
 // registered picks the kernel variant and the block size like on the device.
 int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, const abl_grid_view *grid, int reach,
-                 unsigned char *dead, unsigned *bin_key, unsigned *bin_local, unsigned *bin_count,
+                 unsigned char *dead, unsigned char *add_flag, void *const *add_cols,
+                 unsigned *bin_key, unsigned *bin_local, unsigned *bin_count,
                  unsigned long long seed, unsigned timestep, int block_size, int flat_loop) {
   if (s < 0 || s >= g_n_steps) return 1;
   abl_step_launch a;
@@ -89,6 +90,8 @@ int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, con
   a.grid = *grid;
   a.reach = reach;
   a.dead = dead;
+  a.add_flag = add_flag;
+  if (add_cols) for (int c = 0; c < ABL_MAX_COLUMNS; c++) a.add_cols[c] = add_cols[c];
   a.bin_key = bin_key; a.bin_local = bin_local; a.bin_count = bin_count;
   a.seed = seed;
   a.timestep = timestep;

@@ -171,3 +171,43 @@ def test_squared_distance_bounds_decide_like_the_square_root(use_float, tmp_path
     out = subprocess.run([exe], stdout=subprocess.PIPE, text=True)
     assert out.returncode == 0, out.stdout
     assert " 0 failures" in out.stdout
+
+
+@pytest.mark.parametrize("flat_loop", [0, 1], ids=["cursor", "flat"])
+def test_predator_prey_kernels_match_frozen_semantics(flat_loop):
+    """BASELINE configs[3] on the CPU: the generated kernels of predator_prey (three agent types,
+    eleven step functions, removeCurrent(), add(), in-step random numbers) under the emulator,
+    with the commit rules of the runtime restated in numpy, against the frozen-semantics oracle:
+    agent counts after every timestep, ids of run-time-added agents and every member, bit for bit."""
+    from oracle import PredatorPreyOracle
+    n, steps = 32000, 12
+    m = EmuModel(os.path.join(REPO, "examples", "predator_prey.abl"), {"num_agents": n})
+    m.flat_loop = flat_loop
+    m.populate()
+    o = PredatorPreyOracle(n)
+    for t in range(3):
+        _, rec = o.read(t)
+        host = m.host_agents(t)
+        assert len(host) == len(rec)
+        for f in host.dtype.names:
+            assert np.array_equal(host[f], rec[f]), "initial %s differs" % f
+    initial = [len(m.pools[t].ids) for t in range(3)]
+    removed_any = added_any = False
+    for step in range(steps):
+        before = [o.count(t) for t in range(3)]
+        m.timestep()
+        o.timestep(GRID)
+        counts = [len(m.pools[t].ids) for t in range(3)]
+        assert counts == [o.count(t) for t in range(3)], "agent counts differ after timestep %d" % step
+        removed_any |= counts[1] < before[1]
+    for t in range(3):
+        ids, want = o.read(t)
+        got = m.host_agents(t)
+        assert np.array_equal(np.sort(m.pools[t].ids), ids), "agent ids differ"
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[f]), "type %d member %s differs" % (t, f)
+        added_any |= bool(len(ids) and ids.max() >= initial[t])
+    o.close()
+    assert removed_any and added_any
+    from emu.emu import modes
+    assert (3 in modes(m.kernels)) == bool(flat_loop)
