@@ -211,3 +211,30 @@ def test_predator_prey_kernels_match_frozen_semantics(flat_loop):
     assert removed_any and added_any
     from emu.emu import modes
     assert (3 in modes(m.kernels)) == bool(flat_loop)
+
+
+REF_EXAMPLES = "/root/reference/examples"
+needs_ref = pytest.mark.skipif(not os.path.isdir(REF_EXAMPLES), reason="reference tree not present")
+
+
+@needs_ref
+@pytest.mark.parametrize("example,params,steps", [
+    ("ants.abl", {"num_agents": 3000}, 6),                # two agent types reading each other, in-step RNG
+    ("sugarscape.abl", {"num_agents": 3000}, 6),          # four chained step functions, partial `out` writes
+    ("boids2d_flockers.abl", {"num_agents": 3000}, 6),    # in-step random(), wraparound
+    ("boids.abl", {"num_agents": 3000}, 4),               # 3-D: no flat loop, but squared-distance comparisons
+    ("keratinocyte.abl", {}, 3),                          # constant tables, while, count(member, value)
+])
+def test_loop_variants_agree_on_the_reference_examples(example, params, steps):
+    """Differential check on the models that have no oracle: the kernels printed with every
+    optimisation off (cursor loop, distances through the square root) and the default kernels
+    (flat loop where it applies, comparisons on the squared distance) give identical state —
+    every agent type, every member, bit for bit."""
+    path = os.path.join(REF_EXAMPLES, example)
+    _, _, plain = emulate(path, params, False, steps, {"cuda.flat": False, "cuda.sqcmp": False}, flat_loop=0)
+    m, _, tuned = emulate(path, params, False, steps, None, flat_loop=1)
+    assert len(plain) == len(tuned)
+    for a, b in zip(plain, tuned):
+        assert len(a) == len(b)
+        for f in (a.dtype.names or []):
+            assert np.array_equal(a[f], b[f], equal_nan=True), "%s: member %s differs" % (example, f)
