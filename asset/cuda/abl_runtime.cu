@@ -120,6 +120,7 @@ struct Pool {
   u32 halo_pad = 0;                        // host-side upper bound of arrivals (rest is sentinel padding)
   bool halo_pending = false;               // device-side counts of the last exchange not verified yet
   u32 halo_prev_ob = 0, halo_prev_own = 0, halo_last_arrivals = 0, halo_room = 0;
+  u64 order_serial = 0;   // bumped whenever records are moved, added or removed (validity of cached neighbour lists)
   bool binned = false;
   bool ever_binned = false;
   bool counted = false;   // key/local/cell_count already hold the histogram of the current positions
@@ -142,10 +143,25 @@ struct ScanState {
   size_t max_tiles = 0;
 };
 
+// Cached neighbour lists of one step function (abl_step_desc.nlist): per agent of the stepped
+// pool the pool indices of its accepted candidates, k-major (word k * stride + i), valid while
+// neither pool of the for-near loop is reordered, resized or re-uploaded.
+struct NeighbourLists {
+  u32 *cnt = nullptr, *idx = nullptr;
+  size_t cnt_cap = 0, idx_cap = 0;     // words
+  u32 stride = 0, max_degree = 0;
+  u64 self_serial = 0, nbr_serial = 0;
+  size_t n_self = 0, n_nbr = 0;
+  bool valid = false;
+  bool off = false;                    // lists would exceed the memory budget: use the ordinary loops
+  unsigned builds = 0;
+};
+
 struct Step {
   abl_step_desc desc;
   std::string name;
   int reach = 1;
+  NeighbourLists nl;
 };
 
 struct ColTable {
@@ -229,6 +245,8 @@ struct abl_runtime {
   bool device_range = false;
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
+  bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
+  size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
   int flat_loop = -1;          // ABL_CUDA_FLAT=0/1 pins the candidate loop of sparse 2-D step kernels (default: timed at run time)
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
@@ -1033,6 +1051,8 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
+  if (const char *nlv = getenv("ABL_CUDA_NLIST")) rt->nlist = atoi(nlv) != 0;
+  if (const char *mb = getenv("ABL_CUDA_NLIST_MB")) rt->nlist_budget = (size_t)std::max(1, atoi(mb)) << 20;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
   if (getenv("ABL_CUDA_TRACE")) {
     rt->trace = true;
@@ -1091,6 +1111,10 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     free_pool_scratch(nullptr, p);
     if (p.cell_count) cudaFree(p.cell_count);
     if (p.cell_start) cudaFree(p.cell_start);
+  }
+  for (Step &st : rt->steps) {
+    if (st.nl.cnt) cudaFree(st.nl.cnt);
+    if (st.nl.idx) cudaFree(st.nl.idx);
   }
   for (auto &pr : rt->pinned_ranges) cudaHostUnregister(pr.first);
   rt->pinned_ranges.clear();
@@ -1304,6 +1328,7 @@ static int upload_impl(abl_runtime *rt, int pool, const void *host_aos, const un
     CU(cudaGetLastError());
   }
   p->n = n;
+  p->order_serial++;
   p->next_id = ids ? next_id : (u32)n;
   p->binned = false;
   p->own_valid = false;
@@ -1525,6 +1550,7 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
     CU(cudaGetLastError());
     flip_all(p);
   }
+  p.order_serial++;
   trace_stamp(rt, TR_MOVE);
   const u32 src_before = p.src_begin;
   p.src_begin = 0;
@@ -1663,6 +1689,7 @@ static int commit_removals(abl_runtime *rt, Pool &p, u32 first, u32 n, bool slab
   rt->launches++;
   CU(cudaGetLastError());
   flip_all(p);
+  p.order_serial++;
   p.ever_removed = true;
   p.binned = false;
   TRY(drop_fused_histogram(rt, p));  // stable compaction keeps cell order, but cell_start is stale
@@ -1708,6 +1735,7 @@ static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const 
     CU(cudaFree(tmp));
   }
   target.n += m;
+  target.order_serial++;
   target.next_id += m;
   target.binned = false;
   TRY(drop_fused_histogram(rt, target));
@@ -1816,6 +1844,68 @@ static int drain_timing(abl_runtime *rt) {
   rt->last.bin_ms = (float)(bin / quads);
   rt->last.kernel_ms = (float)(kernel / quads);
   rt->last.commit_ms = (float)(commit / quads);
+  return ABL_OK;
+}
+
+// Builds the neighbour lists of step `s` for the views in `a` (count pass -> size by the largest
+// count -> fill pass; both passes are launches of the generated kernel that store nothing of the
+// step itself).  One host synchronisation, once per build.
+static int build_neighbour_lists(abl_runtime *rt, Step &s, const abl_step_launch &a, const Pool &self, const Pool &nbr) {
+  NeighbourLists &nl = s.nl;
+  nl.valid = false;
+  const size_t n = a.self.n;
+  if (nl.cnt_cap < n) {
+    if (nl.cnt) CU(cudaFree(nl.cnt));
+    nl.cnt = nullptr;
+    nl.cnt_cap = round_up(n + n / 8, 1024);
+    CU(cudaMalloc(&nl.cnt, nl.cnt_cap * sizeof(u32)));
+  }
+  u32 *d_max = rt->d_scalar + 1020;   // a word of the 4 KB scratch no other path uses
+  CU(cudaMemsetAsync(d_max, 0, sizeof(u32), rt->stream));
+  abl_step_launch b = a;
+  b.bin_key = b.bin_local = b.bin_count = nullptr;
+  b.nlist_phase = 1;
+  b.nlist_cnt = nl.cnt;
+  b.nlist_idx = nullptr;
+  b.nlist_stride = 0;
+  b.nlist_max = d_max;
+  int rc = s.desc.launch(&b);
+  rt->launches++;
+  if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: neighbour-list count pass failed: %s", s.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+  u32 max_degree = 0;
+  TRY(read_scalar(rt, d_max, &max_degree));
+  const size_t words = (size_t)std::max(max_degree, 1u) * n;
+  if (words * sizeof(u32) > rt->nlist_budget) {
+    nl.off = true;   // e.g. a crowd in one cell: the k-major layout pads every agent to the largest list
+    if (getenv("ABL_CUDA_VERBOSE"))
+      fprintf(stderr, "abl_cuda: step %s: neighbour lists need %.1f MB (largest list %u), over the budget: ordinary loop\n",
+              s.name.c_str(), words * 4.0 / 1048576.0, max_degree);
+    return ABL_OK;
+  }
+  if (nl.idx_cap < words) {
+    if (nl.idx) CU(cudaFree(nl.idx));
+    nl.idx = nullptr;
+    nl.idx_cap = words;
+    CU(cudaMalloc(&nl.idx, nl.idx_cap * sizeof(u32)));
+  }
+  b.nlist_phase = 2;
+  b.nlist_idx = nl.idx;
+  b.nlist_stride = (u32)n;
+  rc = s.desc.launch(&b);
+  rt->launches++;
+  if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: neighbour-list fill pass failed: %s", s.name.c_str(), cudaGetErrorString((cudaError_t)rc));
+  CU(cudaGetLastError());
+  nl.stride = (u32)n;
+  nl.max_degree = max_degree;
+  nl.self_serial = self.order_serial;
+  nl.nbr_serial = nbr.order_serial;
+  nl.n_self = self.n;
+  nl.n_nbr = nbr.n;
+  nl.valid = true;
+  nl.builds++;
+  if (getenv("ABL_CUDA_VERBOSE"))
+    fprintf(stderr, "abl_cuda: step %s: neighbour lists built (%zu agents, largest list %u, %.1f MB)\n", s.name.c_str(), n,
+            max_degree, words * 4.0 / 1048576.0);
   return ABL_OK;
 }
 
@@ -1928,6 +2018,19 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.flat_loop = rt->flat_loop;
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
+    // cached neighbour lists: neither pool of this step's for-near loop ever moves (the code
+    // generator's guarantee), so the accepted candidates are found once and walked afterwards
+    if (s.desc.nlist && rt->nlist && nbr && !rt->slab && !s.nl.off) {
+      NeighbourLists &nl = s.nl;
+      const bool current = nl.valid && nl.self_serial == self.order_serial && nl.nbr_serial == nbr->order_serial &&
+                           nl.n_self == self.n && nl.n_nbr == nbr->n && nl.stride == a.self.n;
+      if (!current) TRY(build_neighbour_lists(rt, s, a, self, *nbr));
+      if (nl.valid) {
+        a.nlist_cnt = nl.cnt;
+        a.nlist_idx = nl.idx;
+        a.nlist_stride = nl.stride;
+      }
+    }
     trace_stamp(rt, TR_OTHER);
     int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches++;

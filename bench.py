@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
     ap.add_argument("--tile", action="store_true", help="stage neighbour rows in shared memory (ABL_MODE 2 kernels)")
     ap.add_argument("--unroll", action="store_true", help="-C cuda.unroll=true: for-near candidate loop unrolled by two")
+    ap.add_argument("--nlist", action="store_true", help="-C cuda.nlist=true: cached neighbour lists for step functions whose "
+                    "neighbourhoods never change (game_of_life)")
     ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
     ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
                     help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
@@ -228,7 +230,7 @@ def main():
         # which the model derives from num_agents) grows with the number of GPUs
         params["num_agents"] = params["num_agents"] * world
     m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float,
-              config={"cuda.unroll": True} if args.unroll else None)
+              config=dict(([("cuda.unroll", True)] if args.unroll else []) + ([("cuda.nlist", True)] if args.nlist else [])) or None)
     m.populate()
     host = [m.host_agents(t) for t in range(m.n_types)]
     n_agents = sum(len(h) for h in host)          # whole job, all ranks
@@ -374,7 +376,7 @@ def main():
                 "config": {"workload": args.workload, "model": model_file, "num_agents": n_agents,
                            "agents_per_gpu": n_agents // world,
                            "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
-                           "block_size": args.block_size,
+                           "block_size": args.block_size, "neighbour_lists": bool(args.nlist),
                            "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
                                os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor loop against flat loop, the faster is kept"),
                            "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))

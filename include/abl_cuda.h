@@ -210,6 +210,19 @@ typedef struct {
                                               -1 the launcher times both bit-identical variants over its first launches and keeps the faster */
   int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
+  /* Cached neighbour lists (steps registered with abl_step_desc.nlist != 0: neither pool of the
+   * for-near loop ever moves, so the set of accepted candidates of every agent is the same in
+   * every timestep).  nlist_phase 1: the kernel only counts the accepted candidates of each
+   * agent into nlist_cnt[i] and folds the maximum into *nlist_max; phase 2: it stores their pool
+   * indices, in visiting order, at nlist_idx[k * nlist_stride + i] (k-major: the lanes of a warp
+   * read consecutive words); phase 0 with nlist_cnt != NULL: the step kernel walks that list
+   * instead of the cell rows — no position loads, no filter.  Same candidates in the same order:
+   * bit-identical results. */
+  int nlist_phase;
+  unsigned *nlist_cnt;
+  unsigned *nlist_idx;
+  unsigned nlist_stride;
+  unsigned *nlist_max;
 } abl_step_launch;
 
 typedef int (*abl_step_launcher)(const abl_step_launch *args);
@@ -226,6 +239,8 @@ typedef struct {
   int uses_removal;
   int added_pool;            /* -1: no run-time add() */
   abl_step_launcher launch;
+  int nlist;                 /* 1: list kernels were generated and no step function of the model moves, adds or
+                                removes agents of either pool of the for-near loop (`-C cuda.nlist=true`) */
 } abl_step_desc;
 
 int abl_cuda_register_step(abl_runtime *rt, const abl_step_desc *desc, int *step);

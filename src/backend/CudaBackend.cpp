@@ -97,6 +97,8 @@ private:
   bool curStepHasLimit = false;
   bool curStepTile = false;     // the step's for-near loop can run from a shared-memory tile
   bool curStepFlat = false;     // `-C cuda.flat=true` and a 2-D for-near loop: ABL_MODE 3 is printed
+  bool curStepList = false;     // `-C cuda.nlist=true` and a static neighbourhood: list kernels (ABL_MODE 4/5/6) are printed
+  bool stepListEligible(const StepInfo &si) const;
   // one neighbour column staged in shared memory by a tiled kernel
   struct TileCol {
     int member;          // member of the neighbour agent
@@ -147,6 +149,7 @@ private:
   std::string nearContinueLabel;   // non-empty: `continue` of the for-near body jumps there (unrolled loop)
   int innerLoopDepth = 0;
   std::vector<StepInfo> steps;
+  std::set<const FuncDecl *> listSteps;   // steps whose kernels were printed with the list modes
 
   std::string label() { return "_var" + std::to_string(anon++); }
   bool dev() const { return target == Target::Device; }
@@ -724,6 +727,66 @@ void CudaPrinter::nearLoop(const Stmt &s) {
 
   w << "{";
   w.indent(); w.nl();
+  if (curStepList) {
+    // ABL_MODE 4: walk the cached list of accepted candidates (k-major, abl_cuda.h); 5 / 6: the
+    // two list-building passes — the cursor loop's filter with a counter instead of the body
+    const bool needPos = curFn->nearMembers.count(pos->name) != 0;
+    std::string ptypeL = typeName(pos->type);
+    w << "if (ABL_MODE == 4) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "ln = _a.nlist_cnt[_i];"; w.nl();
+    w << "for (unsigned " << it << "lk = 0; " << it << "lk < " << it << "ln; " << it << "lk++) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "j = __ldg(_a.nlist_idx + (size_t)" << it << "lk * _a.nlist_stride + _i);"; w.nl();
+    w << nbr->name << " " << s.varName << ";";
+    if (needPos) {
+      w.nl();
+      loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+      w.nl();
+      w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+        << pos->name << ", " << selfPosText << "));";
+    }
+    loadOthers(it + "j");
+    w.nl();
+    {
+      std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
+      int savedDepth = innerLoopDepth;
+      nearBreakLabel.clear();
+      nearContinueLabel.clear();
+      innerLoopDepth = 0;
+      if (needPos) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+      stmt(*s.body[0]);
+      clearNearContext();
+      nearBreakLabel = savedLabel;
+      nearContinueLabel = savedContinue;
+      innerLoopDepth = savedDepth;
+    }
+    w.outdent(); w.nl();
+    w << "}";
+    w.outdent(); w.nl();
+    w << "} else if (ABL_MODE == 5 || ABL_MODE == 6) {";
+    w.indent(); w.nl();
+    w << "abl_near_iter<" << sdim << "> " << it << "b;"; w.nl();
+    w << it << "b.init" << sdim << "(_a, " << selfPosText << ", true);"; w.nl();
+    w << "unsigned " << it << "c = 0;"; w.nl();
+    w << "while (" << it << "b.valid()) {";
+    w.indent(); w.nl();
+    w << "const unsigned " << it << "j = " << it << "b.index();"; w.nl();
+    w << it << "b.next();"; w.nl();
+    w << ptypeL << " " << it << "q;"; w.nl();
+    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "j"); w.nl();
+    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText << ")) > _near_limit) continue;"; w.nl();
+    w << "if (ABL_MODE == 6) _a.nlist_idx[(size_t)" << it << "c * _a.nlist_stride + _i] = " << it << "j;"; w.nl();
+    w << it << "c++;";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "if (ABL_MODE == 5) { _a.nlist_cnt[_i] = " << it << "c; atomicMax(_a.nlist_max, " << it << "c); }";
+    w.outdent(); w.nl();
+    w << "} else";
+    w.nl();
+  }
+  w << "{";
+  w.indent(); w.nl();
   const bool tile = curStepTile;
   if (tile) {
     // ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
@@ -1107,6 +1170,8 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   if (curStepFlat) { w.outdent(); w.nl(); w << "}"; }
   if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
   if (tile) { w.outdent(); w.nl(); w << "}"; }
+  w.outdent(); w.nl();
+  w << "}";
   w.outdent(); w.nl();
   w << "}";
 }
@@ -1551,6 +1616,26 @@ bool CudaPrinter::hostEvaluable(const Expr &e) {
   }
 }
 
+// Cached neighbour lists (`-C cuda.nlist=true`): the accepted candidates of an agent are the same
+// in every timestep when no step function of the model writes the position of, removes or adds
+// agents of either type of the for-near loop — and the step itself neither removes nor adds
+// (the list-building launches run the function body without its side effects on the pool only).
+bool CudaPrinter::stepListEligible(const StepInfo &si) const {
+  const FuncDecl &f = *si.fn;
+  if (!config.getBool("cuda.nlist", false) || !f.nearAgent || !curStepHasLimit) return false;
+  if (f.usesRemoval || f.addedAgent) return false;
+  AgentDecl *types[2] = { si.self, f.nearAgent };
+  for (AgentDecl *t : types) {
+    AgentMember *pos = t ? t->position() : nullptr;
+    if (!pos) return false;
+    for (const StepInfo &o : steps) {
+      if (o.self == t && (o.writes.count(pos->name) || o.fn->usesRemoval)) return false;
+      if (o.fn->addedAgent == t) return false;
+    }
+  }
+  return true;
+}
+
 void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   FuncDecl &f = *si.fn;
   AgentDecl &self = *si.self;
@@ -1575,6 +1660,9 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     }
   }
   const std::string trows = tdim == 2 ? "3" : "9";
+  curStepList = stepListEligible(si) && nearStmt && nearStmt->e[0]->kids[0]->kind == Expr::Var &&
+                nearStmt->e[0]->kids[0]->sym == p.sym;
+  if (curStepList) listSteps.insert(&f);
   curStepFlat = config.getBool("cuda.flat", true) && curStepHasLimit && nearStmt && nearStmt->declTy.agent &&
                 nearStmt->declTy.agent->position() && nearStmt->declTy.agent->position()->type.vecLen() == 2;
 
@@ -1658,6 +1746,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
   w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
+  if (curStepList) { w.nl(); w << "if (ABL_MODE == 5 || ABL_MODE == 6) return;   // list-building launch: nothing of the step is stored"; }
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
     if (!si.writes.count(self.members[m]->name)) continue;
@@ -1725,6 +1814,12 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w << "        return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<2>, grid, bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
     w << "    }"; w.nl();
   }
+  if (curStepList) {
+    // cached neighbour lists: count / fill launches of the runtime, then the list walk
+    w << "    if (a->nlist_phase == 1) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<5>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+    w << "    if (a->nlist_phase == 2) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<6>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+    w << "    if (a->nlist_cnt) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<4>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+  }
   if (curStepFlat) {
     // sparse 2-D neighbourhoods with one cell of reach: the flat candidate loop (ABL_MODE 3)
     // (a->flat_loop < 0: the first launches time both variants, abl_device.cuh: abl_tuner)
@@ -1752,6 +1847,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepHasLimit = false;
   curStepTile = false;
   curStepFlat = false;
+  curStepList = false;
 }
 
 std::string CudaPrinter::kernelSource() {
@@ -1861,6 +1957,7 @@ std::string CudaPrinter::kernelSource() {
     else w << "        d.added_pool = -1;";
     w.nl();
     w << "        d.launch = abl_launch_" << f.emitName << ";"; w.nl();
+    w << "        d.nlist = " << (listSteps.count(&f) ? 1 : 0) << ";"; w.nl();
     w << "        if ((rc = abl_cuda_register_step(rt, &d, &abl_model_step_ids[" << i << "]))) return rc;"; w.nl();
     w << "    }"; w.nl();
   }

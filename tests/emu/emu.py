@@ -41,6 +41,36 @@ class GridView(C.Structure):      # abl_grid_view
                 ("key_base", C.c_uint)]
 
 
+def _generate(abl_path, params, config):
+    """Generated sources + host objects of a model WITHOUT the nvcc build (the emulator does not
+    need the device code): reuses a full build when one exists, else runs the code generator and
+    gcc into build/emu/<key>/."""
+    key = _build.model_key(abl_path, params, config)
+    full = os.path.join(_build.MODEL_CACHE, key)
+    if os.path.exists(os.path.join(full, "libmodel.so")):
+        return full
+    out = os.path.join(os.path.dirname(_build.MODEL_CACHE), "emu", key)
+    if os.path.exists(os.path.join(out, "abl_host.o")):
+        return out
+    _build.build_compiler()
+    _build.build_runtime()
+    os.makedirs(out, exist_ok=True)
+    cmd = [_build.COMPILER, "-i", abl_path, "-b", "cuda", "-o", out, "-A", ASSET_DIR]
+    for k, v in params.items():
+        cmd += ["-P", "%s=%s" % (k, _build._fmt(v))]
+    for k, v in config.items():
+        cmd += ["-C", "%s=%s" % (k, _build._fmt(v))]
+    _build._run(cmd, cwd=_build.REPO_ROOT)
+    define = ["-DLIBABL_USE_FLOAT=1", "-DABL_USE_FLOAT=1"] if config.get("use_float") else []
+    with open(os.path.join(out, "build.sh")) as f:
+        script = f.read()
+    # the host objects exactly as build.sh compiles them (same flags and defines)
+    for line in script.splitlines():
+        if line.startswith("$CC ") and ("-DABL_MODEL_NO_MAIN" in line or "abl_host.c" in line):
+            _build._run(["sh", "-c", "CC=gcc; " + line], cwd=out)
+    return out
+
+
 def _build_emu(model_dir):
     lib = os.path.join(model_dir, "libmodel_emu.so")
     srcs = [os.path.join(HERE, "cuda_runtime.h"), os.path.join(HERE, "emu_kernels.cpp"),
@@ -130,7 +160,7 @@ class EmuModel:
             cfg["use_float"] = True
         self.use_float = bool(use_float)
         self.real = np.float32 if use_float else np.float64
-        self.dir = _build.build_model(abl_path, dict(params or {}), cfg)
+        self.dir = _generate(abl_path, dict(params or {}), cfg)
         load_library()   # the host part of the model resolves against libabl_cuda.so (never called here)
         self.lib = C.CDLL(lib_path or _build_emu(self.dir), mode=C.RTLD_LOCAL)
         with open(abl_path) as f:
@@ -146,6 +176,10 @@ class EmuModel:
                                           C.c_void_p, C.c_void_p, C.c_void_p,
                                           C.c_ulonglong, C.c_uint, C.c_int, C.c_int]
         self.lib.emu_set_cost.argtypes = [C.c_int, C.c_float]
+        self.lib.emu_set_nlist.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p]
+        self.use_nlist = False     # drive steps registered with desc.nlist through cached neighbour lists
+        self.nlists = {}           # step -> (ids of self pool, ids of nbr pool, cnt, idx, stride)
+        self.nlist_builds = 0
         self.steps = []
         for s in range(self.n_steps):
             sp, nb, ap, ur = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -283,6 +317,34 @@ class EmuModel:
         sv = self._view(me, out)
         nv = self._view(nb, None) if nb is not None else None
         grid = self.grid if self.grid is not None else GridView()
+        listed = self.use_nlist and nb is not None and self.lib.emu_step_nlist(s)
+        if listed:
+            # the runtime's protocol (abl_cuda_step): count pass, size the lists by the largest count,
+            # fill pass; rebuilt whenever the order of either pool changed
+            cached = self.nlists.get(s)
+            if cached is None or not (np.array_equal(cached[0], me.ids) and np.array_equal(cached[1], nb.ids)):
+                cnt = np.zeros(n, dtype=np.uint32)
+                mx = np.zeros(1, dtype=np.uint32)
+                self.lib.emu_set_nlist(1, cnt.ctypes.data, None, 0, mx.ctypes.data)
+                assert self.lib.emu_run_step(s, C.byref(sv), C.byref(nv), C.byref(grid), reach, None, None, None,
+                                             None, None, None, self.seed, self.timestep_no, self.block_size, 0) == 0
+                self.kernels.add(self.lib.emu_last_kernel_name().decode())
+                assert int(mx[0]) == int(cnt.max()) if n else True
+                stride = n
+                idx = np.full(max(1, int(mx[0])) * stride, 0xffffffff, dtype=np.uint32)
+                self.lib.emu_set_nlist(2, cnt.ctypes.data, idx.ctypes.data, stride, mx.ctypes.data)
+                assert self.lib.emu_run_step(s, C.byref(sv), C.byref(nv), C.byref(grid), reach, None, None, None,
+                                             None, None, None, self.seed, self.timestep_no, self.block_size, 0) == 0
+                self.kernels.add(self.lib.emu_last_kernel_name().decode())
+                for c, o in zip(me.cols, out):
+                    assert np.array_equal(c, o, equal_nan=True) if c.dtype.kind == "f" else np.array_equal(c, o), \
+                        "a list-building launch stored something"
+                cached = (me.ids.copy(), nb.ids.copy(), cnt, idx, stride)
+                self.nlists[s] = cached
+                self.nlist_builds += 1
+            self.lib.emu_set_nlist(0, cached[2].ctypes.data, cached[3].ctypes.data, cached[4], None)
+        else:
+            self.lib.emu_set_nlist(0, None, None, 0, None)
         rc = self.lib.emu_run_step(s, C.byref(sv), C.byref(nv) if nv is not None else None, C.byref(grid), reach,
                                    dead.ctypes.data if dead is not None else None,
                                    add_flag.ctypes.data if add_flag is not None else None,

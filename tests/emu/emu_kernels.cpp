@@ -30,6 +30,7 @@ struct StepRec { abl_step_desc desc; };
 StepRec g_steps[64];
 int g_n_steps = 0;
 int g_n_pools = 0;
+struct { int phase; unsigned *cnt, *idx, stride, *max; } g_nlist = {0, nullptr, nullptr, 0, nullptr};
 }
 
 extern "C" int emu_set_environment(abl_runtime *, int dim, const double *env_min, const double *env_max, double granularity) {
@@ -71,6 +72,12 @@ int emu_step_info(int s, int *self_pool, int *nbr_pool, double *radius, unsigned
   return 0;
 }
 
+// neighbour-list arguments of the next emu_run_step calls (abl_step_launch.nlist_*)
+void emu_set_nlist(int phase, unsigned *cnt, unsigned *idx, unsigned stride, unsigned *max) {
+  g_nlist.phase = phase; g_nlist.cnt = cnt; g_nlist.idx = idx; g_nlist.stride = stride; g_nlist.max = max;
+}
+int emu_step_nlist(int s) { return s >= 0 && s < g_n_steps ? g_steps[s].desc.nlist : 0; }
+
 int emu_real_size(void) { return (int)sizeof(abl_real); }
 unsigned long long emu_thread_count(void) { return emu_threads_run; }
 const char *emu_last_kernel_name(void) { return emu_last_kernel; }
@@ -99,6 +106,8 @@ int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, con
   a.block_size = block_size;
   a.tile_neighbours = 0;   // block-cooperative kernels cannot be emulated sequentially
   a.flat_loop = flat_loop;
+  a.nlist_phase = g_nlist.phase; a.nlist_cnt = g_nlist.cnt; a.nlist_idx = g_nlist.idx;
+  a.nlist_stride = g_nlist.stride; a.nlist_max = g_nlist.max;
   a.pdl = 0;
   return a.self.n ? g_steps[s].desc.launch(&a) : 0;
 }

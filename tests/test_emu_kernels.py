@@ -238,3 +238,55 @@ def test_loop_variants_agree_on_the_reference_examples(example, params, steps):
         assert len(a) == len(b)
         for f in (a.dtype.names or []):
             assert np.array_equal(a[f], b[f], equal_nan=True), "%s: member %s differs" % (example, f)
+
+
+@pytest.mark.parametrize("use_float", [False, True], ids=["f64", "f32"])
+def test_cached_neighbour_lists_equal_grid_oracle(use_float):
+    """-C cuda.nlist=true on game_of_life (no step function moves a cell): the count pass, the fill
+    pass and the list-walking kernel (ABL_MODE 5, 6, 4) against the grid-ordered oracle; the lists
+    are built once and reused for every timestep."""
+    from emu.emu import modes
+    params = {"num_agents": 65536}
+    m = EmuModel(os.path.join(REPO, "examples", "game_of_life.abl"), params, use_float=use_float,
+                 config={"cuda.nlist": True})
+    m.use_nlist = True
+    m.populate()
+    for _ in range(5):
+        m.timestep()
+    got = m.host_agents(0)
+    o = Oracle(use_float)
+    want = o.run_for("game_of_life.abl", params, o.init_for("game_of_life.abl", params), 5, GRID)
+    assert np.array_equal(got["alive"], want["alive"]) and np.array_equal(got["pos"], want["pos"])
+    assert m.nlist_builds == 1
+    assert modes(m.kernels) == [4, 5, 6]
+
+
+def test_neighbour_lists_are_only_offered_for_static_neighbourhoods():
+    """boids2d moves its agents, predator_prey's steps remove/add or read moving agents: the code
+    generator must not mark their steps; game_of_life without the option neither."""
+    for model, cfg in [("boids2d.abl", {"cuda.nlist": True}), ("predator_prey.abl", {"cuda.nlist": True}),
+                       ("circle3d.abl", {"cuda.nlist": True}), ("game_of_life.abl", None)]:
+        m = EmuModel(os.path.join(REPO, "examples", model), {"num_agents": 4096}, config=cfg)
+        assert not any(m.lib.emu_step_nlist(s) for s in range(m.n_steps)), model
+
+
+def test_neighbour_lists_on_a_model_with_static_and_moving_types():
+    """tests/models/static_sites.abl: Sites never move (their diffusion step reads neighbouring
+    Sites through dist(), a float and a bool member, with `continue` and `break`), Walkers do.
+    Only the Site-Site step is marked; its lists are built once although the other pools change
+    every timestep; the state equals the plain kernels' bit for bit."""
+    from emu.emu import modes
+    path = os.path.join(REPO, "tests", "models", "static_sites.abl")
+    _, _, plain = emulate(path, {"num_agents": 3000}, False, 5, {"cuda.flat": False, "cuda.sqcmp": False})
+    m = EmuModel(path, {"num_agents": 3000}, config={"cuda.nlist": True})
+    m.use_nlist = True
+    m.populate()
+    for _ in range(5):
+        m.timestep()
+    assert [m.lib.emu_step_nlist(s) for s in range(m.n_steps)] == [1, 0, 0]
+    assert m.nlist_builds == 1 and {4, 5, 6} <= set(modes(m.kernels))
+    for t in range(m.n_types):
+        got = m.host_agents(t)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], plain[t][f]), "type %d member %s differs" % (t, f)
+    assert plain[0]["visitors"].sum() > 0 and not np.array_equal(plain[0]["heat"], emulate(path, {"num_agents": 3000}, False, 0)[2][0]["heat"])

@@ -15,6 +15,10 @@ for w in boids2d-1M-f64 boids2d-1M-f32 game_of_life-16M-f64; do
       > $out/r2_flat_${w}_$flat.json 2> $out/r2_flat_${w}_$flat.err
   done
 done
+# cached neighbour lists (game_of_life): guarded GPU tests first, then the A/B
+python -m pytest tests/test_gpu_zz_nlist.py -m gpu -q -rxX > $out/r2_pytest_nlist.log 2>&1
+ABL_CUDA_VERBOSE=1 python bench.py --workload game_of_life-16M-f64 --nlist --no-cpu-baseline --steps 100 --warmup 10 \
+  > $out/r2_nlist_game_of_life-16M-f64.json 2> $out/r2_nlist_game_of_life-16M-f64.err
 ABL_CUDA_FLAT=0 python tools/quick_step.py predator_prey-4M-f64 --steps 50 > $out/r2_pp4M_flat0.txt 2>&1
 ABL_CUDA_FLAT=1 python tools/quick_step.py predator_prey-4M-f64 --steps 50 > $out/r2_pp4M_flat1.txt 2>&1
 python bench.py > $out/r2_bench_default_n1.json 2> $out/r2_bench_default_n1.err
