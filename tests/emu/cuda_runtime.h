@@ -92,8 +92,8 @@ static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { unsigned o = *p; *p = v; return o; }
 static inline unsigned atomicMin(unsigned *p, unsigned v) { unsigned o = *p; if (v < o) *p = v; return o; }
 static inline unsigned atomicMax(unsigned *p, unsigned v) { unsigned o = *p; if (v > o) *p = v; return o; }
-// a warp of one lane
-static inline unsigned __activemask() { return 1u; }
+// every simulated thread is alone in its warp, at its natural lane
+static inline unsigned __activemask() { return 1u << (threadIdx.x & 31u); }
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <typename T> static inline T __shfl_sync(unsigned, T v, unsigned) { return v; }

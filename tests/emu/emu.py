@@ -286,7 +286,9 @@ class EmuModel:
         v.cell_start = p.cell_start.ctypes.data if p.cell_start is not None else None
         return v
 
-    def run_step(self, s):
+    def run_step(self, s, own_range=None):
+        """own_range = (begin, end): step only that part of the (binned) pool, like the runtime does
+        under slab decomposition (views offset to the first owned record); no commit stages."""
         st = self.steps[s]
         me = self.pools[st["self"]]
         nb = self.pools[st["nbr"]] if st["nbr"] >= 0 else None
@@ -315,6 +317,14 @@ class EmuModel:
         if nb is not None:
             reach = max(1, int(math.ceil(st["radius"] / self.grid.cell_size - 1e-12)))
         sv = self._view(me, out)
+        if own_range is not None:
+            b, e = own_range
+            sv.n = e - b
+            for c in range(me.n_cols):
+                sv.cin[c] = me.cols[c][b:e].ctypes.data
+                sv.cout[c] = out[c][b:e].ctypes.data
+            sv.id = me.ids[b:e].ctypes.data
+            fuse, bk, bl, bc = False, None, None, None
         nv = self._view(nb, None) if nb is not None else None
         grid = self.grid if self.grid is not None else GridView()
         listed = self.use_nlist and nb is not None and self.lib.emu_step_nlist(s)

@@ -31,6 +31,7 @@ StepRec g_steps[64];
 int g_n_steps = 0;
 int g_n_pools = 0;
 struct { int phase; unsigned *cnt, *idx, stride, *max; } g_nlist = {0, nullptr, nullptr, 0, nullptr};
+abl_slab_view g_slab;   // zero-initialised: inactive
 }
 
 extern "C" int emu_set_environment(abl_runtime *, int dim, const double *env_min, const double *env_max, double granularity) {
@@ -78,6 +79,28 @@ void emu_set_nlist(int phase, unsigned *cnt, unsigned *idx, unsigned stride, uns
 }
 int emu_step_nlist(int s) { return s >= 0 && s < g_n_steps ? g_steps[s].desc.nlist : 0; }
 
+// Slab decomposition as the runtime's halo_fill_view sets it up for the fused send (no
+// boundary-first scheduling, no device range): owned layers [begin, end), the layer ranges of
+// the lower / upper peer ([0,0) = none), ghost flags, message areas and slot counters.
+void emu_set_slab(int active, int dim, int pos_col, int n_layers, double origin, double inv_cell, int begin, int end,
+                  int ghost, int lo_begin, int lo_end, int hi_begin, int hi_end, int lo_ghost, int hi_ghost,
+                  unsigned char *msg_lo, unsigned char *msg_hi, unsigned *counters, unsigned capacity,
+                  unsigned rec_words, int n_cols, const int *elem) {
+  memset(&g_slab, 0, sizeof g_slab);
+  if (!active) return;
+  g_slab.active = 1; g_slab.dim = dim; g_slab.pos_col = pos_col; g_slab.n_layers = n_layers;
+  g_slab.origin = origin; g_slab.inv_cell = inv_cell;
+  g_slab.begin = begin; g_slab.end = end; g_slab.ghost = ghost;
+  g_slab.lo_begin = lo_begin; g_slab.lo_end = lo_end; g_slab.hi_begin = hi_begin; g_slab.hi_end = hi_end;
+  g_slab.lo_ghost = lo_ghost; g_slab.hi_ghost = hi_ghost;
+  g_slab.msg[0] = msg_lo; g_slab.msg[1] = msg_hi;
+  g_slab.count[0] = counters; g_slab.count[1] = counters + 1; g_slab.far = counters + 2;
+  g_slab.late = counters + 3;
+  g_slab.capacity = capacity; g_slab.rec_words = rec_words;
+  g_slab.n_cols = n_cols;
+  for (int c = 0; c < n_cols; c++) g_slab.elem[c] = elem[c];
+}
+
 int emu_real_size(void) { return (int)sizeof(abl_real); }
 unsigned long long emu_thread_count(void) { return emu_threads_run; }
 const char *emu_last_kernel_name(void) { return emu_last_kernel; }
@@ -106,6 +129,7 @@ int emu_run_step(int s, const abl_pool_view *self, const abl_pool_view *nbr, con
   a.block_size = block_size;
   a.tile_neighbours = 0;   // block-cooperative kernels cannot be emulated sequentially
   a.flat_loop = flat_loop;
+  a.slab = g_slab;
   a.nlist_phase = g_nlist.phase; a.nlist_cnt = g_nlist.cnt; a.nlist_idx = g_nlist.idx;
   a.nlist_stride = g_nlist.stride; a.nlist_max = g_nlist.max;
   a.pdl = 0;

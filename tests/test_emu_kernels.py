@@ -290,3 +290,60 @@ def test_neighbour_lists_on_a_model_with_static_and_moving_types():
         for f in got.dtype.names:
             assert np.array_equal(got[f], plain[t][f]), "type %d member %s differs" % (t, f)
     assert plain[0]["visitors"].sum() > 0 and not np.array_equal(plain[0]["heat"], emulate(path, {"num_agents": 3000}, False, 0)[2][0]["heat"])
+
+
+@pytest.mark.parametrize("me", [0, 1, 3])
+def test_fused_halo_send_packs_what_the_decomposition_rules_say(me):
+    """Slab decomposition, direct transport: the step kernel itself routes every owned agent by
+    the cell layer of its NEW position and appends the record to the outgoing messages
+    (abl_slab_epilogue / abl_slab_send / abl_slab_route).  Emulated for one of four slabs and
+    compared with the rules restated in numpy (openabl_b200.slab.send_masks, the ones the gloo
+    test runs): same agents per direction, word-major records equal to the stored columns."""
+    import ctypes as C
+    from openabl_b200.slab import send_masks, slab_layer, split_layers
+    params = {"num_agents": 100000}
+    m = EmuModel(os.path.join(REPO, "examples", "boids2d.abl"), params)
+    m.populate()
+    m.bin(0)
+    g, p = m.grid, m.pools[0]
+    n_layers = g.n_cell[1]
+    bounds = split_layers(n_layers, 4)
+    pairs = [(bounds[k], bounds[k + 1]) for k in range(4)] if not isinstance(bounds[0], (tuple, list)) else list(bounds)
+    begin, end = pairs[me]
+    layer_now = slab_layer(p.position()[1], g.origin[1], g.cell_size, n_layers)
+    owned = np.nonzero((layer_now >= begin) & (layer_now < end))[0]
+    ob, oe = int(owned[0]), int(owned[-1]) + 1
+    assert oe - ob == len(owned)                      # sorted by cell key: the owned agents are contiguous
+    N = 4
+    lo = me - 1 if me > 0 else N - 1                  # peers form a ring (halo_fill_view)
+    hi = me + 1 if me < N - 1 else 0
+    capacity, rec_words = 20000, 4 + 4 + 1            # pos + velocity (2 doubles each) + id
+    msgs = [np.zeros(rec_words * capacity, dtype=np.uint32) for _ in range(2)]
+    counters = np.zeros(8, dtype=np.uint32)
+    elem = (C.c_int * 2)(16, 16)
+    m.lib.emu_set_slab.argtypes = [C.c_int] * 4 + [C.c_double] * 2 + [C.c_int] * 9 + [C.c_void_p] * 3 + [C.c_uint] * 2 + \
+        [C.c_int, C.c_void_p]
+    m.lib.emu_set_slab(1, 2, 0, n_layers, g.origin[1], g.inv_cell_size, begin, end, 1,
+                       pairs[lo][0], pairs[lo][1], pairs[hi][0], pairs[hi][1], int(me > 0), int(me < N - 1),
+                       msgs[0].ctypes.data, msgs[1].ctypes.data, counters.ctypes.data, capacity, rec_words, 2, elem)
+    try:
+        m.run_step(0, own_range=(ob, oe))
+    finally:
+        m.lib.emu_set_slab(*([0] * 4 + [0.0, 0.0] + [0] * 9 + [None] * 3 + [0, 0, 0, None]))
+    new_pos, new_vel, ids = p.cols[0][ob:oe], p.cols[1][ob:oe], p.ids[ob:oe]
+    layer_new = slab_layer(new_pos[:, 1], g.origin[1], g.cell_size, n_layers)
+    want_lo, want_hi = send_masks(layer_new, pairs, me, 1)
+    assert counters[2] == 0 and counters[3] == 0      # nobody moved farther than a neighbouring slab
+    assert want_lo.sum() > 0 or want_hi.sum() > 0
+    if me == 1:
+        assert want_lo.sum() > 100 and want_hi.sum() > 100      # ghost copies for both true neighbours
+    for d, want in enumerate((want_lo, want_hi)):
+        cnt = int(counters[d])
+        assert cnt == int(want.sum()), "direction %d: %d records, rules say %d" % (d, cnt, want.sum())
+        words = msgs[d].reshape(rec_words, capacity)[:, :cnt]
+        got_ids = words[8]
+        order = np.argsort(got_ids)
+        assert np.array_equal(got_ids[order], np.sort(ids[want]))
+        rec = np.ascontiguousarray(words[:8, order].T).view(np.float64)      # pos.x pos.y vel.x vel.y
+        sel = np.nonzero(want)[0][np.argsort(ids[want])]
+        assert np.array_equal(rec[:, 0:2], new_pos[sel]) and np.array_equal(rec[:, 2:4], new_vel[sel])
