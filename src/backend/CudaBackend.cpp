@@ -767,7 +767,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w << "} else if (ABL_MODE == 5 || ABL_MODE == 6) {";
     w.indent(); w.nl();
     w << "abl_near_iter<" << sdim << "> " << it << "b;"; w.nl();
-    w << it << "b.init" << sdim << "(_a, " << selfPosText << ", true);"; w.nl();
+    w << it << "b.init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);"; w.nl();
     w << "unsigned " << it << "c = 0;"; w.nl();
     w << "while (" << it << "b.valid()) {";
     w.indent(); w.nl();
@@ -895,8 +895,8 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   }
   w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
-  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true); else ";
-  w << it << ".init" << sdim << "(_a, " << selfPosText << ", true);";
+  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true, _near_cull); else ";
+  w << it << ".init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);";
   w.nl();
   // Radius filter: inclusive radius, self included, same operand order as the reference's
   // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
@@ -1670,7 +1670,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "template <int ABL_MODE>"; w.nl();
   sqLimits.clear();
   const bool sql = sqcmpOn() && curStepHasLimit;   // comparison bounds on the squared distance travel as a kernel parameter
-  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, "
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const abl_real _near_cull, "
     << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok, const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
@@ -1679,7 +1679,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
 
   w << "template <int ABL_MODE>"; w.nl();
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
-    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, "
+    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull, "
     << (sql ? "const abl_sq_limits _sql, " : "") << "const unsigned _tile_cap) {";
   w.indent(); w.nl();
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
@@ -1716,7 +1716,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w.indent(); w.nl();
     w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
     w << "abl_near_iter<" << tdim << "> _rows;"; w.nl();
-    w << "_rows.rows" << tdim << "(_a, " << p.name << "." << selfPosM->name << ", _active);"; w.nl();
+    w << "_rows.rows" << tdim << "(_a, " << p.name << "." << selfPosM->name << ", _active, _near_cull);"; w.nl();
     w << "_tile_ok = abl_tile_plan<" << tdim << ">(_rows, _tile_cap, _abl_smem);"; w.nl();
     w << "if (_tile_ok) {";
     w.indent(); w.nl();
@@ -1745,7 +1745,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "abl_ctx _ctx;"; w.nl();
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
-  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, _near_cull, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
   if (curStepList) { w.nl(); w << "if (ABL_MODE == 5 || ABL_MODE == 6) return;   // list-building launch: nothing of the step is stored"; }
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
@@ -1792,7 +1792,13 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w << "        have_sql = true;"; w.nl();
     w << "    }"; w.nl();
   }
-  const std::string lim = sql ? "limit, sql" : "limit";
+  // cell-range culling for radii well below the cell size (`-C cuda.cull=false` turns it off)
+  if (curStepHasLimit && config.getBool("cuda.cull", true)) {
+    w << "    const abl_real cull = abl_near_cull_range(limit, a->grid.cell_size);"; w.nl();
+  } else {
+    w << "    const abl_real cull = ABL_R(-1.0);"; w.nl();
+  }
+  const std::string lim = sql ? "limit, cull, sql" : "limit, cull";
   if (curStepHasLimit) {
     // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
     w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();

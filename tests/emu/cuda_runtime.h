@@ -86,7 +86,8 @@ static inline void __syncthreads() {
   fprintf(stderr, "emu: __syncthreads() reached — block-cooperative kernels cannot run on the sequential emulator\n");
   abort();
 }
-template <typename T> static inline T __ldg(const T *p) { return *p; }
+extern unsigned long long emu_ldg_count;   // read-only loads executed (a proxy for candidates visited)
+template <typename T> static inline T __ldg(const T *p) { emu_ldg_count++; return *p; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p = o + v; return o; }
 static inline int atomicAdd(int *p, int v) { int o = *p; *p = o + v; return o; }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { unsigned o = *p; *p = v; return o; }

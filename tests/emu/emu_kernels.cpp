@@ -9,6 +9,7 @@
 
 emu_idx threadIdx, blockIdx, blockDim, gridDim;
 unsigned long long emu_threads_run = 0;
+unsigned long long emu_ldg_count = 0;
 char emu_last_kernel[256];
 float emu_clock_ms = 0.f, emu_cost_ms[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
 
@@ -103,6 +104,7 @@ void emu_set_slab(int active, int dim, int pos_col, int n_layers, double origin,
 
 int emu_real_size(void) { return (int)sizeof(abl_real); }
 unsigned long long emu_thread_count(void) { return emu_threads_run; }
+unsigned long long emu_load_count(void) { return emu_ldg_count; }
 const char *emu_last_kernel_name(void) { return emu_last_kernel; }
 void emu_set_cost(int mode, float ms) { if (mode >= 0 && mode < 8) emu_cost_ms[mode] = ms; }
 

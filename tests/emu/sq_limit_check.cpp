@@ -4,6 +4,7 @@
 #include "cuda_runtime.h"
 emu_idx threadIdx, blockIdx, blockDim, gridDim;
 unsigned long long emu_threads_run = 0;
+unsigned long long emu_ldg_count = 0;
 char emu_last_kernel[256];
 float emu_clock_ms = 0.f, emu_cost_ms[8];
 #include "abl_device.cuh"

@@ -347,3 +347,48 @@ def test_fused_halo_send_packs_what_the_decomposition_rules_say(me):
         rec = np.ascontiguousarray(words[:8, order].T).view(np.float64)      # pos.x pos.y vel.x vel.y
         sel = np.nonzero(want)[0][np.argsort(ids[want])]
         assert np.array_equal(rec[:, 0:2], new_pos[sel]) and np.array_equal(rec[:, 2:4], new_vel[sel])
+
+
+def test_cell_range_culling_keeps_every_candidate_on_the_radius():
+    """Cell-range culling (radius well below the cell size: only the cells [cell(p - R), cell(p + R)]
+    per axis are visited).  static_sites counts Walkers within 1.0 of each Site on a grid of 2.5:
+    Walkers are placed exactly ON the radius around Sites that sit on / next to cell borders, in
+    all directions and one ulp inside / outside; the kernel's counts must equal a brute-force
+    count with the reference's predicate, and the culled kernel must visit fewer candidates."""
+    import ctypes as C
+    path = os.path.join(REPO, "tests", "models", "static_sites.abl")
+    rng = np.random.default_rng(7)
+    R, cell, W = 1.0, 2.5, float(np.sqrt(np.float64(3000) / 0.5))
+    n_sites = 1500
+    k = rng.integers(2, 28, size=(n_sites, 2)).astype(np.float64)
+    off = rng.choice([0.0, 1e-13, -1e-13, 0.4, 1.0, 1.5, 2.4999999999], size=(n_sites, 2))
+    site_pos = np.clip(k * cell + off, 0.0, W)
+    theta = np.concatenate([np.arange(8) * np.pi / 4, rng.uniform(0, 2 * np.pi, 4)])
+    walkers = []
+    for s in site_pos[:600]:
+        for t in theta:
+            q = s + R * np.array([np.cos(t), np.sin(t)])
+            walkers += [q, np.nextafter(q, s), np.nextafter(q, q + (q - s))]
+    walker_pos = np.clip(np.array(walkers), 0.0, W)
+
+    def run(cfg):
+        m = EmuModel(path, {"num_agents": 3000}, config=cfg)
+        m.lib.emu_load_count.restype = C.c_ulonglong
+        m.populate()
+        sites = np.zeros(n_sites, dtype=m.dtypes[0]); sites["pos"] = site_pos; sites["heat"] = 1.0
+        wk = np.zeros(len(walker_pos), dtype=m.dtypes[1]); wk["pos"] = walker_pos
+        m.pools[0].load(sites); m.pools[1].load(wk)
+        before = m.lib.emu_load_count()
+        m.run_step(1)                                  # site_count_walkers
+        return m.host_agents(0)["visitors"], m.lib.emu_load_count() - before
+
+    got, loads = run(None)
+    plain, loads_plain = run({"cuda.cull": False})
+    # the reference's filter (CPrinter.cpp:166-169, libabl.h:156-168): skip if (double)sqrtf((float)d2) > R
+    dx = walker_pos[None, :, 0] - site_pos[:, None, 0]
+    dy = walker_pos[None, :, 1] - site_pos[:, None, 1]
+    d2 = dx * dx + dy * dy
+    want = (~(np.sqrt(d2.astype(np.float32)).astype(np.float64) > R)).sum(axis=1)
+    assert np.array_equal(plain, want)
+    assert np.array_equal(got, want)
+    assert want.max() >= 20 and loads < 0.6 * loads_plain
