@@ -261,9 +261,9 @@ def main():
         rt.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
-    # (at least 10 warm-up timesteps: the launchers' run-time tuner times its two candidate-loop
-    # variants over the first 8 launches of a step function, asset/cuda/abl_device.cuh)
-    n_warmup = max(10, args.warmup)
+    # (at least 16 warm-up timesteps: the launchers' run-time tuner times up to three candidate-loop
+    # variants over the first 12 launches of a step function, asset/cuda/abl_device.cuh)
+    n_warmup = max(16, args.warmup)
     upload()
     for _ in range(n_warmup):
         timestep()
@@ -378,7 +378,7 @@ def main():
                            "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
                            "block_size": args.block_size, "neighbour_lists": bool(args.nlist),
                            "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
-                               os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor loop against flat loop, the faster is kept"),
+                               os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor, flat and chunked loop over the first launches, the fastest is kept"),
                            "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))
                                  if args.no_l2_flush else
                                  ("flushed: a %d MB write before every timed timestep (state: %.0f MB per GPU, L2: 126 MB); "

@@ -1799,53 +1799,79 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
     w << "    const abl_real cull = ABL_R(-1.0);"; w.nl();
   }
   const std::string lim = sql ? "limit, cull, sql" : "limit, cull";
+  const std::string K = "abl_kernel_" + f.emitName;
+  // Which loop: the density rule for pinned runs, a timed choice otherwise.  row_occ = mean number
+  // of candidates in one visited row (cells of a row after culling x agents per cell).
+  w << "    const double occ = a->grid.n_cells ? (double)a->nbr.n / (double)a->grid.n_cells : 0.0;"; w.nl();
+  w << "    const double row_cells = cull > ABL_R(0.0) ? fmin(3.0, 1.0 + 2.0 * (double)cull / a->grid.cell_size) : 2.0 * a->reach + 1.0;"; w.nl();
+  w << "    const double row_occ = occ * row_cells;"; w.nl();
   if (curStepHasLimit) {
-    // dense neighbourhoods (mean row of 3 cells holds >= 8 agents): chunked two-phase loop
-    w << "    const bool chunked = a->grid.n_cells && 3ull * a->nbr.n >= 8ull * a->grid.n_cells;"; w.nl();
+    // dense neighbourhoods (mean row holds >= 8 candidates): chunked two-phase loop
+    w << "    const bool chunked = row_occ >= 8.0;"; w.nl();
   } else {
     w << "    const bool chunked = false;"; w.nl();
   }
-  // block size 0 = automatic: 128 threads for sparse neighbourhoods, 256 for dense ones
-  // (measured on circle3d 1 M: 3.9 ms against 4.5 ms per step)
-  w << "    if (bs == 0) bs = chunked ? 256 : 128;"; w.nl();
-  w << "    unsigned grid = abl_grid_blocks(a, bs);"; w.nl();
-  if (curStepTile) {
-    // sparse neighbourhoods: stage the block's candidate rows in shared memory (ABL_MODE 2)
-    w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
-    w << "    const unsigned tile_cap = (a->tile_neighbours && !chunked && bs % 32 == 0) ? abl_tile_capacity(a, " << trows << ", bs, tile_entry, 64u * 1024u) : 0u;"; w.nl();
-    w << "    if (tile_cap) {"; w.nl();
-    w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
-    w << "        static bool tile_set = false;"; w.nl();
-    w << "        if (!tile_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
-    w << "        return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<2>, grid, bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
-    w << "    }"; w.nl();
-  }
+  w << "    const bool can_flat = " << (curStepFlat ? "a->reach == 1" : "false") << ";"; w.nl();
+  w << "    int mode = chunked ? 1 : (a->flat_loop > 0 && can_flat ? 3 : 0);"; w.nl();
+  w << "    bool timed = false;"; w.nl();
+  w << "    static abl_tuner tune[ABL_TUNE_DEVICES];"; w.nl();
   if (curStepList) {
     // cached neighbour lists: count / fill launches of the runtime, then the list walk
-    w << "    if (a->nlist_phase == 1) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<5>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
-    w << "    if (a->nlist_phase == 2) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<6>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
-    w << "    if (a->nlist_cnt) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<4>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+    w << "    const bool listed = a->nlist_phase != 0 || a->nlist_cnt != nullptr;"; w.nl();
+    w << "    if (listed) mode = a->nlist_phase == 1 ? 5 : a->nlist_phase == 2 ? 6 : 4;"; w.nl();
+  } else {
+    w << "    const bool listed = false;"; w.nl();
   }
-  if (curStepFlat) {
-    // sparse 2-D neighbourhoods with one cell of reach: the flat candidate loop (ABL_MODE 3)
-    // (a->flat_loop < 0: the first launches time both variants, abl_device.cuh: abl_tuner)
-    w << "    static abl_tuner tune[ABL_TUNE_DEVICES];"; w.nl();
-    w << "    if (!chunked && a->reach == 1" << (curStepTile ? " && !tile_cap" : "") << ") {"; w.nl();
-    w << "        const int flat = abl_tune_begin(tune, a->flat_loop, \"" << f.emitName << ": flat candidate loop\", a->stream);"; w.nl();
-    w << "        const int rc = flat ? (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<3>, grid, bs, 0, *a, " << lim << ", 0u)"; w.nl();
-    w << "                            : (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
-    w << "        abl_tune_end(tune, a->flat_loop, a->stream);"; w.nl();
-    w << "        return rc;"; w.nl();
+  if (curStepTile) {
+    // opt-in: stage the block's candidate rows in shared memory (ABL_MODE 2), sparse neighbourhoods only
+    w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
+    w << "    const int tile_bs = bs ? bs : 128;"; w.nl();
+    w << "    const unsigned tile_cap = (a->tile_neighbours && !chunked && !listed && tile_bs % 32 == 0) ? abl_tile_capacity(a, " << trows << ", tile_bs, tile_entry, 64u * 1024u) : 0u;"; w.nl();
+    w << "    if (tile_cap) {"; w.nl();
+    w << "        const unsigned tile_grid = abl_grid_blocks(a, tile_bs);"; w.nl();
+    w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * tile_bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
+    w << "        static bool tile_set = false;"; w.nl();
+    w << "        if (!tile_set) { cudaFuncSetAttribute(" << K << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
+    w << "        return (int)abl_launch_kernel(a, " << K << "<2>, tile_grid, tile_bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
     w << "    }"; w.nl();
   }
   if (curStepHasLimit) {
-    w << "    static bool smem_set = false;"; w.nl();
-    w << "    if (chunked && !smem_set) { cudaFuncSetAttribute(abl_kernel_" << f.emitName << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
-    w << "    if (chunked) return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, " << lim << ", 0u);"; w.nl();
-    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
-  } else {
-    w << "    return (int)abl_launch_kernel(a, abl_kernel_" << f.emitName << "<0>, grid, bs, 0, *a, " << lim << ", 0u);"; w.nl();
+    // a->flat_loop < 0 (the runtime's default): the plausible variants are timed over the first
+    // launches (abl_device.cuh: abl_tuner) — cursor loop and flat loop unless the rows are
+    // crowded, the chunked loop unless they are nearly empty
+    w << "    if (a->flat_loop < 0 && !listed) {"; w.nl();
+    w << "        int var[ABL_TUNE_VARIANTS], nvar = 0;"; w.nl();
+    w << "        unsigned vmask = 0;"; w.nl();
+    w << "        if (row_occ <= 48.0) { var[nvar++] = 0; vmask |= 1u; if (can_flat) { var[nvar++] = 3; vmask |= 2u; } }"; w.nl();
+    w << "        if (row_occ >= 2.0) { var[nvar++] = 1; vmask |= 4u; }"; w.nl();
+    w << "        timed = nvar > 1;"; w.nl();
+    w << "        mode = var[abl_tune_begin(tune, vmask, nvar, \"" << f.emitName << ": candidate loop (0 cursor, 3 flat, 1 chunked; in that order)\", a->stream)];"; w.nl();
+    w << "    }"; w.nl();
   }
+  // block size 0 = automatic: 128 threads for the per-candidate loops, 256 for the chunked one
+  // (measured on circle3d 1 M: 3.9 ms against 4.5 ms per step)
+  w << "    if (bs == 0) bs = mode == 1 ? 256 : 128;"; w.nl();
+  w << "    const unsigned grid = abl_grid_blocks(a, bs);"; w.nl();
+  w << "    int rc;"; w.nl();
+  w << "    switch (mode) {"; w.nl();
+  if (curStepHasLimit) {
+    w << "    case 1: {"; w.nl();
+    w << "        static bool smem_set = false;"; w.nl();
+    w << "        if (!smem_set) { cudaFuncSetAttribute(" << K << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
+    w << "        rc = (int)abl_launch_kernel(a, " << K << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, " << lim << ", 0u);"; w.nl();
+    w << "        break;"; w.nl();
+    w << "    }"; w.nl();
+  }
+  if (curStepFlat) { w << "    case 3: rc = (int)abl_launch_kernel(a, " << K << "<3>, grid, bs, 0, *a, " << lim << ", 0u); break;"; w.nl(); }
+  if (curStepList) {
+    for (int mlist = 4; mlist <= 6; mlist++) {
+      w << "    case " << mlist << ": rc = (int)abl_launch_kernel(a, " << K << "<" << mlist << ">, grid, bs, 0, *a, " << lim << ", 0u); break;"; w.nl();
+    }
+  }
+  w << "    default: rc = (int)abl_launch_kernel(a, " << K << "<0>, grid, bs, 0, *a, " << lim << ", 0u); break;"; w.nl();
+  w << "    }"; w.nl();
+  w << "    if (timed) abl_tune_end(tune, a->stream);"; w.nl();
+  w << "    return rc;"; w.nl();
   w << "}"; w.nl(); w.nl();
   (void)index;
   curFn = nullptr;

@@ -121,18 +121,18 @@ def test_launchers_pick_the_expected_kernel_variant():
     assert modes(emulate(c3, {"num_agents": 20000}, False, 1, flat_loop=1)[0].kernels) == [1]
 
 
-@pytest.mark.parametrize("faster", [0, 3])
-def test_run_time_tuner_times_both_variants_and_keeps_the_faster(faster):
-    """flat_loop = -1: the first eight launches alternate between the cursor loop and the flat loop
-    (events on the launch stream; here a simulated clock), afterwards every launch uses the variant
-    with the smaller time.  Results are those of any fixed choice, bit for bit."""
-    import ctypes as C
+@pytest.mark.parametrize("faster", [0, 3, 1])
+def test_run_time_tuner_times_the_variants_and_keeps_the_fastest(faster):
+    """flat_loop = -1: the first twelve launches rotate through the cursor loop, the flat loop and
+    the chunked loop (events on the launch stream; here a simulated clock), afterwards every launch
+    uses the variant with the smallest time.  Results are those of any fixed choice, bit for bit."""
+    import shutil
+    import tempfile
     from emu.emu import modes
     params = {"num_agents": 4000, "num_timesteps": 10}
     path = os.path.join(REPO, "examples", "boids2d.abl")
     # (the tuner is static in the launcher: a private copy of the library gives this test its own)
     m = EmuModel(path, params)
-    import shutil, tempfile
     with tempfile.TemporaryDirectory() as tmp:
         private = os.path.join(tmp, "libmodel_emu_%d.so" % faster)
         shutil.copy(os.path.join(m.dir, "libmodel_emu.so"), private)
@@ -142,16 +142,26 @@ def test_run_time_tuner_times_both_variants_and_keeps_the_faster(faster):
         m.flat_loop = -1
         m.populate()
         seen = []
-        for _ in range(12):
+        for _ in range(16):
             m.kernels = set()
             m.timestep()
             seen += modes(m.kernels)
-        assert seen[:8] == [0, 3, 0, 3, 0, 3, 0, 3]
-        assert seen[8:] == [faster] * 4
-        _, _, want = emulate(path, params, False, 12)
+        assert seen[:12] == [0, 3, 1] * 4
+        assert seen[12:] == [faster] * 4
+        _, _, want = emulate(path, params, False, 16)
         got = m.host_agents(0)
         for f in got.dtype.names:
             assert np.array_equal(got[f], want[0][f])
+
+
+def test_tuner_only_compares_plausible_variants():
+    """Crowded rows (circle3d: 49 agents per cell) go straight to the chunked loop; nearly empty
+    rows (predators: 0.04 per cell) are never tried on it."""
+    from emu.emu import modes
+    m, _, _ = emulate(os.path.join(REPO, "examples", "circle3d.abl"), {"num_agents": 20000}, False, 2, flat_loop=-1)
+    assert modes(m.kernels) == [1]
+    m, _, _ = emulate(os.path.join(REPO, "examples", "circle.abl"), {"num_agents": 50000}, False, 3, flat_loop=-1)
+    assert 0 in modes(m.kernels) and 3 in modes(m.kernels)
 
 
 @pytest.mark.parametrize("use_float", [False, True], ids=["f64", "f32"])
