@@ -359,7 +359,8 @@ def test_fused_halo_send_packs_what_the_decomposition_rules_say(me):
         assert np.array_equal(rec[:, 0:2], new_pos[sel]) and np.array_equal(rec[:, 2:4], new_vel[sel])
 
 
-def test_cell_range_culling_keeps_every_candidate_on_the_radius():
+@pytest.mark.parametrize("outside", [False, True], ids=["inside", "beyond-the-bounds"])
+def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside):
     """Cell-range culling (radius well below the cell size: only the cells [cell(p - R), cell(p + R)]
     per axis are visited).  static_sites counts Walkers within 1.0 of each Site on a grid of 2.5:
     Walkers are placed exactly ON the radius around Sites that sit on / next to cell borders, in
@@ -373,13 +374,17 @@ def test_cell_range_culling_keeps_every_candidate_on_the_radius():
     k = rng.integers(2, 28, size=(n_sites, 2)).astype(np.float64)
     off = rng.choice([0.0, 1e-13, -1e-13, 0.4, 1.0, 1.5, 2.4999999999], size=(n_sites, 2))
     site_pos = np.clip(k * cell + off, 0.0, W)
+    if outside:
+        # a third of the Sites beyond the environment (clamped into the border cells by the binning)
+        site_pos[:500, 0] = rng.choice([-0.5, -3.0, W + 0.25, W + 7.0, 0.0, W], size=500)
+        site_pos[250:750, 1] = rng.choice([-0.75, -1e-9, W + 1e-9, W + 2.0, 0.0, W], size=500)
     theta = np.concatenate([np.arange(8) * np.pi / 4, rng.uniform(0, 2 * np.pi, 4)])
     walkers = []
     for s in site_pos[:600]:
         for t in theta:
             q = s + R * np.array([np.cos(t), np.sin(t)])
             walkers += [q, np.nextafter(q, s), np.nextafter(q, q + (q - s))]
-    walker_pos = np.clip(np.array(walkers), 0.0, W)
+    walker_pos = np.array(walkers) if outside else np.clip(np.array(walkers), 0.0, W)
 
     def run(cfg):
         m = EmuModel(path, {"num_agents": 3000}, config=cfg)
@@ -401,4 +406,59 @@ def test_cell_range_culling_keeps_every_candidate_on_the_radius():
     want = (~(np.sqrt(d2.astype(np.float32)).astype(np.float64) > R)).sum(axis=1)
     assert np.array_equal(plain, want)
     assert np.array_equal(got, want)
-    assert want.max() >= 20 and loads < 0.6 * loads_plain
+    assert want.max() >= 20 and loads < (1.0 if outside else 0.6) * loads_plain
+
+
+# ---- the GPU edge cases (tests/test_gpu_edge_cases.py) under the emulator, for every loop choice ----
+@pytest.mark.parametrize("flat_loop", [0, 1, -1], ids=["cursor", "flat", "timed"])
+def test_edge_reach_two_cells_matches_oracle(flat_loop):
+    """granularity 5 < radius 10: the on-demand row path of the iterator (no flat loop, no culling)."""
+    from oracle import BRUTE
+    n, steps = 20000, 4
+    m, _, got = emulate(os.path.join(REPO, "tests", "models", "circle_fine_grid.abl"), {"num_agents": n}, False, steps,
+                        flat_loop=flat_loop)
+    o = Oracle(False)
+    state = o.circle_init(2, n)
+    want = o.circle_run(2, state, steps, GRID, granularity=5.0)
+    assert np.array_equal(got[0]["pos"], want["pos"])
+    ref = o.circle_run(2, state, steps, BRUTE)
+    assert np.max(np.abs(got[0]["pos"] - ref["pos"]) / np.maximum(np.abs(ref["pos"]), 1.0)) <= 1e-9
+
+
+@pytest.mark.parametrize("flat_loop", [0, 1, -1], ids=["cursor", "flat", "timed"])
+@pytest.mark.parametrize("n", [0, 1, 2, 3])
+def test_edge_empty_and_tiny_populations(n, flat_loop):
+    m = EmuModel(os.path.join(REPO, "examples", "boids2d.abl"), {"num_agents": 100000})
+    m.flat_loop = flat_loop
+    m.populate()
+    sub = np.ascontiguousarray(m.host_agents(0)[:n])
+    m.pools[0].load(sub)
+    for _ in range(3):
+        m.timestep()
+    got = m.host_agents(0)
+    assert len(got) == n
+    if n:
+        want = Oracle(False).boids_run(sub, 3, GRID, num_agents=100000)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[f])
+
+
+@pytest.mark.parametrize("flat_loop", [0, 1, -1], ids=["cursor", "flat", "timed"])
+def test_edge_one_cell_crowd_and_agents_outside_the_environment(flat_loop):
+    m = EmuModel(os.path.join(REPO, "examples", "boids2d.abl"), {"num_agents": 100000})
+    m.flat_loop = flat_loop
+    m.populate()
+    rng = np.random.default_rng(7)
+    n = 6000
+    a = np.zeros(n, dtype=m.dtypes[0])
+    a["pos"][:5000] = 5.0 + rng.random((5000, 2)) * 0.04          # one 0.05 x 0.05 cell
+    a["pos"][5000:5500] = -3.0 + rng.random((500, 2))             # below the lower bound
+    a["pos"][5500:] = 14.2 + rng.random((500, 2)) * 5.0           # beyond max_pos (= 14.14)
+    a["velocity"] = rng.random((n, 2)) * 2 - 1
+    m.pools[0].load(a)
+    for _ in range(2):
+        m.timestep()
+    got = m.host_agents(0)
+    want = Oracle(False).boids_run(a, 2, GRID, num_agents=100000)
+    for f in got.dtype.names:
+        assert np.array_equal(got[f], want[f]), f
