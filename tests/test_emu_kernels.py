@@ -359,8 +359,9 @@ def test_fused_halo_send_packs_what_the_decomposition_rules_say(me):
         assert np.array_equal(rec[:, 0:2], new_pos[sel]) and np.array_equal(rec[:, 2:4], new_vel[sel])
 
 
+@pytest.mark.parametrize("use_float", [False, True], ids=["f64", "f32"])
 @pytest.mark.parametrize("outside", [False, True], ids=["inside", "beyond-the-bounds"])
-def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside):
+def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside, use_float):
     """Cell-range culling (radius well below the cell size: only the cells [cell(p - R), cell(p + R)]
     per axis are visited).  static_sites counts Walkers within 1.0 of each Site on a grid of 2.5:
     Walkers are placed exactly ON the radius around Sites that sit on / next to cell borders, in
@@ -385,9 +386,15 @@ def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside):
             q = s + R * np.array([np.cos(t), np.sin(t)])
             walkers += [q, np.nextafter(q, s), np.nextafter(q, q + (q - s))]
     walker_pos = np.array(walkers) if outside else np.clip(np.array(walkers), 0.0, W)
+    real = np.float32 if use_float else np.float64
+    site_pos, walker_pos = site_pos.astype(real), walker_pos.astype(real)
+    if use_float:
+        # one float ulp either side of the rounded positions as well
+        extra = walker_pos[::3]
+        walker_pos = np.concatenate([walker_pos, np.nextafter(extra, np.float32(0)), np.nextafter(extra, np.float32(1e9))])
 
     def run(cfg):
-        m = EmuModel(path, {"num_agents": 3000}, config=cfg)
+        m = EmuModel(path, {"num_agents": 3000}, use_float=use_float, config=cfg)
         m.lib.emu_load_count.restype = C.c_ulonglong
         m.populate()
         sites = np.zeros(n_sites, dtype=m.dtypes[0]); sites["pos"] = site_pos; sites["heat"] = 1.0
@@ -403,7 +410,7 @@ def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside):
     dx = walker_pos[None, :, 0] - site_pos[:, None, 0]
     dy = walker_pos[None, :, 1] - site_pos[:, None, 1]
     d2 = dx * dx + dy * dy
-    want = (~(np.sqrt(d2.astype(np.float32)).astype(np.float64) > R)).sum(axis=1)
+    want = (~(np.sqrt(d2.astype(np.float32)).astype(real) > real(R))).sum(axis=1)     # dx, dy, d2 in abl_float
     assert np.array_equal(plain, want)
     assert np.array_equal(got, want)
     assert want.max() >= 20 and loads < (1.0 if outside else 0.6) * loads_plain
