@@ -51,3 +51,23 @@ def test_circle3d_1M_is_independent_of_block_size_and_tiling():
     assert len(a) == n == 1000000
     assert np.array_equal(a["pos"], b["pos"])
     assert np.isfinite(a["pos"]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_file,n,steps", [("boids2d.abl", 1000000, 14), ("game_of_life.abl", 1048576, 14)],
+                         ids=["boids2d-1M", "game_of_life-1M"])
+def test_candidate_loop_variants_agree_bitwise_at_full_size(model_file, n, steps, monkeypatch):
+    """Cursor loop (ABL_CUDA_FLAT=0), flat loop (=1) and the timed choice (unset: the first twelve
+    launches rotate through cursor, flat and chunked loop) must give the same bits; 14 timesteps
+    take the timed run through all its trial launches and into the chosen variant."""
+    params = {"num_agents": n}
+    outs = {}
+    for setting in ("0", "1", None):
+        if setting is None:
+            monkeypatch.delenv("ABL_CUDA_FLAT", raising=False)
+        else:
+            monkeypatch.setenv("ABL_CUDA_FLAT", setting)
+        outs[setting] = run(model_file, params, False, steps)[1]
+    for f in outs["0"].dtype.names:
+        assert np.array_equal(outs["0"][f], outs["1"][f]), "flat loop differs from the cursor loop in %s" % f
+        assert np.array_equal(outs["0"][f], outs[None][f]), "timed run differs from the cursor loop in %s" % f
