@@ -469,3 +469,19 @@ def test_edge_one_cell_crowd_and_agents_outside_the_environment(flat_loop):
     want = Oracle(False).boids_run(a, 2, GRID, num_agents=100000)
     for f in got.dtype.names:
         assert np.array_equal(got[f], want[f]), f
+
+
+@pytest.mark.parametrize("flat_loop", [1, -1], ids=["flat", "timed"])
+def test_break_and_continue_inside_the_loop_body_under_every_variant(flat_loop):
+    """static_sites.site_diffuse leaves its for-near loop with `break` after twelve neighbours and
+    skips itself with `continue`: the flat loop (two candidates per iteration, `continue` of the
+    first must still reach the second, `break` of the first must not) and the chunked loop give
+    the plain cursor loop's state bit for bit."""
+    path = os.path.join(REPO, "tests", "models", "static_sites.abl")
+    _, _, plain = emulate(path, {"num_agents": 3000}, False, 5, {"cuda.flat": False, "cuda.sqcmp": False, "cuda.cull": False})
+    m, _, got = emulate(path, {"num_agents": 3000}, False, 5, None, flat_loop=flat_loop)
+    from emu.emu import modes
+    assert 3 in modes(m.kernels)
+    for a, b in zip(plain, got):
+        for f in a.dtype.names:
+            assert np.array_equal(a[f], b[f]), "member %s differs" % f
