@@ -162,7 +162,7 @@ def run_reference_arm(args):
         return
     workload = args.workload
     model, params, use_float, S, M, P = WORKLOADS[workload]
-    vals, last = [], None
+    vals, times, last = [], [], None
     total = args.warmup + args.steps
     # each "step" is a bounded sample; the whole run stays within about half a minute of CPU work
     # at ~1e10 candidate tests per second (16 threads)
@@ -171,12 +171,14 @@ def run_reference_arm(args):
         base, dt = cpu_baseline(workload, budget_pairs=budget)
         if i >= args.warmup:
             vals.append(base["value"])
+            times.append(dt)
         last = base
     value = sum(vals) / len(vals)
     last["value"] = value
     line = {"impl": "reference", "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": None, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * sum(times) / len(times),   # one step = one bounded sample (see cpu_baseline.sample)
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if use_float else "f64", "data": "synthetic",
             "config": {"workload": workload, "model": model, "num_agents": params["num_agents"]},
             "cpu_baseline": last,
