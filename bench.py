@@ -367,6 +367,8 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = n_agents * args.steps / float(te.item())
+    mode_names = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", -1: "not launched"}
+    variants = {m.step_names[s]: mode_names.get(m.step_variant(s), str(m.step_variant(s))) for s in range(m.n_steps)}
     m.close()
 
     if rank == 0:
@@ -379,6 +381,7 @@ def main():
                            "agents_per_gpu": n_agents // world,
                            "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
                            "block_size": args.block_size, "neighbour_lists": bool(args.nlist),
+                           "candidate_loop_in_use": variants,     # ABL_MODE of each step function's latest launch (rank 0)
                            "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
                                os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor, flat and chunked loop over the first launches, the fastest is kept"),
                            "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))

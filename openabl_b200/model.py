@@ -55,6 +55,8 @@ class Model:
             getattr(self.lib, fn).argtypes = [C.c_void_p]
             getattr(self.lib, fn).restype = C.c_int
         self.lib.abl_model_run_step.argtypes = [C.c_void_p, C.c_int]
+        self.lib.abl_model_step_variant.argtypes = [C.c_int]
+        self.lib.abl_model_step_variant.restype = C.c_int
         self.lib.abl_model_step_flags.argtypes = [C.c_int]
         self.lib.abl_model_step_flags.restype = C.c_int
         self.lib.abl_model_sequential_step.argtypes = [C.c_void_p]
@@ -113,6 +115,12 @@ class Model:
     def step_flags(self, s):
         """bit 0: step function `s` removes agents, bit 1: it adds agents at run time."""
         return self.lib.abl_model_step_flags(s)
+
+    def step_variant(self, s):
+        """ABL_MODE of the kernel the latest launch of step function `s` used (-1 before the first):
+        0 cursor loop, 1 chunked, 2 shared-memory tile, 3 flat loop, 4 neighbour-list walk.  After the
+        tuning phase this is the variant the launcher's run-time tuner kept."""
+        return self.lib.abl_model_step_variant(s)
 
     def sequential_step(self):
         check(self.lib.abl_model_sequential_step(self.rt.handle), "abl_model_sequential_step")

@@ -1767,6 +1767,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w.outdent(); w.nl();
   w << "}"; w.nl(); w.nl();
 
+  w << "static int abl_last_mode_" << f.emitName << " = -1;   // ABL_MODE of the most recent launch (abl_model_step_variant)"; w.nl();
   w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *_args) {"; w.nl();
   w << "    abl_step_launch _copy = *_args;   // block counts of the boundary parts are filled in below"; w.nl();
   w << "    abl_step_launch *a = &_copy;"; w.nl();
@@ -1853,6 +1854,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "    if (bs == 0) bs = mode == 1 ? 256 : 128;"; w.nl();
   w << "    const unsigned grid = abl_grid_blocks(a, bs);"; w.nl();
   w << "    int rc;"; w.nl();
+  w << "    abl_last_mode_" << f.emitName << " = mode;"; w.nl();
   w << "    switch (mode) {"; w.nl();
   if (curStepHasLimit) {
     w << "    case 1: {"; w.nl();
@@ -1944,6 +1946,18 @@ std::string CudaPrinter::kernelSource() {
   for (const StepInfo &si : steps) w << " " << ((si.fn->usesRemoval ? 1 : 0) | (si.fn->addedAgent ? 2 : 0)) << ",";
   w << " 0 };"; w.nl();
   w << "    return flags[s];"; w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  w << "/* ABL_MODE of the kernel the most recent launch of step function s used (-1: not launched yet): 0 cursor"; w.nl();
+  w << " * loop, 1 chunked, 2 shared-memory tile, 3 flat loop, 4 neighbour-list walk — after the tuning phase"; w.nl();
+  w << " * this is the variant the launcher's run-time tuner kept */"; w.nl();
+  w << "extern \"C\" int abl_model_step_variant(int s) {"; w.nl();
+  w << "    switch (s) {"; w.nl();
+  for (size_t i = 0; i < steps.size(); i++) {
+    w << "    case " << i << ": return abl_last_mode_" << steps[i].fn->emitName << ";"; w.nl();
+  }
+  w << "    default: return -1;"; w.nl();
+  w << "    }"; w.nl();
   w << "}"; w.nl(); w.nl();
 
   w << "extern \"C\" int abl_model_setup(abl_runtime *rt) {"; w.nl();

@@ -148,6 +148,7 @@ def test_run_time_tuner_times_the_variants_and_keeps_the_fastest(faster):
             seen += modes(m.kernels)
         assert seen[:12] == [0, 3, 1] * 4
         assert seen[12:] == [faster] * 4
+        assert m.lib.abl_model_step_variant(0) == faster      # what bench.py reports as candidate_loop_in_use
         _, _, want = emulate(path, params, False, 16)
         got = m.host_agents(0)
         for f in got.dtype.names:
