@@ -19,8 +19,13 @@ done
 python -m pytest tests/test_gpu_zz_nlist.py -m gpu -q -rxX > $out/r2_pytest_nlist.log 2>&1
 ABL_CUDA_VERBOSE=1 python bench.py --workload game_of_life-16M-f64 --nlist --no-cpu-baseline --steps 100 --warmup 10 \
   > $out/r2_nlist_game_of_life-16M-f64.json 2> $out/r2_nlist_game_of_life-16M-f64.err
+# predator_prey 4 M: round-1 kernels (no culling, no flat loop, square roots) / pinned cursor / tuned default
+python tools/quick_step.py predator_prey-4M-f64 --steps 50 -C cuda.cull=false -C cuda.flat=false -C cuda.sqcmp=false > $out/r2_pp4M_round1_kernels.txt 2>&1
 ABL_CUDA_FLAT=0 python tools/quick_step.py predator_prey-4M-f64 --steps 50 > $out/r2_pp4M_flat0.txt 2>&1
-ABL_CUDA_FLAT=1 python tools/quick_step.py predator_prey-4M-f64 --steps 50 > $out/r2_pp4M_flat1.txt 2>&1
+python tools/quick_step.py predator_prey-4M-f64 --steps 50 > $out/r2_pp4M_tuned.txt 2>&1
+# round-1 kernels of the headline workload, same box, same run
+python tools/quick_step.py boids2d-1M-f64 -C cuda.flat=false -C cuda.sqcmp=false > $out/r2_boids1M_round1_kernels.txt 2>&1
+python tools/quick_step.py boids2d-1M-f64 > $out/r2_boids1M_tuned.txt 2>&1
 python bench.py > $out/r2_bench_default_n1.json 2> $out/r2_bench_default_n1.err
 # launch list + one full capture of the flat-loop kernel (numbers under ncu are never bench values)
 ABL_CUDA_FLAT=1 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
@@ -39,4 +44,4 @@ for f in sorted(glob.glob("gpurun_out/r2_*.json")):
                   "bin_ms", r.get("bin_ms"), "whole", r.get("whole_step_frac"))
 PY
 grep -h "variant" gpurun_out/r2_flat_*_auto.err
-tail -2 $out/r2_pp4M_flat0.txt $out/r2_pp4M_flat1.txt
+tail -n 1 $out/r2_pp4M_*.txt $out/r2_boids1M_*.txt

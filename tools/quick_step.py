@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Quick device-side timing of one workload: ms per timestep and per-stage times.
-usage: quick_step.py WORKLOAD [--tile] [--steps K] [--bs B]"""
+usage: quick_step.py WORKLOAD [--tile] [--steps K] [--bs B] [-C key=value ...]"""
 import argparse, os, sys
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -13,14 +13,19 @@ ap.add_argument("workload")
 ap.add_argument("--tile", action="store_true")
 ap.add_argument("--steps", type=int, default=100)
 ap.add_argument("--bs", type=int, default=0)
+ap.add_argument("-C", dest="config", action="append", default=[], help="code-generator option, e.g. -C cuda.cull=false")
 args = ap.parse_args()
+config = {}
+for kv in args.config:
+    k, v = kv.split("=", 1)
+    config[k] = {"true": True, "false": False}.get(v, v)
 model_file, params, use_float, S, M, P = bench.WORKLOADS[args.workload]
-m = Model(os.path.join(REPO, "examples", model_file), dict(params), use_float=use_float)
+m = Model(os.path.join(REPO, "examples", model_file), dict(params), use_float=use_float, config=config or None)
 m.populate()
 m.create_runtime(device=0, block_size=args.bs, tile=args.tile)
 m.upload_host()
 stream = torch.cuda.ExternalStream(m.rt.stream())
-for _ in range(10):
+for _ in range(16):      # covers the launchers' tuning phase (12 trial launches per step function)
     m.timestep()
 m.rt.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -39,5 +44,6 @@ for _ in range(20):
         for k in st:
             st[k] += lt[k] / 20
 n = sum(m.host_count(t) for t in range(m.n_types))
-print("%s tile=%s bs=%d: %.4f ms/step, %.2f G agent-steps/s; stages %s" % (
-    args.workload, args.tile, args.bs, ms, n / ms / 1e6, {k: round(v, 4) for k, v in st.items()}))
+modes = {m.step_names[s]: m.step_variant(s) for s in range(m.n_steps)}
+print("%s tile=%s bs=%d %s: %.4f ms/step, %.2f G agent-steps/s; stages %s; ABL_MODE per step %s" % (
+    args.workload, args.tile, args.bs, config, ms, n / ms / 1e6, {k: round(v, 4) for k, v in st.items()}, modes))
