@@ -206,8 +206,9 @@ typedef struct {
   unsigned step_index;
   int block_size;
   int tile_neighbours;
-  int flat_loop;                           /* flat candidate loop of sparse 2-D for-near loops (ABL_MODE 3 kernels): 1 always, 0 never,
-                                              -1 the launcher times both bit-identical variants over its first launches and keeps the faster */
+  int flat_loop;                           /* candidate loop of the step kernels: 0 cursor loop, 1 flat loop (sparse 2-D loops, ABL_MODE 3) — both
+                                              leave dense neighbourhoods to the chunked loop by the density rule; -1 (runtime default) the launcher
+                                              times the plausible bit-identical variants (cursor, flat, chunked) over its first launches and keeps the fastest */
   int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
   /* Cached neighbour lists (steps registered with abl_step_desc.nlist != 0: neither pool of the
