@@ -186,6 +186,24 @@ private:
   void stmts(const std::vector<StmtP> &v);
   void forStmt(const Stmt &s);
   void nearLoop(const Stmt &s);
+  // what the per-variant emitters of a for-near loop share
+  struct NearLoop {
+    const Stmt &s;
+    const Expr &agentExpr, &radius;
+    AgentDecl *nbr;
+    AgentMember *pos, *selfPos;
+    int dim, posIndex;
+    std::string it, sdim, selfPosText;
+    std::vector<int> others;      // neighbour members the body reads (besides the position)
+    bool prefetchOthers;          // ... fetched one candidate ahead / with the position
+    std::string ptypeS;
+  };
+  void nearLoadOthers(const NearLoop &L, const std::string &idx);
+  void nearListLoops(const NearLoop &L);
+  void nearTileLoop(const NearLoop &L);
+  void nearChunkedLoop(const NearLoop &L);
+  void nearFlatLoop(const NearLoop &L);
+  void nearCursorLoop(const NearLoop &L);
   void constDecl(const ConstDecl &c);
   void function(const FuncDecl &f);
   void agentStruct(const AgentDecl &a);
@@ -198,6 +216,16 @@ private:
   void reachableStmt(const Stmt &s, std::set<const FuncDecl *> &seen);
 
   void stepKernel(const StepInfo &si, int index);
+  struct StepKernelCtx {
+    const StepInfo &si;
+    const Expr *radius;
+    const std::vector<TileCol> &tcols;
+    int tdim;
+    const std::string &trows;
+    bool sql;
+  };
+  void stepKernelWrapper(const StepKernelCtx &C);
+  void stepLauncher(const StepKernelCtx &C);
   static const Expr *findNearRadius(const std::vector<StmtP> &body);
   static bool hostEvaluable(const Expr &e);
   void loadMember(const AgentDecl &a, int m, const std::string &dst, const std::string &view,
@@ -698,63 +726,364 @@ void CudaPrinter::forStmt(const Stmt &s) {
   w.outdent(); w.nl(); w << "}";
 }
 
-// for (T nx : near(agent, radius)) body   — device only
-void CudaPrinter::nearLoop(const Stmt &s) {
-  if (!dev() || !curStep)
-    throw BackendError("cuda backend: for-near loops are only supported directly inside step functions");
-  const Expr &call = *s.e[0];
-  const Expr &agentExpr = *call.kids[0];
-  const Expr &radius = *call.kids[1];
-  AgentDecl *nbr = s.declTy.agent;
-  AgentMember *pos = nbr->position();
-  AgentDecl *selfTy = agentExpr.type.agent;
-  AgentMember *selfPos = selfTy ? selfTy->position() : nullptr;
-  if (!selfPos) throw BackendError("cuda backend: near() needs an agent with a position");
-  int dim = pos->type.vecLen();
-  std::string it = label();
-  std::string sdim = std::to_string(dim);
+// members the loop body reads are fetched only for accepted candidates
+void CudaPrinter::nearLoadOthers(const NearLoop &L, const std::string &idx) {
+  for (size_t m = 0; m < L.nbr->members.size(); m++) {
+    if ((int)m == L.posIndex || !curFn->nearMembers.count(L.nbr->members[m]->name)) continue;
+    w.nl();
+    loadMember(*L.nbr, (int)m, L.s.varName + "." + L.nbr->members[m]->name, "_a.nbr.in", idx);
+  }
+}
 
-  int posIndex = nbr->memberIndex(pos->name);
-  auto loadOthers = [&](const std::string &idx) {
-    // members the body reads are fetched only for accepted candidates
-    for (size_t m = 0; m < nbr->members.size(); m++) {
-      if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
-      w.nl();
-      loadMember(*nbr, (int)m, s.varName + "." + nbr->members[m]->name, "_a.nbr.in", idx);
+// ABL_MODE 4: walk the cached list of accepted candidates (k-major, abl_cuda.h); 5 / 6: the two
+// list-building passes — the cursor loop's filter with a counter instead of the body.  Leaves an
+// open `else` for the ordinary variants.
+void CudaPrinter::nearListLoops(const NearLoop &L) {
+  const Stmt &s = L.s;
+  const Expr &agentExpr = L.agentExpr, &radius = L.radius;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos, *selfPos = L.selfPos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  auto loadOthers = [&](const std::string &idx) { nearLoadOthers(L, idx); };
+  (void)agentExpr; (void)radius; (void)pos; (void)selfPos; (void)dim; (void)posIndex; (void)loadOthers;
+  // ABL_MODE 4: walk the cached list of accepted candidates (k-major, abl_cuda.h); 5 / 6: the
+  // two list-building passes — the cursor loop's filter with a counter instead of the body
+  const bool needPos = curFn->nearMembers.count(pos->name) != 0;
+  std::string ptypeL = typeName(pos->type);
+  w << "if (ABL_MODE == 4) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "ln = _a.nlist_cnt[_i];"; w.nl();
+  w << "for (unsigned " << it << "lk = 0; " << it << "lk < " << it << "ln; " << it << "lk++) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "j = __ldg(_a.nlist_idx + (size_t)" << it << "lk * _a.nlist_stride + _i);"; w.nl();
+  w << nbr->name << " " << s.varName << ";";
+  if (needPos) {
+    w.nl();
+    loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+    w.nl();
+    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+      << pos->name << ", " << selfPosText << "));";
+  }
+  loadOthers(it + "j");
+  w.nl();
+  {
+    std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
+    int savedDepth = innerLoopDepth;
+    nearBreakLabel.clear();
+    nearContinueLabel.clear();
+    innerLoopDepth = 0;
+    if (needPos) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+    stmt(*s.body[0]);
+    clearNearContext();
+    nearBreakLabel = savedLabel;
+    nearContinueLabel = savedContinue;
+    innerLoopDepth = savedDepth;
+  }
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "} else if (ABL_MODE == 5 || ABL_MODE == 6) {";
+  w.indent(); w.nl();
+  w << "abl_near_iter<" << sdim << "> " << it << "b;"; w.nl();
+  w << it << "b.init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);"; w.nl();
+  w << "unsigned " << it << "c = 0;"; w.nl();
+  w << "while (" << it << "b.valid()) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "j = " << it << "b.index();"; w.nl();
+  w << it << "b.next();"; w.nl();
+  w << ptypeL << " " << it << "q;"; w.nl();
+  loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "j"); w.nl();
+  w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText << ")) > _near_limit) continue;"; w.nl();
+  w << "if (ABL_MODE == 6) _a.nlist_idx[(size_t)" << it << "c * _a.nlist_stride + _i] = " << it << "j;"; w.nl();
+  w << it << "c++;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "if (ABL_MODE == 5) { _a.nlist_cnt[_i] = " << it << "c; atomicMax(_a.nlist_max, " << it << "c); }";
+  w.outdent(); w.nl();
+  w << "} else";
+  w.nl();
+}
+
+// ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
+// (abl_device.cuh: abl_tile_plan); same visiting order as abl_near_iter.  Leaves its `else` open.
+void CudaPrinter::nearTileLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  const Expr &agentExpr = L.agentExpr, &radius = L.radius;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos, *selfPos = L.selfPos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  auto loadOthers = [&](const std::string &idx) { nearLoadOthers(L, idx); };
+  (void)agentExpr; (void)radius; (void)pos; (void)selfPos; (void)dim; (void)posIndex; (void)loadOthers;
+  // ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
+  // (abl_device.cuh: abl_tile_plan); same visiting order as abl_near_iter
+  std::vector<TileCol> cols = tileColumns(*curFn, *nbr);
+  const std::string rows = dim == 2 ? "3" : "9";
+  std::string done = "_near_done" + it + "t";
+  w << "if (ABL_MODE == 2 && _tile_ok) {";
+  w.indent(); w.nl();
+  w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
+  w << "const uint2 *" << it << "seg = reinterpret_cast<const uint2 *>(_abl_smem + ABL_TILE_HDR_BYTES) + threadIdx.x;"; w.nl();
+  w << "const unsigned char *const " << it << "cols = _abl_smem + ABL_TILE_HDR_BYTES + " << rows << " * blockDim.x * sizeof(uint2);"; w.nl();
+  // Two phases per row and chunk of up to 32 candidates: phase 1 only evaluates the radius
+  // filter and collects one acceptance bit per candidate in a register; phase 2 runs the
+  // loop body for the set bits, in candidate order.  A warp then pays for the body
+  // max-popcount times per chunk instead of once per candidate (in the single-phase loop
+  // nearly every iteration has some lane that accepts).
+  w << "for (int " << it << "k = 0; " << it << "k < " << rows << "; " << it << "k++) {";
+  w.indent(); w.nl();
+  w << "const uint2 " << it << "sg = " << it << "seg[" << it << "k * blockDim.x];"; w.nl();
+  w << "for (unsigned " << it << "b = " << it << "sg.x, " << it << "e = " << it << "sg.x + " << it << "sg.y; "
+    << it << "b < " << it << "e; " << it << "b += 32) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "n = min(32u, " << it << "e - " << it << "b);"; w.nl();
+  w << "unsigned " << it << "m = 0;"; w.nl();
+  std::string posSrc = "reinterpret_cast<const " + cols[0].ctype + " *>(" + it + "cols)";
+  auto tilePos = [&](const std::string &dst, const std::string &idx) {
+    // position columns come first in the tile (offsets 0, 1, 2 scalar columns for float3)
+    if (dim == 2) {
+      w << dst << " = reinterpret_cast<const abl_float2 *>(" << it << "cols)[" << idx << "];";
+    } else {
+      for (int c = 0; c < 3; c++) {
+        if (c) w.nl();
+        w << dst << "." << "xyz"[c] << " = reinterpret_cast<const abl_real *>(" << it << "cols + (size_t)_tile_cap * "
+          << tileOffset(cols, (size_t)c) << ")[" << idx << "];";
+      }
     }
   };
-  std::string selfPosText = exprText(agentExpr) + "." + selfPos->name;
-
-  w << "{";
+  (void)posSrc;
+  std::string ptypeT = typeName(pos->type);
+  w << "for (unsigned " << it << "c = 0; " << it << "c < " << it << "n; " << it << "c++) {";
   w.indent(); w.nl();
-  if (curStepList) {
-    // ABL_MODE 4: walk the cached list of accepted candidates (k-major, abl_cuda.h); 5 / 6: the
-    // two list-building passes — the cursor loop's filter with a counter instead of the body
-    const bool needPos = curFn->nearMembers.count(pos->name) != 0;
-    std::string ptypeL = typeName(pos->type);
-    w << "if (ABL_MODE == 4) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "ln = _a.nlist_cnt[_i];"; w.nl();
-    w << "for (unsigned " << it << "lk = 0; " << it << "lk < " << it << "ln; " << it << "lk++) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "j = __ldg(_a.nlist_idx + (size_t)" << it << "lk * _a.nlist_stride + _i);"; w.nl();
-    w << nbr->name << " " << s.varName << ";";
-    if (needPos) {
+  w << ptypeT << " " << it << "q;"; w.nl();
+  tilePos(it + "q", it + "b + " + it + "c");
+  w.nl();
+  if (curStepHasLimit) {
+    w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
+      << ")) > _near_limit)) " << it << "m |= 1u << " << it << "c;";
+  } else {
+    w << "if (!(dist_float" << sdim << "(" << it << "q, " << selfPosText << ") > ";
+    expr(radius);
+    w << ")) " << it << "m |= 1u << " << it << "c;";
+  }
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "while (" << it << "m) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "s = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
+  w << it << "m &= " << it << "m - 1;"; w.nl();
+  w << nbr->name << " " << s.varName << ";";
+  auto tileLoad = [&](int member) {
+    const Ty &mt = nbr->members[member]->type;
+    std::string dst = s.varName + "." + nbr->members[member]->name;
+    for (size_t q = 0; q < cols.size(); q++) {
+      if (cols[q].member != member) continue;
       w.nl();
-      loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
-      w.nl();
-      w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
-        << pos->name << ", " << selfPosText << "));";
+      std::string src = "reinterpret_cast<const " + cols[q].ctype + " *>(" + it + "cols + (size_t)_tile_cap * " +
+                        tileOffset(cols, q) + ")[" + it + "s]";
+      if (mt.k == TK::Vec3) w << dst << "." << "xyz"[cols[q].comp] << " = " << src << ";";
+      else if (mt.k == TK::Bool) w << dst << " = " << src << " != 0;";
+      else w << dst << " = " << src << ";";
     }
-    loadOthers(it + "j");
+  };
+  tileLoad(posIndex);
+  if (curStepHasLimit) {
+    w.nl();
+    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+      << pos->name << ", " << selfPosText << "));";
+  }
+  for (size_t m = 0; m < nbr->members.size(); m++) {
+    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
+    tileLoad((int)m);
+  }
+  w.nl();
+  {
+    std::string savedLabel = nearBreakLabel;
+    int savedDepth = innerLoopDepth;
+    nearBreakLabel = done;
+    innerLoopDepth = 0;
+    if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+    stmt(*s.body[0]);
+    clearNearContext();
+    nearBreakLabel = savedLabel;
+    innerLoopDepth = savedDepth;
+  }
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << done << ": ;";
+  w.outdent(); w.nl();
+  w << "} else {";
+  w.indent(); w.nl();
+}
+
+// ABL_MODE 1: chunked two-phase loop for dense neighbourhoods.  Leaves its `else` open.
+void CudaPrinter::nearChunkedLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  const Expr &agentExpr = L.agentExpr, &radius = L.radius;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos, *selfPos = L.selfPos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  auto loadOthers = [&](const std::string &idx) { nearLoadOthers(L, idx); };
+  (void)agentExpr; (void)radius; (void)pos; (void)selfPos; (void)dim; (void)posIndex; (void)loadOthers;
+  // Dense populations (ABL_MODE 1, chosen by the launcher from the mean cell occupancy):
+  // two phases per chunk of up to 32 candidates.  Phase 1 only evaluates the filter and
+  // records a bit per accepted candidate; phase 2 runs the loop body for the set bits, in
+  // order.  In a warp the expensive body then executes max-popcount times per chunk instead
+  // of once per candidate (with the plain loop nearly every iteration has *some* lane that
+  // accepts, so the whole warp pays for the body every time).
+  std::string done = "_near_done" + it;
+  std::string ptype = typeName(pos->type);
+  w << "if (ABL_MODE == 1) {";
+  w.indent(); w.nl();
+  w << "// phase 1 writes one acceptance bit per candidate into shared memory (32 candidates"; w.nl();
+  w << "// per word, ABL_MASK_WORDS words per thread and round); phase 2 replays the same"; w.nl();
+  w << "// chunks and runs the loop body for the set bits only, in candidate order"; w.nl();
+  w << "extern __shared__ unsigned _abl_masks[];"; w.nl();
+  w << "unsigned " << it << "nw, " << it << "w, " << it << "m, " << it << "b;"; w.nl();
+  w << "for (;;) {";
+  w.indent(); w.nl();
+  w << "abl_near_iter<" << sdim << "> " << it << "s = " << it << ";"; w.nl();
+  w << it << "nw = 0;"; w.nl();
+  w << "while (" << it << "s.valid() && " << it << "nw < ABL_MASK_WORDS) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "sb = " << it << "s.index();"; w.nl();
+  w << "const unsigned " << it << "sn = min(" << it << "s.remaining(), 32u);"; w.nl();
+  w << "unsigned " << it << "sm = 0;"; w.nl();
+  w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "sn; " << it << "k++) {";
+  w.indent(); w.nl();
+  w << ptype << " " << it << "q;"; w.nl();
+  loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "sb + " + it + "k");
+  w.nl();
+  w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
+    << ")) > _near_limit)) " << it << "sm |= 1u << " << it << "k;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "_abl_masks[" << it << "nw * blockDim.x + threadIdx.x] = " << it << "sm;"; w.nl();
+  w << it << "nw++;"; w.nl();
+  w << it << "s.skip(" << it << "sn);";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "if (" << it << "nw == 0) break;"; w.nl();
+  w << it << "w = 0; " << it << "m = 0; " << it << "b = 0;"; w.nl();
+  w << "for (;;) {";
+  w.indent(); w.nl();
+  w << "while (" << it << "m == 0 && " << it << "w < " << it << "nw) {";
+  w.indent(); w.nl();
+  w << it << "b = " << it << ".index();"; w.nl();
+  w << it << "m = _abl_masks[" << it << "w * blockDim.x + threadIdx.x];"; w.nl();
+  w << it << "w++;"; w.nl();
+  w << it << ".skip(min(" << it << ".remaining(), 32u));";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "if (" << it << "m == 0) break;"; w.nl();
+  w << "const unsigned " << it << "j = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
+  w << it << "m &= " << it << "m - 1;"; w.nl();
+  w << nbr->name << " " << s.varName << ";"; w.nl();
+  loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
+  w.nl();
+  w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+    << pos->name << ", " << selfPosText << "));";
+  loadOthers(it + "j");
+  w.nl();
+  {
+    std::string savedLabel = nearBreakLabel;
+    int savedDepth = innerLoopDepth;
+    nearBreakLabel = done;
+    innerLoopDepth = 0;
+    setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+    stmt(*s.body[0]);
+    clearNearContext();
+    nearBreakLabel = savedLabel;
+    innerLoopDepth = savedDepth;
+  }
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << done << ": ;";
+  w.outdent(); w.nl();
+  w << "} else {";
+  w.indent(); w.nl();
+}
+
+// `-C cuda.flat=true` (ABL_MODE 3, 2-D grids, reach 1): ONE flat candidate counter over the
+// three row ranges instead of a cursor that switches rows.  The pool index of candidate k is
+// k plus a per-row offset picked with two compares and two selects, so no lane ever leaves the
+// loop body to open its next row — in the cursor loop nearly every iteration has *some* lane
+// doing that, and the whole warp pays for the divergent path.  Two candidates are handled per
+// iteration: both positions (and prefetched members) are requested up front and both filters
+// evaluated back to back (independent dependency chains), then the bodies run in candidate
+// order.  Same candidates, same order as abl_near_iter: bit-identical results.
+// Leaves its `else` open.
+void CudaPrinter::nearFlatLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  const Expr &agentExpr = L.agentExpr, &radius = L.radius;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos, *selfPos = L.selfPos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  auto loadOthers = [&](const std::string &idx) { nearLoadOthers(L, idx); };
+  (void)agentExpr; (void)radius; (void)pos; (void)selfPos; (void)dim; (void)posIndex; (void)loadOthers;
+  const std::vector<int> &others = L.others;
+  const bool prefetchOthers = L.prefetchOthers;
+  const std::string &ptypeS = L.ptypeS;
+  (void)others; (void)prefetchOthers; (void)ptypeS;
+  w << "if (ABL_MODE == 3) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "T1 = " << it << ".re[0] - " << it << ".rb[0];"; w.nl();
+  w << "const unsigned " << it << "T2 = " << it << "T1 + (" << it << ".re[1] - " << it << ".rb[1]);"; w.nl();
+  w << "const unsigned " << it << "N = " << it << "T2 + (" << it << ".re[2] - " << it << ".rb[2]);"; w.nl();
+  w << "const unsigned " << it << "O0 = " << it << ".rb[0], " << it << "O1 = " << it << ".rb[1] - " << it << "T1, "
+    << it << "O2 = " << it << ".rb[2] - " << it << "T2;"; w.nl();
+  w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "N; " << it << "k += 2) {";
+  w.indent(); w.nl();
+  w << "const bool " << it << "hB = " << it << "k + 1u < " << it << "N;"; w.nl();
+  w << "const unsigned " << it << "kB = " << it << "hB ? " << it << "k + 1u : " << it << "k;"; w.nl();
+  w << "const unsigned " << it << "jA = " << it << "k + (" << it << "k < " << it << "T1 ? " << it << "O0 : (" << it << "k < "
+    << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
+  w << "const unsigned " << it << "jB = " << it << "kB + (" << it << "kB < " << it << "T1 ? " << it << "O0 : (" << it << "kB < "
+    << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << ptypeS << " " << it << "p" << H << ";"; w.nl();
+    loadMember(*nbr, posIndex, it + "p" + H, "_a.nbr.in", it + "j" + H); w.nl();
+    if (prefetchOthers)
+      for (int m : others) {
+        w << typeName(nbr->members[m]->type) << " " << it << "m" << m << H << ";"; w.nl();
+        loadMember(*nbr, m, it + "m" + std::to_string(m) + H, "_a.nbr.in", it + "j" + H); w.nl();
+      }
+  }
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << "const abl_real " << it << "d2" << H << " = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "p" << H
+      << ", " << selfPosText << "));"; w.nl();
+  }
+  const std::string second = "_near_flatB" + it;
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << "if (" << (h ? it + "hB && " : std::string()) << "!(" << it << "d2" << H << " > _near_limit)) {";
+    w.indent(); w.nl();
+    w << nbr->name << " " << s.varName << ";"; w.nl();
+    w << s.varName << "." << pos->name << " = " << it << "p" << H << ";";
+    if (prefetchOthers) {
+      for (int m : others) { w.nl(); w << s.varName << "." << nbr->members[m]->name << " = " << it << "m" << m << H << ";"; }
+    } else {
+      loadOthers(it + "j" + H);
+    }
     w.nl();
     {
       std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
       int savedDepth = innerLoopDepth;
       nearBreakLabel.clear();
-      nearContinueLabel.clear();
+      nearContinueLabel = h ? std::string() : second;
       innerLoopDepth = 0;
-      if (needPos) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
+      setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2" + H);
       stmt(*s.body[0]);
       clearNearContext();
       nearBreakLabel = savedLabel;
@@ -762,251 +1091,30 @@ void CudaPrinter::nearLoop(const Stmt &s) {
       innerLoopDepth = savedDepth;
     }
     w.outdent(); w.nl();
-    w << "}";
-    w.outdent(); w.nl();
-    w << "} else if (ABL_MODE == 5 || ABL_MODE == 6) {";
-    w.indent(); w.nl();
-    w << "abl_near_iter<" << sdim << "> " << it << "b;"; w.nl();
-    w << it << "b.init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);"; w.nl();
-    w << "unsigned " << it << "c = 0;"; w.nl();
-    w << "while (" << it << "b.valid()) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "j = " << it << "b.index();"; w.nl();
-    w << it << "b.next();"; w.nl();
-    w << ptypeL << " " << it << "q;"; w.nl();
-    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "j"); w.nl();
-    w << "if (abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText << ")) > _near_limit) continue;"; w.nl();
-    w << "if (ABL_MODE == 6) _a.nlist_idx[(size_t)" << it << "c * _a.nlist_stride + _i] = " << it << "j;"; w.nl();
-    w << it << "c++;";
-    w.outdent(); w.nl();
     w << "}"; w.nl();
-    w << "if (ABL_MODE == 5) { _a.nlist_cnt[_i] = " << it << "c; atomicMax(_a.nlist_max, " << it << "c); }";
-    w.outdent(); w.nl();
-    w << "} else";
-    w.nl();
+    if (h == 0) { w << second << ": ;"; w.nl(); }
   }
-  w << "{";
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "} else {";
   w.indent(); w.nl();
-  const bool tile = curStepTile;
-  if (tile) {
-    // ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
-    // (abl_device.cuh: abl_tile_plan); same visiting order as abl_near_iter
-    std::vector<TileCol> cols = tileColumns(*curFn, *nbr);
-    const std::string rows = dim == 2 ? "3" : "9";
-    std::string done = "_near_done" + it + "t";
-    w << "if (ABL_MODE == 2 && _tile_ok) {";
-    w.indent(); w.nl();
-    w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
-    w << "const uint2 *" << it << "seg = reinterpret_cast<const uint2 *>(_abl_smem + ABL_TILE_HDR_BYTES) + threadIdx.x;"; w.nl();
-    w << "const unsigned char *const " << it << "cols = _abl_smem + ABL_TILE_HDR_BYTES + " << rows << " * blockDim.x * sizeof(uint2);"; w.nl();
-    // Two phases per row and chunk of up to 32 candidates: phase 1 only evaluates the radius
-    // filter and collects one acceptance bit per candidate in a register; phase 2 runs the
-    // loop body for the set bits, in candidate order.  A warp then pays for the body
-    // max-popcount times per chunk instead of once per candidate (in the single-phase loop
-    // nearly every iteration has some lane that accepts).
-    w << "for (int " << it << "k = 0; " << it << "k < " << rows << "; " << it << "k++) {";
-    w.indent(); w.nl();
-    w << "const uint2 " << it << "sg = " << it << "seg[" << it << "k * blockDim.x];"; w.nl();
-    w << "for (unsigned " << it << "b = " << it << "sg.x, " << it << "e = " << it << "sg.x + " << it << "sg.y; "
-      << it << "b < " << it << "e; " << it << "b += 32) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "n = min(32u, " << it << "e - " << it << "b);"; w.nl();
-    w << "unsigned " << it << "m = 0;"; w.nl();
-    std::string posSrc = "reinterpret_cast<const " + cols[0].ctype + " *>(" + it + "cols)";
-    auto tilePos = [&](const std::string &dst, const std::string &idx) {
-      // position columns come first in the tile (offsets 0, 1, 2 scalar columns for float3)
-      if (dim == 2) {
-        w << dst << " = reinterpret_cast<const abl_float2 *>(" << it << "cols)[" << idx << "];";
-      } else {
-        for (int c = 0; c < 3; c++) {
-          if (c) w.nl();
-          w << dst << "." << "xyz"[c] << " = reinterpret_cast<const abl_real *>(" << it << "cols + (size_t)_tile_cap * "
-            << tileOffset(cols, (size_t)c) << ")[" << idx << "];";
-        }
-      }
-    };
-    (void)posSrc;
-    std::string ptypeT = typeName(pos->type);
-    w << "for (unsigned " << it << "c = 0; " << it << "c < " << it << "n; " << it << "c++) {";
-    w.indent(); w.nl();
-    w << ptypeT << " " << it << "q;"; w.nl();
-    tilePos(it + "q", it + "b + " + it + "c");
-    w.nl();
-    if (curStepHasLimit) {
-      w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
-        << ")) > _near_limit)) " << it << "m |= 1u << " << it << "c;";
-    } else {
-      w << "if (!(dist_float" << sdim << "(" << it << "q, " << selfPosText << ") > ";
-      expr(radius);
-      w << ")) " << it << "m |= 1u << " << it << "c;";
-    }
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << "while (" << it << "m) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "s = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
-    w << it << "m &= " << it << "m - 1;"; w.nl();
-    w << nbr->name << " " << s.varName << ";";
-    auto tileLoad = [&](int member) {
-      const Ty &mt = nbr->members[member]->type;
-      std::string dst = s.varName + "." + nbr->members[member]->name;
-      for (size_t q = 0; q < cols.size(); q++) {
-        if (cols[q].member != member) continue;
-        w.nl();
-        std::string src = "reinterpret_cast<const " + cols[q].ctype + " *>(" + it + "cols + (size_t)_tile_cap * " +
-                          tileOffset(cols, q) + ")[" + it + "s]";
-        if (mt.k == TK::Vec3) w << dst << "." << "xyz"[cols[q].comp] << " = " << src << ";";
-        else if (mt.k == TK::Bool) w << dst << " = " << src << " != 0;";
-        else w << dst << " = " << src << ";";
-      }
-    };
-    tileLoad(posIndex);
-    if (curStepHasLimit) {
-      w.nl();
-      w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
-        << pos->name << ", " << selfPosText << "));";
-    }
-    for (size_t m = 0; m < nbr->members.size(); m++) {
-      if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
-      tileLoad((int)m);
-    }
-    w.nl();
-    {
-      std::string savedLabel = nearBreakLabel;
-      int savedDepth = innerLoopDepth;
-      nearBreakLabel = done;
-      innerLoopDepth = 0;
-      if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-      stmt(*s.body[0]);
-      clearNearContext();
-      nearBreakLabel = savedLabel;
-      innerLoopDepth = savedDepth;
-    }
-    w.outdent(); w.nl();
-    w << "}";
-    w.outdent(); w.nl();
-    w << "}";
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << done << ": ;";
-    w.outdent(); w.nl();
-    w << "} else {";
-    w.indent(); w.nl();
-  }
-  w << "abl_near_iter<" << sdim << "> " << it << ";";
-  w.nl();
-  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true, _near_cull); else ";
-  w << it << ".init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);";
-  w.nl();
-  // Radius filter: inclusive radius, self included, same operand order as the reference's
-  // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
-  // is a host-evaluable constant the launcher precomputes the equivalent bound on the
-  // squared distance (abl_near_sq_limit) and the kernel skips the square root.
-  if (curStepHasLimit) {
-    // Dense populations (ABL_MODE 1, chosen by the launcher from the mean cell occupancy):
-    // two phases per chunk of up to 32 candidates.  Phase 1 only evaluates the filter and
-    // records a bit per accepted candidate; phase 2 runs the loop body for the set bits, in
-    // order.  In a warp the expensive body then executes max-popcount times per chunk instead
-    // of once per candidate (with the plain loop nearly every iteration has *some* lane that
-    // accepts, so the whole warp pays for the body every time).
-    std::string done = "_near_done" + it;
-    std::string ptype = typeName(pos->type);
-    w << "if (ABL_MODE == 1) {";
-    w.indent(); w.nl();
-    w << "// phase 1 writes one acceptance bit per candidate into shared memory (32 candidates"; w.nl();
-    w << "// per word, ABL_MASK_WORDS words per thread and round); phase 2 replays the same"; w.nl();
-    w << "// chunks and runs the loop body for the set bits only, in candidate order"; w.nl();
-    w << "extern __shared__ unsigned _abl_masks[];"; w.nl();
-    w << "unsigned " << it << "nw, " << it << "w, " << it << "m, " << it << "b;"; w.nl();
-    w << "for (;;) {";
-    w.indent(); w.nl();
-    w << "abl_near_iter<" << sdim << "> " << it << "s = " << it << ";"; w.nl();
-    w << it << "nw = 0;"; w.nl();
-    w << "while (" << it << "s.valid() && " << it << "nw < ABL_MASK_WORDS) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "sb = " << it << "s.index();"; w.nl();
-    w << "const unsigned " << it << "sn = min(" << it << "s.remaining(), 32u);"; w.nl();
-    w << "unsigned " << it << "sm = 0;"; w.nl();
-    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "sn; " << it << "k++) {";
-    w.indent(); w.nl();
-    w << ptype << " " << it << "q;"; w.nl();
-    loadMember(*nbr, posIndex, it + "q", "_a.nbr.in", it + "sb + " + it + "k");
-    w.nl();
-    w << "if (!(abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "q, " << selfPosText
-      << ")) > _near_limit)) " << it << "sm |= 1u << " << it << "k;";
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << "_abl_masks[" << it << "nw * blockDim.x + threadIdx.x] = " << it << "sm;"; w.nl();
-    w << it << "nw++;"; w.nl();
-    w << it << "s.skip(" << it << "sn);";
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << "if (" << it << "nw == 0) break;"; w.nl();
-    w << it << "w = 0; " << it << "m = 0; " << it << "b = 0;"; w.nl();
-    w << "for (;;) {";
-    w.indent(); w.nl();
-    w << "while (" << it << "m == 0 && " << it << "w < " << it << "nw) {";
-    w.indent(); w.nl();
-    w << it << "b = " << it << ".index();"; w.nl();
-    w << it << "m = _abl_masks[" << it << "w * blockDim.x + threadIdx.x];"; w.nl();
-    w << it << "w++;"; w.nl();
-    w << it << ".skip(min(" << it << ".remaining(), 32u));";
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << "if (" << it << "m == 0) break;"; w.nl();
-    w << "const unsigned " << it << "j = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
-    w << it << "m &= " << it << "m - 1;"; w.nl();
-    w << nbr->name << " " << s.varName << ";"; w.nl();
-    loadMember(*nbr, posIndex, s.varName + "." + pos->name, "_a.nbr.in", it + "j");
-    w.nl();
-    w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
-      << pos->name << ", " << selfPosText << "));";
-    loadOthers(it + "j");
-    w.nl();
-    {
-      std::string savedLabel = nearBreakLabel;
-      int savedDepth = innerLoopDepth;
-      nearBreakLabel = done;
-      innerLoopDepth = 0;
-      setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-      stmt(*s.body[0]);
-      clearNearContext();
-      nearBreakLabel = savedLabel;
-      innerLoopDepth = savedDepth;
-    }
-    w.outdent(); w.nl();
-    w << "}";
-    w.outdent(); w.nl();
-    w << "}"; w.nl();
-    w << done << ": ;";
-    w.outdent(); w.nl();
-    w << "} else {";
-    w.indent(); w.nl();
-  }
-  // Software-pipelined candidate loop: the position of the *next* candidate is requested
-  // before the current one is tested and processed, so the load latency (L1 miss -> L2) is
-  // overlapped with the body instead of stalling every iteration.  The iterator is advanced
-  // at the top, which also makes `continue` in the body do the right thing.
-  // Besides the position, up to two further neighbour members are fetched one candidate
-  // ahead as well (speculatively: a rejected candidate wastes the load, an accepted one no
-  // longer waits for a dependent L2 round trip).
-  std::vector<int> others;
-  int otherCols = 0;
-  for (size_t m = 0; m < nbr->members.size(); m++) {
-    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
-    others.push_back((int)m);
-    otherCols += nbr->members[m]->type.k == TK::Vec3 ? 3 : 1;
-  }
-  // (only floating-point members: integer/bool flags usually guard cheap bodies, where the
-  // extra load per rejected candidate costs more than the stall it hides — measured on
-  // game_of_life)
-  bool allFloat = true;
-  for (int m : others) {
-    const Ty &mt = nbr->members[m]->type;
-    allFloat = allFloat && (mt.isFloat() || mt.isVec());
-  }
-  const bool prefetchOthers = !others.empty() && otherCols <= 2 && allFloat;
-  std::string ptypeS = typeName(pos->type);
+}
+
+// ABL_MODE 0: the cursor loop (abl_near_iter), software-pipelined, optionally unrolled by two.
+void CudaPrinter::nearCursorLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  const Expr &agentExpr = L.agentExpr, &radius = L.radius;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos, *selfPos = L.selfPos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  auto loadOthers = [&](const std::string &idx) { nearLoadOthers(L, idx); };
+  (void)agentExpr; (void)radius; (void)pos; (void)selfPos; (void)dim; (void)posIndex; (void)loadOthers;
+  const std::vector<int> &others = L.others;
+  const bool prefetchOthers = L.prefetchOthers;
+  const std::string &ptypeS = L.ptypeS;
+  (void)others; (void)prefetchOthers; (void)ptypeS;
   // `-C cuda.unroll=true`: the loop is unrolled by two with alternating prefetch registers, so
   // that handing the prefetched candidate to the body costs no register copies (8 moves per
   // iteration for a double-precision float2 position + float2 member)
@@ -1025,81 +1133,6 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w.outdent(); w.nl();
     w << "}";
   };
-  // `-C cuda.flat=true` (ABL_MODE 3, 2-D grids, reach 1): ONE flat candidate counter over the
-  // three row ranges instead of a cursor that switches rows.  The pool index of candidate k is
-  // k plus a per-row offset picked with two compares and two selects, so no lane ever leaves the
-  // loop body to open its next row — in the cursor loop nearly every iteration has *some* lane
-  // doing that, and the whole warp pays for the divergent path.  Two candidates are handled per
-  // iteration: both positions (and prefetched members) are requested up front and both filters
-  // evaluated back to back (independent dependency chains), then the bodies run in candidate
-  // order.  Same candidates, same order as abl_near_iter: bit-identical results.
-  if (curStepFlat) {
-    w << "if (ABL_MODE == 3) {";
-    w.indent(); w.nl();
-    w << "const unsigned " << it << "T1 = " << it << ".re[0] - " << it << ".rb[0];"; w.nl();
-    w << "const unsigned " << it << "T2 = " << it << "T1 + (" << it << ".re[1] - " << it << ".rb[1]);"; w.nl();
-    w << "const unsigned " << it << "N = " << it << "T2 + (" << it << ".re[2] - " << it << ".rb[2]);"; w.nl();
-    w << "const unsigned " << it << "O0 = " << it << ".rb[0], " << it << "O1 = " << it << ".rb[1] - " << it << "T1, "
-      << it << "O2 = " << it << ".rb[2] - " << it << "T2;"; w.nl();
-    w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "N; " << it << "k += 2) {";
-    w.indent(); w.nl();
-    w << "const bool " << it << "hB = " << it << "k + 1u < " << it << "N;"; w.nl();
-    w << "const unsigned " << it << "kB = " << it << "hB ? " << it << "k + 1u : " << it << "k;"; w.nl();
-    w << "const unsigned " << it << "jA = " << it << "k + (" << it << "k < " << it << "T1 ? " << it << "O0 : (" << it << "k < "
-      << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
-    w << "const unsigned " << it << "jB = " << it << "kB + (" << it << "kB < " << it << "T1 ? " << it << "O0 : (" << it << "kB < "
-      << it << "T2 ? " << it << "O1 : " << it << "O2));"; w.nl();
-    for (int h = 0; h < 2; h++) {
-      const std::string H = h ? "B" : "A";
-      w << ptypeS << " " << it << "p" << H << ";"; w.nl();
-      loadMember(*nbr, posIndex, it + "p" + H, "_a.nbr.in", it + "j" + H); w.nl();
-      if (prefetchOthers)
-        for (int m : others) {
-          w << typeName(nbr->members[m]->type) << " " << it << "m" << m << H << ";"; w.nl();
-          loadMember(*nbr, m, it + "m" + std::to_string(m) + H, "_a.nbr.in", it + "j" + H); w.nl();
-        }
-    }
-    for (int h = 0; h < 2; h++) {
-      const std::string H = h ? "B" : "A";
-      w << "const abl_real " << it << "d2" << H << " = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "p" << H
-        << ", " << selfPosText << "));"; w.nl();
-    }
-    const std::string second = "_near_flatB" + it;
-    for (int h = 0; h < 2; h++) {
-      const std::string H = h ? "B" : "A";
-      w << "if (" << (h ? it + "hB && " : std::string()) << "!(" << it << "d2" << H << " > _near_limit)) {";
-      w.indent(); w.nl();
-      w << nbr->name << " " << s.varName << ";"; w.nl();
-      w << s.varName << "." << pos->name << " = " << it << "p" << H << ";";
-      if (prefetchOthers) {
-        for (int m : others) { w.nl(); w << s.varName << "." << nbr->members[m]->name << " = " << it << "m" << m << H << ";"; }
-      } else {
-        loadOthers(it + "j" + H);
-      }
-      w.nl();
-      {
-        std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
-        int savedDepth = innerLoopDepth;
-        nearBreakLabel.clear();
-        nearContinueLabel = h ? std::string() : second;
-        innerLoopDepth = 0;
-        setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2" + H);
-        stmt(*s.body[0]);
-        clearNearContext();
-        nearBreakLabel = savedLabel;
-        nearContinueLabel = savedContinue;
-        innerLoopDepth = savedDepth;
-      }
-      w.outdent(); w.nl();
-      w << "}"; w.nl();
-      if (h == 0) { w << second << ": ;"; w.nl(); }
-    }
-    w.outdent(); w.nl();
-    w << "}";
-    w.outdent(); w.nl();
-    w << "} else {";
-    w.indent(); w.nl();
-  }
   for (int set = 0; set < (unroll ? 2 : 1); set++) {
     w << ptypeS << " " << setName(set, it + "p") << ";"; w.nl();
     if (prefetchOthers)
@@ -1167,6 +1200,76 @@ void CudaPrinter::nearLoop(const Stmt &s) {
     w.outdent(); w.nl();
     w << "}";
   }
+}
+
+// for (T nx : near(agent, radius)) body   — device only
+void CudaPrinter::nearLoop(const Stmt &s) {
+  if (!dev() || !curStep)
+    throw BackendError("cuda backend: for-near loops are only supported directly inside step functions");
+  const Expr &call = *s.e[0];
+  const Expr &agentExpr = *call.kids[0];
+  const Expr &radius = *call.kids[1];
+  AgentDecl *nbr = s.declTy.agent;
+  AgentMember *pos = nbr->position();
+  AgentDecl *selfTy = agentExpr.type.agent;
+  AgentMember *selfPos = selfTy ? selfTy->position() : nullptr;
+  if (!selfPos) throw BackendError("cuda backend: near() needs an agent with a position");
+  int dim = pos->type.vecLen();
+  std::string it = label();
+  std::string sdim = std::to_string(dim);
+
+  int posIndex = nbr->memberIndex(pos->name);
+  std::string selfPosText = exprText(agentExpr) + "." + selfPos->name;
+
+  // Variants are template instances of one kernel (`if (ABL_MODE == k)`), printed in this order:
+  // list walk / list building (4, 5, 6), shared-memory tile (2), chunked (1), flat (3), cursor (0);
+  // every emitter but the last leaves an `else` open, closed at the end of this function.
+  w << "{";
+  w.indent(); w.nl();
+  NearLoop L{s, agentExpr, radius, nbr, pos, selfPos, dim, posIndex, it, sdim, selfPosText, {}, false, std::string()};
+  if (curStepList) nearListLoops(L);
+  w << "{";
+  w.indent(); w.nl();
+  const bool tile = curStepTile;
+  if (tile) nearTileLoop(L);
+  w << "abl_near_iter<" << sdim << "> " << it << ";";
+  w.nl();
+  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true, _near_cull); else ";
+  w << it << ".init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);";
+  w.nl();
+  // Radius filter: inclusive radius, self included, same operand order as the reference's
+  // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
+  // is a host-evaluable constant the launcher precomputes the equivalent bound on the
+  // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  if (curStepHasLimit) nearChunkedLoop(L);
+  // Software-pipelined candidate loop: the position of the *next* candidate is requested
+  // before the current one is tested and processed, so the load latency (L1 miss -> L2) is
+  // overlapped with the body instead of stalling every iteration.  The iterator is advanced
+  // at the top, which also makes `continue` in the body do the right thing.
+  // Besides the position, up to two further neighbour members are fetched one candidate
+  // ahead as well (speculatively: a rejected candidate wastes the load, an accepted one no
+  // longer waits for a dependent L2 round trip).
+  std::vector<int> &others = L.others;
+  int otherCols = 0;
+  for (size_t m = 0; m < nbr->members.size(); m++) {
+    if ((int)m == posIndex || !curFn->nearMembers.count(nbr->members[m]->name)) continue;
+    others.push_back((int)m);
+    otherCols += nbr->members[m]->type.k == TK::Vec3 ? 3 : 1;
+  }
+  // (only floating-point members: integer/bool flags usually guard cheap bodies, where the
+  // extra load per rejected candidate costs more than the stall it hides — measured on
+  // game_of_life)
+  bool allFloat = true;
+  for (int m : others) {
+    const Ty &mt = nbr->members[m]->type;
+    allFloat = allFloat && (mt.isFloat() || mt.isVec());
+  }
+  const bool prefetchOthers = !others.empty() && otherCols <= 2 && allFloat;
+  std::string ptypeS = typeName(pos->type);
+  L.prefetchOthers = prefetchOthers;
+  L.ptypeS = ptypeS;
+  if (curStepFlat) nearFlatLoop(L);
+  nearCursorLoop(L);
   if (curStepFlat) { w.outdent(); w.nl(); w << "}"; }
   if (curStepHasLimit) { w.outdent(); w.nl(); w << "}"; }
   if (tile) { w.outdent(); w.nl(); w << "}"; }
@@ -1636,47 +1739,21 @@ bool CudaPrinter::stepListEligible(const StepInfo &si) const {
   return true;
 }
 
-void CudaPrinter::stepKernel(const StepInfo &si, int index) {
+// The __global__ wrapper of a step function: thread -> agent, loads of the members the step reads,
+// the tile staging of ABL_MODE 2, the call, stores of the written members, the fused histogram of
+// the next binning and the slab epilogue.
+void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
+  const StepInfo &si = C.si;
   FuncDecl &f = *si.fn;
   AgentDecl &self = *si.self;
   const Param &p = f.params[0];
-  curFn = &f;
-  curStep = &si;
-  const Expr *radius = f.nearAgent ? findNearRadius(f.body) : nullptr;
-  curStepHasLimit = radius && hostEvaluable(*radius);
-  // Shared-memory tiling needs the loop to range over the neighbourhood of the stepped agent
-  // itself (`near(in, r)`): the kernel prologue plans the tile from in.pos of every thread.
-  const Stmt *nearStmt = f.nearAgent ? findNearStmt(f.body) : nullptr;
+  const Expr *radius = C.radius;
   AgentMember *selfPosM = self.position();
-  curStepTile = false;
-  std::vector<TileCol> tcols;
-  int tdim = 0;
-  if (nearStmt && selfPosM && nearStmt->declTy.agent && nearStmt->declTy.agent->position()) {
-    const Expr &ae = *nearStmt->e[0]->kids[0];
-    curStepTile = ae.kind == Expr::Var && ae.sym && ae.sym == p.sym;
-    if (curStepTile) {
-      tcols = tileColumns(f, *nearStmt->declTy.agent);
-      tdim = nearStmt->declTy.agent->position()->type.vecLen();
-    }
-  }
-  const std::string trows = tdim == 2 ? "3" : "9";
-  curStepList = stepListEligible(si) && nearStmt && nearStmt->e[0]->kids[0]->kind == Expr::Var &&
-                nearStmt->e[0]->kids[0]->sym == p.sym;
-  if (curStepList) listSteps.insert(&f);
-  curStepFlat = config.getBool("cuda.flat", true) && curStepHasLimit && nearStmt && nearStmt->declTy.agent &&
-                nearStmt->declTy.agent->position() && nearStmt->declTy.agent->position()->type.vecLen() == 2;
-
-  // the user's step function
-  w << "template <int ABL_MODE>"; w.nl();
-  sqLimits.clear();
-  const bool sql = sqcmpOn() && curStepHasLimit;   // comparison bounds on the squared distance travel as a kernel parameter
-  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const abl_real _near_cull, "
-    << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok, const "
-    << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
-  w.indent(); stmts(f.body); w.outdent();
-  w.nl();
-  w << "}"; w.nl(); w.nl();
-
+  const std::vector<TileCol> &tcols = C.tcols;
+  const int tdim = C.tdim;
+  const std::string &trows = C.trows;
+  const bool sql = C.sql;
+  (void)p; (void)radius; (void)selfPosM; (void)tcols; (void)tdim; (void)trows; (void)sql;
   w << "template <int ABL_MODE>"; w.nl();
   w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull, "
@@ -1767,6 +1844,23 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w.outdent(); w.nl();
   w << "}"; w.nl(); w.nl();
 
+}
+
+// The host-side launcher registered with the runtime (abl_step_desc.launch): bounds on the squared
+// distance, culling range, choice of the kernel variant (density rule or run-time tuner) and of
+// the block size, launch.
+void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
+  const StepInfo &si = C.si;
+  FuncDecl &f = *si.fn;
+  AgentDecl &self = *si.self;
+  const Param &p = f.params[0];
+  const Expr *radius = C.radius;
+  AgentMember *selfPosM = self.position();
+  const std::vector<TileCol> &tcols = C.tcols;
+  const int tdim = C.tdim;
+  const std::string &trows = C.trows;
+  const bool sql = C.sql;
+  (void)p; (void)radius; (void)selfPosM; (void)tcols; (void)tdim; (void)trows; (void)sql;
   w << "static int abl_last_mode_" << f.emitName << " = -1;   // ABL_MODE of the most recent launch (abl_model_step_variant)"; w.nl();
   w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *_args) {"; w.nl();
   w << "    abl_step_launch _copy = *_args;   // block counts of the boundary parts are filled in below"; w.nl();
@@ -1875,6 +1969,52 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   w << "    if (timed) abl_tune_end(tune, a->stream);"; w.nl();
   w << "    return rc;"; w.nl();
   w << "}"; w.nl(); w.nl();
+}
+
+void CudaPrinter::stepKernel(const StepInfo &si, int index) {
+  FuncDecl &f = *si.fn;
+  AgentDecl &self = *si.self;
+  const Param &p = f.params[0];
+  curFn = &f;
+  curStep = &si;
+  const Expr *radius = f.nearAgent ? findNearRadius(f.body) : nullptr;
+  curStepHasLimit = radius && hostEvaluable(*radius);
+  // Shared-memory tiling needs the loop to range over the neighbourhood of the stepped agent
+  // itself (`near(in, r)`): the kernel prologue plans the tile from in.pos of every thread.
+  const Stmt *nearStmt = f.nearAgent ? findNearStmt(f.body) : nullptr;
+  AgentMember *selfPosM = self.position();
+  curStepTile = false;
+  std::vector<TileCol> tcols;
+  int tdim = 0;
+  if (nearStmt && selfPosM && nearStmt->declTy.agent && nearStmt->declTy.agent->position()) {
+    const Expr &ae = *nearStmt->e[0]->kids[0];
+    curStepTile = ae.kind == Expr::Var && ae.sym && ae.sym == p.sym;
+    if (curStepTile) {
+      tcols = tileColumns(f, *nearStmt->declTy.agent);
+      tdim = nearStmt->declTy.agent->position()->type.vecLen();
+    }
+  }
+  const std::string trows = tdim == 2 ? "3" : "9";
+  curStepList = stepListEligible(si) && nearStmt && nearStmt->e[0]->kids[0]->kind == Expr::Var &&
+                nearStmt->e[0]->kids[0]->sym == p.sym;
+  if (curStepList) listSteps.insert(&f);
+  curStepFlat = config.getBool("cuda.flat", true) && curStepHasLimit && nearStmt && nearStmt->declTy.agent &&
+                nearStmt->declTy.agent->position() && nearStmt->declTy.agent->position()->type.vecLen() == 2;
+
+  // the user's step function
+  w << "template <int ABL_MODE>"; w.nl();
+  sqLimits.clear();
+  const bool sql = sqcmpOn() && curStepHasLimit;   // comparison bounds on the squared distance travel as a kernel parameter
+  w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const abl_real _near_cull, "
+    << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok, const "
+    << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
+  w.indent(); stmts(f.body); w.outdent();
+  w.nl();
+  w << "}"; w.nl(); w.nl();
+
+  StepKernelCtx ctx{si, radius, tcols, tdim, trows, sql};
+  stepKernelWrapper(ctx);
+  stepLauncher(ctx);
   (void)index;
   curFn = nullptr;
   curStep = nullptr;
