@@ -199,6 +199,7 @@ private:
     std::string ptypeS;
   };
   void nearLoadOthers(const NearLoop &L, const std::string &idx);
+  void nearLoopBody(const NearLoop &L, const std::string &d2, const std::string &breakLabel, const std::string &continueLabel);
   void nearListLoops(const NearLoop &L);
   void nearTileLoop(const NearLoop &L);
   void nearChunkedLoop(const NearLoop &L);
@@ -726,6 +727,25 @@ void CudaPrinter::forStmt(const Stmt &s) {
   w.outdent(); w.nl(); w << "}";
 }
 
+// The DSL loop body for one accepted candidate.  d2: variable holding the squared distance of the
+// near pair (dist(in.pos, nx.pos) in the body reuses it; empty: not available); breakLabel /
+// continueLabel: where `break` / `continue` of the body must jump when the variant wraps the body
+// in loops of its own (empty: the plain statement).
+void CudaPrinter::nearLoopBody(const NearLoop &L, const std::string &d2, const std::string &breakLabel,
+                           const std::string &continueLabel) {
+  const std::string savedBreak = nearBreakLabel, savedContinue = nearContinueLabel;
+  const int savedDepth = innerLoopDepth;
+  nearBreakLabel = breakLabel;
+  nearContinueLabel = continueLabel;
+  innerLoopDepth = 0;
+  if (!d2.empty()) setNearContext(L.s, L.agentExpr, L.pos->name, L.selfPos->name, d2);
+  stmt(*L.s.body[0]);
+  clearNearContext();
+  nearBreakLabel = savedBreak;
+  nearContinueLabel = savedContinue;
+  innerLoopDepth = savedDepth;
+}
+
 // members the loop body reads are fetched only for accepted candidates
 void CudaPrinter::nearLoadOthers(const NearLoop &L, const std::string &idx) {
   for (size_t m = 0; m < L.nbr->members.size(); m++) {
@@ -767,19 +787,7 @@ void CudaPrinter::nearListLoops(const NearLoop &L) {
   }
   loadOthers(it + "j");
   w.nl();
-  {
-    std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
-    int savedDepth = innerLoopDepth;
-    nearBreakLabel.clear();
-    nearContinueLabel.clear();
-    innerLoopDepth = 0;
-    if (needPos) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-    stmt(*s.body[0]);
-    clearNearContext();
-    nearBreakLabel = savedLabel;
-    nearContinueLabel = savedContinue;
-    innerLoopDepth = savedDepth;
-  }
+  nearLoopBody(L, needPos ? it + "d2" : std::string(), std::string(), std::string());
   w.outdent(); w.nl();
   w << "}";
   w.outdent(); w.nl();
@@ -898,17 +906,7 @@ void CudaPrinter::nearTileLoop(const NearLoop &L) {
     tileLoad((int)m);
   }
   w.nl();
-  {
-    std::string savedLabel = nearBreakLabel;
-    int savedDepth = innerLoopDepth;
-    nearBreakLabel = done;
-    innerLoopDepth = 0;
-    if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-    stmt(*s.body[0]);
-    clearNearContext();
-    nearBreakLabel = savedLabel;
-    innerLoopDepth = savedDepth;
-  }
+  nearLoopBody(L, curStepHasLimit ? it + "d2" : std::string(), done, nearContinueLabel);
   w.outdent(); w.nl();
   w << "}";
   w.outdent(); w.nl();
@@ -991,17 +989,7 @@ void CudaPrinter::nearChunkedLoop(const NearLoop &L) {
     << pos->name << ", " << selfPosText << "));";
   loadOthers(it + "j");
   w.nl();
-  {
-    std::string savedLabel = nearBreakLabel;
-    int savedDepth = innerLoopDepth;
-    nearBreakLabel = done;
-    innerLoopDepth = 0;
-    setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-    stmt(*s.body[0]);
-    clearNearContext();
-    nearBreakLabel = savedLabel;
-    innerLoopDepth = savedDepth;
-  }
+  nearLoopBody(L, it + "d2", done, nearContinueLabel);
   w.outdent(); w.nl();
   w << "}";
   w.outdent(); w.nl();
@@ -1077,19 +1065,7 @@ void CudaPrinter::nearFlatLoop(const NearLoop &L) {
       loadOthers(it + "j" + H);
     }
     w.nl();
-    {
-      std::string savedLabel = nearBreakLabel, savedContinue = nearContinueLabel;
-      int savedDepth = innerLoopDepth;
-      nearBreakLabel.clear();
-      nearContinueLabel = h ? std::string() : second;
-      innerLoopDepth = 0;
-      setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2" + H);
-      stmt(*s.body[0]);
-      clearNearContext();
-      nearBreakLabel = savedLabel;
-      nearContinueLabel = savedContinue;
-      innerLoopDepth = savedDepth;
-    }
+    nearLoopBody(L, it + "d2" + H, std::string(), h ? std::string() : second);
     w.outdent(); w.nl();
     w << "}"; w.nl();
     if (h == 0) { w << second << ": ;"; w.nl(); }
@@ -1164,17 +1140,7 @@ void CudaPrinter::nearCursorLoop(const NearLoop &L) {
     }
     if (!prefetchOthers) loadOthers(it + "j");
     w.nl();
-    {
-      std::string savedLabel = nearBreakLabel;
-      int savedDepth = innerLoopDepth;
-      nearBreakLabel.clear();
-      innerLoopDepth = 0;
-      if (curStepHasLimit) setNearContext(s, agentExpr, pos->name, selfPos->name, it + "d2");
-      stmt(*s.body[0]);
-      clearNearContext();
-      nearBreakLabel = savedLabel;
-      innerLoopDepth = savedDepth;
-    }
+    nearLoopBody(L, curStepHasLimit ? it + "d2" : std::string(), std::string(), nearContinueLabel);
   };
   if (!unroll) {
     w << "while (" << it << ".valid()) {";
