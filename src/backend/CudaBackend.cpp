@@ -1872,6 +1872,8 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   } else {
     w << "    const bool chunked = false;"; w.nl();
   }
+  w << "    int dev = 0;"; w.nl();
+  w << "    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ABL_TUNE_DEVICES) dev = 0;"; w.nl();
   w << "    const bool can_flat = " << (curStepFlat ? "a->reach == 1" : "false") << ";"; w.nl();
   w << "    int mode = chunked ? 1 : (a->flat_loop > 0 && can_flat ? 3 : 0);"; w.nl();
   w << "    bool timed = false;"; w.nl();
@@ -1891,8 +1893,8 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
     w << "    if (tile_cap) {"; w.nl();
     w << "        const unsigned tile_grid = abl_grid_blocks(a, tile_bs);"; w.nl();
     w << "        const size_t smem = ABL_TILE_HDR_BYTES + (size_t)" << trows << " * tile_bs * sizeof(uint2) + (size_t)tile_cap * tile_entry;"; w.nl();
-    w << "        static bool tile_set = false;"; w.nl();
-    w << "        if (!tile_set) { cudaFuncSetAttribute(" << K << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set = true; }"; w.nl();
+    w << "        static bool tile_set[ABL_TUNE_DEVICES];   // the attribute is per device"; w.nl();
+    w << "        if (!tile_set[dev]) { cudaFuncSetAttribute(" << K << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set[dev] = true; }"; w.nl();
     w << "        return (int)abl_launch_kernel(a, " << K << "<2>, tile_grid, tile_bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
     w << "    }"; w.nl();
   }
@@ -1918,8 +1920,8 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   w << "    switch (mode) {"; w.nl();
   if (curStepHasLimit) {
     w << "    case 1: {"; w.nl();
-    w << "        static bool smem_set = false;"; w.nl();
-    w << "        if (!smem_set) { cudaFuncSetAttribute(" << K << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set = true; }"; w.nl();
+    w << "        static bool smem_set[ABL_TUNE_DEVICES];   // the attribute is per device"; w.nl();
+    w << "        if (!smem_set[dev]) { cudaFuncSetAttribute(" << K << "<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, ABL_MASK_WORDS * 256 * (int)sizeof(unsigned)); smem_set[dev] = true; }"; w.nl();
     w << "        rc = (int)abl_launch_kernel(a, " << K << "<1>, grid, bs, (size_t)ABL_MASK_WORDS * bs * sizeof(unsigned), *a, " << lim << ", 0u);"; w.nl();
     w << "        break;"; w.nl();
     w << "    }"; w.nl();
