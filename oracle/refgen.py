@@ -96,6 +96,10 @@ EXTRA_FIXTURES = {
     "two_species_n3000_t0": ("tests/models/two_species.abl", {"num_agents": 3000, "num_timesteps": 0}, False),
     "table_cells_n2500_t10": ("tests/models/table_cells.abl", {"num_agents": 2500, "num_timesteps": 10}, False),
     "table_cells_n2500_t10_f32": ("tests/models/table_cells.abl", {"num_agents": 2500, "num_timesteps": 10}, True),
+    # radii below the cell size (cell-range culling), a static type next to a moving one (neighbour lists),
+    # a distance compared with a constant
+    "sites_walkers_n3000_t10": ("tests/models/sites_walkers.abl", {"num_agents": 3000, "num_timesteps": 10}, False),
+    "sites_walkers_n3000_t10_f32": ("tests/models/sites_walkers.abl", {"num_agents": 3000, "num_timesteps": 10}, True),
 }
 
 

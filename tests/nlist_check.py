@@ -58,6 +58,18 @@ def static_sites():
     m.close()
 
 
+def sites_walkers():
+    """Lists for the static Sites, against the golden vector of the real reference `c` backend."""
+    import refgen
+    from openabl_b200.state import exact_members_equal, max_rel_error
+    info, gold = refgen.load_fixture("sites_walkers_n3000_t10")
+    params = dict(info["params"])
+    got = run(refgen.model_path(info["model"]), params, params["num_timesteps"], {"cuda.nlist": True})
+    for g, ref in zip(got, gold):
+        assert len(g) == len(ref) and exact_members_equal(g, ref)
+        assert max_rel_error(g, ref) <= 1e-9, max_rel_error(g, ref)
+
+
 if __name__ == "__main__":
-    {"game_of_life": game_of_life, "static_sites": static_sites}[sys.argv[1]]()
+    {"game_of_life": game_of_life, "static_sites": static_sites, "sites_walkers": sites_walkers}[sys.argv[1]]()
     print("ok")

@@ -486,3 +486,28 @@ def test_break_and_continue_inside_the_loop_body_under_every_variant(flat_loop):
     for a, b in zip(plain, got):
         for f in a.dtype.names:
             assert np.array_equal(a[f], b[f]), "member %s differs" % f
+
+
+@pytest.mark.parametrize("use_float", [False, True], ids=["f64", "f32"])
+def test_neighbour_lists_and_culling_match_the_real_reference(use_float):
+    """tests/models/sites_walkers.abl against the golden vectors of the unmodified reference compiler
+    + libabl (10 timesteps): radii below the cell size (culled cell ranges), a distance compared
+    with a constant, and — with cuda.nlist — cached lists for the static Sites.  Counts and
+    integer/bool state exact, floating point within 1e-9 (double) / 1e-4 (use_float)."""
+    name = "sites_walkers_n3000_t10" + ("_f32" if use_float else "")
+    info, gold = refgen.load_fixture(name)
+    params = dict(info["params"])
+    tol = 1e-4 if use_float else 1e-9
+    for config, lists in ((None, False), ({"cuda.nlist": True}, True)):
+        m = EmuModel(refgen.model_path(info["model"]), params, use_float=use_float, config=config)
+        m.use_nlist = lists
+        m.flat_loop = 1
+        m.populate()
+        for _ in range(params["num_timesteps"]):
+            m.timestep()
+        assert m.nlist_builds == (1 if lists else 0)
+        for t, ref in enumerate(gold):
+            got = m.host_agents(t)
+            assert len(got) == len(ref)
+            assert exact_members_equal(got, ref), "integer/bool state differs"
+            assert max_rel_error(got, ref) <= tol, "max relative error %.3e" % max_rel_error(got, ref)

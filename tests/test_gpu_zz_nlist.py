@@ -33,3 +33,10 @@ def test_lists_of_static_sites_survive_moving_walkers():
     """Site-Site lists are built once while the Walker pool is re-binned every timestep; the state
     equals the run without lists bit for bit, and re-uploading the population rebuilds the lists."""
     check("static_sites")
+
+
+@pytest.mark.gpu
+@first_run
+def test_lists_match_the_real_reference():
+    """sites_walkers with lists for the static Sites against the reference `c` backend's golden vector."""
+    check("sites_walkers")
