@@ -1934,6 +1934,13 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   }
   w << "    default: rc = (int)abl_launch_kernel(a, " << K << "<0>, grid, bs, 0, *a, " << lim << ", 0u); break;"; w.nl();
   w << "    }"; w.nl();
+  // a trial variant that cannot even be launched must not stop the simulation: back to the cursor loop
+  w << "    if (rc != 0 && timed && mode != 0) {"; w.nl();
+  w << "        abl_tune_abort(tune);"; w.nl();
+  w << "        timed = false;"; w.nl();
+  w << "        abl_last_mode_" << f.emitName << " = 0;"; w.nl();
+  w << "        rc = (int)abl_launch_kernel(a, " << K << "<0>, abl_grid_blocks(a, 128), 128, 0, *a, " << lim << ", 0u);"; w.nl();
+  w << "    }"; w.nl();
   w << "    if (timed) abl_tune_end(tune, a->stream);"; w.nl();
   w << "    return rc;"; w.nl();
   w << "}"; w.nl(); w.nl();

@@ -72,6 +72,7 @@ extern char emu_last_kernel[256];   // mangled name of the kernel launched last 
 struct emu_event { float t; };
 typedef emu_event *cudaEvent_t;
 extern float emu_clock_ms, emu_cost_ms[8];
+extern int emu_fail_mode;   // launches of this ABL_MODE fail (-1: none)
 static inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emu_event{0.f}; return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
@@ -124,6 +125,7 @@ static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t *cfg, void
   }
   if (const char *m = strstr(emu_last_kernel, "ILi")) {
     const int mode = atoi(m + 3);
+    if (mode == emu_fail_mode) return 1;   // simulated launch failure (e.g. too much dynamic shared memory)
     emu_clock_ms += emu_cost_ms[mode >= 0 && mode < 8 ? mode : 0];
   }
   for (unsigned b = 0; b < cfg->gridDim.x; b++) {

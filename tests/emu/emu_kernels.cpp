@@ -12,6 +12,7 @@ unsigned long long emu_threads_run = 0;
 unsigned long long emu_ldg_count = 0;
 char emu_last_kernel[256];
 float emu_clock_ms = 0.f, emu_cost_ms[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+int emu_fail_mode = -1;
 
 #define abl_cuda_set_environment emu_set_environment
 #define abl_cuda_add_pool emu_add_pool
@@ -106,6 +107,7 @@ int emu_real_size(void) { return (int)sizeof(abl_real); }
 unsigned long long emu_thread_count(void) { return emu_threads_run; }
 unsigned long long emu_load_count(void) { return emu_ldg_count; }
 const char *emu_last_kernel_name(void) { return emu_last_kernel; }
+void emu_set_fail_mode(int mode) { emu_fail_mode = mode; }
 void emu_set_cost(int mode, float ms) { if (mode >= 0 && mode < 8) emu_cost_ms[mode] = ms; }
 
 // Runs step function `s` over the given (already binned) pools: the launcher the generated code

@@ -7,6 +7,7 @@ unsigned long long emu_threads_run = 0;
 unsigned long long emu_ldg_count = 0;
 char emu_last_kernel[256];
 float emu_clock_ms = 0.f, emu_cost_ms[8];
+int emu_fail_mode = -1;
 #include "abl_device.cuh"
 
 #ifdef ABL_USE_FLOAT

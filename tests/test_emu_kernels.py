@@ -511,3 +511,34 @@ def test_neighbour_lists_and_culling_match_the_real_reference(use_float):
             assert len(got) == len(ref)
             assert exact_members_equal(got, ref), "integer/bool state differs"
             assert max_rel_error(got, ref) <= tol, "max relative error %.3e" % max_rel_error(got, ref)
+
+
+def test_a_trial_variant_that_cannot_be_launched_falls_back_to_the_cursor_loop():
+    """If a variant the tuner tries cannot even be launched (here: every launch of the chunked
+    kernel fails), the launcher stops comparing, repeats the step with the cursor loop and stays
+    there; the simulation goes on with correct results."""
+    import shutil
+    import tempfile
+    from emu.emu import modes
+    params = {"num_agents": 4000, "num_timesteps": 10}
+    path = os.path.join(REPO, "examples", "boids2d.abl")
+    m = EmuModel(path, params)
+    with tempfile.TemporaryDirectory() as tmp:
+        private = os.path.join(tmp, "libmodel_emu_fail.so")
+        shutil.copy(os.path.join(m.dir, "libmodel_emu.so"), private)
+        m = EmuModel(path, params, lib_path=private)
+        m.lib.emu_set_fail_mode(1)
+        m.flat_loop = -1
+        m.populate()
+        seen = []
+        for _ in range(8):
+            m.kernels = set()
+            m.timestep()
+            seen.append(modes(m.kernels))
+        m.lib.emu_set_fail_mode(-1)
+        assert seen[:2] == [[0], [3]] and all(s == [0] for s in seen[2:])    # third launch: chunked fails, cursor runs
+        assert m.lib.abl_model_step_variant(0) == 0
+        _, _, want = emulate(path, params, False, 8)
+        got = m.host_agents(0)
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[0][f])
