@@ -1,0 +1,152 @@
+"""GPU parity AT THE SIZES THE BENCHMARK RUNS (BASELINE.json configs[1..4]), against the grid-ordered
+plain-C oracle (oracle/abl_oracle.c, pinned bit-equal to the real reference by tests/test_oracle.py;
+its GRID mode performs the reference's per-pair arithmetic of /root/reference/src/backend/
+CPrinter.cpp:148-173, 189-233 with the candidates visited in the kernels' order).
+
+The brute-force reference is O(N^2) (1 400 s per boids2d step at 1 M agents); the grid oracle does
+boids2d 1 M x 10 steps in 2 s, so the comparison is made where the numbers are reported:
+
+  * double precision: every member BIT-EXACT;
+  * use_float: 1e-4 relative (north_star; the reference evaluates unsuffixed literals in double
+    even with LIBABL_USE_FLOAT, the kernels stay in float);
+  * integer / bool state and agent counts: exact;
+  * undecomposed AND decomposed into 2 / 4 / 8 slabs (direct peer-memory transport: the code path
+    of the multi-GPU runs).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import GRID, Oracle, PredatorPreyOracle
+from openabl_b200.model import Model
+from openabl_b200.slab import LocalSlabs
+from openabl_b200.state import F32_FLOOR_ULPS, exact_members_equal, max_rel_error
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+# (model, num_agents, use_float, timesteps)
+CASES = [
+    ("boids2d.abl", 1000000, False, 10),          # configs[1], double
+    ("boids2d.abl", 1000000, True, 10),           # configs[1], use_float
+    ("circle3d.abl", 1000000, False, 2),          # configs[2]'s model at 1 M (16 M: 2.6e10 pair tests per step on the CPU)
+    ("game_of_life.abl", 16777216, False, 10),    # configs[4]: 4096 x 4096
+]
+_IDS = ["%s-%d-%s" % (c[0][:-4], c[1], "f32" if c[2] else "f64") for c in CASES]
+
+_want = {}
+
+
+def oracle_result(model_file, n, use_float, steps):
+    """(initial state, state after `steps` timesteps) of the grid-ordered oracle; cached, the slab
+    tests compare with the same arrays."""
+    key = (model_file, n, use_float, steps)
+    if key not in _want:
+        o = Oracle(use_float)
+        init = o.init_for(model_file, {"num_agents": n})
+        _want[key] = (init, o.run_for(model_file, {"num_agents": n}, init, steps, GRID))
+    return _want[key]
+
+
+def check(got, want, use_float, what):
+    assert len(got) == len(want), "%s: population %d, oracle %d" % (what, len(got), len(want))
+    assert exact_members_equal(got, want), "%s: integer/bool state differs" % what
+    if use_float:
+        err = max_rel_error(got, want, floor_ulps=F32_FLOOR_ULPS)
+        assert err <= 1e-4, "%s: max relative error %.3e > 1e-4" % (what, err)
+    else:
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[f]), "%s: member %s is not bit-equal (max rel err %.3e)" % (
+                what, f, max_rel_error(got, want))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_file,n,use_float,steps", CASES, ids=_IDS)
+def test_single_gpu_equals_grid_oracle_at_benchmark_size(model_file, n, use_float, steps):
+    init, want = oracle_result(model_file, n, use_float, steps)
+    m = Model(os.path.join(REPO, "examples", model_file), {"num_agents": n}, use_float=use_float)
+    m.populate()
+    host = m.host_agents(0)
+    for f in host.dtype.names:
+        assert np.array_equal(host[f], init[f]), "initial %s differs from the oracle's" % f
+    m.create_runtime()
+    m.upload_host()
+    for _ in range(steps):
+        m.timestep()
+    got = m.download(0)
+    m.close()
+    check(got, want, use_float, "1 GPU")
+
+
+SLAB_CASES = [
+    ("boids2d.abl", 1000000, False, 10, 2),
+    ("boids2d.abl", 1000000, False, 10, 8),
+    ("boids2d.abl", 1000000, True, 10, 4),
+    ("circle3d.abl", 1000000, False, 2, 4),
+    ("game_of_life.abl", 16777216, False, 10, 8),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model_file,n,use_float,steps,slabs", SLAB_CASES,
+                         ids=["%s-%d-%s-%dslabs" % (c[0][:-4], c[1], "f32" if c[2] else "f64", c[4]) for c in SLAB_CASES])
+def test_slabs_equal_grid_oracle_at_benchmark_size(model_file, n, use_float, steps, slabs):
+    _, want = oracle_result(model_file, n, use_float, steps)
+    m = Model(os.path.join(REPO, "examples", model_file), {"num_agents": n}, use_float=use_float)
+    m.populate()
+    host = [m.host_agents(0)]
+    ls = LocalSlabs(m, slabs, transport="direct")
+    ls.upload(host)
+    for _ in range(steps):
+        ls.timestep()
+    ids, got = ls.download(0)
+    ls.close()
+    m.close()
+    assert np.array_equal(ids, np.arange(len(host[0]), dtype=np.uint32))
+    check(got, want, use_float, "%d slabs" % slabs)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("slabs", [1, 2], ids=["1gpu", "2slabs"])
+def test_predator_prey_4M_equals_frozen_semantics(slabs):
+    """configs[3]: 4 M agents, run-time add/remove.  Parity UNPINNED by the reference (its `c`
+    backend refuses add/remove, CBackend.cpp:30-32); the checker is the frozen-semantics section
+    of oracle/abl_oracle.c plus the hand-traced scenario of tests/test_predator_prey_trace.py.
+    Agent counts after every timestep, sum(Grass.avail), ids and every member: bit-exact."""
+    n, steps = 4000000, 5
+    m = Model(os.path.join(REPO, "examples", "predator_prey.abl"), {"num_agents": n})
+    m.populate()
+    o = PredatorPreyOracle(n)
+    host = [m.host_agents(t) for t in range(3)]
+    for t in range(3):
+        _, rec = o.read(t)
+        assert len(host[t]) == len(rec)
+    if slabs == 1:
+        m.create_runtime()
+        m.upload_host()
+        run = m
+        counts = lambda: [m.rt.count(m.pool(t)) for t in range(3)]
+    else:
+        run = LocalSlabs(m, slabs, transport="direct")
+        run.upload(host)
+        counts = lambda: [sum(run.owned_counts(t)) for t in range(3)]
+    for step in range(steps):
+        run.timestep()
+        o.timestep(GRID)
+        assert counts() == [o.count(t) for t in range(3)], "agent counts differ after timestep %d" % step
+    changed = False
+    for t in range(3):
+        ids, want = o.read(t)
+        if slabs == 1:
+            got, got_ids = m.download(t), m.rt.download_ids(m.pool(t))
+        else:
+            got_ids, got = run.download(t)
+        assert np.array_equal(got_ids, ids), "%s: ids differ" % m.names[t]
+        for f in got.dtype.names:
+            assert np.array_equal(got[f], want[f]), "%s.%s differs" % (m.names[t], f)
+        changed |= len(got) != len(host[t])
+    if slabs != 1:
+        run.close()
+    m.close()
+    o.close()
+    assert changed, "population never changed"

@@ -13,7 +13,7 @@ import pytest
 
 from oracle import GRID, Oracle
 from openabl_b200.model import Model
-from openabl_b200.state import exact_members_equal, max_rel_error
+from openabl_b200.state import F32_FLOOR_ULPS, exact_members_equal, max_rel_error
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -59,7 +59,7 @@ def test_gpu_equals_grid_oracle(model_file, params, use_float, steps, tile):
     assert len(got) == len(want)
     assert exact_members_equal(got, want), "integer/bool state differs"
     if use_float:
-        assert max_rel_error(got, want) <= 1e-4
+        assert max_rel_error(got, want, floor_ulps=F32_FLOOR_ULPS) <= 1e-4
     else:
         for f in got.dtype.names:
             assert np.array_equal(got[f], want[f]), "member %s is not bit-equal (max rel err %.3e)" % (
@@ -82,7 +82,7 @@ def test_unrolled_candidate_loop_equals_grid_oracle(model_file, params, use_floa
     assert len(got) == len(want)
     assert exact_members_equal(got, want), "integer/bool state differs"
     if use_float:
-        assert max_rel_error(got, want) <= 1e-4
+        assert max_rel_error(got, want, floor_ulps=F32_FLOOR_ULPS) <= 1e-4
     else:
         for f in got.dtype.names:
             assert np.array_equal(got[f], want[f]), "member %s is not bit-equal" % f

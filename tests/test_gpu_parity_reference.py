@@ -13,7 +13,7 @@ import pytest
 
 import refgen
 from openabl_b200.model import Model
-from openabl_b200.state import exact_members_equal, max_rel_error
+from openabl_b200.state import F32_FLOOR_ULPS, exact_members_equal, max_rel_error
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # 10-step runs: the bar of BASELINE.json north_star.  The 100-step circle run is order-
@@ -48,7 +48,7 @@ def test_matches_reference_c_backend(name):
     for g, ref in zip(got, gold):
         assert len(g) == len(ref), "agent count differs"
         assert exact_members_equal(g, ref), "integer/bool state differs"
-        err = max_rel_error(g, ref)
+        err = max_rel_error(g, ref, floor_ulps=F32_FLOOR_ULPS if info["use_float"] else 0)
         assert err <= tol, "max relative error %.3e > %.1e" % (err, tol)
 
 

@@ -1,10 +1,10 @@
 """Cached neighbour lists (-C cuda.nlist=true) on the GPU.
 
 The list kernels are verified bit for bit under the CPU emulator (tests/test_emu_kernels.py);
-the runtime side (count pass -> sizing -> fill pass, validity tracking) was written after the
-round's GPU budget had been spent and has not run on a device yet — hence the non-strict xfail
-guard (a pass shows up as XPASS) and the child process (a device fault cannot poison the CUDA
-context of the session).  Remove the guard after the first green run."""
+the runtime side (count pass -> sizing -> fill pass, validity tracking) passed on a B200 at the
+end of round 1 (GPUTEST_r01.json: three XPASS), so the xfail guard of that round is gone and a
+regression fails.  The checks still run in a child process (a device fault cannot poison the CUDA
+context of the session)."""
 import os
 import subprocess
 import sys
@@ -12,7 +12,6 @@ import sys
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-first_run = pytest.mark.xfail(reason="neighbour-list runtime path not yet validated on a GPU", strict=False)
 
 
 def check(case):
@@ -22,13 +21,11 @@ def check(case):
 
 
 @pytest.mark.gpu
-@first_run
 def test_game_of_life_with_neighbour_lists_equals_grid_oracle():
     check("game_of_life")
 
 
 @pytest.mark.gpu
-@first_run
 def test_lists_of_static_sites_survive_moving_walkers():
     """Site-Site lists are built once while the Walker pool is re-binned every timestep; the state
     equals the run without lists bit for bit, and re-uploading the population rebuilds the lists."""
@@ -36,7 +33,6 @@ def test_lists_of_static_sites_survive_moving_walkers():
 
 
 @pytest.mark.gpu
-@first_run
 def test_lists_match_the_real_reference():
     """sites_walkers with lists for the static Sites against the reference `c` backend's golden vector."""
     check("sites_walkers")
