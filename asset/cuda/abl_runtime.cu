@@ -1154,14 +1154,20 @@ extern "C" int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *
   if (!(granularity > 0)) return fail(ABL_ERR_ARGUMENT, "granularity must be positive");
   GridParams &g = rt->grid;
   g.dim = dim;
-  g.cell = granularity;
-  g.inv_cell = rt->real_size == 8 ? 1.0 / granularity : (double)(1.0f / (float)granularity);
+  // Cells are a shade larger than the granularity (ABL_CELL_PAD_*, abl_cuda.h): the reference's
+  // filter `sqrtf((float)s) > R` accepts true distances up to R(1 + 6e-8), and the cell index is a
+  // floor of a rounded product, so with cell == R two agents the reference pairs up could land
+  // two cells apart (p = 9.999999999999998, q = p + 5.0, cell 5.0 -> cells 1 and 3) and the 3^d
+  // search would miss the pair.  With the padding |dx| <= R(1 + 6e-8) implies |d index| <= 1 with a
+  // margin far above the rounding of the index computation.
+  g.cell = granularity * (1.0 + (rt->real_size == 8 ? ABL_CELL_PAD_F64 : ABL_CELL_PAD_F32));
+  g.inv_cell = rt->real_size == 8 ? 1.0 / g.cell : (double)(1.0f / (float)g.cell);
   u64 cells = 1;
   for (int a = 0; a < 3; a++) {
     if (a < dim) {
       double size = env_max[a] - env_min[a];
       if (size < 0) return fail(ABL_ERR_ARGUMENT, "environment max < min");
-      long nc = (long)ceil(size / granularity);
+      long nc = (long)ceil(size / g.cell);
       if (nc < 1) nc = 1;
       g.n_cell[a] = (int)nc;
       g.origin[a] = env_min[a];

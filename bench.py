@@ -116,31 +116,48 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml"}
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel, from the
-# `ncu --set full` captures summarised under profiles/ (None where no capture exists)
-NCU_TRAFFIC = {
-    "boids2d-1M-f64": (43.2e6, "profiles/r1d_boids_summary.txt"),
-    "circle3d-1M-f64": (25.39e6, "profiles/r1c_circle3d_summary.txt"),
-}
+def ncu_traffic(workload, variant):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel VARIANT this run
+    used, from the `ncu --set full` captures summarised under profiles/ (profiles/traffic.json,
+    written by profiles/summarize.py --traffic); (None, None) when that variant was never captured."""
+    path = os.path.join(REPO, "profiles", "traffic.json")
+    if not os.path.exists(path):
+        return None, None
+    with open(path) as f:
+        table = json.load(f)
+    hit = table.get("%s/%s" % (workload, variant))
+    return (hit["bytes"], hit["source"]) if hit else (None, None)
 
 
-def cpu_baseline(workload, budget_pairs=1.5e11):
-    """Times the oracle's brute-force (reference-order) step on a bounded sample of agents."""
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(workload, budget_pairs=1.5e11, num_agents=None):
+    """Times the oracle's brute-force (reference-order) step on a bounded sample of agents.
+    `num_agents`: population of the run this baseline stands next to (weak scaling multiplies the
+    workload's by the number of GPUs).  The OpenMP thread count is SET here (torchrun exports
+    OMP_NUM_THREADS=1 to its children) and the number reported is the one the library uses."""
     sys.path.insert(0, os.path.join(REPO, "oracle"))
     from oracle import BRUTE, Oracle
     model, params, use_float, _, _, _ = WORKLOADS[workload]
     if model not in ("boids2d.abl", "circle.abl", "circle3d.abl", "game_of_life.abl"):
         raise SystemExit("no CPU baseline for %s: the reference `c` backend rejects run-time add/remove "
                          "(use --no-cpu-baseline)" % model)
+    if num_agents:
+        params = dict(params, num_agents=int(num_agents))
     n = params["num_agents"]
     o = Oracle(use_float)
+    cores = o.set_threads(host_threads())
     if model == "game_of_life.abl":
         size = int(n ** 0.5)
         n = size * size
     state = o.init_for(model, params)
     n = len(state)
     sample = int(max(256, min(n, budget_pairs / n)))
-    cores = os.cpu_count() or 1
     t0 = time.perf_counter()
     if model == "boids2d.abl":
         o.boids_run(state, 1, BRUTE, sample=(0, sample))
@@ -157,18 +174,21 @@ def cpu_baseline(workload, budget_pairs=1.5e11):
 
 
 def run_reference_arm(args):
+    """The reference's CPU path for the same metric and population as the repo arm (weak scaling:
+    workload population x GPUs), rank 0 only, all host threads."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     workload = args.workload
     model, params, use_float, S, M, P = WORKLOADS[workload]
+    n_agents = params["num_agents"] * (1 if args.strong else max(1, args.gpus))
     vals, times, last = [], [], None
     total = args.warmup + args.steps
     # each "step" is a bounded sample; the whole run stays within about half a minute of CPU work
     # at ~1e10 candidate tests per second (16 threads)
     budget = max(2e9, 3e11 / max(1, total))
     for i in range(total):
-        base, dt = cpu_baseline(workload, budget_pairs=budget)
+        base, dt = cpu_baseline(workload, budget_pairs=budget, num_agents=n_agents)
         if i >= args.warmup:
             vals.append(base["value"])
             times.append(dt)
@@ -178,55 +198,42 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": "agent-steps/s", "value": value, "unit": "agent-steps/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * sum(times) / len(times),   # one step = one bounded sample (see cpu_baseline.sample)
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if (args.strong and args.gpus > 1) else "weak", "vs_baseline": None,
             "dtype": "f32" if use_float else "f64", "data": "synthetic",
-            "config": {"workload": workload, "model": model, "num_agents": params["num_agents"]},
+            "config": {"workload": workload, "model": model, "num_agents": n_agents},
             "cpu_baseline": last,
             "e2e": {"value": value, "unit": "agent-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
-    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-l2-flush", action="store_true", help="report the back-to-back (steady state) time as `value`")
-    ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
-    ap.add_argument("--tile", action="store_true", help="stage neighbour rows in shared memory (ABL_MODE 2 kernels)")
-    ap.add_argument("--unroll", action="store_true", help="-C cuda.unroll=true: for-near candidate loop unrolled by two")
-    ap.add_argument("--nlist", action="store_true", help="-C cuda.nlist=true: cached neighbour lists for step functions whose "
-                    "neighbourhoods never change (game_of_life)")
-    ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
-    ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
-                    help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
-                         "NVLink (direct) or grouped ncclSend/ncclRecv (nccl)")
-    args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference_arm(args)
-        return
+MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", -1: "not launched"}
 
-    import numpy as np
+# FP64 operations per agent-step of circle3d's step kernel (SURVEY.md 8d asks for this view next to
+# the HBM one): per candidate 3 sub + 3 mul + 2 add + 1 compare = 9, per accepted candidate the
+# force (normalize: sqrt + 3 IEEE divisions, scale, accumulate) ~ 80; candidates = 27 cells x
+# agents per cell, accepted = (4/3 pi) / 27 of them.  Peak: 64 FP64 lanes per SM and clock.
+def fp64_roofline(workload, n_agents, kernel_ms, clocks):
+    if not workload.startswith("circle3d") or kernel_ms <= 0:
+        return None
+    candidates, accepted = 27 * 49.0, 27 * 49.0 * 0.1551
+    ops = 9 * candidates + 80 * accepted
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 148 * 64 * mhz * 1e6 / 1e12          # T lane-ops/s
+    achieved = ops * n_agents / (kernel_ms / 1e3) / 1e12
+    return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "T FP64 lane-ops/s", "frac": achieved / peak,
+            "ops_per_agent_step": ops,
+            "definition": "9 FP64 operations per candidate (1323 per agent) + ~80 per accepted candidate (205 per agent); "
+                          "peak = 148 SMs x 64 FP64 lanes x SM clock (an FMA counted as one operation)"}
+
+
+def measure(args, workload, env, strong, steps, warmup, with_cpu_baseline):
+    """One workload through the device-resident, per-stage and end-to-end passes -> JSON object."""
     import torch
-    import torch.distributed as dist
-
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device: the cuda backend has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
     from openabl_b200.model import Model
     from openabl_b200.slab import RankSlab
-    model_file, params, use_float, S, M, P = WORKLOADS[args.workload]
+    rank, local_rank, world, dist = env
+    model_file, params, use_float, S, M, P = WORKLOADS[workload]
     params = dict(params)
-    strong = args.strong or world == 1
     if not strong:
         # weak scaling: the per-GPU population stays fixed, the world (and the environment,
         # which the model derives from num_agents) grows with the number of GPUs
@@ -234,8 +241,8 @@ def main():
     m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float,
               config=dict(([("cuda.unroll", True)] if args.unroll else []) + ([("cuda.nlist", True)] if args.nlist else [])) or None)
     m.populate()
-    host = [m.host_agents(t) for t in range(m.n_types)]
-    n_agents = sum(len(h) for h in host)          # whole job, all ranks
+    n_agents = sum(m.host_count(t) for t in range(m.n_types))          # whole job, all ranks
+    host_bytes = sum(m.host_count(t) * m.dtypes[t].itemsize for t in range(m.n_types))
     slab = None
     if world > 1:
         slab = RankSlab(m, rank, world, dist, device=local_rank, transport=args.transport,
@@ -265,7 +272,7 @@ def main():
     # ---- device-resident throughput ------------------------------------------------------
     # (at least 16 warm-up timesteps: the launchers' run-time tuner times up to three candidate-loop
     # variants over the first 12 launches of a step function, asset/cuda/abl_device.cuh)
-    n_warmup = max(16, args.warmup)
+    n_warmup = max(16, warmup)
     upload()
     for _ in range(n_warmup):
         timestep()
@@ -279,7 +286,7 @@ def main():
     ev1 = torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(steps):
         timestep()
     ev1.record(stream)
     barrier()
@@ -293,7 +300,7 @@ def main():
         ms = ms_steady
     else:
         scratch = torch.empty(flush_bytes, dtype=torch.uint8, device=torch.device("cuda", local_rank))
-        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        pairs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         with torch.cuda.stream(stream):
             for k, (a, b) in enumerate(pairs):
@@ -309,10 +316,10 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max, ms_steady_max = float(t[0].item()), float(t[1].item())
-    value = n_agents * args.steps / (ms_max / 1e3)
-    steady = {"value": n_agents * args.steps / (ms_steady_max / 1e3), "unit": "agent-steps/s",
-              "ms_per_step": ms_steady_max / args.steps,
-              "definition": "the same %d timesteps back to back without the L2 flush (what a simulation run sees)" % args.steps}
+    value = n_agents * steps / (ms_max / 1e3)
+    steady = {"value": n_agents * steps / (ms_steady_max / 1e3), "unit": "agent-steps/s",
+              "ms_per_step": ms_steady_max / steps,
+              "definition": "the same %d timesteps back to back without the L2 flush (what a simulation run sees)" % steps}
 
     # ---- per-stage device times (separate pass over the same population) --------------------
     # The runtime queues four events per abl_cuda_step and evaluates them when asked, so the
@@ -320,7 +327,7 @@ def main():
     # GPU between them); last_timing() returns the mean per step-function call.
     rt.enable_timing(True)
     stage = {"bin_ms": 0.0, "kernel_ms": 0.0, "commit_ms": 0.0}
-    reps = min(args.steps, 50)
+    reps = max(10, min(200, int(200.0 / max(ms_steady_max / steps, 1e-3))))   # ~0.2 s of device time, 10..200 timesteps
     if not mutating_slabs:
         for _ in range(reps):
             for s in range(m.n_steps):
@@ -333,25 +340,27 @@ def main():
     n_local = rt.pool_size(m.pool(0)) if world > 1 else n_agents
     kernel_bytes = (S + M + S) * n_local
     achieved = kernel_bytes / (stage["kernel_ms"] / 1e3) / 1e9 if stage["kernel_ms"] > 0 else 0.0
-    step_bytes = whole_step_bytes(args.workload) * n_agents / world
-    roofline = {"bound": "hbm", "kernel": "abl_kernel_%s" % m.step_names[0], "achieved": achieved,
+    step_bytes = whole_step_bytes(workload) * n_agents / world
+    variants = {m.step_names[s]: MODE_NAMES.get(m.step_variant(s), str(m.step_variant(s))) for s in range(m.n_steps)}
+    traffic, traffic_src = ncu_traffic(workload, variants[m.step_names[0]]) if world == 1 else (None, None)
+    roofline = {"bound": "hbm", "kernel": "abl_kernel_%s<%s>" % (m.step_names[0], variants[m.step_names[0]]), "achieved": achieved,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0] if world == 1 else None,
-                "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1],
+                "traffic": traffic, "traffic_source": traffic_src,
                 "algorithmic_bytes_per_agent": S + M + S,
                 "kernel_ms": stage["kernel_ms"], "bin_ms": stage["bin_ms"], "commit_ms": stage["commit_ms"],
-                "whole_step_algorithmic_bytes_per_agent": whole_step_bytes(args.workload),
-                "whole_step_frac": step_bytes * args.steps / (ms_max / 1e3) / 1e9 / peak}
+                "stage_pass_timesteps": reps,
+                "whole_step_algorithmic_bytes_per_agent": whole_step_bytes(workload),
+                "whole_step_frac": step_bytes * steps / (ms_max / 1e3) / 1e9 / peak}
 
     # ---- end to end through the C ABI with host buffers -------------------------------------
     e2e_reps = 3
-    h2d = sum(h.nbytes for h in host)
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
+    d2h = h2d = 0
     for _ in range(e2e_reps):
         upload()
-        for _ in range(args.steps):
+        h2d = slab.last_upload_bytes if slab else host_bytes
+        for _ in range(steps):
             timestep()
         if slab:
             out = [m.download(tt) for tt in range(m.n_types)]   # this rank's owned agents
@@ -363,40 +372,96 @@ def main():
     if world > 1:
         dist.barrier()
     e2e_s = (time.perf_counter() - t0) / e2e_reps
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    te = torch.tensor([e2e_s, float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = n_agents * args.steps / float(te.item())
-    mode_names = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", -1: "not launched"}
-    variants = {m.step_names[s]: mode_names.get(m.step_variant(s), str(m.step_variant(s))) for s in range(m.n_steps)}
+        tm = te.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(te, op=dist.ReduceOp.SUM)
+        e2e_s, h2d, d2h = float(tm[0].item()), float(te[1].item()), float(te[2].item())   # bytes: all ranks
+    e2e_value = n_agents * steps / e2e_s
     m.close()
 
+    line = {"metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
+            "steps": steps, "warmup": n_warmup, "ms_per_step": ms_max / steps,
+            "higher_is_better": True, "scaling": "strong" if (strong and world > 1) else "weak",
+            "vs_baseline": None,
+            "dtype": "f32" if use_float else "f64", "data": "synthetic",
+            "config": {"workload": workload, "model": model_file, "num_agents": n_agents,
+                       "agents_per_gpu": n_agents // world,
+                       "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
+                       "block_size": args.block_size, "neighbour_lists": bool(args.nlist),
+                       "candidate_loop_in_use": variants,     # ABL_MODE of each step function's latest launch (rank 0)
+                       "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
+                           os.environ.get("ABL_CUDA_FLAT", ""), "chosen by the launcher (rule; timed at run time where two variants are plausible)"),
+                       "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))
+                             if args.no_l2_flush else
+                             ("flushed: a %d MB write before every timed timestep (state: %.0f MB per GPU, L2: 126 MB); "
+                              "`steady_state` is the same run without the flush" % (flush_bytes >> 20, n_agents * S / 1e6 / world))},
+            "steady_state": steady,
+            "clocks": clocks, "gpu_launches": launches,
+            "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / steps,
+                    "d2h_bytes_per_step": d2h / steps,
+                    "definition": "upload + %d timesteps + download per simulate() call; bytes summed over all ranks" % steps},
+            "roofline": roofline}
+    fp64 = fp64_roofline(workload, n_local, stage["kernel_ms"], clocks)
+    if fp64:
+        line["roofline_fp64"] = fp64
+    if with_cpu_baseline and rank == 0:
+        base, _ = cpu_baseline(workload, num_agents=n_agents)
+        line["cpu_baseline"] = base
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default=None, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-l2-flush", action="store_true", help="report the back-to-back (steady state) time as `value`")
+    ap.add_argument("--block-size", type=int, default=0, help="threads per CTA of step kernels (0 = automatic)")
+    ap.add_argument("--tile", action="store_true", help="stage neighbour rows in shared memory (ABL_MODE 2 kernels)")
+    ap.add_argument("--unroll", action="store_true", help="-C cuda.unroll=true: for-near candidate loop unrolled by two")
+    ap.add_argument("--nlist", action="store_true", help="-C cuda.nlist=true: cached neighbour lists for step functions whose "
+                    "neighbourhoods never change (game_of_life)")
+    ap.add_argument("--strong", action="store_true", help="N>1: keep the total population fixed (strong scaling)")
+    ap.add_argument("--no-companion", action="store_true",
+                    help="skip the circle3d-16M line (the other half of BASELINE.json's metric) that the default run "
+                         "adds to the boids2d line under the key `circle3d`")
+    ap.add_argument("--transport", default="direct", choices=["direct", "nccl"],
+                    help="N>1 halo/migration exchange: step kernels write into the neighbour's memory over "
+                         "NVLink (direct) or grouped ncclSend/ncclRecv (nccl)")
+    args = ap.parse_args()
+    companion = args.workload is None and not args.no_companion
+    if args.workload is None:
+        args.workload = DEFAULT_WORKLOAD
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the cuda backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    env = (rank, local_rank, world, dist)
+    line = measure(args, args.workload, env, args.strong or world == 1, args.steps, args.warmup, not args.no_cpu_baseline)
+    if companion:
+        # BASELINE.json's metric names boids2d AND circle3d; configs[2] is circle3d 16 M agents under
+        # slab decomposition at 1/2/4/8 GPUs with the population fixed (strong scaling).  One timestep
+        # takes tens of milliseconds, so a few of them are enough.
+        c = measure(args, "circle3d-16M-f64", env, True, max(3, min(args.steps, 10)), 3, False)
+        line["circle3d"] = {k: c[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "scaling", "dtype", "config",
+                                               "steady_state", "e2e", "roofline", "roofline_fp64", "gpu_launches") if k in c}
     if rank == 0:
-        line = {"metric": "agent-steps/s", "value": value, "unit": "agent-steps/s", "n_gpus": world,
-                "steps": args.steps, "warmup": n_warmup, "ms_per_step": ms_max / args.steps,
-                "higher_is_better": True, "scaling": "strong" if (args.strong and world > 1) else "weak",
-                "vs_baseline": None,
-                "dtype": "f32" if use_float else "f64", "data": "synthetic",
-                "config": {"workload": args.workload, "model": model_file, "num_agents": n_agents,
-                           "agents_per_gpu": n_agents // world,
-                           "parallelism": ("slab%d (cell layers along the slowest axis; halo + migration %s)" % (world, "written into the neighbour's HBM over NVLink by the step kernel, no host sync" if args.transport == "direct" else "over NCCL send/recv")) if world > 1 else "single",
-                           "block_size": args.block_size, "neighbour_lists": bool(args.nlist),
-                           "candidate_loop_in_use": variants,     # ABL_MODE of each step function's latest launch (rank 0)
-                           "candidate_loop": {"0": "cursor loop (ABL_CUDA_FLAT=0)", "1": "flat loop (ABL_CUDA_FLAT=1)"}.get(
-                               os.environ.get("ABL_CUDA_FLAT", ""), "timed at run time: cursor, flat and chunked loop over the first launches, the fastest is kept"),
-                           "l2": ("no flush: state (%.0f MB per GPU) stays partly L2-resident between timesteps" % (n_agents * S / 1e6 / world))
-                                 if args.no_l2_flush else
-                                 ("flushed: a %d MB write before every timed timestep (state: %.0f MB per GPU, L2: 126 MB); "
-                                  "`steady_state` is the same run without the flush" % (flush_bytes >> 20, n_agents * S / 1e6 / world))},
-                "steady_state": steady,
-                "clocks": clocks, "gpu_launches": launches,
-                "e2e": {"value": e2e_value, "unit": "agent-steps/s", "h2d_bytes_per_step": h2d / args.steps,
-                        "d2h_bytes_per_step": d2h / args.steps,
-                        "definition": "upload + %d timesteps + download per simulate() call" % args.steps},
-                "roofline": roofline}
-        if not args.no_cpu_baseline:
-            base, _ = cpu_baseline(args.workload)
-            line["cpu_baseline"] = base
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -88,7 +88,14 @@ int abl_cuda_destroy(abl_runtime *rt);
 const char *abl_cuda_last_error(void);
 
 /* ---- environment (reference EnvironmentDeclaration: envMin/envMax/envGranularity,
- *      src/AST.hpp:658-662; grid sizing rule ceil(size/granularity) per axis) ----------- */
+ *      src/AST.hpp:658-662; grid sizing rule ceil(size/cell) per axis) -------------------
+ * The cell size is granularity * (1 + ABL_CELL_PAD_*): with cell == radius exactly, two agents at a
+ * distance the reference's float-rounded filter still accepts (up to R(1 + 6e-8)) could be binned two
+ * cells apart (the cell index is the floor of a rounded product) and the 3^d search would miss the
+ * pair.  The padding is far above the rounding of the index computation in either precision and
+ * costs 2e-6 (double) / 2e-3 (float) more candidates. */
+#define ABL_CELL_PAD_F64 (1.0 / 1048576.0)   /* 2^-20 */
+#define ABL_CELL_PAD_F32 (1.0 / 1024.0)      /* 2^-10 */
 int abl_cuda_set_environment(abl_runtime *rt, int dim, const double *env_min,
                              const double *env_max, double granularity);
 

@@ -191,6 +191,7 @@ class RankSlab:
         self.transport = transport if world > 1 else "none"
         self.halo_records = halo_records
         self._connected = False
+        self.last_upload_bytes = 0      # host -> device bytes of the latest upload() on this rank
         self.rt = model.create_runtime(device=device, **rt_kw)
         layers = self.rt.slab_layers()
         self.bounds = split_layers(layers, world)
@@ -216,9 +217,11 @@ class RankSlab:
             self._connect_direct(totals)
         if host_arrays is None:
             m.upload_host()
+            self.last_upload_bytes = sum(m.host_count(t) * m.dtypes[t].itemsize for t in range(m.n_types))
         else:
             for t, arr in enumerate(host_arrays):
                 self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
+            self.last_upload_bytes = sum(a.nbytes for a in host_arrays)
         for t in range(m.n_types):
             self.rt.exchange(m.pool(t))
 

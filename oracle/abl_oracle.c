@@ -37,6 +37,26 @@
 #include <stdlib.h>
 #include <string.h>
 #include <limits.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+/* OpenMP threads the parallel loops below will use, and a way to set them: torchrun exports
+ * OMP_NUM_THREADS=1 to its children, which would silently time the CPU baseline on one core. */
+int oracle_omp_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+void oracle_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
 
 #ifdef LIBABL_USE_FLOAT
 typedef float abl_float;
@@ -113,8 +133,14 @@ static inline int cell_coord(abl_float p, abl_float origin, abl_float inv_cell, 
   return c < 0 ? 0 : (c >= n ? n - 1 : c);
 }
 
+static double oracle_padded_cell(double granularity) {
+  return granularity * (1.0 + (sizeof(abl_float) == 8 ? 0x1p-20 : 0x1p-10));
+}
+
 static void grid_setup(grid_t *g, int dim, const double *env_min, const double *env_max, double granularity) {
   g->dim = dim;
+  /* cells a shade larger than the granularity, as in abl_cuda_set_environment (ABL_CELL_PAD_*) */
+  granularity = oracle_padded_cell(granularity);
   g->cell = (abl_float)granularity;
   g->inv_cell = (abl_float)1 / (abl_float)granularity;
   g->n_cells = 1;
@@ -188,7 +214,7 @@ static void grid_free(grid_t *g) { free(g->cell_start); free(g->order); g->cell_
   }
 
 static int reach_for(double radius, double cell) {
-  int r = (int)ceil(radius / cell - 1e-12);
+  int r = (int)ceil(radius / oracle_padded_cell(cell) - 1e-12);
   return r < 1 ? 1 : r;
 }
 

@@ -34,6 +34,14 @@ class Oracle:
         self.lib.oracle_fold6.restype = C.c_double
         self.lib.oracle_fold6.argtypes = [C.c_double]
 
+    def set_threads(self, n):
+        """OpenMP threads of the parallel loops (torchrun exports OMP_NUM_THREADS=1); -> threads in use."""
+        self.lib.oracle_set_threads(C.c_int(int(n)))
+        return int(self.lib.oracle_omp_threads())
+
+    def threads(self):
+        return int(self.lib.oracle_omp_threads())
+
     def reset_rng(self):
         self.lib.oracle_rng_reset()
 

@@ -206,6 +206,7 @@ class EmuModel:
     def _grid(self, dim, lo, hi, cell):
         g = GridView()
         g.dim = dim
+        cell = cell * (1.0 + (2.0 ** -10 if self.use_float else 2.0 ** -20))   # ABL_CELL_PAD_* (abl_cuda.h)
         g.cell_size = cell
         g.inv_cell_size = 1.0 / cell if not self.use_float else float(np.float32(1.0) / np.float32(cell))
         cells = 1

@@ -542,3 +542,38 @@ def test_a_trial_variant_that_cannot_be_launched_falls_back_to_the_cursor_loop()
         got = m.host_agents(0)
         for f in got.dtype.names:
             assert np.array_equal(got[f], want[0][f])
+
+
+@pytest.mark.parametrize("flat_loop", [0, 1], ids=["cursor", "flat"])
+def test_pairs_exactly_one_radius_apart_across_cell_borders_are_found(flat_loop):
+    """Radius == granularity (the default: the granularity is the largest radius).  The reference
+    (brute force, CPrinter.cpp:148-173) pairs up agents whose distance is exactly R — and, through
+    its float-rounded filter, up to R(1 + 6e-8).  On a lattice of spacing R such partners sit one
+    cell index apart only if the cells are a shade larger than R (ABL_CELL_PAD_*, abl_cuda.h):
+    with cell == R the floor of the rounded product puts some of them TWO cells apart (9.999999999999998
+    and 20.0 with R = 10: cells 0 and 2) and the 3 x 3 search misses them.  circle.abl (R = 2r = 10)
+    on a lattice of spacing 10 plus one ulp either side, against the brute-force oracle."""
+    from oracle import BRUTE
+    R = 10.0
+    k = np.arange(1, 25, dtype=np.float64)
+    axis = np.concatenate([k * R, np.nextafter(k[::2] * R, 0.0), np.nextafter(k[1::3] * R, 1e9)])
+    # the construction must contain what the test is about: accepted partners two UNPADDED cells apart
+    cells = np.floor(axis * (1.0 / R))
+    d = np.abs(axis[:, None] - axis[None, :])
+    accepted = ~(np.sqrt((d * d).astype(np.float32)).astype(np.float64) > R)
+    assert (accepted & (np.abs(cells[:, None] - cells[None, :]) >= 2)).any()
+    xs, ys = np.meshgrid(axis, axis[:30])
+    n_model = 50000                                       # W = sqrt(n / 0.05) = 1000: the lattice fits
+    m = EmuModel(os.path.join(REPO, "examples", "circle.abl"), {"num_agents": n_model})
+    m.flat_loop = flat_loop
+    m.populate()
+    a = np.zeros(xs.size, dtype=m.dtypes[0])
+    a["pos"][:, 0], a["pos"][:, 1] = xs.ravel(), ys.ravel()
+    m.pools[0].load(a)
+    m.timestep()
+    got = m.host_agents(0)
+    o = Oracle(False)
+    want = o.circle_run(2, a, 1, BRUTE, num_agents=n_model)
+    assert max_rel_error(got, want) <= 1e-9
+    grid = o.circle_run(2, a, 1, GRID, num_agents=n_model)
+    assert np.array_equal(got["pos"], grid["pos"])
