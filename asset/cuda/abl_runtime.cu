@@ -510,8 +510,8 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
 // 4096 counters, k_tile_scan lets every CTA add up the sums of the tiles before its own (a few
 // hundred words that sit in L2) and scan its tile.  No CTA ever waits for another one, which
 // for the few hundred tiles of a cell grid beats the look-back chain of the single-pass scan
-// above (all of whose CTAs are resident at once and mostly poll).  The scan pass also clears
-// the histogram for the next binning.
+// above (all of whose CTAs are resident at once and mostly poll).  The histogram is left in
+// place: k_bin_scatter draws the slots of every cell segment by counting it back down to zero.
 __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u32 *tile_sum) {
   __shared__ u32 s_warp[kScanBlock / 32];
   cudaGridDependencySynchronize();
@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
     ScanLoad<u32>::load16(in, i0, v);
 #pragma unroll
     for (int k = 0; k < kScanItems; k++) if (i0 + k >= n) v[k] = 0;
-    ScanLoad<u32>::zero16(in, i0);
+    // (the histogram stays: k_bin_scatter counts it back down to zero)
   }
   u32 t = 0;
 #pragma unroll
@@ -648,7 +648,7 @@ __device__ __forceinline__ void bin_count_one(const void *px, const void *py, co
   if (ids && ids[s] == ABL_SENTINEL_ID) {
     // padding record of a halo message: parked in the trash cell behind all real cells
     key[o] = g.n_local;
-    local[o] = atomicAdd(&cell_count[g.n_local], 1u);
+    atomicAdd(&cell_count[g.n_local], 1u);
     return;
   }
   R x, y, z = 0;
@@ -671,7 +671,7 @@ __device__ __forceinline__ void bin_count_one(const void *px, const void *py, co
   }
   c -= g.key_base;
   key[o] = c;
-  local[o] = atomicAdd(&cell_count[c], 1u);
+  atomicAdd(&cell_count[c], 1u);   // result unused: a RED; slots are handed out by k_bin_scatter
 }
 
 template <typename R, int DIM>
@@ -683,14 +683,20 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
   bin_count_one<R, DIM>(px, py, pz, (size_t)src_begin + i, (size_t)out_begin + i, g, key, local, cell_count, ids);
 }
 
-// seg_ids[slot] = id of the agent that arrived `local`-th in its cell segment
-__global__ void k_bin_scatter(const u32 *key, const u32 *local, const u32 *ids, u32 n, u32 src_begin,
-                              const u32 *cell_start, u32 *seg_ids) {
+// seg_ids[slot] = id of the agent that drew slot `local` of its cell segment.  The slots are drawn
+// here, by counting the histogram back down (the scan leaves it in place): every agent takes one,
+// so the histogram is all zero again when the kernel ends — ready for the next fused histogram
+// without a clearing pass — and the atomic round trip is paid by this short, fully occupied kernel
+// instead of by the last instruction of the step kernel.
+__global__ void k_bin_scatter(const u32 *key, u32 *local, const u32 *ids, u32 n, u32 src_begin,
+                              const u32 *cell_start, u32 *seg_ids, u32 *cell_count) {
   cudaGridDependencySynchronize();
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
-  u32 slot = cell_start[key[t]] + local[t];
-  seg_ids[slot] = ids[src_begin + t];
+  const u32 c = key[t];
+  const u32 l = atomicSub(&cell_count[c], 1u) - 1u;
+  local[t] = l;
+  seg_ids[cell_start[c] + l] = ids[src_begin + t];
 }
 
 __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src, size_t si, int elem) {
@@ -918,7 +924,7 @@ static void trace_stamp(abl_runtime *rt, int bucket) {
 static int run_cell_scan(abl_runtime *rt, u32 *count, u32 *start, size_t n, const ScanReport *report = nullptr,
                          bool *reported = nullptr) {
   if (reported) *reported = false;
-  if (!rt->scan_two_pass) return run_scan<u32, 0, true>(rt, count, start, n, nullptr);
+  if (!rt->scan_two_pass) return run_scan<u32, 0, false>(rt, count, start, n, nullptr);
   TRY(ensure_scan(rt, n));
   const u32 tiles = (u32)((n + kScanTile - 1) / kScanTile);
   u32 *tile_sum = rt->scan.tile_sum;
@@ -1546,8 +1552,8 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
     const u32 *ids = (const u32 *)p.cols[p.id_col].buf[p.cols[p.id_col].cur];
     u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
-    CU(launch_pdl(rt->pdl, k_bin_scatter, dim3(nb), dim3(bs), 0, rt->stream, (const u32 *)p.key, (const u32 *)p.local, ids, n,
-                  p.src_begin, (const u32 *)p.cell_start, seg_ids));
+    CU(launch_pdl(rt->pdl, k_bin_scatter, dim3(nb), dim3(bs), 0, rt->stream, (const u32 *)p.key, p.local, ids, n,
+                  p.src_begin, (const u32 *)p.cell_start, seg_ids, p.cell_count));
     ColTable t;
     fill_table(p, t, true);
     CU(launch_pdl(rt->pdl, k_bin_rank_move, dim3(nb), dim3(bs), 0, rt->stream, t, (const u32 *)seg_ids, (const u32 *)p.key,

@@ -202,8 +202,9 @@ typedef struct {
   unsigned char *dead;                     /* [self.n] removeCurrent() flags, or NULL */
   unsigned char *add_flag;                 /* [self.n] add() flags, or NULL */
   void *add_cols[ABL_MAX_COLUMNS];         /* staging columns of the added type, [self.n] */
-  /* when non-NULL the kernel also bins the positions it writes: bin_key[i] = cell key,
-   * bin_local[i] = atomicAdd(&bin_count[key], 1) (fused histogram of the next binning) */
+  /* when non-NULL the kernel also bins the positions it writes: bin_key[i] = cell key and
+   * bin_count[key] += 1 (fused histogram of the next binning; bin_local is unused since the
+   * slots inside a cell segment are handed out by the scatter pass) */
   unsigned *bin_key;
   unsigned *bin_local;
   unsigned *bin_count;
