@@ -247,7 +247,13 @@ struct abl_runtime {
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
   size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
-  int flat_loop = -1;          // ABL_CUDA_FLAT=0/1 pins the candidate loop of sparse 2-D step kernels (default: timed at run time)
+  // Candidate loop of sparse 2-D step kernels: 1 (default) the flat loop — from a bulk-staged tile when
+  // bulk_tile is set — chosen by the launcher's density rule (measured on B200 in round 2: flat beats
+  // the cursor loop on boids2d f64/f32, game_of_life and predator_prey; the chunked loop wins only for
+  // dense rows); ABL_CUDA_FLAT=0 pins the cursor loop; ABL_CUDA_TUNE=1 (-1) lets the launcher time the
+  // plausible variants over its first launches instead.
+  int flat_loop = 1;
+  int bulk_tile = 1;           // ABL_CUDA_BULK=0: no TMA-staged tiles (ABL_MODE 7)
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
@@ -1057,6 +1063,8 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
+  if (const char *tn = getenv("ABL_CUDA_TUNE")) { if (atoi(tn) != 0) rt->flat_loop = -1; }
+  if (const char *bk = getenv("ABL_CUDA_BULK")) rt->bulk_tile = atoi(bk) < 0 ? 0 : atoi(bk) > 2 ? 2 : atoi(bk);
   if (const char *nlv = getenv("ABL_CUDA_NLIST")) rt->nlist = atoi(nlv) != 0;
   if (const char *mb = getenv("ABL_CUDA_NLIST_MB")) rt->nlist_budget = (size_t)std::max(1, atoi(mb)) << 20;
   if (const char *sc = getenv("ABL_CUDA_SCAN")) rt->scan_two_pass = strcmp(sc, "lookback") != 0;
@@ -2028,6 +2036,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.block_size = rt->cfg.block_size;
     a.tile_neighbours = rt->cfg.tile_neighbours;
     a.flat_loop = rt->flat_loop;
+    a.bulk_tile = rt->bulk_tile;
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
     // cached neighbour lists: neither pool of this step's for-near loop ever moves (the code

@@ -206,7 +206,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", -1: "not launched"}
+MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", 7: "bulk-tile", -1: "not launched"}
 
 # FP64 operations per agent-step of circle3d's step kernel (SURVEY.md 8d asks for this view next to
 # the HBM one): per candidate 3 sub + 3 mul + 2 add + 1 compare = 9, per accepted candidate the
@@ -270,9 +270,10 @@ def measure(args, workload, env, strong, steps, warmup, with_cpu_baseline):
         rt.synchronize()
 
     # ---- device-resident throughput ------------------------------------------------------
-    # (at least 16 warm-up timesteps: the launchers' run-time tuner times up to three candidate-loop
-    # variants over the first 12 launches of a step function, asset/cuda/abl_device.cuh)
-    n_warmup = max(16, warmup)
+    # (ABL_CUDA_TUNE=1: at least 16 warm-up timesteps, because the launchers' run-time tuner then times up
+    # to three candidate-loop variants over the first 12 launches of a step function; by default the
+    # variant follows from a rule and the requested warm-up, at least 3 timesteps, is used as is)
+    n_warmup = max(16 if os.environ.get("ABL_CUDA_TUNE", "0") not in ("", "0") else 3, warmup)
     upload()
     for _ in range(n_warmup):
         timestep()

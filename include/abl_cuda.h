@@ -217,6 +217,9 @@ typedef struct {
   int flat_loop;                           /* candidate loop of the step kernels: 0 cursor loop, 1 flat loop (sparse 2-D loops, ABL_MODE 3) — both
                                               leave dense neighbourhoods to the chunked loop by the density rule; -1 (runtime default) the launcher
                                               times the plausible bit-identical variants (cursor, flat, chunked) over its first launches and keeps the fastest */
+  int bulk_tile;                           /* 1 (default; ABL_CUDA_BULK=0 clears it): sparse 2-D for-near loops run from a shared-memory tile whose rows
+                                              the TMA engine copies (cp.async.bulk + mbarrier, ABL_MODE 7) when the launcher's rule picks the flat loop and
+                                              a tile entry has 32 bytes or more; 2 (ABL_CUDA_BULK=2): for every entry size */
   int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
   /* Cached neighbour lists (steps registered with abl_step_desc.nlist != 0: neither pool of the

@@ -98,6 +98,7 @@ private:
   bool curStepTile = false;     // the step's for-near loop can run from a shared-memory tile
   bool curStepFlat = false;     // `-C cuda.flat=true` and a 2-D for-near loop: ABL_MODE 3 is printed
   bool curStepList = false;     // `-C cuda.nlist=true` and a static neighbourhood: list kernels (ABL_MODE 4/5/6) are printed
+  bool curStepBulk = false;     // tileable 2-D flat loop: ABL_MODE 7 (rows staged by cp.async.bulk, `-C cuda.bulk=false` omits it)
   bool stepListEligible(const StepInfo &si) const;
   // one neighbour column staged in shared memory by a tiled kernel
   struct TileCol {
@@ -202,6 +203,7 @@ private:
   void nearLoopBody(const NearLoop &L, const std::string &d2, const std::string &breakLabel, const std::string &continueLabel);
   void nearListLoops(const NearLoop &L);
   void nearTileLoop(const NearLoop &L);
+  void nearBulkFlatLoop(const NearLoop &L);
   void nearChunkedLoop(const NearLoop &L);
   void nearFlatLoop(const NearLoop &L);
   void nearCursorLoop(const NearLoop &L);
@@ -813,6 +815,68 @@ void CudaPrinter::nearListLoops(const NearLoop &L) {
   w.nl();
 }
 
+// ABL_MODE 7: the flat loop of ABL_MODE 3 over a shared-memory tile whose rows were copied by the
+// TMA engine (abl_device.cuh: abl_btile_plan).  Candidate k of the thread is tile entry
+// k + (k < T1 ? O0 : k < T2 ? O1 : O2); position from the tile, further members only for accepted
+// candidates.  Same candidates in the same order as every other variant.  Leaves its `else` open.
+void CudaPrinter::nearBulkFlatLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos;
+  const int posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  std::vector<TileCol> cols = tileColumns(*curFn, *nbr);
+  w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+  w << "if (ABL_MODE == 7 && _bt.ok) {";
+  w.indent(); w.nl();
+  w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
+  w << "const unsigned char *const " << it << "tc = _abl_smem + ABL_BTILE_HDR_BYTES;"; w.nl();
+  w << "for (unsigned " << it << "k = 0; " << it << "k < _bt.N; " << it << "k += 2) {";
+  w.indent(); w.nl();
+  w << "const bool " << it << "hB = " << it << "k + 1u < _bt.N;"; w.nl();
+  w << "const unsigned " << it << "kB = " << it << "hB ? " << it << "k + 1u : " << it << "k;"; w.nl();
+  w << "const unsigned " << it << "eA = " << it << "k + (" << it << "k < _bt.T1 ? _bt.O0 : (" << it << "k < _bt.T2 ? _bt.O1 : _bt.O2));"; w.nl();
+  w << "const unsigned " << it << "eB = " << it << "kB + (" << it << "kB < _bt.T1 ? _bt.O0 : (" << it << "kB < _bt.T2 ? _bt.O1 : _bt.O2));"; w.nl();
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << "const abl_float2 " << it << "p" << H << " = reinterpret_cast<const abl_float2 *>(" << it << "tc)[" << it << "e" << H << "];"; w.nl();
+  }
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << "const abl_real " << it << "d2" << H << " = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << it << "p" << H
+      << ", " << selfPosText << "));"; w.nl();
+  }
+  const std::string second = "_near_bulkB" + it;
+  for (int h = 0; h < 2; h++) {
+    const std::string H = h ? "B" : "A";
+    w << "if (" << (h ? it + "hB && " : std::string()) << "!(" << it << "d2" << H << " > _near_limit)) {";
+    w.indent(); w.nl();
+    w << nbr->name << " " << s.varName << ";"; w.nl();
+    w << s.varName << "." << pos->name << " = " << it << "p" << H << ";";
+    for (size_t q = 0; q < cols.size(); q++) {
+      if (cols[q].member == posIndex) continue;
+      const Ty &mt = nbr->members[cols[q].member]->type;
+      const std::string dst = s.varName + "." + nbr->members[cols[q].member]->name;
+      const std::string src = "reinterpret_cast<const " + cols[q].ctype + " *>(" + it + "tc + (size_t)_tile_cap * " +
+                              tileOffset(cols, q) + ")[" + it + "e" + H + "]";
+      w.nl();
+      if (mt.k == TK::Vec3) w << dst << "." << "xyz"[cols[q].comp] << " = " << src << ";";
+      else if (mt.k == TK::Bool) w << dst << " = " << src << " != 0;";
+      else w << dst << " = " << src << ";";
+    }
+    w.nl();
+    nearLoopBody(L, it + "d2" + H, std::string(), h ? std::string() : second);
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    if (h == 0) { w << second << ": ;"; w.nl(); }
+  }
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "} else"; w.nl();
+  w << "#endif"; w.nl();
+}
+
 // ABL_MODE 2: candidates come from the shared-memory tile the kernel prologue staged
 // (abl_device.cuh: abl_tile_plan); same visiting order as abl_near_iter.  Leaves its `else` open.
 void CudaPrinter::nearTileLoop(const NearLoop &L) {
@@ -1022,7 +1086,7 @@ void CudaPrinter::nearFlatLoop(const NearLoop &L) {
   const bool prefetchOthers = L.prefetchOthers;
   const std::string &ptypeS = L.ptypeS;
   (void)others; (void)prefetchOthers; (void)ptypeS;
-  w << "if (ABL_MODE == 3) {";
+  w << "if (ABL_MODE == 3 || ABL_MODE == 7) {";   // (7: a thread or block whose rows are not staged)
   w.indent(); w.nl();
   w << "const unsigned " << it << "T1 = " << it << ".re[0] - " << it << ".rb[0];"; w.nl();
   w << "const unsigned " << it << "T2 = " << it << "T1 + (" << it << ".re[1] - " << it << ".rb[1]);"; w.nl();
@@ -1197,10 +1261,11 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   w << "{";
   w.indent(); w.nl();
   const bool tile = curStepTile;
+  if (curStepBulk) nearBulkFlatLoop(L);
   if (tile) nearTileLoop(L);
   w << "abl_near_iter<" << sdim << "> " << it << ";";
   w.nl();
-  if (curStepFlat) w << "if (ABL_MODE == 3) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true, _near_cull); else ";
+  if (curStepFlat) w << "if (ABL_MODE == 3 || ABL_MODE == 7) " << it << ".rows" << sdim << "(_a, " << selfPosText << ", true, _near_cull); else ";
   w << it << ".init" << sdim << "(_a, " << selfPosText << ", true, _near_cull);";
   w.nl();
   // Radius filter: inclusive radius, self included, same operand order as the reference's
@@ -1725,6 +1790,12 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull, "
     << (sql ? "const abl_sq_limits _sql, " : "") << "const unsigned _tile_cap) {";
   w.indent(); w.nl();
+  if (curStepBulk) {
+    // the mbarrier of the bulk-staged tile: no global memory involved, so this overlaps the tail of the preceding kernel
+    w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+    w << "if (ABL_MODE == 7) { extern __shared__ __align__(16) unsigned char _abl_smem0[]; abl_btile_begin(_abl_smem0); }"; w.nl();
+    w << "#endif"; w.nl();
+  }
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
   // _r: index inside the launched (owned) range, _i: index in the pool's columns
   w << "bool _boundary;"; w.nl();
@@ -1738,7 +1809,7 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
   if (curStepTile) {
     // tiled kernels keep surplus threads of the last block alive for the cooperative staging
     w << "const bool _active = _r != 0xffffffffu;"; w.nl();
-    w << "if (ABL_MODE != 2 && !_active) return;"; w.nl();
+    w << "if (ABL_MODE != 2 && ABL_MODE != 7 && !_active) return;"; w.nl();
     w << self.name << " " << p.name << " = {};"; w.nl();
     w << "if (_active) {";
     w.indent();
@@ -1784,11 +1855,48 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
   } else {
     w << "const bool _tile_ok = false;"; w.nl();
   }
+  if (curStepBulk) {
+    // ABL_MODE 7: warp 0 plans the row ranges of the block from its first and last agent and starts
+    // the bulk copies; every thread fetches its own row ranges meanwhile and then waits on the mbarrier
+    const int pc = columnOf(self, self.memberIndex(selfPosM->name));
+    w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+    w << "abl_btile_flat2 _bt;"; w.nl();
+    w << "_bt.ok = false; _bt.T1 = _bt.T2 = _bt.N = _bt.O0 = _bt.O1 = _bt.O2 = 0;"; w.nl();
+    w << "if (ABL_MODE == 7) {";
+    w.indent(); w.nl();
+    w << "extern __shared__ __align__(16) unsigned char _abl_smem[];"; w.nl();
+    w << "const abl_btile_cols _TC = { " << tcols.size() << ", {";
+    for (size_t q = 0; q < tcols.size(); q++) w << (q ? ", " : "") << tcols[q].column;
+    w << "}, {";
+    for (size_t q = 0; q < tcols.size(); q++) w << (q ? ", " : "") << "(int)" << tcols[q].bytes;
+    w << "}, {";
+    for (size_t q = 0; q < tcols.size(); q++) w << (q ? ", " : "") << "(unsigned)" << tileOffset(tcols, q);
+    w << "}, (unsigned)" << tileOffset(tcols, tcols.size()) << " };"; w.nl();
+    w << "if (threadIdx.x < 32) {";
+    w.indent(); w.nl();
+    w << "unsigned _bf = 0, _bl = 0;"; w.nl();
+    w << "const bool _any = abl_block_span(_a, _bf, _bl);"; w.nl();
+    w << "const abl_real *const _pc = static_cast<const abl_real *>(_a.self.in[" << pc << "]);"; w.nl();
+    w << "abl_real _pf[2] = {0, 0}, _pl[2] = {0, 0};"; w.nl();
+    w << "if (_any) { _pf[0] = __ldg(_pc + 2 * (size_t)_bf); _pf[1] = __ldg(_pc + 2 * (size_t)_bf + 1); "
+      << "_pl[0] = __ldg(_pc + 2 * (size_t)_bl); _pl[1] = __ldg(_pc + 2 * (size_t)_bl + 1); }"; w.nl();
+    w << "abl_btile_plan<2>(_a, _pf, _pl, _any, _tile_cap, _abl_smem, _TC);";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "if (!_active) return;"; w.nl();
+    w << "abl_near_iter<2> _rows;"; w.nl();
+    w << "_rows.rows2(_a, " << p.name << "." << selfPosM->name << ", true, _near_cull);"; w.nl();
+    w << "_tile_ok = abl_btile_wait(_abl_smem);"; w.nl();
+    w << "_bt = abl_btile_thread2(_rows, _abl_smem, _tile_ok);";
+    w.outdent(); w.nl();
+    w << "}"; w.nl();
+    w << "#endif"; w.nl();
+  }
   w << self.name << " " << p.outName << " = " << p.name << ";"; w.nl();
   w << "abl_ctx _ctx;"; w.nl();
   if (f.usesRng) { w << "abl_ctx_init(_ctx, _a.seed, _a.timestep, _a.step_index, _a.self.id[_i]);"; w.nl(); }
   else { w << "_ctx.rng = 0; _ctx.dead = false; _ctx.added = false;"; w.nl(); }
-  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, _near_cull, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok, " << p.name << ", " << p.outName << ");";
+  w << f.emitName << "<ABL_MODE>(_ctx, _a, _i, _near_limit, _near_cull, " << (sql ? "_sql, " : "") << "_tile_cap, _tile_ok" << (curStepBulk ? " ABL_BT_ARG" : "") << ", " << p.name << ", " << p.outName << ");";
   if (curStepList) { w.nl(); w << "if (ABL_MODE == 5 || ABL_MODE == 6) return;   // list-building launch: nothing of the step is stored"; }
   AgentMember *selfPos = self.position();
   for (size_t m = 0; m < self.members.size(); m++) {
@@ -1866,15 +1974,18 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   w << "    const double occ = a->grid.n_cells ? (double)a->nbr.n / (double)a->grid.n_cells : 0.0;"; w.nl();
   w << "    const double row_cells = cull > ABL_R(0.0) ? fmin(3.0, 1.0 + 2.0 * (double)cull / a->grid.cell_size) : 2.0 * a->reach + 1.0;"; w.nl();
   w << "    const double row_occ = occ * row_cells;"; w.nl();
-  if (curStepHasLimit) {
-    // dense neighbourhoods (mean row holds >= 8 candidates): chunked two-phase loop
-    w << "    const bool chunked = row_occ >= 8.0;"; w.nl();
-  } else {
-    w << "    const bool chunked = false;"; w.nl();
-  }
   w << "    int dev = 0;"; w.nl();
   w << "    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ABL_TUNE_DEVICES) dev = 0;"; w.nl();
   w << "    const bool can_flat = " << (curStepFlat ? "a->reach == 1" : "false") << ";"; w.nl();
+  if (curStepHasLimit) {
+    // Dense neighbourhoods: chunked two-phase loop.  Against the cursor loop it pays from a mean row
+    // of 8 candidates (round 1); against the flat loop only for crowded rows — measured on B200 in
+    // round 2 (profiles/r2/): game_of_life (7 per row) flat 0.43 ms, chunked 0.94 ms; every loop of
+    // predator_prey 4 M (rows of 2 .. 43) flat, 1.30 ms per timestep against 1.72 ms by the old rule.
+    w << "    const bool chunked = row_occ >= (can_flat && a->flat_loop != 0 ? 64.0 : 8.0);"; w.nl();
+  } else {
+    w << "    const bool chunked = false;"; w.nl();
+  }
   w << "    int mode = chunked ? 1 : (a->flat_loop > 0 && can_flat ? 3 : 0);"; w.nl();
   w << "    bool timed = false;"; w.nl();
   w << "    static abl_tuner tune[ABL_TUNE_DEVICES];"; w.nl();
@@ -1897,6 +2008,29 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
     w << "        if (!tile_set[dev]) { cudaFuncSetAttribute(" << K << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set[dev] = true; }"; w.nl();
     w << "        return (int)abl_launch_kernel(a, " << K << "<2>, tile_grid, tile_bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
     w << "    }"; w.nl();
+  }
+  if (curStepBulk) {
+    // the launcher's rule for sparse 2-D loops: flat loop, from a TMA-staged tile when the block's rows fit
+    w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+    // (only for entries of 32 bytes and more — boids2d in double: +9 % at 1 M agents, +13 % at 16 M;
+    // lighter loops do not wait for their loads enough to repay the planning: boids2d in float
+    // neutral, game_of_life (17 bytes) 13 % slower — profiles/r2/r2b_*.json)
+    w << "    const unsigned bentry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
+    w << "    if (a->bulk_tile && (a->bulk_tile > 1 || bentry >= 32u) && a->flat_loop > 0 && can_flat && !chunked && !listed) {"; w.nl();
+    w << "        const int bbs = bs ? bs : 128;"; w.nl();
+    w << "        const unsigned bcap = bbs % 32 == 0 ? abl_tile_capacity(a, 3, bbs, bentry, 96u * 1024u) : 0u;"; w.nl();
+    w << "        if (bcap) {"; w.nl();
+    w << "            const size_t bsmem = ABL_BTILE_HDR_BYTES + (size_t)bcap * bentry;"; w.nl();
+    w << "            static size_t bulk_set[ABL_TUNE_DEVICES];   // opt-in shared memory size, per device"; w.nl();
+    w << "            if (bsmem > 48u * 1024u && bulk_set[dev] < bsmem) { cudaFuncSetAttribute(" << K << "<7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bsmem); bulk_set[dev] = bsmem; }"; w.nl();
+    w << "            abl_last_mode_" << f.emitName << " = 7;"; w.nl();
+    w << "            const unsigned bgrid = abl_grid_blocks(a, bbs);"; w.nl();
+    w << "            const int brc = (int)abl_launch_kernel(a, " << K << "<7>, bgrid, bbs, bsmem, *a, " << lim << ", bcap);"; w.nl();
+    w << "            if (brc == 0) return 0;"; w.nl();
+    w << "            (void)cudaGetLastError();   // could not be launched: the flat loop over global memory below"; w.nl();
+    w << "        }"; w.nl();
+    w << "    }"; w.nl();
+    w << "#endif"; w.nl();
   }
   if (curStepHasLimit) {
     // a->flat_loop < 0 (the runtime's default): the plausible variants are timed over the first
@@ -1976,12 +2110,15 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepFlat = config.getBool("cuda.flat", true) && curStepHasLimit && nearStmt && nearStmt->declTy.agent &&
                 nearStmt->declTy.agent->position() && nearStmt->declTy.agent->position()->type.vecLen() == 2;
 
+  curStepBulk = curStepTile && curStepFlat && tdim == 2 && config.getBool("cuda.bulk", true) &&
+                tcols.size() <= 8;   // ABL_BTILE_MAX_COLS
+
   // the user's step function
   w << "template <int ABL_MODE>"; w.nl();
   sqLimits.clear();
   const bool sql = sqcmpOn() && curStepHasLimit;   // comparison bounds on the squared distance travel as a kernel parameter
   w << "__device__ __forceinline__ void " << f.emitName << "(abl_ctx& _ctx, const abl_step_launch& _a, unsigned _i, const abl_real _near_limit, const abl_real _near_cull, "
-    << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok, const "
+    << (sql ? "const abl_sq_limits& _sql, " : "") << "const unsigned _tile_cap, const bool _tile_ok" << (curStepBulk ? " ABL_BT_PARAM" : "") << ", const "
     << self.name << "& " << p.name << ", " << self.name << "& " << p.outName << ") {";
   w.indent(); stmts(f.body); w.outdent();
   w.nl();
@@ -1997,6 +2134,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepTile = false;
   curStepFlat = false;
   curStepList = false;
+  curStepBulk = false;
 }
 
 std::string CudaPrinter::kernelSource() {

@@ -57,17 +57,19 @@ def test_circle3d_1M_is_independent_of_block_size_and_tiling():
 @pytest.mark.parametrize("model_file,n,steps", [("boids2d.abl", 1000000, 14), ("game_of_life.abl", 1048576, 14)],
                          ids=["boids2d-1M", "game_of_life-1M"])
 def test_candidate_loop_variants_agree_bitwise_at_full_size(model_file, n, steps, monkeypatch):
-    """Cursor loop (ABL_CUDA_FLAT=0), flat loop (=1) and the timed choice (unset: the first twelve
-    launches rotate through cursor, flat and chunked loop) must give the same bits; 14 timesteps
-    take the timed run through all its trial launches and into the chosen variant."""
+    """Cursor loop (ABL_CUDA_FLAT=0), flat loop over global memory (ABL_CUDA_BULK=0), the default (flat
+    loop over a TMA-staged shared-memory tile, ABL_MODE 7) and the timed choice (ABL_CUDA_TUNE=1: the
+    first twelve launches rotate through cursor, flat and chunked loop) must give the same bits; 14
+    timesteps take the timed run through all its trial launches and into the chosen variant."""
     params = {"num_agents": n}
     outs = {}
-    for setting in ("0", "1", None):
-        if setting is None:
-            monkeypatch.delenv("ABL_CUDA_FLAT", raising=False)
-        else:
-            monkeypatch.setenv("ABL_CUDA_FLAT", setting)
-        outs[setting] = run(model_file, params, False, steps)[1]
-    for f in outs["0"].dtype.names:
-        assert np.array_equal(outs["0"][f], outs["1"][f]), "flat loop differs from the cursor loop in %s" % f
-        assert np.array_equal(outs["0"][f], outs[None][f]), "timed run differs from the cursor loop in %s" % f
+    settings = {"cursor": {"ABL_CUDA_FLAT": "0"}, "flat": {"ABL_CUDA_BULK": "0"}, "bulk": {}, "timed": {"ABL_CUDA_TUNE": "1"}}
+    for name, env in settings.items():
+        for k in ("ABL_CUDA_FLAT", "ABL_CUDA_BULK", "ABL_CUDA_TUNE"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        outs[name] = run(model_file, params, False, steps)[1]
+    for f in outs["cursor"].dtype.names:
+        for name in ("flat", "bulk", "timed"):
+            assert np.array_equal(outs["cursor"][f], outs[name][f]), "%s run differs from the cursor loop in %s" % (name, f)
