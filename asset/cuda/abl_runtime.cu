@@ -92,6 +92,12 @@ struct Pool {
   int pos_member = -1;
   unsigned stride = 0;
   size_t n = 0, cap = 0;
+  // single-precision shadow of the positions (ABL_MODE 8): float4 per record in pool order, valid while
+  // shadow_serial == layout_serial (layout_serial counts every change of the order or the positions)
+  float4 *shadow = nullptr;
+  u32 *shadow_max = nullptr;
+  size_t shadow_cap = 0;
+  u64 shadow_serial = ~(u64)0;   // order_serial the shadow was built for
   u32 next_id = 0;
   // slab decomposition: [own_begin, own_end) is the owned part of the (binned) pool;
   // src_begin is where the live records start before the next binning compacts them
@@ -254,6 +260,7 @@ struct abl_runtime {
   // plausible variants over its first launches instead.
   int flat_loop = 1;
   int bulk_tile = 1;           // ABL_CUDA_BULK=0: no TMA-staged tiles (ABL_MODE 7)
+  int dense_tile = 1;          // ABL_CUDA_DENSE=0: no single-precision shadow of the positions (ABL_MODE 8)
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
@@ -1064,6 +1071,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
   if (const char *tn = getenv("ABL_CUDA_TUNE")) { if (atoi(tn) != 0) rt->flat_loop = -1; }
+  if (const char *dn = getenv("ABL_CUDA_DENSE")) rt->dense_tile = atoi(dn) != 0 ? 1 : 0;
   if (const char *bk = getenv("ABL_CUDA_BULK")) rt->bulk_tile = atoi(bk) < 0 ? 0 : atoi(bk) > 2 ? 2 : atoi(bk);
   if (const char *nlv = getenv("ABL_CUDA_NLIST")) rt->nlist = atoi(nlv) != 0;
   if (const char *mb = getenv("ABL_CUDA_NLIST_MB")) rt->nlist_budget = (size_t)std::max(1, atoi(mb)) << 20;
@@ -1125,6 +1133,8 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     free_pool_scratch(nullptr, p);
     if (p.cell_count) cudaFree(p.cell_count);
     if (p.cell_start) cudaFree(p.cell_start);
+    if (p.shadow) cudaFree(p.shadow);
+    if (p.shadow_max) cudaFree(p.shadow_max);
   }
   for (Step &st : rt->steps) {
     if (st.nl.cnt) cudaFree(st.nl.cnt);
@@ -1870,6 +1880,58 @@ static int drain_timing(abl_runtime *rt) {
 // Builds the neighbour lists of step `s` for the views in `a` (count pass -> size by the largest
 // count -> fill pass; both passes are launches of the generated kernel that store nothing of the
 // step itself).  One host synchronisation, once per build.
+// Single-precision shadow of a pool's positions for the pre-filter of ABL_MODE 8 (abl_device.cuh):
+// float4 (x, y, z, 0) per record in pool order plus the largest coordinate magnitude (the error bound
+// of the pre-filter scales with it).  NaN coordinates do not enter the maximum; such candidates pass
+// the pre-filter by themselves (every comparison with NaN is false) and are decided by the exact test.
+template <int DIM>
+__global__ void k_shadow(const double *px, const double *py, const double *pz, u32 n, float4 *shadow, u32 *max_bits) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  float m = 0.0f;
+  if (i < n) {
+    float4 f;
+    if (DIM == 2) {
+      const double2 p = reinterpret_cast<const double2 *>(px)[i];
+      f = make_float4((float)p.x, (float)p.y, 0.0f, 0.0f);
+    } else {
+      f = make_float4((float)px[i], (float)py[i], (float)pz[i], 0.0f);
+    }
+    shadow[i] = f;
+    m = fmaxf(fabsf(f.x), fmaxf(fabsf(f.y), fabsf(f.z)));
+  }
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, d));
+  if ((threadIdx.x & 31u) == 0u && m > 0.0f) atomicMax(max_bits, __float_as_uint(m));   // non-negative floats order like their bits
+}
+
+static int refresh_shadow(abl_runtime *rt, Pool &p) {
+  if (p.shadow && p.shadow_serial == p.order_serial && p.shadow_cap >= p.n) return ABL_OK;
+  if (p.shadow_cap < std::max(p.n, (size_t)1)) {
+    if (p.shadow) TRY(release_device(rt, p.shadow));
+    p.shadow = nullptr;
+    p.shadow_cap = std::max(p.cap, std::max(p.n, (size_t)1));
+    CU(cudaMalloc(&p.shadow, p.shadow_cap * sizeof(float4)));
+  }
+  if (!p.shadow_max) CU(cudaMalloc(&p.shadow_max, sizeof(u32)));
+  CU(cudaMemsetAsync(p.shadow_max, 0, sizeof(u32), rt->stream));
+  if (p.n) {
+    const Member &pm = p.members[p.pos_member];
+    const double *px = (const double *)p.cols[pm.first_col].buf[p.cols[pm.first_col].cur];
+    const u32 nb = blocks_for(p.n, 256);
+    if (rt->grid.dim == 2) {
+      k_shadow<2><<<nb, 256, 0, rt->stream>>>(px, nullptr, nullptr, (u32)p.n, p.shadow, p.shadow_max);
+    } else {
+      const double *py = (const double *)p.cols[pm.first_col + 1].buf[p.cols[pm.first_col + 1].cur];
+      const double *pz = (const double *)p.cols[pm.first_col + 2].buf[p.cols[pm.first_col + 2].cur];
+      k_shadow<3><<<nb, 256, 0, rt->stream>>>(px, py, pz, (u32)p.n, p.shadow, p.shadow_max);
+    }
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  p.shadow_serial = p.order_serial;
+  return ABL_OK;
+}
+
 static int build_neighbour_lists(abl_runtime *rt, Step &s, const abl_step_launch &a, const Pool &self, const Pool &nbr) {
   NeighbourLists &nl = s.nl;
   nl.valid = false;
@@ -2037,6 +2099,12 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.tile_neighbours = rt->cfg.tile_neighbours;
     a.flat_loop = rt->flat_loop;
     a.bulk_tile = rt->bulk_tile;
+    // dense for-near loops pre-filter on a single-precision shadow of the neighbours' positions
+    if (s.desc.shadow && rt->dense_tile && nbr && rt->real_size == 8 && nbr->pos_member >= 0) {
+      TRY(refresh_shadow(rt, *nbr));
+      a.nbr_shadow = nbr->shadow;
+      a.nbr_shadow_max = nbr->shadow_max;
+    }
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
     // cached neighbour lists: neither pool of this step's for-near loop ever moves (the code

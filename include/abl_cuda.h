@@ -220,6 +220,16 @@ typedef struct {
   int bulk_tile;                           /* 1 (default; ABL_CUDA_BULK=0 clears it): sparse 2-D for-near loops run from a shared-memory tile whose rows
                                               the TMA engine copies (cp.async.bulk + mbarrier, ABL_MODE 7) when the launcher's rule picks the flat loop and
                                               a tile entry has 32 bytes or more; 2 (ABL_CUDA_BULK=2): for every entry size */
+  /* Single-precision shadow of the neighbour pool's positions (double-precision builds, steps registered with
+   * abl_step_desc.shadow != 0; NULL: none, e.g. ABL_CUDA_DENSE=0): one float4 (x, y, z, 0) per agent in pool order,
+   * refreshed by the runtime whenever the pool was re-binned or its positions were rewritten, and the largest
+   * coordinate magnitude in it (float bits).  Dense for-near loops (the launcher's chunked case) pre-filter their
+   * candidates on it and re-test the survivors exactly (ABL_MODE 8). */
+  const void *nbr_shadow;
+  const unsigned *nbr_shadow_max;
+  /* > 0 (set by the generated launcher for dense for-near loops of reach 1): the squared radius bound; the neighbour
+   * iterator then narrows every row of cells along x to the cells within reach of the agent (abl_device.cuh: row_reach) */
+  double row_cull;
   int pdl;                                 /* 1: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first) */
   void *stream;                            /* cudaStream_t */
   /* Cached neighbour lists (steps registered with abl_step_desc.nlist != 0: neither pool of the
@@ -251,6 +261,7 @@ typedef struct {
   int uses_removal;
   int added_pool;            /* -1: no run-time add() */
   abl_step_launcher launch;
+  int shadow;                /* 1: the step's kernels include the shadow pre-filter variant (ABL_MODE 8) */
   int nlist;                 /* 1: list kernels were generated and no step function of the model moves, adds or
                                 removes agents of either pool of the for-near loop (`-C cuda.nlist=true`) */
 } abl_step_desc;

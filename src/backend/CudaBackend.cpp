@@ -98,6 +98,7 @@ private:
   bool curStepTile = false;     // the step's for-near loop can run from a shared-memory tile
   bool curStepFlat = false;     // `-C cuda.flat=true` and a 2-D for-near loop: ABL_MODE 3 is printed
   bool curStepList = false;     // `-C cuda.nlist=true` and a static neighbourhood: list kernels (ABL_MODE 4/5/6) are printed
+  bool curStepDense = false;    // for-near loop with a host-evaluable radius: ABL_MODE 8 (single-precision shadow pre-filter, `-C cuda.dense=false` omits it)
   bool curStepBulk = false;     // tileable 2-D flat loop: ABL_MODE 7 (rows staged by cp.async.bulk, `-C cuda.bulk=false` omits it)
   bool stepListEligible(const StepInfo &si) const;
   // one neighbour column staged in shared memory by a tiled kernel
@@ -151,6 +152,7 @@ private:
   int innerLoopDepth = 0;
   std::vector<StepInfo> steps;
   std::set<const FuncDecl *> listSteps;   // steps whose kernels were printed with the list modes
+  std::set<const FuncDecl *> denseSteps;  // steps whose kernels were printed with the shadow pre-filter (ABL_MODE 8)
 
   std::string label() { return "_var" + std::to_string(anon++); }
   bool dev() const { return target == Target::Device; }
@@ -204,6 +206,7 @@ private:
   void nearListLoops(const NearLoop &L);
   void nearTileLoop(const NearLoop &L);
   void nearBulkFlatLoop(const NearLoop &L);
+  void nearShadowLoop(const NearLoop &L);
   void nearChunkedLoop(const NearLoop &L);
   void nearFlatLoop(const NearLoop &L);
   void nearCursorLoop(const NearLoop &L);
@@ -815,6 +818,133 @@ void CudaPrinter::nearListLoops(const NearLoop &L) {
   w.nl();
 }
 
+// ABL_MODE 8 (abl_device.cuh: shadow pre-filter): the chunked loop with phase 1 in single precision
+// on the pool's float4 shadow and phase 2 over per-thread lists expanded from the acceptance masks,
+// in rounds the lanes of a warp enter together.  Same accepted candidates in the same order as every
+// other variant.  Works for any reach (the iterator is replayed like in ABL_MODE 1).  Leaves its
+// `else` open.
+void CudaPrinter::nearShadowLoop(const NearLoop &L) {
+  const Stmt &s = L.s;
+  AgentDecl *nbr = L.nbr;
+  AgentMember *pos = L.pos;
+  const int dim = L.dim, posIndex = L.posIndex;
+  const std::string &it = L.it, &sdim = L.sdim, &selfPosText = L.selfPosText;
+  const std::string done = "_near_done" + it + "s";
+  const std::string ptype = typeName(pos->type);
+  w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+  w << "if (ABL_MODE == 8) {";
+  w.indent(); w.nl();
+  w << "// dynamic shared memory, words: [ABL_SHADOW_WORDS][blockDim.x] acceptance masks | [ABL_SHADOW_ROWS][blockDim.x] first pool"; w.nl();
+  w << "// index of every row range the masks cover | [ABL_SHADOW_LIST][blockDim.x] survivors of the current round"; w.nl();
+  w << "extern __shared__ unsigned _abl_masks[];"; w.nl();
+  w << "unsigned *const " << it << "mk = _abl_masks + threadIdx.x;"; w.nl();
+  w << "unsigned *const " << it << "rows = " << it << "mk + ABL_SHADOW_WORDS * blockDim.x;"; w.nl();
+  w << "unsigned *const " << it << "list = " << it << "rows + ABL_SHADOW_ROWS * blockDim.x;"; w.nl();
+  w << "const float4 *const " << it << "sh = static_cast<const float4 *>(_a.nbr_shadow);"; w.nl();
+  w << "const float " << it << "sx = (float)" << selfPosText << ".x, " << it << "sy = (float)" << selfPosText << ".y"
+    << (dim == 3 ? ", " + it + "sz = (float)" + selfPosText + ".z" : std::string()) << ";"; w.nl();
+  w << "const float " << it << "limf = abl_shadow_limit(_near_limit, __ldg(_a.nbr_shadow_max), fmaxf(fabsf(" << it << "sx), "
+    << (dim == 3 ? "fmaxf(fabsf(" + it + "sy), fabsf(" + it + "sz))" : "fabsf(" + it + "sy)") << "));"; w.nl();
+  w << "const unsigned " << it << "wm = __activemask();   // the lanes that run this loop go through its rounds together"; w.nl();
+  w << "bool " << it << "stop = false;   // `break` of the loop body"; w.nl();
+  w << "for (;;) {";
+  w.indent(); w.nl();
+  // phase 1: masks of up to ABL_SHADOW_WORDS * 32 candidates out of up to ABL_SHADOW_ROWS row ranges
+  w << "unsigned " << it << "nw = 0, " << it << "nr = 0, " << it << "prev = 0xffffffffu;"; w.nl();
+  w << "unsigned long long " << it << "sbits = 0ull;   // bit w: word w starts a new row range"; w.nl();
+  w << "while (!" << it << "stop && " << it << ".valid() && " << it << "nw < ABL_SHADOW_WORDS) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "sb = " << it << ".index();"; w.nl();
+  w << "if (" << it << "sb != " << it << "prev + 32u) {";
+  w.indent(); w.nl();
+  w << "if (" << it << "nr == ABL_SHADOW_ROWS) break;"; w.nl();
+  w << it << "rows[" << it << "nr * blockDim.x] = " << it << "sb;"; w.nl();
+  w << it << "nr++;"; w.nl();
+  w << it << "sbits |= 1ull << " << it << "nw;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << it << "prev = " << it << "sb;"; w.nl();
+  w << "const unsigned " << it << "sn = min(" << it << ".remaining(), 32u);"; w.nl();
+  w << "unsigned " << it << "sm = 0;"; w.nl();
+  w << "for (unsigned " << it << "k = 0; " << it << "k < " << it << "sn; " << it << "k++) {";
+  w.indent(); w.nl();
+  w << "const float4 " << it << "f = __ldg(" << it << "sh + " << it << "sb + " << it << "k);"; w.nl();
+  w << "const float " << it << "dx = " << it << "f.x - " << it << "sx, " << it << "dy = " << it << "f.y - " << it << "sy"
+    << (dim == 3 ? ", " + it + "dz = " + it + "f.z - " + it + "sz" : std::string()) << ";"; w.nl();
+  if (dim == 3)
+    w << "const float " << it << "d2f = __fmaf_rn(" << it << "dz, " << it << "dz, __fmaf_rn(" << it << "dy, " << it << "dy, " << it << "dx * " << it << "dx));";
+  else
+    w << "const float " << it << "d2f = __fmaf_rn(" << it << "dy, " << it << "dy, " << it << "dx * " << it << "dx);";
+  w.nl();
+  w << "if (!(" << it << "d2f > " << it << "limf)) " << it << "sm |= 1u << " << it << "k;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << it << "mk[" << it << "nw * blockDim.x] = " << it << "sm;"; w.nl();
+  w << it << "nw++;"; w.nl();
+  w << it << ".skip(" << it << "sn);";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "if (!__any_sync(" << it << "wm, " << it << "nw != 0u)) break;"; w.nl();
+  // phase 2: rounds of up to ABL_SHADOW_LIST survivors, expanded from the masks
+  w << "unsigned " << it << "w = 0, " << it << "m = 0, " << it << "b = 0, " << it << "ri = 0;"; w.nl();
+  w << "for (;;) {";
+  w.indent(); w.nl();
+  w << "unsigned " << it << "cnt = 0;"; w.nl();
+  w << "while (" << it << "cnt < ABL_SHADOW_LIST) {";
+  w.indent(); w.nl();
+  w << "if (" << it << "m == 0u) {";
+  w.indent(); w.nl();
+  w << "if (" << it << "w == " << it << "nw) break;"; w.nl();
+  w << it << "m = " << it << "mk[" << it << "w * blockDim.x];"; w.nl();
+  w << "if ((" << it << "sbits >> " << it << "w) & 1ull) { " << it << "b = " << it << "rows[" << it << "ri * blockDim.x]; " << it << "ri++; } else " << it << "b += 32u;"; w.nl();
+  w << it << "w++;"; w.nl();
+  w << "continue;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << it << "list[" << it << "cnt * blockDim.x] = " << it << "b + (__ffs(" << it << "m) - 1);"; w.nl();
+  w << it << "cnt++;"; w.nl();
+  w << it << "m &= " << it << "m - 1u;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "__syncwarp(" << it << "wm);"; w.nl();
+  // the position of the next survivor is requested before the current one is processed
+  w << "unsigned " << it << "jn = " << it << "cnt ? " << it << "list[0] : 0u;"; w.nl();
+  w << ptype << " " << it << "pn = " << ptype << "();"; w.nl();
+  w << "if (" << it << "cnt) {";
+  w.indent(); w.nl();
+  loadMember(*nbr, posIndex, it + "pn", "_a.nbr.in", it + "jn");
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "for (unsigned " << it << "q = 0; " << it << "q < " << it << "cnt; " << it << "q++) {";
+  w.indent(); w.nl();
+  w << "const unsigned " << it << "j = " << it << "jn;"; w.nl();
+  w << nbr->name << " " << s.varName << ";"; w.nl();
+  w << s.varName << "." << pos->name << " = " << it << "pn;"; w.nl();
+  w << "if (" << it << "q + 1u < " << it << "cnt) {";
+  w.indent(); w.nl();
+  w << it << "jn = " << it << "list[(" << it << "q + 1u) * blockDim.x];"; w.nl();
+  loadMember(*nbr, posIndex, it + "pn", "_a.nbr.in", it + "jn");
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "const abl_real " << it << "d2 = abl_sqnorm" << sdim << "(float" << sdim << "_sub(" << s.varName << "."
+    << pos->name << ", " << selfPosText << "));"; w.nl();
+  w << "if (" << it << "d2 > _near_limit) continue;";
+  nearLoadOthers(L, it + "j");
+  w.nl();
+  nearLoopBody(L, it + "d2", done, std::string());
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "if (false) { " << done << ": " << it << "stop = true; " << it << "m = 0u; " << it << "w = " << it << "nw; }   // `break` of the loop body: no further candidates"; w.nl();
+  w << "if (!__any_sync(" << it << "wm, " << it << "m != 0u || " << it << "w != " << it << "nw)) break;";
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "}";
+  w.outdent(); w.nl();
+  w << "} else"; w.nl();
+  w << "#endif"; w.nl();
+}
+
 // ABL_MODE 7: the flat loop of ABL_MODE 3 over a shared-memory tile whose rows were copied by the
 // TMA engine (abl_device.cuh: abl_btile_plan).  Candidate k of the thread is tile entry
 // k + (k < T1 ? O0 : k < T2 ? O1 : O2); position from the tile, further members only for accepted
@@ -1272,6 +1402,7 @@ void CudaPrinter::nearLoop(const Stmt &s) {
   // filter (CPrinter.cpp:166-169): dist(nx.pos, in.pos) > radius -> skip.  When the radius
   // is a host-evaluable constant the launcher precomputes the equivalent bound on the
   // squared distance (abl_near_sq_limit) and the kernel skips the square root.
+  if (curStepDense) nearShadowLoop(L);
   if (curStepHasLimit) nearChunkedLoop(L);
   // Software-pipelined candidate loop: the position of the *next* candidate is requested
   // before the current one is tested and processed, so the load latency (L1 miss -> L2) is
@@ -1786,7 +1917,8 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
   const bool sql = C.sql;
   (void)p; (void)radius; (void)selfPosM; (void)tcols; (void)tdim; (void)trows; (void)sql;
   w << "template <int ABL_MODE>"; w.nl();
-  w << "__global__ void __launch_bounds__(256) abl_kernel_" << f.emitName
+  // (two resident CTAs of 256 threads are all the shadow pre-filter's shared memory allows: let it have the registers)
+  w << "__global__ void __launch_bounds__(256, ABL_MODE == 8 ? 2 : 1) abl_kernel_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull, "
     << (sql ? "const abl_sq_limits _sql, " : "") << "const unsigned _tile_cap) {";
   w.indent(); w.nl();
@@ -1974,6 +2106,13 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   w << "    const double occ = a->grid.n_cells ? (double)a->nbr.n / (double)a->grid.n_cells : 0.0;"; w.nl();
   w << "    const double row_cells = cull > ABL_R(0.0) ? fmin(3.0, 1.0 + 2.0 * (double)cull / a->grid.cell_size) : 2.0 * a->reach + 1.0;"; w.nl();
   w << "    const double row_occ = occ * row_cells;"; w.nl();
+  if (curStepHasLimit && config.getBool("cuda.rowcull", false)) {
+    // `-C cuda.rowcull=true` (off by default): dense rows (8 candidates and more), one cell of reach, radius not clearly below
+    // the cell size: every row is narrowed along x to the cells within reach of the agent, 24 % fewer candidates per AGENT in
+    // 3-D.  Measured on B200 (circle3d 1 M): 3.37 -> 4.02 ms per step — the lanes of a warp then walk different ranges, the
+    // warp still covers their union, and the chunked loops lose their lock step (23 instead of 30 active lanes in phase 1).
+    w << "    a->row_cull = (a->reach == 1 && row_occ >= 8.0 && !(cull > ABL_R(0.0)) && limit > ABL_R(0.0) && limit < (abl_real)INFINITY) ? (double)limit : 0.0;"; w.nl();
+  }
   w << "    int dev = 0;"; w.nl();
   w << "    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= ABL_TUNE_DEVICES) dev = 0;"; w.nl();
   w << "    const bool can_flat = " << (curStepFlat ? "a->reach == 1" : "false") << ";"; w.nl();
@@ -2008,6 +2147,22 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
     w << "        if (!tile_set[dev]) { cudaFuncSetAttribute(" << K << "<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024); tile_set[dev] = true; }"; w.nl();
     w << "        return (int)abl_launch_kernel(a, " << K << "<2>, tile_grid, tile_bs, smem, *a, " << lim << ", tile_cap);"; w.nl();
     w << "    }"; w.nl();
+  }
+  if (curStepDense) {
+    // dense rows: the chunked loop with its filter on the single-precision shadow (ABL_MODE 8) when the runtime keeps one
+    w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+    w << "    if (a->nbr_shadow != nullptr && a->flat_loop != 0 && chunked && !listed) {"; w.nl();
+    w << "        const int dbs = bs ? bs : 256;"; w.nl();
+    w << "        const size_t dsmem = (size_t)(ABL_SHADOW_WORDS + ABL_SHADOW_ROWS + ABL_SHADOW_LIST) * dbs * sizeof(unsigned);"; w.nl();
+    w << "        static size_t dense_set[ABL_TUNE_DEVICES];   // opt-in shared memory size, per device"; w.nl();
+    w << "        if (dsmem > 48u * 1024u && dense_set[dev] < dsmem) { cudaFuncSetAttribute(" << K << "<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); dense_set[dev] = dsmem; }"; w.nl();
+    w << "        abl_last_mode_" << f.emitName << " = 8;"; w.nl();
+    w << "        const unsigned dgrid = abl_grid_blocks(a, dbs);"; w.nl();
+    w << "        const int drc = (int)abl_launch_kernel(a, " << K << "<8>, dgrid, dbs, dsmem, *a, " << lim << ", 0u);"; w.nl();
+    w << "        if (drc == 0) return 0;"; w.nl();
+    w << "        (void)cudaGetLastError();   // could not be launched: the chunked loop below"; w.nl();
+    w << "    }"; w.nl();
+    w << "#endif"; w.nl();
   }
   if (curStepBulk) {
     // the launcher's rule for sparse 2-D loops: flat loop, from a TMA-staged tile when the block's rows fit
@@ -2112,6 +2267,8 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
 
   curStepBulk = curStepTile && curStepFlat && tdim == 2 && config.getBool("cuda.bulk", true) &&
                 tcols.size() <= 8;   // ABL_BTILE_MAX_COLS
+  curStepDense = curStepHasLimit && nearStmt && !useFloat && config.getBool("cuda.dense", true);
+  if (curStepDense) denseSteps.insert(&f);
 
   // the user's step function
   w << "template <int ABL_MODE>"; w.nl();
@@ -2135,6 +2292,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepFlat = false;
   curStepList = false;
   curStepBulk = false;
+  curStepDense = false;
 }
 
 std::string CudaPrinter::kernelSource() {
@@ -2257,6 +2415,7 @@ std::string CudaPrinter::kernelSource() {
     w.nl();
     w << "        d.launch = abl_launch_" << f.emitName << ";"; w.nl();
     w << "        d.nlist = " << (listSteps.count(&f) ? 1 : 0) << ";"; w.nl();
+    w << "        d.shadow = " << (denseSteps.count(&f) ? 1 : 0) << ";"; w.nl();
     w << "        if ((rc = abl_cuda_register_step(rt, &d, &abl_model_step_ids[" << i << "]))) return rc;"; w.nl();
     w << "    }"; w.nl();
   }

@@ -407,6 +407,8 @@ def test_cell_range_culling_keeps_every_candidate_on_the_radius(outside, use_flo
 
     got, loads = run(None)
     plain, loads_plain = run({"cuda.cull": False})
+    rowcull, loads_rowcull = run({"cuda.cull": False, "cuda.rowcull": True})     # rows narrowed along x to the cells within reach (dense rows)
+    assert np.array_equal(rowcull, plain) and loads_rowcull < loads_plain
     # the reference's filter (CPrinter.cpp:166-169, libabl.h:156-168): skip if (double)sqrtf((float)d2) > R
     dx = walker_pos[None, :, 0] - site_pos[:, None, 0]
     dy = walker_pos[None, :, 1] - site_pos[:, None, 1]
