@@ -29,6 +29,7 @@
 #include <atomic>
 #include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "abl_cuda.h"
@@ -1391,6 +1392,156 @@ extern "C" int abl_cuda_upload_with_ids(abl_runtime *rt, int pool, const void *h
   return upload_impl(rt, pool, host_aos, ids, n, next_id);
 }
 
+// ---------------------------------------------------------------------------------------
+// scalable upload under slab decomposition: every slab uploads 1/N of the population BY INDEX,
+// the records are routed to their owners on the devices (one all-to-all), never through a
+// host that holds N copies.  Transit record: the host AoS record followed by the agent id,
+// padded to a multiple of 8 bytes (the stride being a multiple of 4).
+// ---------------------------------------------------------------------------------------
+static int slab_layers(const abl_runtime *rt);
+struct SlabBounds { int n; int b[ABL_MAX_SLABS + 1]; };
+// bytes of a transit record: host record + id, padded so that 8-byte members stay aligned
+static __host__ __device__ inline u32 transit_bytes(u32 stride) { return (stride + 4u + 7u) & ~7u; }
+
+template <typename R>
+__global__ void k_route_classify(const u8 *aos, u32 stride, u32 pos_offset, u32 n, R origin, R inv_cell, int n_layers,
+                                 SlabBounds sb, u32 *owner, u32 *slot, u32 *counts) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const R p = *reinterpret_cast<const R *>(aos + (size_t)i * stride + pos_offset);
+  const int layer = cell_coord<R>(p, origin, inv_cell, n_layers);
+  int o = 0;
+  for (int s = 1; s < sb.n; s++) o += layer >= sb.b[s] ? 1 : 0;
+  owner[i] = (u32)o;
+  slot[i] = atomicAdd(&counts[o], 1u);
+}
+
+__global__ void k_route_pack(const u8 *aos, u32 stride, u32 n, u32 first_id, const u32 *owner, const u32 *slot,
+                             const u32 *offsets, u8 *out) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u32 words = stride / 4u;
+  const u32 *src = reinterpret_cast<const u32 *>(aos + (size_t)i * stride);
+  u32 *dst = reinterpret_cast<u32 *>(out + (size_t)(offsets[owner[i]] + slot[i]) * transit_bytes(stride));
+  for (u32 w = 0; w < words; w++) dst[w] = src[w];
+  dst[words] = first_id + i;
+}
+
+__global__ void k_transit_to_soa(ColTable t, const u8 *transit, u32 stride, u32 n) {
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const u8 *rec = transit + (size_t)i * transit_bytes(stride);
+  for (int c = 0; c < t.ncols; c++) {
+    u8 *dst = (u8 *)t.out[c] + (size_t)i * t.elem[c];
+    if (t.host_off[c] < 0) { *(u32 *)dst = *reinterpret_cast<const u32 *>(rec + stride); continue; }   // the id column
+    for (int k = 0; k < t.ncomp[c]; k++)
+      copy_scalar(dst + k * t.comp[c], rec + t.host_off[c] + k * t.comp[c], t.comp[c]);
+  }
+}
+
+extern "C" int abl_cuda_transit_record_bytes(abl_runtime *rt, int pool, size_t *bytes) {
+  Pool *p;
+  TRY(get_pool(rt, pool, &p));
+  if (p->stride % 4u) return fail(ABL_ERR_STATE, "pool %s: record size %u is not a multiple of 4", p->name.c_str(), p->stride);
+  if (bytes) *bytes = (size_t)transit_bytes(p->stride);
+  return ABL_OK;
+}
+
+// host records [first_id, first_id + n) of the population -> `dev_out` (device memory of this
+// runtime's GPU, room for n transit records): grouped by owning slab, counts[s] records for slab s.
+extern "C" int abl_cuda_partition_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n, unsigned first_id,
+                                         void *dev_out, unsigned *counts) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (!rt->slab) return fail(ABL_ERR_STATE, "partition_upload requires abl_cuda_set_slab");
+  if (p.pos_member < 0) return fail(ABL_ERR_ARGUMENT, "pool %s has no position member", p.name.c_str());
+  if (p.stride % 4u) return fail(ABL_ERR_STATE, "pool %s: record size %u is not a multiple of 4", p.name.c_str(), p.stride);
+  if (n > 0x7fffffffu) return fail(ABL_ERR_ARGUMENT, "chunk too large");
+  if (!counts || (n && (!host_aos || !dev_out))) return fail(ABL_ERR_ARGUMENT, "null argument");
+  CU(cudaSetDevice(rt->device));
+  const int N = rt->n_slabs;
+  for (int s = 0; s < N; s++) counts[s] = 0;
+  if (!n) return ABL_OK;
+  const size_t bytes = n * (size_t)p.stride;
+  const size_t aux = round_up(bytes, 256);
+  TRY(ensure_stage(rt, aux + 2 * round_up(n * sizeof(u32), 256) + 2 * 256 * sizeof(u32)));
+  u8 *aos = (u8 *)rt->stage;
+  u32 *owner = (u32 *)(aos + aux);
+  u32 *slot = (u32 *)((u8 *)owner + round_up(n * sizeof(u32), 256));
+  u32 *cnt = (u32 *)((u8 *)slot + round_up(n * sizeof(u32), 256));
+  u32 *off = cnt + 256;
+  CU(cudaMemcpyAsync(aos, host_aos, bytes, cudaMemcpyHostToDevice, rt->stream));
+  CU(cudaMemsetAsync(cnt, 0, 256 * sizeof(u32), rt->stream));
+  SlabBounds sb;
+  sb.n = N;
+  for (int s = 0; s <= N; s++) sb.b[s] = rt->slab_bounds[s];
+  const GridParams &g = rt->grid;
+  const int axis = g.dim - 1;
+  const Member &pm = p.members[p.pos_member];
+  ColTable t;
+  fill_table(p, t, false);
+  // host offset of the slab-axis coordinate: a packed 2-vector column in 2D, the third of three scalar columns in 3D
+  const u32 pos_off = g.dim == 2 ? (u32)t.host_off[pm.first_col] + (u32)axis * (u32)rt->real_size
+                                 : (u32)t.host_off[pm.first_col + axis];
+  const u32 nb = blocks_for(n, 256);
+  if (rt->real_size == 8)
+    k_route_classify<double><<<nb, 256, 0, rt->stream>>>(aos, p.stride, pos_off, (u32)n, g.origin[axis], g.inv_cell,
+                                                        slab_layers(rt), sb, owner, slot, cnt);
+  else
+    k_route_classify<float><<<nb, 256, 0, rt->stream>>>(aos, p.stride, pos_off, (u32)n, (float)g.origin[axis],
+                                                       (float)g.inv_cell, slab_layers(rt), sb, owner, slot, cnt);
+  u32 h_cnt[ABL_MAX_SLABS];
+  CU(cudaMemcpyAsync(h_cnt, cnt, N * sizeof(u32), cudaMemcpyDeviceToHost, rt->stream));
+  CU(cudaStreamSynchronize(rt->stream));
+  u32 h_off[ABL_MAX_SLABS];
+  u32 run = 0;
+  for (int s = 0; s < N; s++) { h_off[s] = run; run += h_cnt[s]; counts[s] = h_cnt[s]; }
+  CU(cudaMemcpyAsync(off, h_off, N * sizeof(u32), cudaMemcpyHostToDevice, rt->stream));
+  k_route_pack<<<nb, 256, 0, rt->stream>>>(aos, p.stride, (u32)n, first_id, owner, slot, off, (u8 *)dev_out);
+  rt->launches += 2;
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(rt->stream));   // the caller hands dev_out to another stream / device next
+  return ABL_OK;
+}
+
+// n transit records in device memory (all of them owned by this slab) become the pool's population;
+// next_id: first id a run-time add() may hand out (the size of the whole population).
+extern "C" int abl_cuda_adopt_records(abl_runtime *rt, int pool, const void *dev_records, size_t n, unsigned next_id) {
+  Pool *pp;
+  TRY(get_pool(rt, pool, &pp));
+  Pool &p = *pp;
+  if (p.stride % 4u) return fail(ABL_ERR_STATE, "pool %s: record size %u is not a multiple of 4", p.name.c_str(), p.stride);
+  if (n > 0x7fffffffu) return fail(ABL_ERR_ARGUMENT, "pool too large");
+  if (n && !dev_records) return fail(ABL_ERR_ARGUMENT, "null records");
+  CU(cudaSetDevice(rt->device));
+  p.n = 0;
+  TRY(reserve_pool(rt, p, std::max(n, (size_t)1) + (halo_direct(p) ? 2 * p.halo_cap + 1024 : 0)));
+  if (n) {
+    ColTable t;
+    fill_table(p, t, false);
+    k_transit_to_soa<<<blocks_for(n, 256), 256, 0, rt->stream>>>(t, (const u8 *)dev_records, p.stride, (u32)n);
+    rt->launches++;
+    CU(cudaGetLastError());
+  }
+  p.n = n;
+  p.order_serial++;
+  p.next_id = next_id;
+  p.binned = false;
+  p.own_valid = false;
+  p.report_pending = false;
+  p.exch_deferred = false;
+  p.halo_pending = false;
+  p.halo_sync_check = false;
+  p.src_begin = 0;
+  p.own_begin = 0;
+  p.own_end = (u32)n;
+  TRY(drop_fused_histogram(rt, p));
+  p.ever_removed = false;
+  CU(cudaStreamSynchronize(rt->stream));   // the caller may release dev_records
+  return ABL_OK;
+}
+
 extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity,
                                  size_t *n_out) {
   Pool *p;
@@ -2100,10 +2251,16 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     a.flat_loop = rt->flat_loop;
     a.bulk_tile = rt->bulk_tile;
     // dense for-near loops pre-filter on a single-precision shadow of the neighbours' positions
-    if (s.desc.shadow && rt->dense_tile && nbr && rt->real_size == 8 && nbr->pos_member >= 0) {
-      TRY(refresh_shadow(rt, *nbr));
-      a.nbr_shadow = nbr->shadow;
-      a.nbr_shadow_max = nbr->shadow_max;
+    // (only when the launcher's rule picks that variant for this launch: it is asked first)
+    if (s.desc.shadow && rt->dense_tile && nbr && rt->real_size == 8 && nbr->pos_member >= 0 && a.self.n) {
+      a.probe = 1;
+      const int wants = s.desc.launch(&a);
+      a.probe = 0;
+      if (wants == 1) {
+        TRY(refresh_shadow(rt, *nbr));
+        a.nbr_shadow = nbr->shadow;
+        a.nbr_shadow_max = nbr->shadow_max;
+      }
     }
     a.pdl = rt->pdl ? 1 : 0;
     a.stream = (void *)rt->stream;
@@ -3434,4 +3591,178 @@ extern "C" int abl_cuda_exchange_end(abl_runtime *rt, int pool) {
   TRY(exchange_unpack(rt, p, incoming));
   CU(cudaStreamSynchronize(rt->stream));
   return ABL_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// one process, several GPUs: the driver behind `-C cuda.gpus=N` (see abl_cuda.h)
+// ---------------------------------------------------------------------------------------
+namespace {
+struct GroupSlab {
+  abl_runtime *rt = nullptr;
+  int device = 0;
+  int rc = ABL_OK;
+  std::string err;
+  std::vector<u8 *> send;                  // per type: transit records grouped by owner (device memory)
+  std::vector<std::vector<u32>> counts;    // per type: records for every slab
+};
+
+template <typename F> int for_each_slab(std::vector<GroupSlab> &slabs, F f) {
+  std::vector<std::thread> th;
+  for (size_t r = 0; r < slabs.size(); r++)
+    th.emplace_back([&, r] {
+      GroupSlab &g = slabs[r];
+      if (g.rc != ABL_OK) return;
+      cudaSetDevice(g.device);
+      g.rc = f((int)r, g);
+      if (g.rc != ABL_OK) g.err = abl_cuda_last_error();
+    });
+  for (auto &t : th) t.join();
+  for (GroupSlab &g : slabs)
+    if (g.rc != ABL_OK) return fail(g.rc, "device %d: %s", g.device, g.err.c_str());
+  return ABL_OK;
+}
+}  // namespace
+
+extern "C" int abl_cuda_group_simulate(const abl_config *cfg_in, int n_gpus, int (*setup)(abl_runtime *),
+                                       int (*timestep)(abl_runtime *), int timesteps, const abl_group_population *pop) {
+  if (!cfg_in || !setup || !timestep || !pop || n_gpus < 1 || n_gpus > ABL_MAX_SLABS)
+    return fail(ABL_ERR_ARGUMENT, "bad arguments to group_simulate");
+  int visible = 0;
+  CU(cudaGetDeviceCount(&visible));
+  // (ABL_CUDA_OVERSUBSCRIBE=1: more slabs than devices, several slabs share a GPU — how the single-GPU test tier runs this driver)
+  const bool share = getenv("ABL_CUDA_OVERSUBSCRIBE") && atoi(getenv("ABL_CUDA_OVERSUBSCRIBE")) != 0;
+  if (visible < 1 || (n_gpus > visible && !share)) return fail(ABL_ERR_ARGUMENT, "%d GPUs requested, %d visible", n_gpus, visible);
+  const int N = n_gpus, T = pop->n_types;
+  std::vector<GroupSlab> slabs(N);
+  auto cleanup = [&] { for (GroupSlab &g : slabs) { for (u8 *p : g.send) if (p) { cudaSetDevice(g.device); cudaFree(p); } if (g.rt) abl_cuda_destroy(g.rt); g.rt = nullptr; } };
+  // 1. one runtime per device, same pools and steps everywhere
+  for (int r = 0; r < N; r++) {
+    slabs[r].device = ((cfg_in->device >= 0 ? cfg_in->device : 0) + r) % visible;
+    slabs[r].send.assign(T, nullptr);
+    slabs[r].counts.assign(T, std::vector<u32>(N, 0));
+  }
+  int rc = for_each_slab(slabs, [&](int, GroupSlab &g) -> int {
+    abl_config cfg = *cfg_in;
+    cfg.device = g.device;
+    TRY(abl_cuda_create(&g.rt, &cfg));
+    if (setup(g.rt) != 0) return fail(ABL_ERR_STATE, "model setup failed: %s", abl_cuda_last_error());
+    for (const Step &s : g.rt->steps)
+      if (s.desc.added_pool >= 0)
+        return fail(ABL_ERR_STATE, "step %s adds agents at run time: not supported with cuda.gpus > 1 (the ids of new agents are "
+                                   "resolved across the slabs by the host; use the torchrun harness openabl_b200.slab.RankSlab)", s.name.c_str());
+    return ABL_OK;
+  });
+  if (rc != ABL_OK) { cleanup(); return rc; }
+  // 2. slabs of whole cell layers, ring of peer-mapped receive areas
+  int layers = 0;
+  rc = abl_cuda_slab_axis_layers(slabs[0].rt, &layers);
+  if (rc == ABL_OK && layers < N) rc = fail(ABL_ERR_ARGUMENT, "more GPUs (%d) than cell layers (%d)", N, layers);
+  if (rc != ABL_OK) { cleanup(); return rc; }
+  std::vector<int> bounds(N + 1);
+  for (int r = 0; r <= N; r++) bounds[r] = (int)(((long long)layers * r) / N);
+  rc = for_each_slab(slabs, [&](int r, GroupSlab &g) -> int { return abl_cuda_set_slab(g.rt, bounds.data(), N, r); });
+  if (rc == ABL_OK && N > 1) {
+    rc = for_each_slab(slabs, [&](int, GroupSlab &g) -> int {
+      for (int t = 0; t < T; t++) {
+        if (!pop->has_position[t]) continue;
+        const size_t cap = std::max<size_t>(16384, 4 * pop->len[t] / (size_t)std::max(layers, 1) + 4096);
+        TRY(abl_cuda_halo_setup(g.rt, pop->pool[t], cap, nullptr));
+      }
+      return ABL_OK;
+    });
+    if (rc == ABL_OK)
+      rc = for_each_slab(slabs, [&](int r, GroupSlab &g) -> int {
+        const bool ring = N > 2;
+        abl_runtime *lo = r > 0 ? slabs[r - 1].rt : (ring ? slabs[N - 1].rt : nullptr);
+        abl_runtime *hi = r + 1 < N ? slabs[r + 1].rt : (ring ? slabs[0].rt : nullptr);
+        for (int t = 0; t < T; t++)
+          if (pop->has_position[t]) TRY(abl_cuda_halo_connect_local(g.rt, pop->pool[t], lo, hi));
+        return ABL_OK;
+      });
+  }
+  if (rc != ABL_OK) { cleanup(); return rc; }
+  // 3. upload: slab r takes the r-th part of every array by index, classifies it on its device ...
+  rc = for_each_slab(slabs, [&](int r, GroupSlab &g) -> int {
+    for (int t = 0; t < T; t++) {
+      const size_t n = pop->len[t];
+      if (!pop->has_position[t]) { TRY(abl_cuda_upload(g.rt, pop->pool[t], pop->data[t], n)); continue; }
+      const size_t b = n * (size_t)r / N, e = n * (size_t)(r + 1) / N;
+      if (e > b) CU(cudaMalloc(&g.send[t], (e - b) * (size_t)transit_bytes((u32)pop->stride[t])));
+      TRY(abl_cuda_partition_upload(g.rt, pop->pool[t], (const u8 *)pop->data[t] + b * pop->stride[t], e - b, (unsigned)b,
+                                    g.send[t], g.counts[t].data()));
+    }
+    return ABL_OK;
+  });
+  // ... and every slab fetches the records it owns from all of them (peer copies), then adopts them
+  if (rc == ABL_OK)
+    rc = for_each_slab(slabs, [&](int d, GroupSlab &g) -> int {
+      for (int t = 0; t < T; t++) {
+        if (!pop->has_position[t]) continue;
+        const size_t rec = transit_bytes((u32)pop->stride[t]);
+        size_t total = 0;
+        for (int r = 0; r < N; r++) total += slabs[r].counts[t][d];
+        u8 *recv = nullptr;
+        if (total) CU(cudaMalloc(&recv, total * rec));
+        size_t at = 0;
+        for (int r = 0; r < N; r++) {
+          const size_t cnt = slabs[r].counts[t][d];
+          if (!cnt) continue;
+          size_t before = 0;
+          for (int q = 0; q < d; q++) before += slabs[r].counts[t][q];
+          CU(cudaMemcpyPeer(recv + at * rec, g.device, slabs[r].send[t] + before * rec, slabs[r].device, cnt * rec));
+          at += cnt;
+        }
+        int arc = abl_cuda_adopt_records(g.rt, pop->pool[t], recv, total, (unsigned)pop->len[t]);
+        if (recv) cudaFree(recv);
+        TRY(arc);
+      }
+      return ABL_OK;
+    });
+  if (rc == ABL_OK)
+    rc = for_each_slab(slabs, [&](int, GroupSlab &g) -> int {
+      for (u8 *&p : g.send) if (p) { cudaFree(p); p = nullptr; }
+      if (N > 1)
+        for (int t = 0; t < T; t++)
+          if (pop->has_position[t]) TRY(abl_cuda_exchange(g.rt, pop->pool[t]));   // ghosts of the initial state
+      return ABL_OK;
+    });
+  // 4. the simulation: every device runs its slab, coupled only through the halo messages
+  if (rc == ABL_OK)
+    rc = for_each_slab(slabs, [&](int, GroupSlab &g) -> int {
+      for (int s = 0; s < timesteps; s++)
+        if (timestep(g.rt) != 0) return fail(ABL_ERR_STATE, "timestep %d failed: %s", s, abl_cuda_last_error());
+      return abl_cuda_synchronize(g.rt);
+    });
+  // 5. download: owned records of every slab, placed by agent id
+  if (rc == ABL_OK) {
+    for (int t = 0; t < T && rc == ABL_OK; t++) {
+      const size_t stride = pop->stride[t], n = pop->len[t];
+      if (!pop->has_position[t]) { size_t got = 0; rc = abl_cuda_download(slabs[0].rt, pop->pool[t], pop->data[t], n, &got); continue; }
+      std::vector<std::vector<u8>> rec(N);
+      std::vector<std::vector<unsigned>> ids(N);
+      rc = for_each_slab(slabs, [&](int r, GroupSlab &g) -> int {
+        size_t own = 0;
+        TRY(abl_cuda_owned_size(g.rt, pop->pool[t], &own));
+        rec[r].resize(own * stride);
+        ids[r].resize(own);
+        size_t got = 0;
+        TRY(abl_cuda_download(g.rt, pop->pool[t], rec[r].data(), own, &got));
+        TRY(abl_cuda_download_ids(g.rt, pop->pool[t], ids[r].data(), own, &got));
+        return ABL_OK;
+      });
+      if (rc != ABL_OK) break;
+      size_t total = 0;
+      for (int r = 0; r < N; r++) total += ids[r].size();
+      if (total != n) { rc = fail(ABL_ERR_STATE, "%zu agents came back, %zu were uploaded", total, n); break; }
+      for (int r = 0; r < N && rc == ABL_OK; r++)
+        for (size_t k = 0; k < ids[r].size(); k++) {
+          if (ids[r][k] >= n) { rc = fail(ABL_ERR_STATE, "agent id %u out of range", ids[r][k]); break; }
+          memcpy((u8 *)pop->data[t] + (size_t)ids[r][k] * stride, rec[r].data() + k * stride, stride);
+        }
+    }
+  }
+  std::string keep = g_err;
+  cleanup();
+  if (rc != ABL_OK) snprintf(g_err, sizeof g_err, "%s", keep.c_str());
+  return rc;
 }

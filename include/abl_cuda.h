@@ -227,6 +227,7 @@ typedef struct {
    * candidates on it and re-test the survivors exactly (ABL_MODE 8). */
   const void *nbr_shadow;
   const unsigned *nbr_shadow_max;
+  int probe;   /* != 0: launch nothing; return 1 if this launch would use the shadow (ABL_MODE 8), else 0 */
   /* > 0 (set by the generated launcher for dense for-near loops of reach 1): the squared radius bound; the neighbour
    * iterator then narrows every row of cells along x to the cells within reach of the agent (abl_device.cuh: row_reach) */
   double row_cull;
@@ -337,6 +338,37 @@ int abl_cuda_halo_connect_local(abl_runtime *rt, int pool, abl_runtime *lower, a
  * runs a step on every slab, then exchange_begin on every slab, then exchange_end on every
  * slab; abl_cuda_step does not exchange by itself in this mode. */
 int abl_cuda_set_local_peers(abl_runtime *rt, abl_runtime *lower, abl_runtime *upper);
+/* ---- scalable upload + one-process multi-GPU driver -------------------------------------------------
+ * Under slab decomposition no participant has to touch the whole population: slab r uploads the r-th part
+ * of the host records BY INDEX (abl_cuda_partition_upload: H2D, owner of every record from its position,
+ * records grouped by owner in device memory), the parts are exchanged between the devices (NCCL all-to-all
+ * under torchrun, peer copies inside one process) and adopted (abl_cuda_adopt_records).  Transit record =
+ * host record + u32 id (abl_cuda_transit_record_bytes). */
+int abl_cuda_transit_record_bytes(abl_runtime *rt, int pool, size_t *bytes);
+int abl_cuda_partition_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n, unsigned first_id,
+                              void *dev_out, unsigned *counts /* [n_slabs] */);
+int abl_cuda_adopt_records(abl_runtime *rt, int pool, const void *dev_records, size_t n, unsigned next_id);
+
+/* `simulate(timesteps)` of a generated program on n_gpus devices of this machine (`-C cuda.gpus=N`,
+ * ABL_CUDA_GPUS=N): one runtime and one host thread per device, slabs of whole cell layers along the
+ * slowest axis, halo cells and migrating agents written into the neighbour's memory by the step kernels
+ * (peer access over NVLink), scalable upload as above, download merged by agent id into the host arrays.
+ * The reference's precedent for putting the decomposition into the generated program:
+ * src/backend/DMasonPrinter.cpp:30-32 (dmason.grid_rows/cols), src/backend/FlameMainPrinter.cpp:40-41.
+ * setup(rt): registers pools and steps (abl_model_setup); timestep(rt): one timestep of the parallel step
+ * functions, callable from several threads at once, one runtime each.  Models whose timestep needs the
+ * host between step functions (run-time add(), a sequential step) are refused. */
+typedef struct {
+  int n_types;
+  const int *pool;          /* [n_types] pool index of every agent type (the same in every runtime) */
+  void *const *data;        /* [n_types] host record arrays */
+  const size_t *len;        /* [n_types] records in them */
+  const size_t *stride;     /* [n_types] */
+  const int *has_position;  /* [n_types] agent types without a position are replicated on every device */
+} abl_group_population;
+int abl_cuda_group_simulate(const abl_config *cfg, int n_gpus, int (*setup)(abl_runtime *rt),
+                            int (*timestep)(abl_runtime *rt), int timesteps, const abl_group_population *pop);
+
 int abl_cuda_exchange_begin(abl_runtime *rt, int pool);
 int abl_cuda_exchange_end(abl_runtime *rt, int pool);
 

@@ -78,6 +78,15 @@ class Model:
         buf = (C.c_char * (n * self.dtypes[t].itemsize)).from_address(arr.data)
         return np.frombuffer(buf, dtype=self.dtypes[t]).copy()
 
+    def host_view(self, t):
+        """The host records of agent type index `t` WITHOUT a copy (valid until the array is resized)."""
+        arr = self._types[t].agents.contents
+        n = arr.len
+        if n == 0:
+            return np.zeros(0, dtype=self.dtypes[t])
+        buf = (C.c_char * (n * self.dtypes[t].itemsize)).from_address(arr.data)
+        return np.frombuffer(buf, dtype=self.dtypes[t])
+
     def host_count(self, t):
         """Number of host records of agent type index `t` (no copy)."""
         return self._types[t].agents.contents.len

@@ -48,6 +48,10 @@ ABI = {
     "abl_cuda_upload_with_ids": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_size_t, C.c_uint]),
     "abl_cuda_download": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "abl_cuda_pool_size": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_transit_record_bytes": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
+    "abl_cuda_partition_upload": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.c_uint, _VP, C.POINTER(C.c_uint)]),
+    "abl_cuda_adopt_records": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.c_uint]),
+    "abl_cuda_group_simulate": (C.c_int, [_VP, C.c_int, _VP, _VP, C.c_int, _VP]),
     "abl_cuda_download_ids": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, C.POINTER(C.c_size_t)]),
     "abl_cuda_pin_host": (C.c_int, [_VP, _VP, C.c_size_t]),
     "abl_cuda_unpin_host": (C.c_int, [_VP, _VP]),
@@ -173,6 +177,23 @@ class Runtime:
         got = C.c_size_t()
         check(self.lib.abl_cuda_download_ids(self.handle, pool, out.ctypes.data_as(_VP), n, C.byref(got)), "download_ids")
         return out
+
+    # ---- scalable upload under slab decomposition (abl_cuda.h) ----------------------------
+    def transit_record_bytes(self, pool):
+        n = C.c_size_t()
+        check(self.lib.abl_cuda_transit_record_bytes(self.handle, pool, C.byref(n)), "transit_record_bytes")
+        return n.value
+
+    def partition_upload(self, pool, array, first_id, dev_out, n_slabs):
+        """Host records `array` (ids first_id ...) -> device buffer `dev_out` (a device pointer with room for
+        len(array) transit records), grouped by owning slab.  -> records per slab."""
+        counts = (C.c_uint * n_slabs)()
+        check(self.lib.abl_cuda_partition_upload(self.handle, pool, array.ctypes.data_as(_VP), len(array), int(first_id),
+                                                 C.c_void_p(dev_out), counts), "partition_upload")
+        return [int(c) for c in counts]
+
+    def adopt_records(self, pool, dev_records, n, next_id):
+        check(self.lib.abl_cuda_adopt_records(self.handle, pool, C.c_void_p(dev_records), int(n), int(next_id)), "adopt_records")
 
     # ---- slab decomposition ------------------------------------------------------------
     def slab_layers(self):

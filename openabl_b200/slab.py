@@ -69,6 +69,31 @@ def all_gather_ids(dist, world, mine):
     return [e[:c].cpu().numpy().astype(np.uint32) for e, c in zip(every, counts)]
 
 
+def owner_of(layer, bounds):
+    """Slab that owns cell layer `layer` (array) for contiguous bounds [(begin, end)] — the rule of
+    k_route_classify (asset/cuda/abl_runtime.cu)."""
+    starts = np.array([b for b, _ in bounds])
+    return np.searchsorted(starts, layer, side="right") - 1
+
+
+def exchange_partitions(dist, rank, world, send, counts, rec):
+    """All-to-all of transit records.  send: uint8 tensor, the records this rank uploaded grouped by owning
+    slab (counts[d] records of `rec` bytes for rank d).  -> (uint8 tensor with the records this rank owns, in
+    source-rank order; their number)."""
+    import torch
+    dev = send.device
+    mine = torch.tensor(counts, dtype=torch.int64, device=dev)
+    every = [torch.zeros(world, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(every, mine)
+    incoming = [int(e[rank].item()) for e in every]       # records rank r holds for me
+    total = sum(incoming)
+    recv = torch.empty(max(1, total * rec), dtype=torch.uint8, device=dev)
+    dist.all_to_all_single(recv[:total * rec], send[:sum(counts) * rec],
+                           output_split_sizes=[c * rec for c in incoming],
+                           input_split_sizes=[c * rec for c in counts])
+    return recv, total
+
+
 ADDS = 2      # abl_model_step_flags bits
 REMOVES = 1
 
@@ -116,14 +141,37 @@ class LocalSlabs:
                                       self.rts[hi] if hi is not None else None)
         self._connected = True
 
-    def upload(self, host_arrays):
-        """Every slab receives the whole population and keeps its own part."""
+    def upload(self, host_arrays, scalable=False):
+        """Every slab receives the whole population and keeps its own part; scalable=True: slab r uploads
+        the r-th part by index and the records are routed between the slabs on the device (the path of
+        RankSlab.upload and of abl_cuda_group_simulate, with torch copies standing in for the all-to-all)."""
         m = self.model
         if self.transport == "direct" and not self._connected:
             self._connect_direct([len(a) for a in host_arrays])
-        for rt in self.rts:
+        if not scalable:
+            for rt in self.rts:
+                for t, arr in enumerate(host_arrays):
+                    rt.upload(m.pool(t), np.ascontiguousarray(arr))
+        else:
+            import torch
+            S = len(self.rts)
             for t, arr in enumerate(host_arrays):
-                rt.upload(m.pool(t), np.ascontiguousarray(arr))
+                pool, n = m.pool(t), len(arr)
+                rec = self.rts[0].transit_record_bytes(pool)
+                sends, counts = [], []
+                for r, rt in enumerate(self.rts):
+                    lo, hi = n * r // S, n * (r + 1) // S
+                    send = torch.empty(max(1, (hi - lo) * rec), dtype=torch.uint8, device="cuda")
+                    counts.append(rt.partition_upload(pool, np.ascontiguousarray(arr[lo:hi]), lo, send.data_ptr(), S))
+                    sends.append(send)
+                for d, rt in enumerate(self.rts):
+                    parts = []
+                    for r in range(S):
+                        before = sum(counts[r][:d]) * rec
+                        parts.append(sends[r][before:before + counts[r][d] * rec])
+                    recv = torch.cat(parts) if parts else torch.empty(0, dtype=torch.uint8, device="cuda")
+                    torch.cuda.synchronize()
+                    rt.adopt_records(pool, recv.data_ptr() if recv.numel() else 0, recv.numel() // rec, n)
         for t in range(m.n_types):
             self._exchange(m.pool(t))
 
@@ -207,23 +255,51 @@ class RankSlab:
         if world > 1 and dist is not None:
             self._install_reduce_hook()
 
-    def upload(self, host_arrays=None):
-        """Every rank uploads the whole population from the model's own page-locked host arrays
-        (as the generated program does), keeps its slab and fetches ghosts with one exchange."""
+    def upload(self, host_arrays=None, scalable=True):
+        """scalable (default): rank r uploads the r-th part of every agent array BY INDEX, the runtime
+        groups the records by owning slab on the device (abl_cuda_partition_upload), one all-to-all over
+        torch.distributed routes them, and every rank adopts what it owns — H2D traffic and host work per
+        rank are 1/N of the population.  scalable=False: the round-1 path (every rank uploads everything
+        and crops).  Either way one exchange fetches the ghosts."""
+        import torch
         m = self.model
+        arrays = [m.host_view(t) for t in range(m.n_types)] if host_arrays is None else list(host_arrays)
         if self.transport == "direct" and not self._connected:
-            totals = [len(m.host_agents(t)) for t in range(m.n_types)] if host_arrays is None \
-                else [len(a) for a in host_arrays]
-            self._connect_direct(totals)
-        if host_arrays is None:
-            m.upload_host()
-            self.last_upload_bytes = sum(m.host_count(t) * m.dtypes[t].itemsize for t in range(m.n_types))
+            self._connect_direct([len(a) for a in arrays])
+        import os
+        if os.environ.get("ABL_UPLOAD_SCALABLE", "1") in ("0", ""):
+            scalable = False
+        if not scalable or self.world == 1 or self.dist is None:
+            if host_arrays is None:
+                m.upload_host()
+            else:
+                for t, arr in enumerate(arrays):
+                    self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
+            self.last_upload_bytes = sum(a.nbytes for a in arrays)
         else:
-            for t, arr in enumerate(host_arrays):
-                self.rt.upload(m.pool(t), np.ascontiguousarray(arr))
-            self.last_upload_bytes = sum(a.nbytes for a in host_arrays)
+            self.last_upload_bytes = 0
+            dev = torch.device("cuda", torch.cuda.current_device())
+            for t, arr in enumerate(arrays):
+                pool = m.pool(t)
+                if not self._has_position(t):
+                    self.rt.upload(pool, np.ascontiguousarray(arr))
+                    self.last_upload_bytes += arr.nbytes
+                    continue
+                n = len(arr)
+                lo, hi = n * self.rank // self.world, n * (self.rank + 1) // self.world
+                rec = self.rt.transit_record_bytes(pool)
+                part = np.ascontiguousarray(arr[lo:hi])
+                send = torch.empty(max(1, (hi - lo) * rec), dtype=torch.uint8, device=dev)
+                counts = self.rt.partition_upload(pool, part, lo, send.data_ptr(), self.world)
+                self.last_upload_bytes += part.nbytes
+                recv, total = exchange_partitions(self.dist, self.rank, self.world, send, counts, rec)
+                torch.cuda.synchronize()
+                self.rt.adopt_records(pool, recv.data_ptr(), total, n)
         for t in range(m.n_types):
             self.rt.exchange(m.pool(t))
+
+    def _has_position(self, t):
+        return any(is_pos for _, _, is_pos in self.model.agents[t][1])
 
     def _connect_direct(self, total_agents):
         """Every rank allocates its receive areas and learns its ring neighbours' IPC handles."""

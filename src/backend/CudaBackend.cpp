@@ -1816,6 +1816,23 @@ void CudaPrinter::hostSimulate() {
   w << "    for (int t = 0; t < abl_model_n_types; t++) abl_cuda_unpin_host(rt, abl_model_types[t].agents->data);"; w.nl();
   w << "}"; w.nl(); w.nl();
 
+  // `-C cuda.gpus=N` / ABL_CUDA_GPUS=N: the same simulate statement on N devices of this machine.  The decomposition is part
+  // of the generated program, as in the reference's distributed backends (DMasonPrinter.cpp:30-32 dmason.grid_rows/cols,
+  // FlameMainPrinter.cpp:40-41 `mpirun -np 4`); the runtime does the work (abl_cuda_group_simulate).
+  const int gpus = config.getInt("cuda.gpus", 1);
+  if (gpus < 1) throw BackendError("cuda backend: cuda.gpus must be at least 1");
+  bool addsAtRunTime = false;
+  for (const StepInfo &si : steps) addsAtRunTime = addsAtRunTime || si.fn->addedAgent != nullptr;
+  if (gpus > 1 && (seq || addsAtRunTime))
+    throw BackendError("cuda backend: cuda.gpus > 1 is not supported for models with a sequential step or run-time add(): "
+                       "their timestep needs the host between step functions");
+  w << "/* one timestep of the parallel step functions; callable from several host threads, one runtime each */"; w.nl();
+  w << "static int abl_model_timestep_mt(abl_runtime *rt) {"; w.nl();
+  w << "    int rc;"; w.nl();
+  w << "    if ((rc = abl_cuda_begin_timestep(rt))) return rc;"; w.nl();
+  w << "    if ((rc = abl_model_parallel_steps(rt))) return rc;"; w.nl();
+  w << "    return abl_cuda_end_timestep(rt);"; w.nl();
+  w << "}"; w.nl(); w.nl();
   w << "/* the `simulate` statement: upload, run, download (replaces the reference's inline"; w.nl();
   w << "   double-buffered OpenMP loop) */"; w.nl();
   w << "static void abl_model_simulate(int timesteps) {"; w.nl();
@@ -1825,6 +1842,27 @@ void CudaPrinter::hostSimulate() {
   w << "    cfg.block_size = " << config.getInt("cuda.block_size", 0) << ";"; w.nl();
   w << "    cfg.tile_neighbours = " << (config.getBool("cuda.tile", false) ? 1 : 0) << ";"; w.nl();
   w << "    if (getenv(\"ABL_CUDA_DEVICE\")) cfg.device = atoi(getenv(\"ABL_CUDA_DEVICE\"));"; w.nl();
+  w << "    int gpus = " << gpus << ";   /* -C cuda.gpus */"; w.nl();
+  w << "    if (getenv(\"ABL_CUDA_GPUS\")) gpus = atoi(getenv(\"ABL_CUDA_GPUS\"));"; w.nl();
+  w << "    if (gpus > 1) {"; w.nl();
+  if (seq || addsAtRunTime) {
+    w << "        fprintf(stderr, \"ABL_CUDA_GPUS > 1 is not supported for this model (sequential step or run-time add())\\n\");"; w.nl();
+    w << "        exit(1);"; w.nl();
+  } else {
+    w << "        int pools[" << script.agents.size() << "], has_pos[" << script.agents.size() << "];"; w.nl();
+    w << "        void *data[" << script.agents.size() << "]; size_t len[" << script.agents.size() << "], stride[" << script.agents.size() << "];"; w.nl();
+    w << "        /* pool indices follow the order of registration in abl_model_setup: agent declaration order */"; w.nl();
+    w << "        for (int t = 0; t < abl_model_n_types; t++) {"; w.nl();
+    w << "            abl_host_type *ty = &abl_model_types[t];"; w.nl();
+    w << "            pools[t] = t; data[t] = ty->agents->data; len[t] = ty->agents->len; stride[t] = ty->desc.stride;"; w.nl();
+    w << "            has_pos[t] = 0;"; w.nl();
+    w << "            for (int m = 0; m < ty->desc.n_members; m++) if (ty->desc.members[m].is_pos) has_pos[t] = 1;"; w.nl();
+    w << "        }"; w.nl();
+    w << "        abl_group_population pop = { abl_model_n_types, pools, data, len, stride, has_pos };"; w.nl();
+    w << "        abl_host_check(abl_cuda_group_simulate(&cfg, gpus, abl_model_setup, abl_model_timestep_mt, timesteps, &pop), \"simulate on several GPUs\");"; w.nl();
+    w << "        return;"; w.nl();
+  }
+  w << "    }"; w.nl();
   w << "    abl_runtime *rt = NULL;"; w.nl();
   w << "    abl_host_check(abl_cuda_create(&rt, &cfg), \"create\");"; w.nl();
   w << "    abl_host_check(abl_model_setup(rt), \"setup\");"; w.nl();
@@ -1918,7 +1956,7 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
   (void)p; (void)radius; (void)selfPosM; (void)tcols; (void)tdim; (void)trows; (void)sql;
   w << "template <int ABL_MODE>"; w.nl();
   // (two resident CTAs of 256 threads are all the shadow pre-filter's shared memory allows: let it have the registers)
-  w << "__global__ void __launch_bounds__(256, ABL_MODE == 8 ? 2 : 1) abl_kernel_" << f.emitName
+  w << "__global__ void __launch_bounds__(256, ABL_MODE == 8 ? 2 : 0) abl_kernel_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull, "
     << (sql ? "const abl_sq_limits _sql, " : "") << "const unsigned _tile_cap) {";
   w.indent(); w.nl();
@@ -2070,6 +2108,7 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   w << "static int abl_last_mode_" << f.emitName << " = -1;   // ABL_MODE of the most recent launch (abl_model_step_variant)"; w.nl();
   w << "static int abl_launch_" << f.emitName << "(const abl_step_launch *_args) {"; w.nl();
   w << "    abl_step_launch _copy = *_args;   // block counts of the boundary parts are filled in below"; w.nl();
+  if (!curStepDense) { w << "    if (_args->probe) return 0;   // no variant of this step uses the single-precision shadow"; w.nl(); }
   w << "    abl_step_launch *a = &_copy;"; w.nl();
   w << "    int bs = a->block_size > 0 && a->block_size <= 256 ? a->block_size : 0;"; w.nl();
   if (curStepHasLimit) {
@@ -2149,7 +2188,9 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
     w << "    }"; w.nl();
   }
   if (curStepDense) {
-    // dense rows: the chunked loop with its filter on the single-precision shadow (ABL_MODE 8) when the runtime keeps one
+    // dense rows: the chunked loop with its filter on the single-precision shadow (ABL_MODE 8) when the runtime keeps one.
+    // The runtime first asks (probe != 0, nothing is launched) whether this launch would use the shadow, and only then builds it.
+    w << "    if (a->probe) return (a->flat_loop != 0 && chunked && !listed) ? 1 : 0;"; w.nl();
     w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
     w << "    if (a->nbr_shadow != nullptr && a->flat_loop != 0 && chunked && !listed) {"; w.nl();
     w << "        const int dbs = bs ? bs : 256;"; w.nl();

@@ -94,7 +94,16 @@ static void printHelp() {
                "Available configuration options:\n"
                " * bool use_float       (default: false) single precision agent state\n"
                " * int  cuda.block_size (default: 0)     threads per CTA of step kernels (0 = automatic)\n"
-               " * bool cuda.tile       (default: false) stage neighbour cells in shared memory\n"
+               " * int  cuda.gpus       (default: 1)     GPUs of this machine the generated program runs on (slab\n"
+               "                                          decomposition; ABL_CUDA_GPUS overrides it at run time)\n"
+               " * bool cuda.tile       (default: false) stage neighbour cells in shared memory (ABL_MODE 2)\n"
+               " * bool cuda.bulk       (default: true)  print the TMA-staged tile variant of sparse 2-D loops (ABL_MODE 7)\n"
+               " * bool cuda.dense      (default: true)  print the single-precision pre-filter variant of dense loops (ABL_MODE 8)\n"
+               " * bool cuda.flat       (default: true)  print the flat candidate loop of 2-D loops (ABL_MODE 3)\n"
+               " * bool cuda.cull       (default: true)  skip cells a small radius cannot reach\n"
+               " * bool cuda.rowcull    (default: false) narrow every row of cells to the agent's reach (dense loops)\n"
+               " * bool cuda.sqcmp      (default: true)  compare squared distances instead of taking square roots\n"
+               " * bool cuda.nlist      (default: false) cache neighbour lists of step functions whose agents never move\n"
                " * bool cuda.unroll     (default: false) unroll the for-near candidate loop by two\n"
                " * str  cuda.save_format (default: json) save() output: json, flame_xml or flamegpu_xml\n"
                " * int  cuda.dump_state (default: 0)     also write raw binary state on save()\n"

@@ -65,6 +65,29 @@ def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, s
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("model_file,params,use_float,slabs,steps", [CASES[0], CASES[3], CASES[4]],
+                         ids=["%s-%dslabs" % (c[0][:-4], c[3]) for c in (CASES[0], CASES[3], CASES[4])])
+def test_scalable_upload_is_bit_identical(model_file, params, use_float, slabs, steps):
+    """Slab r uploads the r-th part of the population by index; the records are grouped by owner on the
+    device (abl_cuda_partition_upload), routed and adopted (abl_cuda_adopt_records): same state as the
+    upload-everything-and-crop path, hence the same results as the undecomposed run."""
+    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
+    m.populate()
+    host = [m.host_agents(t) for t in range(m.n_types)]
+    single = single_run(m, steps)
+    ls = LocalSlabs(m, slabs, transport="direct")
+    ls.upload(host, scalable=True)
+    assert sum(ls.owned_counts(0)) == len(host[0])
+    for _ in range(steps):
+        ls.timestep()
+    ids, rec = ls.download(0)
+    ls.close()
+    assert np.array_equal(ids, np.arange(len(host[0]), dtype=np.uint32))
+    for f in rec.dtype.names:
+        assert np.array_equal(rec[f], single[f]), "member %s differs from the single-slab run" % f
+
+
+@pytest.mark.gpu
 def test_direct_transport_recovers_from_underestimated_padding(monkeypatch):
     """The host bins `owned + pad` records without knowing how many arrive; when more arrive
     than it assumed, the next binning notices and bins again over the true range."""

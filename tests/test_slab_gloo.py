@@ -147,3 +147,58 @@ def test_new_agent_ids_are_resolved_across_ranks(tmp_path):
     got = [np.load(os.path.join(str(tmp_path), "ids%d.npy" % r), allow_pickle=True).tolist() for r in range(world)]
     assert got[0] == [[[100, 102, 103], 4], [[], 0], [[], 2]]
     assert got[1] == [[[101], 4], [[], 0], [[104, 105], 2]]
+
+
+# ---- scalable upload: every rank uploads 1/N of the population by index, one all-to-all routes the
+# ---- records to their owners (RankSlab.upload; rules of k_route_classify restated in numpy) -----------
+def _route_rank_main(rank, world, port, n, out_dir):
+    import sys
+    sys.path.insert(0, REPO)
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from oracle import Oracle
+    from openabl_b200.slab import exchange_partitions, owner_of, slab_layer, split_layers
+
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    o = Oracle(False)
+    pop = o.boids_init(n)                          # every process can rebuild the population; it touches only its part
+    W = float(np.sqrt(n / 500.0)) if n else 1.0
+    cell = 0.05 * (1.0 + 2.0 ** -20)               # ABL_CELL_PAD_F64
+    layers = max(1, int(np.ceil(o.lib.oracle_fold6(W) / cell)))
+    bounds = split_layers(layers, world)
+    lo, hi = n * rank // world, n * (rank + 1) // world
+    part = pop[lo:hi]
+    owner = owner_of(slab_layer(part["pos"][:, 1], 0.0, cell, layers), bounds)
+    order = np.argsort(owner, kind="stable")
+    counts = [int((owner == d).sum()) for d in range(world)]
+    transit = np.dtype([("rec", pop.dtype), ("id", np.uint32)])
+    send = np.zeros(len(part), dtype=transit)
+    send["rec"] = part[order]
+    send["id"] = (lo + order).astype(np.uint32)
+    raw = torch.from_numpy(np.frombuffer(send.tobytes(), dtype=np.uint8).copy()) if len(send) else torch.zeros(1, dtype=torch.uint8)
+    recv, total = exchange_partitions(dist, rank, world, raw, counts, transit.itemsize)
+    got = np.frombuffer(recv.numpy()[:total * transit.itemsize].tobytes(), dtype=transit)
+    np.save(os.path.join(out_dir, "ids_%d.npy" % rank), got["id"])
+    np.save(os.path.join(out_dir, "pos_%d.npy" % rank), got["rec"]["pos"])
+    dist.destroy_process_group()
+
+
+def test_scalable_upload_routes_every_agent_to_its_owner(tmp_path):
+    import sys
+    sys.path.insert(0, os.path.join(REPO, "oracle"))
+    from oracle import Oracle
+    from openabl_b200.slab import owner_of, slab_layer, split_layers
+    n, world = 20000, 2
+    mp.spawn(_route_rank_main, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    o = Oracle(False)
+    pop = o.boids_init(n)
+    cell = 0.05 * (1.0 + 2.0 ** -20)
+    layers = int(np.ceil(o.lib.oracle_fold6(float(np.sqrt(n / 500.0))) / cell))
+    owner = owner_of(slab_layer(pop["pos"][:, 1], 0.0, cell, layers), split_layers(layers, world))
+    seen = []
+    for r in range(world):
+        ids = np.load(os.path.join(str(tmp_path), "ids_%d.npy" % r))
+        pos = np.load(os.path.join(str(tmp_path), "pos_%d.npy" % r))
+        assert np.array_equal(np.sort(ids), np.nonzero(owner == r)[0]), "rank %d did not receive exactly its agents" % r
+        assert np.array_equal(pos, pop["pos"][ids]), "records do not travel with their ids"
+        seen.append(ids)
+    assert len(np.concatenate(seen)) == n
