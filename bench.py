@@ -355,16 +355,19 @@ def measure(args, workload, env, strong, steps, warmup, with_cpu_baseline):
 
     # ---- end to end through the C ABI with host buffers -------------------------------------
     e2e_reps = 3
-    barrier()
-    t0 = time.perf_counter()
     d2h = h2d = 0
-    for _ in range(e2e_reps):
+    # (one untimed call first: page-locked staging buffers are allocated, host arrays registered and NCCL
+    # connections made once per process, not once per simulate())
+    for rep in range(e2e_reps + 1):
+        if rep == 1:
+            barrier()
+            t0 = time.perf_counter()
         upload()
         h2d = slab.last_upload_bytes if slab else host_bytes
         for _ in range(steps):
             timestep()
         if slab:
-            out = [m.download(tt) for tt in range(m.n_types)]   # this rank's owned agents
+            out = [slab.download_owned(tt) for tt in range(m.n_types)]   # this rank's owned agents, page-locked buffers
             d2h = sum(o.nbytes for o in out)
         else:
             m.download_host()

@@ -178,6 +178,16 @@ class Runtime:
         check(self.lib.abl_cuda_download_ids(self.handle, pool, out.ctypes.data_as(_VP), n, C.byref(got)), "download_ids")
         return out
 
+    def pin_host(self, array):
+        """Page-locks the memory of a numpy array for direct DMA (idempotent; best effort)."""
+        check(self.lib.abl_cuda_pin_host(self.handle, array.ctypes.data_as(_VP), array.nbytes), "pin_host")
+
+    def download_into(self, pool, out):
+        """abl_cuda_download into a caller-provided (ideally page-locked) structured array; -> records written."""
+        got = C.c_size_t()
+        check(self.lib.abl_cuda_download(self.handle, pool, out.ctypes.data_as(_VP), len(out), C.byref(got)), "download")
+        return got.value
+
     # ---- scalable upload under slab decomposition (abl_cuda.h) ----------------------------
     def transit_record_bytes(self, pool):
         n = C.c_size_t()

@@ -240,6 +240,7 @@ class RankSlab:
         self.halo_records = halo_records
         self._connected = False
         self.last_upload_bytes = 0      # host -> device bytes of the latest upload() on this rank
+        self._dl = {}                   # page-locked download buffers, per agent type
         self.rt = model.create_runtime(device=device, **rt_kw)
         layers = self.rt.slab_layers()
         self.bounds = split_layers(layers, world)
@@ -289,6 +290,8 @@ class RankSlab:
                 lo, hi = n * self.rank // self.world, n * (self.rank + 1) // self.world
                 rec = self.rt.transit_record_bytes(pool)
                 part = np.ascontiguousarray(arr[lo:hi])
+                if host_arrays is None and len(part):
+                    self.rt.pin_host(part)         # this rank's part of the model's own array: page-locked once, DMA from then on
                 send = torch.empty(max(1, (hi - lo) * rec), dtype=torch.uint8, device=dev)
                 counts = self.rt.partition_upload(pool, part, lo, send.data_ptr(), self.world)
                 self.last_upload_bytes += part.nbytes
@@ -361,6 +364,21 @@ class RankSlab:
 
     def owned(self, t):
         return self.rt.pool_size(self.model.pool(t))
+
+    def download_owned(self, t):
+        """This rank's owned agents of type `t` (ascending id) into a page-locked buffer that is reused
+        from call to call: the device -> host half of an end-to-end simulate()."""
+        import torch
+        m = self.model
+        n = self.owned(t)
+        buf = self._dl.get(t)
+        need = max(1, n) * m.dtypes[t].itemsize
+        if buf is None or buf.numel() < need:
+            buf = torch.empty(need + need // 8, dtype=torch.uint8, pin_memory=True)
+            self._dl[t] = buf
+        out = buf.numpy()[:n * m.dtypes[t].itemsize].view(m.dtypes[t])
+        got = self.rt.download_into(m.pool(t), out)
+        return out[:got]
 
 
 # ---- the decomposition rules, stated once more in numpy ------------------------------------

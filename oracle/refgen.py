@@ -103,6 +103,29 @@ EXTRA_FIXTURES = {
 }
 
 
+# The reference examples the `c` backend can run besides the four above (keratinocyte, ants, sugarscape,
+# boids2d_flockers and predator_prey use run-time add/remove or in-step random(), which it rejects or
+# leaves racy): boids.abl, 3-D flocking, pinned on the real model instead of a look-alike.
+EXTRA_FIXTURES.update({
+    "boids_n2000_t10": ("boids.abl", {"num_agents": 2000, "num_timesteps": 10}, False),
+    "boids_n2000_t10_f32": ("boids.abl", {"num_agents": 2000, "num_timesteps": 10}, True),
+})
+
+# save() text of the reference (libabl.c:46-124), byte for byte: name -> (model, params, use_float, output file).
+# Stored under tests/golden/text/<name>.txt; tests/test_gpu_save_text.py compares the file the generated
+# ./main writes with it (integer / bool models byte-identical, floating point within the last printed digit).
+TEXT_FIXTURES = {
+    "game_of_life_n1024_t10": ("game_of_life.abl", {"num_agents": 1024, "num_timesteps": 10}, False),
+    "circle_n500_t10": ("circle.abl", {"num_agents": 500, "num_timesteps": 10}, False),
+    "boids2d_n1000_t10": ("boids2d.abl", {"num_agents": 1000, "num_timesteps": 10}, False),
+    "circle3d_n500_t10_f32": ("circle3d.abl", {"num_agents": 500, "num_timesteps": 10}, True),
+}
+
+
+def text_fixture_path(name):
+    return os.path.join(GOLDEN, "text", name + ".txt")
+
+
 def model_path(model):
     """Fixture model names are relative to examples/ unless they carry a directory."""
     return os.path.join(REPO, model) if os.sep in model or "/" in model else os.path.join(REPO, "examples", model)
@@ -138,6 +161,14 @@ def main():
                        "generator": "oracle/refgen.py (reference c backend, gcc -O2 -std=c99 -fopenmp)"},
                       f, indent=1)
         print(name, [len(s) for s in state])
+    os.makedirs(os.path.join(GOLDEN, "text"), exist_ok=True)
+    for name, (model, params, use_float) in TEXT_FIXTURES.items():
+        if only and name not in only:
+            continue
+        _, text = run_reference(model_path(model), params, use_float)
+        with open(text_fixture_path(name), "w") as f:
+            f.write(text)
+        print(name, len(text), "bytes of save() text")
 
 
 if __name__ == "__main__":

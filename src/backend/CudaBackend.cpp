@@ -2269,7 +2269,8 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   w << "        abl_tune_abort(tune);"; w.nl();
   w << "        timed = false;"; w.nl();
   w << "        abl_last_mode_" << f.emitName << " = 0;"; w.nl();
-  w << "        rc = (int)abl_launch_kernel(a, " << K << "<0>, abl_grid_blocks(a, 128), 128, 0, *a, " << lim << ", 0u);"; w.nl();
+  w << "        const unsigned g0 = abl_grid_blocks(a, 128);   // fills in the block counts of *a: its own statement, before *a is copied"; w.nl();
+  w << "        rc = (int)abl_launch_kernel(a, " << K << "<0>, g0, 128, 0, *a, " << lim << ", 0u);"; w.nl();
   w << "    }"; w.nl();
   w << "    if (timed) abl_tune_end(tune, a->stream);"; w.nl();
   w << "    return rc;"; w.nl();
