@@ -206,7 +206,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", 7: "bulk-tile", -1: "not launched"}
+MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", 7: "bulk-tile", 8: "shadow-prefilter", -1: "not launched"}
 
 # FP64 operations per agent-step of circle3d's step kernel (SURVEY.md 8d asks for this view next to
 # the HBM one): per candidate 3 sub + 3 mul + 2 add + 1 compare = 9, per accepted candidate the
@@ -222,8 +222,10 @@ def fp64_roofline(workload, n_agents, kernel_ms, clocks):
     achieved = ops * n_agents / (kernel_ms / 1e3) / 1e12
     return {"bound": "fp64", "achieved": achieved, "peak": peak, "unit": "T FP64 lane-ops/s", "frac": achieved / peak,
             "ops_per_agent_step": ops,
-            "definition": "9 FP64 operations per candidate (1323 per agent) + ~80 per accepted candidate (205 per agent); "
-                          "peak = 148 SMs x 64 FP64 lanes x SM clock (an FMA counted as one operation)"}
+            "definition": "ALGORITHMIC double-precision operations of the reference formulation (9 per candidate, 1323 candidates per "
+                          "agent, + ~80 per accepted candidate, 205 per agent) / kernel time, against 148 SMs x 64 FP64 lanes x SM clock "
+                          "(an FMA counted as one operation).  The shadow pre-filter variant evaluates the 9 per candidate in single "
+                          "precision, so fewer FP64 instructions are EXECUTED than this figure counts (ncu: FP64 pipe 16 % busy)"}
 
 
 def measure(args, workload, env, strong, steps, warmup, with_cpu_baseline):

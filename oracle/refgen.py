@@ -118,7 +118,9 @@ TEXT_FIXTURES = {
     "game_of_life_n1024_t10": ("game_of_life.abl", {"num_agents": 1024, "num_timesteps": 10}, False),
     "circle_n500_t10": ("circle.abl", {"num_agents": 500, "num_timesteps": 10}, False),
     "boids2d_n1000_t10": ("boids2d.abl", {"num_agents": 1000, "num_timesteps": 10}, False),
-    "circle3d_n500_t10_f32": ("circle3d.abl", {"num_agents": 500, "num_timesteps": 10}, True),
+    # (single precision on the 2-D model: circle3d with use_float is order-sensitive beyond any tolerance after 10 steps —
+    # 200 neighbours per agent and a force that jumps at distance r; tests/test_oracle.py::test_circle3d_float_is_order_sensitive)
+    "circle_n500_t10_f32": ("circle.abl", {"num_agents": 500, "num_timesteps": 10}, True),
 }
 
 

@@ -2174,6 +2174,10 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   } else {
     w << "    const bool listed = false;"; w.nl();
   }
+  if (curStepDense) {
+    // the runtime's question before the launch proper (nothing is launched): would this launch use the single-precision shadow?
+    w << "    if (a->probe) return (a->flat_loop != 0 && chunked && !listed) ? 1 : 0;"; w.nl();
+  }
   if (curStepTile) {
     // opt-in: stage the block's candidate rows in shared memory (ABL_MODE 2), sparse neighbourhoods only
     w << "    const unsigned tile_entry = " << tileOffset(tcols, tcols.size()) << ";"; w.nl();
@@ -2190,7 +2194,6 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   if (curStepDense) {
     // dense rows: the chunked loop with its filter on the single-precision shadow (ABL_MODE 8) when the runtime keeps one.
     // The runtime first asks (probe != 0, nothing is launched) whether this launch would use the shadow, and only then builds it.
-    w << "    if (a->probe) return (a->flat_loop != 0 && chunked && !listed) ? 1 : 0;"; w.nl();
     w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
     w << "    if (a->nbr_shadow != nullptr && a->flat_loop != 0 && chunked && !listed) {"; w.nl();
     w << "        const int dbs = bs ? bs : 256;"; w.nl();
