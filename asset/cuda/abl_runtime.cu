@@ -164,7 +164,10 @@ struct NeighbourLists {
   unsigned builds = 0;
 };
 
+static const int kPfWords = 56, kPfRows = 12;   // ABL_SHADOW_WORDS / ABL_SHADOW_ROWS of abl_device.cuh
 struct Step {
+  u32 *pf_buf = nullptr;     // scratch of the split pre-filter (ABL_MODE 9)
+  size_t pf_cap = 0;         // words
   abl_step_desc desc;
   std::string name;
   int reach = 1;
@@ -262,6 +265,7 @@ struct abl_runtime {
   int flat_loop = 1;
   int bulk_tile = 1;           // ABL_CUDA_BULK=0: no TMA-staged tiles (ABL_MODE 7)
   int dense_tile = 1;          // ABL_CUDA_DENSE=0: no single-precision shadow of the positions (ABL_MODE 8)
+  int split_prefilter = 1;     // ABL_CUDA_SPLIT=0: the shadow pre-filter stays inside the step kernel (no ABL_MODE 9)
   bool scan_two_pass = true;   // ABL_CUDA_SCAN=lookback selects the single-pass scan for the cell histogram
   std::vector<void *> garbage;
   bool defer_free = false;
@@ -1073,6 +1077,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
   if (const char *tn = getenv("ABL_CUDA_TUNE")) { if (atoi(tn) != 0) rt->flat_loop = -1; }
   if (const char *dn = getenv("ABL_CUDA_DENSE")) rt->dense_tile = atoi(dn) != 0 ? 1 : 0;
+  if (const char *sp = getenv("ABL_CUDA_SPLIT")) rt->split_prefilter = atoi(sp) != 0 ? 1 : 0;
   if (const char *bk = getenv("ABL_CUDA_BULK")) rt->bulk_tile = atoi(bk) < 0 ? 0 : atoi(bk) > 2 ? 2 : atoi(bk);
   if (const char *nlv = getenv("ABL_CUDA_NLIST")) rt->nlist = atoi(nlv) != 0;
   if (const char *mb = getenv("ABL_CUDA_NLIST_MB")) rt->nlist_budget = (size_t)std::max(1, atoi(mb)) << 20;
@@ -1138,6 +1143,7 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
     if (p.shadow_max) cudaFree(p.shadow_max);
   }
   for (Step &st : rt->steps) {
+    if (st.pf_buf) cudaFree(st.pf_buf);
     if (st.nl.cnt) cudaFree(st.nl.cnt);
     if (st.nl.idx) cudaFree(st.nl.idx);
   }
@@ -2256,10 +2262,29 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       a.probe = 1;
       const int wants = s.desc.launch(&a);
       a.probe = 0;
-      if (wants == 1) {
+      if (wants == 1 || wants == 2) {
         TRY(refresh_shadow(rt, *nbr));
         a.nbr_shadow = nbr->shadow;
         a.nbr_shadow_max = nbr->shadow_max;
+      }
+      if (wants == 2 && rt->split_prefilter) {
+        // scratch columns of the pre-filter kernel: words per agent = masks + row table + header + 64-bit map; when the
+        // memory is not to be had the launcher stays with the in-kernel pre-filter
+        const size_t per = (size_t)kPfWords + kPfRows + 1 + 2, need = (size_t)a.self.n * per;
+        if (s.pf_cap < need) {
+          if (s.pf_buf) TRY(release_device(rt, s.pf_buf));
+          s.pf_buf = nullptr;
+          s.pf_cap = need + need / 16;
+          if (cudaMalloc(&s.pf_buf, s.pf_cap * sizeof(u32)) != cudaSuccess) { cudaGetLastError(); s.pf_buf = nullptr; s.pf_cap = 0; }
+        }
+        if (s.pf_buf) {
+          const size_t n = a.self.n;
+          a.pf_sbits = (unsigned long long *)s.pf_buf;          // the 8-byte aligned part first
+          a.pf_masks = s.pf_buf + 2 * n;
+          a.pf_rows = a.pf_masks + (size_t)kPfWords * n;
+          a.pf_hdr = a.pf_rows + (size_t)kPfRows * n;
+          a.pf_stride = (unsigned)n;
+        }
       }
     }
     a.pdl = rt->pdl ? 1 : 0;

@@ -227,7 +227,16 @@ typedef struct {
    * candidates on it and re-test the survivors exactly (ABL_MODE 8). */
   const void *nbr_shadow;
   const unsigned *nbr_shadow_max;
-  int probe;   /* != 0: launch nothing; return 1 if this launch would use the shadow (ABL_MODE 8), else 0 */
+  int probe;   /* != 0: launch nothing; return 1 if this launch would use the shadow (ABL_MODE 8), 2 if it would also
+                  use the pre-filter scratch below (ABL_MODE 9), else 0 */
+  /* Scratch of the split pre-filter (ABL_MODE 9; NULL: none): the step's pre-filter kernel leaves, per agent of the
+   * launched range and column-wise with stride pf_stride, up to ABL_SHADOW_WORDS acceptance masks (pf_masks), the
+   * first pool index of up to ABL_SHADOW_ROWS row ranges (pf_rows), the map of the words that start a new range
+   * (pf_sbits) and a header (pf_hdr: number of words; bit 31: the candidates did not fit); the step kernel, launched
+   * right behind it, walks them. */
+  unsigned *pf_masks, *pf_rows, *pf_hdr;
+  unsigned long long *pf_sbits;
+  unsigned pf_stride;
   /* > 0 (set by the generated launcher for dense for-near loops of reach 1): the squared radius bound; the neighbour
    * iterator then narrows every row of cells along x to the cells within reach of the agent (abl_device.cuh: row_reach) */
   double row_cull;

@@ -99,6 +99,7 @@ private:
   bool curStepFlat = false;     // `-C cuda.flat=true` and a 2-D for-near loop: ABL_MODE 3 is printed
   bool curStepList = false;     // `-C cuda.nlist=true` and a static neighbourhood: list kernels (ABL_MODE 4/5/6) are printed
   bool curStepDense = false;    // for-near loop with a host-evaluable radius: ABL_MODE 8 (single-precision shadow pre-filter, `-C cuda.dense=false` omits it)
+  bool curStepSplit = false;    // ... whose loop ranges over the stepped agent itself: the pre-filter can run as a kernel of its own (ABL_MODE 9)
   bool curStepBulk = false;     // tileable 2-D flat loop: ABL_MODE 7 (rows staged by cp.async.bulk, `-C cuda.bulk=false` omits it)
   bool stepListEligible(const StepInfo &si) const;
   // one neighbour column staged in shared memory by a tiled kernel
@@ -231,6 +232,7 @@ private:
     bool sql;
   };
   void stepKernelWrapper(const StepKernelCtx &C);
+  void stepPrefilterKernel(const StepKernelCtx &C);
   void stepLauncher(const StepKernelCtx &C);
   static const Expr *findNearRadius(const std::vector<StmtP> &body);
   static bool hostEvaluable(const Expr &e);
@@ -832,33 +834,46 @@ void CudaPrinter::nearShadowLoop(const NearLoop &L) {
   const std::string done = "_near_done" + it + "s";
   const std::string ptype = typeName(pos->type);
   w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
-  w << "if (ABL_MODE == 8) {";
+  // ABL_MODE 9: masks, row table and header were written to global memory by the step's pre-filter kernel
+  // (abl_prefilter_<step>, one launch earlier); an agent whose candidates did not fit them takes the cursor loop
+  if (curStepSplit) w << "if (ABL_MODE == 8 || (ABL_MODE == 9 && !(_a.pf_hdr[_i] >> 31))) {";
+  else w << "if (ABL_MODE == 8) {";
   w.indent(); w.nl();
   w << "// dynamic shared memory, words: [ABL_SHADOW_WORDS][blockDim.x] acceptance masks | [ABL_SHADOW_ROWS][blockDim.x] first pool"; w.nl();
   w << "// index of every row range the masks cover | [ABL_SHADOW_LIST][blockDim.x] survivors of the current round"; w.nl();
+  w << "// (ABL_MODE 9: masks and row table are one column per agent in global memory, only the lists are shared memory)"; w.nl();
   w << "extern __shared__ unsigned _abl_masks[];"; w.nl();
-  w << "unsigned *const " << it << "mk = _abl_masks + threadIdx.x;"; w.nl();
-  w << "unsigned *const " << it << "rows = " << it << "mk + ABL_SHADOW_WORDS * blockDim.x;"; w.nl();
-  w << "unsigned *const " << it << "list = " << it << "rows + ABL_SHADOW_ROWS * blockDim.x;"; w.nl();
+  w << "const unsigned " << it << "str = ABL_MODE == 8 ? blockDim.x : _a.pf_stride;"; w.nl();
+  w << "unsigned *const " << it << "mk = ABL_MODE == 8 ? _abl_masks + threadIdx.x : _a.pf_masks + _i;"; w.nl();
+  w << "unsigned *const " << it << "rows = ABL_MODE == 8 ? " << it << "mk + ABL_SHADOW_WORDS * blockDim.x : _a.pf_rows + _i;"; w.nl();
+  w << "unsigned *const " << it << "list = ABL_MODE == 8 ? " << it << "rows + ABL_SHADOW_ROWS * blockDim.x : _abl_masks + threadIdx.x;"; w.nl();
   w << "const float4 *const " << it << "sh = static_cast<const float4 *>(_a.nbr_shadow);"; w.nl();
   w << "const float " << it << "sx = (float)" << selfPosText << ".x, " << it << "sy = (float)" << selfPosText << ".y"
     << (dim == 3 ? ", " + it + "sz = (float)" + selfPosText + ".z" : std::string()) << ";"; w.nl();
-  w << "const float " << it << "limf = abl_shadow_limit(_near_limit, __ldg(_a.nbr_shadow_max), fmaxf(fabsf(" << it << "sx), "
-    << (dim == 3 ? "fmaxf(fabsf(" + it + "sy), fabsf(" + it + "sz))" : "fabsf(" + it + "sy)") << "));"; w.nl();
+  w << "const float " << it << "limf = ABL_MODE == 8 ? abl_shadow_limit(_near_limit, __ldg(_a.nbr_shadow_max), fmaxf(fabsf(" << it << "sx), "
+    << (dim == 3 ? "fmaxf(fabsf(" + it + "sy), fabsf(" + it + "sz))" : "fabsf(" + it + "sy)") << ")) : 0.0f;"; w.nl();
   w << "const unsigned " << it << "wm = __activemask();   // the lanes that run this loop go through its rounds together"; w.nl();
   w << "bool " << it << "stop = false;   // `break` of the loop body"; w.nl();
+  w << "bool " << it << "first = true;"; w.nl();
   w << "for (;;) {";
   w.indent(); w.nl();
   // phase 1: masks of up to ABL_SHADOW_WORDS * 32 candidates out of up to ABL_SHADOW_ROWS row ranges
   w << "unsigned " << it << "nw = 0, " << it << "nr = 0, " << it << "prev = 0xffffffffu;"; w.nl();
   w << "unsigned long long " << it << "sbits = 0ull;   // bit w: word w starts a new row range"; w.nl();
+  w << "if (ABL_MODE == 9) {";
+  w.indent(); w.nl();
+  w << "if (" << it << "first && !" << it << "stop) { " << it << "nw = _a.pf_hdr[_i] & 0xffffu; " << it << "sbits = _a.pf_sbits[_i]; }"; w.nl();
+  w << it << "first = false;";
+  w.outdent(); w.nl();
+  w << "} else";
+  w.nl();
   w << "while (!" << it << "stop && " << it << ".valid() && " << it << "nw < ABL_SHADOW_WORDS) {";
   w.indent(); w.nl();
   w << "const unsigned " << it << "sb = " << it << ".index();"; w.nl();
   w << "if (" << it << "sb != " << it << "prev + 32u) {";
   w.indent(); w.nl();
   w << "if (" << it << "nr == ABL_SHADOW_ROWS) break;"; w.nl();
-  w << it << "rows[" << it << "nr * blockDim.x] = " << it << "sb;"; w.nl();
+  w << it << "rows[" << it << "nr * " << it << "str] = " << it << "sb;"; w.nl();
   w << it << "nr++;"; w.nl();
   w << it << "sbits |= 1ull << " << it << "nw;";
   w.outdent(); w.nl();
@@ -879,7 +894,7 @@ void CudaPrinter::nearShadowLoop(const NearLoop &L) {
   w << "if (!(" << it << "d2f > " << it << "limf)) " << it << "sm |= 1u << " << it << "k;";
   w.outdent(); w.nl();
   w << "}"; w.nl();
-  w << it << "mk[" << it << "nw * blockDim.x] = " << it << "sm;"; w.nl();
+  w << it << "mk[" << it << "nw * " << it << "str] = " << it << "sm;"; w.nl();
   w << it << "nw++;"; w.nl();
   w << it << ".skip(" << it << "sn);";
   w.outdent(); w.nl();
@@ -887,6 +902,7 @@ void CudaPrinter::nearShadowLoop(const NearLoop &L) {
   w << "if (!__any_sync(" << it << "wm, " << it << "nw != 0u)) break;"; w.nl();
   // phase 2: rounds of up to ABL_SHADOW_LIST survivors, expanded from the masks
   w << "unsigned " << it << "w = 0, " << it << "m = 0, " << it << "b = 0, " << it << "ri = 0;"; w.nl();
+  w << "unsigned " << it << "mn = " << it << "nw ? " << it << "mk[0] : 0u;   // mask word w, requested one fetch ahead (global memory in ABL_MODE 9)"; w.nl();
   w << "for (;;) {";
   w.indent(); w.nl();
   w << "unsigned " << it << "cnt = 0;"; w.nl();
@@ -895,9 +911,10 @@ void CudaPrinter::nearShadowLoop(const NearLoop &L) {
   w << "if (" << it << "m == 0u) {";
   w.indent(); w.nl();
   w << "if (" << it << "w == " << it << "nw) break;"; w.nl();
-  w << it << "m = " << it << "mk[" << it << "w * blockDim.x];"; w.nl();
-  w << "if ((" << it << "sbits >> " << it << "w) & 1ull) { " << it << "b = " << it << "rows[" << it << "ri * blockDim.x]; " << it << "ri++; } else " << it << "b += 32u;"; w.nl();
+  w << it << "m = " << it << "mn;"; w.nl();
+  w << "if ((" << it << "sbits >> " << it << "w) & 1ull) { " << it << "b = " << it << "rows[" << it << "ri * " << it << "str]; " << it << "ri++; } else " << it << "b += 32u;"; w.nl();
   w << it << "w++;"; w.nl();
+  w << "if (" << it << "w < " << it << "nw) " << it << "mn = " << it << "mk[" << it << "w * " << it << "str];"; w.nl();
   w << "continue;";
   w.outdent(); w.nl();
   w << "}"; w.nl();
@@ -943,6 +960,81 @@ void CudaPrinter::nearShadowLoop(const NearLoop &L) {
   w.outdent(); w.nl();
   w << "} else"; w.nl();
   w << "#endif"; w.nl();
+}
+
+// The pre-filter kernel of ABL_MODE 9: phase 1 of the shadow pre-filter as a kernel of its own.  It needs the
+// positions only, so it runs with fewer registers than the step kernel and no shared memory, and leaves per agent
+// (one column each, so that a warp reads and writes consecutive words): up to ABL_SHADOW_WORDS acceptance masks,
+// the first pool index of up to ABL_SHADOW_ROWS row ranges, the 64-bit map of the words that start a new range,
+// and a header (number of words; bit 31: the candidates did not fit).  Measured on circle3d 1 M (ncu): 0.86 ms for
+// this kernel + 1.78 ms for the step kernel that walks the masks, against 3.05 ms for ABL_MODE 8; writing survivor
+// LISTS from here instead (no expansion in the step kernel) was tried and lost (1.60 + 1.62 ms: the predicated
+// appends cost more than the expansion they save).
+void CudaPrinter::stepPrefilterKernel(const StepKernelCtx &C) {
+  const StepInfo &si = C.si;
+  FuncDecl &f = *si.fn;
+  AgentDecl &self = *si.self;
+  AgentMember *selfPosM = self.position();
+  const int dim = C.tdim;
+  const std::string sdim = std::to_string(dim);
+  const std::string ptype = typeName(selfPosM->type);
+  w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
+  w << "__global__ void __launch_bounds__(256, 4) abl_prefilter_" << f.emitName
+    << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull) {";
+  w.indent(); w.nl();
+  w << "cudaGridDependencySynchronize();"; w.nl();
+  w << "bool _boundary;"; w.nl();
+  w << "unsigned _ob;"; w.nl();
+  w << "const unsigned _r = abl_agent_index(_a, _boundary, _ob);"; w.nl();
+  w << "if (_r == 0xffffffffu) return;"; w.nl();
+  w << "const unsigned _i = _r + _ob;"; w.nl();
+  w << ptype << " _p;"; w.nl();
+  loadMember(self, self.memberIndex(selfPosM->name), "_p", "_a.self.in", "_i"); w.nl();
+  w << "abl_near_iter<" << sdim << "> _it;"; w.nl();
+  w << "_it.init" << sdim << "(_a, _p, true, _near_cull);"; w.nl();
+  w << "const unsigned _str = _a.pf_stride;"; w.nl();
+  w << "unsigned *const _mk = _a.pf_masks + _i, *const _rows = _a.pf_rows + _i;"; w.nl();
+  w << "const float4 *const _sh = static_cast<const float4 *>(_a.nbr_shadow);"; w.nl();
+  w << "const float _sx = (float)_p.x, _sy = (float)_p.y" << (dim == 3 ? ", _sz = (float)_p.z" : "") << ";"; w.nl();
+  w << "const float _limf = abl_shadow_limit(_near_limit, __ldg(_a.nbr_shadow_max), fmaxf(fabsf(_sx), "
+    << (dim == 3 ? "fmaxf(fabsf(_sy), fabsf(_sz))" : "fabsf(_sy)") << "));"; w.nl();
+  w << "unsigned _nw = 0, _nr = 0, _prev = 0xffffffffu, _over = 0;"; w.nl();
+  w << "unsigned long long _sbits = 0ull;"; w.nl();
+  w << "while (_it.valid()) {";
+  w.indent(); w.nl();
+  w << "if (_nw == ABL_SHADOW_WORDS) { _over = 1; break; }"; w.nl();
+  w << "const unsigned _sb = _it.index();"; w.nl();
+  w << "if (_sb != _prev + 32u) {";
+  w.indent(); w.nl();
+  w << "if (_nr == ABL_SHADOW_ROWS) { _over = 1; break; }"; w.nl();
+  w << "_rows[_nr * _str] = _sb;"; w.nl();
+  w << "_nr++;"; w.nl();
+  w << "_sbits |= 1ull << _nw;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "_prev = _sb;"; w.nl();
+  w << "const unsigned _sn = min(_it.remaining(), 32u);"; w.nl();
+  w << "unsigned _sm = 0;"; w.nl();
+  w << "for (unsigned _k = 0; _k < _sn; _k++) {";
+  w.indent(); w.nl();
+  w << "const float4 _f = __ldg(_sh + _sb + _k);"; w.nl();
+  w << "const float _dx = _f.x - _sx, _dy = _f.y - _sy" << (dim == 3 ? ", _dz = _f.z - _sz" : "") << ";"; w.nl();
+  if (dim == 3) w << "const float _d2f = __fmaf_rn(_dz, _dz, __fmaf_rn(_dy, _dy, _dx * _dx));";
+  else w << "const float _d2f = __fmaf_rn(_dy, _dy, _dx * _dx);";
+  w.nl();
+  w << "if (!(_d2f > _limf)) _sm |= 1u << _k;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "_mk[_nw * _str] = _sm;"; w.nl();
+  w << "_nw++;"; w.nl();
+  w << "_it.skip(_sn);";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "_a.pf_hdr[_i] = _nw | (_over << 31);"; w.nl();
+  w << "_a.pf_sbits[_i] = _sbits;";
+  w.outdent(); w.nl();
+  w << "}"; w.nl();
+  w << "#endif"; w.nl(); w.nl();
 }
 
 // ABL_MODE 7: the flat loop of ABL_MODE 3 over a shared-memory tile whose rows were copied by the
@@ -2176,7 +2268,9 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   }
   if (curStepDense) {
     // the runtime's question before the launch proper (nothing is launched): would this launch use the single-precision shadow?
-    w << "    if (a->probe) return (a->flat_loop != 0 && chunked && !listed) ? 1 : 0;"; w.nl();
+    // (2: it would also use the pre-filter kernel's scratch columns, ABL_MODE 9 — the candidates of an agent fit ABL_SHADOW_WORDS masks)
+    w << "    const bool split = " << (curStepSplit ? "a->reach == 1 && row_occ * " + std::string(tdim == 3 ? "9.0" : "3.0") + " <= 0.75 * 32.0 * ABL_SHADOW_WORDS" : "false") << ";"; w.nl();
+    w << "    if (a->probe) return (a->flat_loop != 0 && chunked && !listed) ? (split ? 2 : 1) : 0;"; w.nl();
   }
   if (curStepTile) {
     // opt-in: stage the block's candidate rows in shared memory (ABL_MODE 2), sparse neighbourhoods only
@@ -2197,6 +2291,17 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
     w << "#ifdef ABL_HAVE_BULK_TILE"; w.nl();
     w << "    if (a->nbr_shadow != nullptr && a->flat_loop != 0 && chunked && !listed) {"; w.nl();
     w << "        const int dbs = bs ? bs : 256;"; w.nl();
+    if (curStepSplit) {
+      w << "        if (split && a->pf_masks != nullptr) {"; w.nl();
+      w << "            // phase 1 as a kernel of its own, then the step kernel walks the masks it left in global memory"; w.nl();
+      w << "            const unsigned pgrid = abl_grid_blocks(a, 256);"; w.nl();
+      w << "            int prc = (int)abl_launch_kernel(a, abl_prefilter_" << f.emitName << ", pgrid, 256, 0, *a, limit, cull);"; w.nl();
+      w << "            const unsigned sgrid = abl_grid_blocks(a, dbs);"; w.nl();
+      w << "            if (prc == 0) prc = (int)abl_launch_kernel(a, " << K << "<9>, sgrid, dbs, (size_t)ABL_SHADOW_LIST * dbs * sizeof(unsigned), *a, " << lim << ", 0u);"; w.nl();
+      w << "            if (prc == 0) { abl_last_mode_" << f.emitName << " = 9; return 0; }"; w.nl();
+      w << "            (void)cudaGetLastError();"; w.nl();
+      w << "        }"; w.nl();
+    }
     w << "        const size_t dsmem = (size_t)(ABL_SHADOW_WORDS + ABL_SHADOW_ROWS + ABL_SHADOW_LIST) * dbs * sizeof(unsigned);"; w.nl();
     w << "        static size_t dense_set[ABL_TUNE_DEVICES];   // opt-in shared memory size, per device"; w.nl();
     w << "        if (dsmem > 48u * 1024u && dense_set[dev] < dsmem) { cudaFuncSetAttribute(" << K << "<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem); dense_set[dev] = dsmem; }"; w.nl();
@@ -2314,6 +2419,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
                 tcols.size() <= 8;   // ABL_BTILE_MAX_COLS
   curStepDense = curStepHasLimit && nearStmt && !useFloat && config.getBool("cuda.dense", true);
   if (curStepDense) denseSteps.insert(&f);
+  curStepSplit = curStepDense && curStepTile && (tdim == 2 || tdim == 3) && config.getBool("cuda.split", true);
 
   // the user's step function
   w << "template <int ABL_MODE>"; w.nl();
@@ -2328,6 +2434,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
 
   StepKernelCtx ctx{si, radius, tcols, tdim, trows, sql};
   stepKernelWrapper(ctx);
+  if (curStepSplit) stepPrefilterKernel(ctx);
   stepLauncher(ctx);
   (void)index;
   curFn = nullptr;
@@ -2338,6 +2445,7 @@ void CudaPrinter::stepKernel(const StepInfo &si, int index) {
   curStepList = false;
   curStepBulk = false;
   curStepDense = false;
+  curStepSplit = false;
 }
 
 std::string CudaPrinter::kernelSource() {
