@@ -111,7 +111,7 @@ def test_slabs_equal_grid_oracle_at_benchmark_size(model_file, n, use_float, ste
 def test_predator_prey_4M_equals_frozen_semantics(slabs):
     """configs[3]: 4 M agents, run-time add/remove.  Parity UNPINNED by the reference (its `c`
     backend refuses add/remove, CBackend.cpp:30-32); the checker is the frozen-semantics section
-    of oracle/abl_oracle.c plus the hand-traced scenario of tests/test_predator_prey_trace.py.
+    of oracle/abl_oracle.c plus the hand-traced scenario of tests/test_lifecycle_trace.py (the add / remove rules restated in Python for a model without random numbers).
     Agent counts after every timestep, sum(Grass.avail), ids and every member: bit-exact."""
     n, steps = 4000000, 5
     m = Model(os.path.join(REPO, "examples", "predator_prey.abl"), {"num_agents": n})
