@@ -2304,7 +2304,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     }
     trace_stamp(rt, TR_OTHER);
     int rc = a.self.n ? s.desc.launch(&a) : 0;
-    rt->launches++;
+    rt->launches += a.pf_masks ? 2 : 1;   // (ABL_MODE 9: the pre-filter kernel and the step kernel)
     trace_stamp(rt, TR_STEP);
     if (rc != 0) return fail(ABL_ERR_CUDA, "step %s: kernel launch failed: %s", s.name.c_str(),
                              cudaGetErrorString((cudaError_t)rc));

@@ -206,7 +206,7 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
-MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", 7: "bulk-tile", 8: "shadow-prefilter", -1: "not launched"}
+MODE_NAMES = {0: "cursor", 1: "chunked", 2: "tile", 3: "flat", 4: "neighbour-list walk", 7: "bulk-tile", 8: "shadow-prefilter", 9: "split-prefilter", -1: "not launched"}
 
 # FP64 operations per agent-step of circle3d's step kernel (SURVEY.md 8d asks for this view next to
 # the HBM one): per candidate 3 sub + 3 mul + 2 add + 1 compare = 9, per accepted candidate the

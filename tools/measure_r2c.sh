@@ -23,7 +23,7 @@ cap() { # name workload kernel-regex skip count extra-args
 cap boids_f64 boids2d-1M-f64 abl_kernel_update_boid 8 1 --no-companion
 cap boids_f32 boids2d-1M-f32 abl_kernel_update_boid 8 1
 cap boids_binning boids2d-1M-f64 'k_bin_|k_tile_' 24 4 --no-companion
-cap circle3d_1M circle3d-1M-f64 abl_kernel_ 6 1
+cap circle3d_1M circle3d-1M-f64 'abl_kernel_|abl_prefilter_' 12 2
 cap gol_16M game_of_life-16M-f64 abl_kernel_ 6 1
 cap gol_16M_nlist game_of_life-16M-f64 abl_kernel_ 8 1 --nlist
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:abl_kernel_ -s 60 -c 13 -f -o $out/prof_r2c_pp_4M \
