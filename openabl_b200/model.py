@@ -127,8 +127,9 @@ class Model:
 
     def step_variant(self, s):
         """ABL_MODE of the kernel the latest launch of step function `s` used (-1 before the first):
-        0 cursor loop, 1 chunked, 2 shared-memory tile, 3 flat loop, 4 neighbour-list walk.  After the
-        tuning phase this is the variant the launcher's run-time tuner kept."""
+        0 cursor loop, 1 chunked, 2 shared-memory tile, 3 flat loop, 4 neighbour-list walk, 7 TMA-staged tile,
+        8 single-precision shadow pre-filter, 9 split pre-filter.  Chosen by the launcher's rule (with
+        ABL_CUDA_TUNE=1: by its run-time tuner, after the tuning phase)."""
         return self.lib.abl_model_step_variant(s)
 
     def sequential_step(self):

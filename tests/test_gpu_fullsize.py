@@ -1,7 +1,8 @@
-"""BASELINE-size checks that need no oracle: at 1 M agents the brute-force reference would take
-hours, so the full-size runs are pinned through properties instead — the shared-memory tile
-path must give bit-identical results to the plain global-memory loop, for every block size; populations are conserved; boids stay
-inside their periodic world."""
+"""BASELINE-size consistency checks between the kernel variants: the shared-memory tile path, the plain
+global-memory loop, the TMA-staged tile, the flat / cursor / timed choices and every block size must give
+bit-identical results at 1 M agents; populations are conserved; boids stay inside their periodic world.
+(Parity with the ORACLE at these sizes — boids2d 1 M, circle3d 1 M, game_of_life 16.7 M, predator_prey 4 M,
+single GPU and slabs — is in tests/test_gpu_parity_fullsize.py.)"""
 import os
 
 import numpy as np
