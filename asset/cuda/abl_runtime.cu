@@ -209,6 +209,8 @@ struct abl_runtime {
   std::vector<Step> steps;
   ScanState scan;
   void *stage = nullptr;       // device staging for AoS transfers
+  u32 *rank_buf = nullptr;     // presence flags + their scan, one word per agent id each (commit_adds with many adds)
+  size_t rank_cap = 0;         // words
   size_t stage_cap = 0;
   void *pinned = nullptr;      // pinned host bounce buffer
   size_t pinned_cap = 0;
@@ -254,7 +256,16 @@ struct abl_runtime {
   // 0.1467 ms per step, profiles/scaling/r1d_weak2_device_range_*.json)
   bool device_range = false;
   bool halo_overlap = true;    // ABL_CUDA_HALO_OVERLAP=0: publish after the whole step kernel instead of boundary-first
+  // ABL_CUDA_HALO_ASYNC=0: the exchange kernel follows the step kernel on the runtime's stream.  Default: it runs
+  // NEXT TO the step kernel on a high-priority side stream (forked before the step kernel is queued, joined before
+  // the next binning) whenever the step kernel publishes by itself (boundary-first scheduling): the neighbours'
+  // records arrive while the interior is still being stepped, so waiting for them, appending them and entering
+  // them into the histogram costs the step nothing.
+  bool halo_async = true;
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
+  bool pdl_trigger = true;     // ABL_CUDA_PDL_TRIGGER=0: successors are launched when a kernel has ended, not when its last wave runs
   bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
   size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
   // Candidate loop of sparse 2-D step kernels: 1 (default) the flat loop — from a bulk-staged tile when
@@ -307,6 +318,12 @@ static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim
   cfg.numAttrs = pdl ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
+
+// ABL_CUDA_PDL_TRIGGER (default 1): every kernel of the per-step chain lets the blocks of its successor become
+// resident as soon as its own last wave is running (they wait in cudaGridDependencySynchronize).
+__constant__ int c_pdl_trigger;
+// ABL_CUDA_BIN_PREFETCH (default 1): k_bin_rank_move requests the lines of a record before it ranks it
+__constant__ int c_bin_prefetch;
 
 static const int kScanBlock = 256;
 static const int kScanItems = 16;                      // per thread
@@ -532,6 +549,7 @@ k_scan(T *in, u32 *out, u32 n, u64 *desc, u32 *ctrl, u32 *total_out) {
 // place: k_bin_scatter draws the slots of every cell segment by counting it back down to zero.
 __global__ void __launch_bounds__(kScanBlock) k_tile_sum(const u32 *in, u32 n, u32 *tile_sum) {
   __shared__ u32 s_warp[kScanBlock / 32];
+  if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const size_t i0 = (size_t)blockIdx.x * kScanTile + (size_t)tid * kScanItems;
@@ -577,6 +595,7 @@ __global__ void __launch_bounds__(kScanBlock) k_tile_scan(u32 *in, u32 *out, u32
                                                           ScanReport report) {
   __shared__ u32 s_warp[kScanBlock / 32];
   __shared__ u32 s_pre[kScanBlock / 32];
+  if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const u32 tile = blockIdx.x;
@@ -708,6 +727,7 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
 // instead of by the last instruction of the step kernel.
 __global__ void k_bin_scatter(const u32 *key, u32 *local, const u32 *ids, u32 n, u32 src_begin,
                               const u32 *cell_start, u32 *seg_ids, u32 *cell_count) {
+  if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n) return;
@@ -733,12 +753,22 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
 // close to the reads (near-coalesced).
 __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *local,
                                 const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start) {
+  if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const u32 src = src_begin + i;
   const u32 c = key[i];
   const u32 mine = ids[src];
+  // the record itself is needed only after three dependent round trips (key -> cell_start -> seg_ids): request
+  // its lines now (one lane per 128-byte line and column)
+  if (c_bin_prefetch) {
+    for (int k = 0; k < t.ncols; k++) {
+      const unsigned char *q = (const unsigned char *)t.in[k] + (size_t)src * t.elem[k];
+      if ((threadIdx.x & 31u) == 0u || ((size_t)q & 127u) < (size_t)t.elem[k])
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+    }
+  }
   const u32 b = cell_start[c], e = cell_start[c + 1];
   u32 rank = 0;
   if (mine == ABL_SENTINEL_ID) rank = local[i];  // padding records: any distinct slot will do
@@ -778,6 +808,32 @@ __global__ void k_append(ColTable t, const u64 *list, u32 m, u32 base, u32 first
   for (u32 q = 0; q < m; q++) rank += (list[q] < mine) ? 1u : 0u;
   u32 src = (u32)mine;
   u32 dst = base + rank;
+  for (int k = 0; k < t.ncols; k++) {
+    if (t.host_off[k] < 0) ((u32 *)t.out[k])[dst] = first_id + rank;  // id column
+    else copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
+  }
+}
+
+// Many adds in one step (m above kAppendScanThreshold): counting costs m compares per new agent.
+// The rank of a parent among the adding parents is then read from an exclusive scan over a
+// presence flag per agent id (k_mark_parents + the runtime's scan: O(next_id + m) instead of
+// O(m^2)); same order, same ids.
+static const u32 kAppendScanThreshold = 2048;
+static u32 append_scan_threshold() {   // ABL_CUDA_APPEND_SCAN=<m>: tests force either path
+  const char *e = getenv("ABL_CUDA_APPEND_SCAN");
+  return e && *e ? (u32)strtoul(e, nullptr, 10) : kAppendScanThreshold;
+}
+__global__ void k_mark_parents(const u64 *list, u32 m, u32 *present) {
+  u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < m) present[(u32)(list[a] >> 32)] = 1u;
+}
+__global__ void k_append_by_id(ColTable t, const u64 *list, const u32 *rank_of_id, u32 m, u32 base, u32 first_id) {
+  u32 a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= m) return;
+  const u64 mine = list[a];
+  const u32 rank = rank_of_id[(u32)(mine >> 32)];
+  const u32 src = (u32)mine;
+  const u32 dst = base + rank;
   for (int k = 0; k < t.ncols; k++) {
     if (t.host_off[k] < 0) ((u32 *)t.out[k])[dst] = first_id + rank;  // id column
     else copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
@@ -1073,7 +1129,16 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *ms = getenv("ABL_CUDA_HALO_TIMEOUT_MS")) rt->halo_timeout_ns = atoll(ms) * 1000000ll;
   if (const char *dr = getenv("ABL_CUDA_DEVICE_RANGE")) rt->device_range = atoi(dr) != 0;
   if (const char *ov = getenv("ABL_CUDA_HALO_OVERLAP")) rt->halo_overlap = atoi(ov) != 0;
+  if (const char *as = getenv("ABL_CUDA_HALO_ASYNC")) rt->halo_async = atoi(as) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
+  if (const char *pt = getenv("ABL_CUDA_PDL_TRIGGER")) rt->pdl_trigger = atoi(pt) != 0;
+  {
+    const int trig = rt->pdl && rt->pdl_trigger ? 1 : 0;
+    CU(cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof trig));
+    const char *bp = getenv("ABL_CUDA_BIN_PREFETCH");
+    const int pre = bp ? (atoi(bp) != 0 ? 1 : 0) : 1;
+    CU(cudaMemcpyToSymbol(c_bin_prefetch, &pre, sizeof pre));
+  }
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
   if (const char *tn = getenv("ABL_CUDA_TUNE")) { if (atoi(tn) != 0) rt->flat_loop = -1; }
   if (const char *dn = getenv("ABL_CUDA_DENSE")) rt->dense_tile = atoi(dn) != 0 ? 1 : 0;
@@ -1153,6 +1218,7 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   if (rt->scan.tile_sum) cudaFree(rt->scan.tile_sum);
   if (rt->scan.ctrl) cudaFree(rt->scan.ctrl);
   if (rt->stage) cudaFree(rt->stage);
+  if (rt->rank_buf) cudaFree(rt->rank_buf);
   if (rt->pinned) cudaFreeHost(rt->pinned);
   if (rt->d_scalar) cudaFree(rt->d_scalar);
   if (rt->h_scalar) cudaFreeHost(rt->h_scalar);
@@ -1161,6 +1227,9 @@ extern "C" int abl_cuda_destroy(abl_runtime *rt) {
   rt->timing_log.clear();
   for (int i = 0; i < 2; i++) if (rt->ev_ts[i]) cudaEventDestroy(rt->ev_ts[i]);
   if (rt->ev_own) cudaEventDestroy(rt->ev_own);
+  if (rt->ev_fork) cudaEventDestroy(rt->ev_fork);
+  if (rt->ev_join) cudaEventDestroy(rt->ev_join);
+  if (rt->side_stream) cudaStreamDestroy(rt->side_stream);
   cudaStreamDestroy(rt->stream);
   delete rt;
   return ABL_OK;
@@ -1283,7 +1352,7 @@ static int slab_settle(abl_runtime *rt, Pool &p);
 static bool halo_direct(const Pool &p);
 static int halo_reserve(abl_runtime *rt, Pool &p);
 static int halo_fill_view(abl_runtime *rt, Pool &p, abl_slab_view &v, bool step_kernel, bool dev_range);
-static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range);
+static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range, bool forked = false);
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
@@ -1914,7 +1983,26 @@ static int commit_adds(abl_runtime *rt, Pool &parent, Pool &target, void *const 
   ColTable t;
   fill_table(target, t, false);
   for (int c = 0; c < t.ncols; c++) t.in[c] = t.host_off[c] < 0 ? nullptr : staging[c];
-  k_append<<<blocks_for(m, 128), 128, 0, rt->stream>>>(t, list, m, (u32)target.n, target.next_id);
+  if (m > append_scan_threshold()) {
+    const size_t padded = round_up((size_t)parent.next_id + 1, kScanTile);
+    if (rt->rank_cap < 2 * padded) {
+      CU(cudaStreamSynchronize(rt->stream));
+      if (rt->rank_buf) CU(cudaFree(rt->rank_buf));
+      rt->rank_buf = nullptr;
+      rt->rank_cap = 0;
+      const size_t cap = round_up(2 * padded + padded / 4, kScanTile);
+      CU(cudaMalloc(&rt->rank_buf, cap * sizeof(u32)));
+      rt->rank_cap = cap;
+    }
+    u32 *present = rt->rank_buf, *rank_of_id = rt->rank_buf + rt->rank_cap / 2;
+    CU(cudaMemsetAsync(present, 0, padded * sizeof(u32), rt->stream));
+    k_mark_parents<<<blocks_for(m, 256), 256, 0, rt->stream>>>(list, m, present);
+    rt->launches++;
+    TRY((run_scan<u32, 0, false>(rt, present, rank_of_id, (size_t)parent.next_id, nullptr)));
+    k_append_by_id<<<blocks_for(m, 128), 128, 0, rt->stream>>>(t, list, rank_of_id, m, (u32)target.n, target.next_id);
+  } else {
+    k_append<<<blocks_for(m, 128), 128, 0, rt->stream>>>(t, list, m, (u32)target.n, target.next_id);
+  }
   rt->launches++;
   CU(cudaGetLastError());
   if (tmp) {
@@ -2287,7 +2375,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
         }
       }
     }
-    a.pdl = rt->pdl ? 1 : 0;
+    a.pdl = rt->pdl ? (rt->pdl_trigger ? 3 : 1) : 0;
     a.stream = (void *)rt->stream;
     // cached neighbour lists: neither pool of this step's for-near loop ever moves (the code
     // generator's guarantee), so the accepted candidates are found once and walked afterwards
@@ -2303,6 +2391,19 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       }
     }
     trace_stamp(rt, TR_OTHER);
+    // the exchange of this step next to its kernel (see halo_async): fork point
+    const bool fork_exchange = direct && !use_dev_range && rt->halo_async && !rt->timing && !rt->trace &&
+                               a.slab.active && a.slab.boundary_first && a.self.n;
+    if (fork_exchange) {
+      if (!rt->side_stream) {
+        int lo_prio = 0, hi_prio = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo_prio, &hi_prio));
+        CU(cudaStreamCreateWithPriority(&rt->side_stream, cudaStreamNonBlocking, hi_prio));
+        CU(cudaEventCreateWithFlags(&rt->ev_fork, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&rt->ev_join, cudaEventDisableTiming));
+      }
+      CU(cudaEventRecord(rt->ev_fork, rt->stream));
+    }
     int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches += a.pf_masks ? 2 : 1;   // (ABL_MODE 9: the pre-filter kernel and the step kernel)
     trace_stamp(rt, TR_STEP);
@@ -2334,7 +2435,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     }
     // slab mode: ghosts of this pool are stale (and agents may have left the slab)
     if (direct) {
-      TRY(halo_finish(rt, self, !use_dev_range && a.slab.boundary_first && a.self.n, use_dev_range));
+      TRY(halo_finish(rt, self, !use_dev_range && a.slab.boundary_first && a.self.n, use_dev_range, fork_exchange));
       trace_stamp(rt, TR_EXCHANGE);
     }
     else if (rt->slab && !rt->peer_lo && !rt->peer_hi && s.desc.written_members && self.pos_member >= 0)
@@ -3298,7 +3399,7 @@ static int halo_reserve(abl_runtime *rt, Pool &p) {
 
 // publish + wait + unpack of exchange number ++halo_seq; records have been packed by the
 // kernel launched just before
-static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range) {
+static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range, bool forked) {
   const u32 seq = ++p.halo_seq;
   // (dev_range: the host's owned range is stale; the kernel reads it from cell_start)
   const u32 ob = p.own_begin, oe = p.own_end, n_own = oe - ob;
@@ -3348,16 +3449,27 @@ static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range)
   // peers, single host thread) the spinning blocks of one slab must leave room for the kernels
   // of the others, so the grid stays small there; across GPUs it covers the device.
   const bool local_peers = (p.halo_peer[0] && !p.halo_ipc[0]) || (p.halo_peer[1] && !p.halo_ipc[1]);
-  const u32 nb = std::max(1u, std::min(blocks_for(pad, 256), local_peers ? 32u : 4u * 148u));
+  // (forked: the kernel runs next to the step kernel and waits there for the neighbours — a few blocks only)
+  const u32 nb = std::max(1u, std::min(blocks_for(pad, 256), forked ? 16u : local_peers ? 32u : 4u * 148u));
+  cudaStream_t xs = rt->stream;
+  if (forked) {
+    // everything queued before the step kernel (the binning that used key / local / histogram) first
+    CU(cudaStreamWaitEvent(rt->side_stream, rt->ev_fork, 0));
+    xs = rt->side_stream;
+  }
   if (rt->real_size == 8) {
-    if (g.dim == 2) k_halo_exchange<double, 2><<<nb, 256, 0, rt->stream>>>(t, a, g);
-    else k_halo_exchange<double, 3><<<nb, 256, 0, rt->stream>>>(t, a, g);
+    if (g.dim == 2) k_halo_exchange<double, 2><<<nb, 256, 0, xs>>>(t, a, g);
+    else k_halo_exchange<double, 3><<<nb, 256, 0, xs>>>(t, a, g);
   } else {
-    if (g.dim == 2) k_halo_exchange<float, 2><<<nb, 256, 0, rt->stream>>>(t, a, g);
-    else k_halo_exchange<float, 3><<<nb, 256, 0, rt->stream>>>(t, a, g);
+    if (g.dim == 2) k_halo_exchange<float, 2><<<nb, 256, 0, xs>>>(t, a, g);
+    else k_halo_exchange<float, 3><<<nb, 256, 0, xs>>>(t, a, g);
   }
   rt->launches++;
   CU(cudaGetLastError());
+  if (forked) {
+    CU(cudaEventRecord(rt->ev_join, rt->side_stream));
+    CU(cudaStreamWaitEvent(rt->stream, rt->ev_join, 0));
+  }
   p.halo_pending = true;
   p.binned = false;
   if (dev_range) {

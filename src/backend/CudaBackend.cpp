@@ -982,6 +982,7 @@ void CudaPrinter::stepPrefilterKernel(const StepKernelCtx &C) {
   w << "__global__ void __launch_bounds__(256, 4) abl_prefilter_" << f.emitName
     << "(const __grid_constant__ abl_step_launch _a, const abl_real _near_limit, const abl_real _near_cull) {";
   w.indent(); w.nl();
+  w << "if (_a.pdl & 2) cudaTriggerProgrammaticLaunchCompletion();"; w.nl();
   w << "cudaGridDependencySynchronize();"; w.nl();
   w << "bool _boundary;"; w.nl();
   w << "unsigned _ob;"; w.nl();
@@ -2058,6 +2059,9 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
     w << "if (ABL_MODE == 7) { extern __shared__ __align__(16) unsigned char _abl_smem0[]; abl_btile_begin(_abl_smem0); }"; w.nl();
     w << "#endif"; w.nl();
   }
+  // (pdl bit 1: the blocks of the NEXT kernel of the stream may become resident while this kernel's last wave
+  // is still running — they wait in their own cudaGridDependencySynchronize until this grid has completed)
+  w << "if (_a.pdl & 2) cudaTriggerProgrammaticLaunchCompletion();"; w.nl();
   w << "cudaGridDependencySynchronize();   // programmatic dependent launch: wait for the preceding kernel"; w.nl();
   // _r: index inside the launched (owned) range, _i: index in the pool's columns
   w << "bool _boundary;"; w.nl();

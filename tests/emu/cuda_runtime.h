@@ -81,6 +81,7 @@ static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess
 static inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) { *ms = b->t - a->t; return cudaSuccess; }
 
 static inline void cudaGridDependencySynchronize() {}
+static inline void cudaTriggerProgrammaticLaunchCompletion() {}
 static inline void __threadfence() {}
 static inline void __threadfence_system() {}
 static inline void __syncthreads() {

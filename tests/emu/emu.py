@@ -78,13 +78,15 @@ def _build_emu(model_dir):
     if os.path.exists(lib) and all(os.path.getmtime(s) <= os.path.getmtime(lib) for s in srcs):
         return lib
     rt_dir = os.path.join(ASSET_DIR, "cuda")
+    tmp = "%s.%d.tmp" % (lib, os.getpid())   # (parallel test workers: never expose a half-written library)
     cmd = ["g++", "-O1", "-ffp-contract=off", "-std=c++17", "-fPIC", "-w", "-I", HERE, "-I", model_dir, "-shared",
-           "-o", lib, "-x", "c++", os.path.join(HERE, "emu_kernels.cpp"), "-x", "none",
+           "-o", tmp, "-x", "c++", os.path.join(HERE, "emu_kernels.cpp"), "-x", "none",
            os.path.join(model_dir, "model_host_lib.o"), os.path.join(model_dir, "abl_host.o"),
            "-L", rt_dir, "-labl_cuda", "-ldl", "-Wl,-rpath," + rt_dir]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulator build failed:\n" + proc.stdout)
+    os.replace(tmp, lib)
     return lib
 
 

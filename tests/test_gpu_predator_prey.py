@@ -17,8 +17,13 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,steps", [(32000, 20), (200000, 6)])
-def test_predator_prey_matches_frozen_semantics(n, steps):
+@pytest.mark.parametrize("n,steps,append_scan", [(32000, 20, None), (200000, 6, None), (32000, 12, "0"), (32000, 12, "1000000000")])
+def test_predator_prey_matches_frozen_semantics(n, steps, append_scan, monkeypatch):
+    # append_scan: ABL_CUDA_APPEND_SCAN pins how new agents are ranked by parent id (commit_adds in
+    # abl_runtime.cu): "0" = always through the scan over per-id presence flags, huge = always by counting;
+    # None = the runtime's rule (counting up to 2048 adds per step function).  Same ids either way.
+    if append_scan is not None:
+        monkeypatch.setenv("ABL_CUDA_APPEND_SCAN", append_scan)
     m = Model(os.path.join(REPO, "examples", "predator_prey.abl"), {"num_agents": n})
     m.populate()
     o = PredatorPreyOracle(n)
