@@ -209,6 +209,8 @@ struct abl_runtime {
   std::vector<Step> steps;
   ScanState scan;
   void *stage = nullptr;       // device staging for AoS transfers
+  int replay_reps = 0;         // abl_cuda_time_kernel: the next abl_cuda_step times its kernel over this many extra launches
+  float replay_ms = 0.f;       // ... average duration of one of them
   u32 *rank_buf = nullptr;     // presence flags + their scan, one word per agent id each (commit_adds with many adds)
   size_t rank_cap = 0;         // words
   size_t stage_cap = 0;
@@ -265,7 +267,7 @@ struct abl_runtime {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
-  bool pdl_trigger = true;     // ABL_CUDA_PDL_TRIGGER=0: successors are launched when a kernel has ended, not when its last wave runs
+  bool pdl_trigger = false;    // ABL_CUDA_PDL_TRIGGER=1: successors become resident while a kernel's last wave runs (measured neutral, off)
   bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
   size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
   // Candidate loop of sparse 2-D step kernels: 1 (default) the flat loop — from a bulk-staged tile when
@@ -319,8 +321,9 @@ static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
-// ABL_CUDA_PDL_TRIGGER (default 1): every kernel of the per-step chain lets the blocks of its successor become
-// resident as soon as its own last wave is running (they wait in cudaGridDependencySynchronize).
+// ABL_CUDA_PDL_TRIGGER=1 (default 0): every kernel of the per-step chain lets the blocks of its successor become
+// resident as soon as its own last wave is running (they wait in cudaGridDependencySynchronize).  Same-box A/B on
+// a B200, boids2d 1 M: 0.0989 / 0.0993 ms per step without / with — neutral, hence off.
 __constant__ int c_pdl_trigger;
 // ABL_CUDA_BIN_PREFETCH (default 1): k_bin_rank_move requests the lines of a record before it ranks it
 __constant__ int c_bin_prefetch;
@@ -2212,8 +2215,18 @@ static int build_neighbour_lists(abl_runtime *rt, Step &s, const abl_step_launch
   if (nl.idx_cap < words) {
     if (nl.idx) CU(cudaFree(nl.idx));
     nl.idx = nullptr;
+    nl.idx_cap = 0;
+    // the lists are an optimisation: when the device has no room for them the step keeps the ordinary loop
+    if (cudaMalloc(&nl.idx, words * sizeof(u32)) != cudaSuccess) {
+      cudaGetLastError();
+      nl.idx = nullptr;
+      nl.off = true;
+      if (getenv("ABL_CUDA_VERBOSE"))
+        fprintf(stderr, "abl_cuda: step %s: no device memory for %.1f MB of neighbour lists: ordinary loop\n",
+                s.name.c_str(), words * 4.0 / 1048576.0);
+      return ABL_OK;
+    }
     nl.idx_cap = words;
-    CU(cudaMalloc(&nl.idx, nl.idx_cap * sizeof(u32)));
   }
   b.nlist_phase = 2;
   b.nlist_idx = nl.idx;
@@ -2404,6 +2417,33 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
       }
       CU(cudaEventRecord(rt->ev_fork, rt->stream));
     }
+    if (rt->replay_reps > 0) {
+      // abl_cuda_time_kernel: the kernel's own duration, undisturbed by events between the kernels of the chain.
+      // The launch is repeated on the same input buffers (a step kernel reads `in` and writes `out`: every
+      // repetition stores the same values), one untimed launch first, then `reps` between two events; the fused
+      // histogram the repetitions add to is cleared again before the launch that counts.
+      const int reps = rt->replay_reps;
+      rt->replay_reps = 0;
+      rt->replay_ms = 0.f;
+      if (a.self.n && !rt->slab && !mutating) {
+        cudaEvent_t e0, e1;
+        CU(cudaEventCreate(&e0));
+        CU(cudaEventCreate(&e1));
+        int rrc = s.desc.launch(&a);
+        CU(cudaEventRecord(e0, rt->stream));
+        for (int r = 0; r < reps && rrc == 0; r++) rrc = s.desc.launch(&a);
+        CU(cudaEventRecord(e1, rt->stream));
+        if (a.bin_count) CU(cudaMemsetAsync(self.cell_count, 0, ((size_t)rt->grid.n_local + 2) * sizeof(u32), rt->stream));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        if (rrc != 0) return fail(ABL_ERR_CUDA, "step %s: kernel launch failed: %s", s.name.c_str(), cudaGetErrorString((cudaError_t)rrc));
+        rt->replay_ms = ms / (float)reps;
+        rt->launches += (unsigned)(reps + 1) * (a.pf_masks ? 2 : 1);
+      }
+    }
     int rc = a.self.n ? s.desc.launch(&a) : 0;
     rt->launches += a.pf_masks ? 2 : 1;   // (ABL_MODE 9: the pre-filter kernel and the step kernel)
     trace_stamp(rt, TR_STEP);
@@ -2492,6 +2532,17 @@ extern "C" int abl_cuda_last_exec_time(abl_runtime *rt, double *seconds) {
   }
   if (seconds) *seconds = ms / 1000.0;
   return ABL_OK;
+}
+
+extern "C" int abl_cuda_time_kernel(abl_runtime *rt, int step, int reps, float *ms_per_launch) {
+  if (!rt) return fail(ABL_ERR_ARGUMENT, "null runtime");
+  if (reps < 1) return fail(ABL_ERR_ARGUMENT, "time_kernel: reps must be positive");
+  rt->replay_reps = reps;
+  rt->replay_ms = 0.f;
+  int rc = abl_cuda_step(rt, step);
+  rt->replay_reps = 0;
+  if (ms_per_launch) *ms_per_launch = rt->replay_ms;
+  return rc;
 }
 
 extern "C" int abl_cuda_enable_timing(abl_runtime *rt, int on) {

@@ -312,6 +312,11 @@ typedef struct {
   unsigned launches;       /* kernels launched by the runtime since creation */
 } abl_step_timing;
 int abl_cuda_enable_timing(abl_runtime *rt, int on);
+/* Runs step function `step` once (like abl_cuda_step) and, before the launch that counts, times `reps` further
+ * launches of its kernel on the same input buffers between two events on the runtime's stream: the average
+ * duration of ONE launch, without the idle time an event between two kernels of the per-step chain adds.
+ * *ms_per_launch = 0 when the step cannot be repeated (it adds or removes agents, slab decomposition, empty pool). */
+int abl_cuda_time_kernel(abl_runtime *rt, int step, int reps, float *ms_per_launch);
 int abl_cuda_last_timing(abl_runtime *rt, abl_step_timing *t);
 void *abl_cuda_stream(abl_runtime *rt);
 

@@ -70,6 +70,7 @@ ABI = {
     "abl_cuda_debug_binning": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t, _VP, C.c_size_t]),
     "abl_cuda_grid_cells": (C.c_int, [_VP, C.POINTER(C.c_uint), C.POINTER(C.c_int * 3)]),
     "abl_cuda_enable_timing": (C.c_int, [_VP, C.c_int]),
+    "abl_cuda_time_kernel": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(C.c_float)]),
     "abl_cuda_last_timing": (C.c_int, [_VP, C.POINTER(StepTiming)]),
     "abl_cuda_stream": (_VP, [_VP]),
     "abl_cuda_nccl_unique_id": (C.c_int, [_VP]),
@@ -329,6 +330,12 @@ class Runtime:
 
     def enable_timing(self, on=True):
         check(self.lib.abl_cuda_enable_timing(self.handle, 1 if on else 0), "enable_timing")
+
+    def time_kernel(self, step, reps=20):
+        """One call of step function `step`; -> average ms of one launch of its kernel over `reps` repetitions."""
+        ms = C.c_float()
+        check(self.lib.abl_cuda_time_kernel(self.handle, step, reps, C.byref(ms)), "time_kernel")
+        return ms.value
 
     def last_timing(self):
         t = StepTiming()
