@@ -267,6 +267,7 @@ struct abl_runtime {
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
+  bool report_in_scan = false; // ABL_CUDA_REPORT_IN_SCAN=1: the owned range is reported by k_tile_scan instead of k_bin_scatter
   bool pdl_trigger = false;    // ABL_CUDA_PDL_TRIGGER=1: successors become resident while a kernel's last wave runs (measured neutral, off)
   bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
   size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
@@ -688,7 +689,9 @@ __device__ __forceinline__ void bin_count_one(const void *px, const void *py, co
   if (ids && ids[s] == ABL_SENTINEL_ID) {
     // padding record of a halo message: parked in the trash cell behind all real cells
     key[o] = g.n_local;
-    atomicAdd(&cell_count[g.n_local], 1u);
+    // (one update per group of converged lanes: the padding records sit next to each other)
+    const unsigned grp = __activemask();
+    if ((threadIdx.x & 31u) == (unsigned)__ffs(grp) - 1u) atomicAdd(&cell_count[g.n_local], (u32)__popc(grp));
     return;
   }
   R x, y, z = 0;
@@ -728,14 +731,39 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
 // so the histogram is all zero again when the kernel ends — ready for the next fused histogram
 // without a clearing pass — and the atomic round trip is paid by this short, fully occupied kernel
 // instead of by the last instruction of the step kernel.
+// Slab decomposition: the first thread also reports the owned range (ScanReport, see k_tile_scan) — from here
+// rather than from the scan, whose few short blocks would all wait for the two round trips to host memory of
+// the reporting threads (device timeline on 2 B200: scan 9 -> 16 us); this kernel runs longer than the report.
 __global__ void k_bin_scatter(const u32 *key, u32 *local, const u32 *ids, u32 n, u32 src_begin,
-                              const u32 *cell_start, u32 *seg_ids, u32 *cell_count) {
+                              const u32 *cell_start, u32 *seg_ids, u32 *cell_count, ScanReport report) {
   if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (report.host && t == 0) {
+    volatile u32 *hw = report.host;
+    hw[0] = cell_start[report.lo_cell];
+    hw[1] = cell_start[report.hi_cell];
+    for (int k = 0; k < 6; k++) hw[2 + k] = report.halo_ctr ? report.halo_ctr[2 + k] : 0;
+    hw[8] = cell_start[report.lo2_cell];
+    hw[9] = cell_start[report.hi2_cell];
+    hw[10] = report.halo_ctr ? report.halo_ctr[12] : 0;  // late
+    hw[11] = report.halo_ctr ? report.halo_ctr[14] : 0;  // sequence number of that exchange
+    hw[12] = report.halo_ctr ? 1u : 0u;
+    __threadfence_system();
+    for (int k = 16; k <= 20; k++) hw[k] = report.stamp;
+  }
   if (t >= n) return;
   const u32 c = key[t];
-  const u32 l = atomicSub(&cell_count[c], 1u) - 1u;
+  // lanes of a warp that share a cell draw their slots with ONE atomic (the pool is almost in cell order, so
+  // cell mates sit in neighbouring lanes; the padding records of a halo exchange all share the trash cell and
+  // would otherwise queue up on a single counter, as would a crowd in one cell)
+  const unsigned peers = __match_any_sync(__activemask(), c);
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned leader = __ffs(peers) - 1u;
+  u32 base = 0;
+  if (lane == leader) base = atomicSub(&cell_count[c], (u32)__popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  const u32 l = base - 1u - (u32)__popc(peers & ((1u << lane) - 1u));
   local[t] = l;
   seg_ids[cell_start[c] + l] = ids[src_begin + t];
 }
@@ -1135,6 +1163,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *as = getenv("ABL_CUDA_HALO_ASYNC")) rt->halo_async = atoi(as) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *pt = getenv("ABL_CUDA_PDL_TRIGGER")) rt->pdl_trigger = atoi(pt) != 0;
+  if (const char *rs = getenv("ABL_CUDA_REPORT_IN_SCAN")) rt->report_in_scan = atoi(rs) != 0;
   {
     const int trig = rt->pdl && rt->pdl_trigger ? 1 : 0;
     CU(cudaMemcpyToSymbol(c_pdl_trigger, &trig, sizeof trig));
@@ -1777,6 +1806,9 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
   p.counted = false;
   // 2. cell_start[c] = number of agents in cells < c; entry n_cells = n.  The scan also
   //    clears the histogram for the next binning.
+  bool scatter_reports = false;
+  ScanReport scatter_rep;
+  memset(&scatter_rep, 0, sizeof scatter_rep);
   if (rt->slab) {
     ScanReport rep;
     bool reported = false;
@@ -1786,8 +1818,11 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
     rep.stamp = p.report_stamp = ++rt->bin_stamp;
     rep.halo_ctr = p.halo_pending ? p.halo_ctr : nullptr;
     p.halo_pending = false;
-    TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, &rep, &reported));
-    TRY(slab_request_owned_range(rt, p, reported, rep));
+    // (the report travels with k_bin_scatter when there is one; ABL_CUDA_REPORT_IN_SCAN=1: with the scan)
+    scatter_reports = n != 0 && !rt->report_in_scan;
+    if (scatter_reports) scatter_rep = rep;
+    TRY(run_cell_scan(rt, p.cell_count, p.cell_start, (size_t)g.n_local + 2, scatter_reports ? nullptr : &rep, &reported));
+    if (!scatter_reports) TRY(slab_request_owned_range(rt, p, reported, rep));
     p.report_pending = true;
     p.own_valid = false;
   } else {
@@ -1800,7 +1835,7 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
     u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
     CU(launch_pdl(rt->pdl, k_bin_scatter, dim3(nb), dim3(bs), 0, rt->stream, (const u32 *)p.key, p.local, ids, n,
-                  p.src_begin, (const u32 *)p.cell_start, seg_ids, p.cell_count));
+                  p.src_begin, (const u32 *)p.cell_start, seg_ids, p.cell_count, scatter_rep));
     ColTable t;
     fill_table(p, t, true);
     CU(launch_pdl(rt->pdl, k_bin_rank_move, dim3(nb), dim3(bs), 0, rt->stream, t, (const u32 *)seg_ids, (const u32 *)p.key,

@@ -5,7 +5,7 @@ set -u
 out=gpurun_out
 mkdir -p $out
 N=${1:-2}
-for a in 1 0 1 0; do
+for a in ${ASYNC_LIST:-1 0 1 0}; do
   ABL_CUDA_HALO_ASYNC=$a timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus $N --steps 100 --warmup 10 --no-companion --no-cpu-baseline > $out/r2d_n${N}_async$a.json 2> $out/r2d_n${N}_async$a.err
   python - $out/r2d_n${N}_async$a.json $a <<'PY'
