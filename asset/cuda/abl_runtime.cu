@@ -268,6 +268,7 @@ struct abl_runtime {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool pdl = true;             // ABL_CUDA_PDL=0 turns programmatic dependent launches off
   bool report_in_scan = false; // ABL_CUDA_REPORT_IN_SCAN=1: the owned range is reported by k_tile_scan instead of k_bin_scatter
+  bool mbar_hint = false;      // ABL_CUDA_MBAR_HINT=1: bulk-tile kernels wait for their tile with a suspend-time hint (pdl bit 2)
   bool pdl_trigger = false;    // ABL_CUDA_PDL_TRIGGER=1: successors become resident while a kernel's last wave runs (measured neutral, off)
   bool nlist = true;           // ABL_CUDA_NLIST=0: ignore abl_step_desc.nlist (A/B against the ordinary loops)
   size_t nlist_budget = (size_t)8 << 30;   // ABL_CUDA_NLIST_MB: largest index array of one step function
@@ -1163,6 +1164,7 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
   if (const char *as = getenv("ABL_CUDA_HALO_ASYNC")) rt->halo_async = atoi(as) != 0;
   if (const char *pd = getenv("ABL_CUDA_PDL")) rt->pdl = atoi(pd) != 0;
   if (const char *pt = getenv("ABL_CUDA_PDL_TRIGGER")) rt->pdl_trigger = atoi(pt) != 0;
+  if (const char *mh = getenv("ABL_CUDA_MBAR_HINT")) rt->mbar_hint = atoi(mh) != 0;
   if (const char *rs = getenv("ABL_CUDA_REPORT_IN_SCAN")) rt->report_in_scan = atoi(rs) != 0;
   {
     const int trig = rt->pdl && rt->pdl_trigger ? 1 : 0;
@@ -2423,7 +2425,7 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
         }
       }
     }
-    a.pdl = rt->pdl ? (rt->pdl_trigger ? 3 : 1) : 0;
+    a.pdl = (rt->pdl ? (rt->pdl_trigger ? 3 : 1) : 0) | (rt->mbar_hint ? 4 : 0);
     a.stream = (void *)rt->stream;
     // cached neighbour lists: neither pool of this step's for-near loop ever moves (the code
     // generator's guarantee), so the accepted candidates are found once and walked afterwards

@@ -240,7 +240,7 @@ typedef struct {
   /* > 0 (set by the generated launcher for dense for-near loops of reach 1): the squared radius bound; the neighbour
    * iterator then narrows every row of cells along x to the cells within reach of the agent (abl_device.cuh: row_reach) */
   double row_cull;
-  int pdl;                                 /* bit 0: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first); bit 1: the kernel triggers the launch of its successor at once (ABL_CUDA_PDL_TRIGGER) */
+  int pdl;                                 /* bit 0: launch with programmatic stream serialization (the kernel calls cudaGridDependencySynchronize first); bit 1: the kernel triggers the launch of its successor at once (ABL_CUDA_PDL_TRIGGER); bit 2: bulk-tile kernels wait for their tile with a suspend-time hint (ABL_CUDA_MBAR_HINT) */
   void *stream;                            /* cudaStream_t */
   /* Cached neighbour lists (steps registered with abl_step_desc.nlist != 0: neither pool of the
    * for-near loop ever moves, so the set of accepted candidates of every agent is the same in

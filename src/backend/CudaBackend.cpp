@@ -2152,7 +2152,7 @@ void CudaPrinter::stepKernelWrapper(const StepKernelCtx &C) {
     w << "if (!_active) return;"; w.nl();
     w << "abl_near_iter<2> _rows;"; w.nl();
     w << "_rows.rows2(_a, " << p.name << "." << selfPosM->name << ", true, _near_cull);"; w.nl();
-    w << "_tile_ok = abl_btile_wait(_abl_smem);"; w.nl();
+    w << "_tile_ok = abl_btile_wait(_abl_smem, (_a.pdl & 4) != 0);"; w.nl();
     w << "_bt = abl_btile_thread2(_rows, _abl_smem, _tile_ok);";
     w.outdent(); w.nl();
     w << "}"; w.nl();
