@@ -6,7 +6,6 @@ out=gpurun_out
 mkdir -p $out
 timeout 900 python -m pytest tests -m gpu -q --durations=5 > $out/r2j_pytest_gpu.log 2>&1; echo "pytest -m gpu rc=$?" | tee -a $out/r2j_pytest_gpu.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $out/r2j_bench_default_n1.json 2> $out/r2j_bench_default_n1.err
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > $out/r2j_bench_reference_n1.json 2> $out/r2j_bench_reference_n1.err
 for w in boids2d-16M-f64 boids2d-1M-f32; do
   timeout 300 python bench.py --workload $w --no-cpu-baseline --no-companion --steps 30 --warmup 10 > $out/r2j_$w.json 2> $out/r2j_$w.err
 done
@@ -16,7 +15,7 @@ cap() { # name workload kernel-regex skip count extra-args
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$3 -s $4 -c $5 -f -o $out/prof_r2j_$1 \
     python bench.py --workload $2 --steps 6 --warmup 3 --no-cpu-baseline ${6:-} > $out/r2j_ncu_$1.log 2>&1
 }
-cap boids_f64 boids2d-1M-f64 abl_kernel_update_boid 8 1 --no-companion
+[ -n "${WITH_STEP_KERNEL:-}" ] && cap boids_f64 boids2d-1M-f64 abl_kernel_update_boid 8 1 --no-companion
 cap boids_binning boids2d-1M-f64 'k_bin_|k_tile_' 24 4 --no-companion
 python - <<'PY'
 import json, glob
