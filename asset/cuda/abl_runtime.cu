@@ -2436,8 +2436,13 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     }
     trace_stamp(rt, TR_OTHER);
     // the exchange of this step next to its kernel (see halo_async): fork point
+    // (a column the step does not write keeps ONE buffer: the exchange would store arrivals behind the owned range
+    // of the very array whose ghost records the neighbour loop may still be reading — only forked when the loop
+    // reads another pool or every member is rewritten, i.e. arrivals land in output buffers)
+    const unsigned all_members = self.members.size() >= 32 ? 0xffffffffu : ((1u << self.members.size()) - 1u);
+    const bool arrivals_hit_outputs = nbr != &self || (s.desc.written_members & all_members) == all_members;
     const bool fork_exchange = direct && !use_dev_range && rt->halo_async && !rt->timing && !rt->trace &&
-                               a.slab.active && a.slab.boundary_first && a.self.n;
+                               a.slab.active && a.slab.boundary_first && a.self.n && arrivals_hit_outputs;
     if (fork_exchange) {
       if (!rt->side_stream) {
         int lo_prio = 0, hi_prio = 0;
