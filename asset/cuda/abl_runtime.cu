@@ -777,28 +777,53 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
 // scan of seg_ids.  All reads of the agent's record are coalesced; because agents move
 // little between two binnings the pool is already almost in cell order and the writes land
 // close to the reads (near-coalesced).
+// Crowded cells (more than kRankCoop agents: a population gathered in one place, or agents beyond the
+// environment's bounds clamped into an edge cell): every agent of such a cell would read the whole
+// segment on its own.  Those agents are ranked by their warp instead, one after the other — the 32
+// lanes count a strided share of the segment each (coalesced) and add up with one redux: 1/32 of the
+// reads and compares, which keeps the rank well below what the neighbour loop over the same cell costs
+// the step kernel.
+static const u32 kRankCoop = 128;
 __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *local,
                                 const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start) {
   if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
-  u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const u32 src = src_begin + i;
-  const u32 c = key[i];
-  const u32 mine = ids[src];
-  // the record itself is needed only after three dependent round trips (key -> cell_start -> seg_ids): request
-  // its lines now (one lane per 128-byte line and column)
-  if (c_bin_prefetch) {
-    for (int k = 0; k < t.ncols; k++) {
-      const unsigned char *q = (const unsigned char *)t.in[k] + (size_t)src * t.elem[k];
-      if ((threadIdx.x & 31u) == 0u || ((size_t)q & 127u) < (size_t)t.elem[k])
-        asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+  const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < n;            // (no early return: whole warps reach the collectives below)
+  const u32 src = src_begin + (valid ? i : 0u);
+  u32 mine = ABL_SENTINEL_ID, b = 0, e = 0;
+  if (valid) {
+    const u32 c = key[i];
+    mine = ids[src];
+    // the record itself is needed only after three dependent round trips (key -> cell_start -> seg_ids): request
+    // its lines now (one lane per 128-byte line and column)
+    if (c_bin_prefetch) {
+      for (int k = 0; k < t.ncols; k++) {
+        const unsigned char *q = (const unsigned char *)t.in[k] + (size_t)src * t.elem[k];
+        if ((threadIdx.x & 31u) == 0u || ((size_t)q & 127u) < (size_t)t.elem[k])
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
+      }
     }
+    b = cell_start[c];
+    e = cell_start[c + 1];
   }
-  const u32 b = cell_start[c], e = cell_start[c + 1];
   u32 rank = 0;
-  if (mine == ABL_SENTINEL_ID) rank = local[i];  // padding records: any distinct slot will do
-  else for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
+  const bool crowded = valid && mine != ABL_SENTINEL_ID && e - b > kRankCoop;
+  if (valid && mine == ABL_SENTINEL_ID) rank = local[i];  // padding records: any distinct slot will do
+  else if (valid && !crowded) for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
+  unsigned todo = __ballot_sync(0xffffffffu, crowded);
+  const u32 lane = threadIdx.x & 31u;
+  while (todo) {
+    const int owner = __ffs(todo) - 1;
+    todo &= todo - 1u;
+    const u32 ob = __shfl_sync(0xffffffffu, b, owner), oe = __shfl_sync(0xffffffffu, e, owner);
+    const u32 oid = __shfl_sync(0xffffffffu, mine, owner);
+    u32 cnt = 0;
+    for (u32 q = ob + lane; q < oe; q += 32u) cnt += (seg_ids[q] < oid) ? 1u : 0u;
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((int)lane == owner) rank = cnt;
+  }
+  if (!valid) return;
   const u32 dst = b + rank;
   for (int k = 0; k < t.ncols; k++) copy_elem(t.out[k], dst, t.in[k], src, t.elem[k]);
 }
