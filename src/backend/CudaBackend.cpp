@@ -2210,23 +2210,24 @@ void CudaPrinter::stepLauncher(const StepKernelCtx &C) {
   if (curStepHasLimit) {
     // host-side evaluation of the radius with the kernel's own arithmetic and constants
     Target saved = target;
-    w << "    static abl_real limit; static bool have_limit = false;"; w.nl();
-    w << "    if (!have_limit) { limit = abl_near_sq_limit((abl_real)(";
+    // (function-local statics with an initialiser: initialised once, thread-safe — the group driver calls the
+    // launcher from one host thread per device)
+    w << "    static const abl_real limit = abl_near_sq_limit((abl_real)(";
     expr(*radius);
-    w << ")); have_limit = true; }"; w.nl();
+    w << "));"; w.nl();
     target = saved;
   } else {
     w << "    const abl_real limit = 0;"; w.nl();
   }
   if (sql) {
-    w << "    static abl_sq_limits sql; static bool have_sql = false;"; w.nl();
-    w << "    if (!have_sql) {"; w.nl();
-    w << "        memset(&sql, 0, sizeof sql);"; w.nl();
+    w << "    static const abl_sq_limits sql = [] {"; w.nl();
+    w << "        abl_sq_limits s;"; w.nl();
+    w << "        memset(&s, 0, sizeof s);"; w.nl();
     for (size_t k = 0; k < sqLimits.size(); k++) {
-      w << "        sql.v[" << k << "] = abl_sq_cmp_limit(" << sqLimits[k].first << ", (abl_real)(" << sqLimits[k].second << "));"; w.nl();
+      w << "        s.v[" << k << "] = abl_sq_cmp_limit(" << sqLimits[k].first << ", (abl_real)(" << sqLimits[k].second << "));"; w.nl();
     }
-    w << "        have_sql = true;"; w.nl();
-    w << "    }"; w.nl();
+    w << "        return s;"; w.nl();
+    w << "    }();"; w.nl();
   }
   // cell-range culling for radii well below the cell size (`-C cuda.cull=false` turns it off)
   if (curStepHasLimit && config.getBool("cuda.cull", true)) {
