@@ -152,3 +152,52 @@ void abl_host_log_open(const char *path) { if (!log_file) log_file = fopen(path,
 void abl_host_log_int(int first, int v) { if (log_file) fprintf(log_file, first ? "%d" : ",%d", v); }
 void abl_host_log_float(int first, double v) { if (log_file) fprintf(log_file, first ? "%f" : ",%f", v); }
 void abl_host_log_end(void) { if (log_file) { fputc('\n', log_file); fflush(log_file); } }
+
+/* ---- frames of a visualised run (abl_host.h) ------------------------------------------------- */
+extern int mkdir(const char *path, unsigned int mode);   /* <sys/stat.h>, POSIX: not declared under -std=c99 */
+void abl_host_make_dir(const char *path) { (void)mkdir(path, 0777); }
+
+int abl_host_frame_begin(abl_frame *f, int size, double min_x, double min_y, double max_x, double max_y) {
+  double w = max_x - min_x, h = max_y - min_y, side = w > h ? w : h;
+  f->size = size;
+  f->min_x = min_x;
+  f->min_y = min_y;
+  f->scale = side > 0 ? size / side : 1.0;
+  f->rgb = (unsigned char *)malloc((size_t)size * size * 3);
+  if (!f->rgb) return 1;
+  memset(f->rgb, 0xff, (size_t)size * size * 3);   /* display.setBackdrop(Color.white) */
+  return 0;
+}
+
+void abl_host_frame_dot(abl_frame *f, double x, double y, int rgb, double size) {
+  if (!(x == x) || !(y == y) || !(size > 0)) return;
+  const double cx = (x - f->min_x) * f->scale, cy = (y - f->min_y) * f->scale;
+  const double r = 2.0 * size;                       /* an oval of 4 * getSize pixels across */
+  int x0 = (int)floor(cx - r), x1 = (int)ceil(cx + r), y0 = (int)floor(cy - r), y1 = (int)ceil(cy + r);
+  if (x1 < 0 || y1 < 0 || x0 >= f->size || y0 >= f->size) return;
+  if (x0 < 0) x0 = 0;
+  if (y0 < 0) y0 = 0;
+  if (x1 >= f->size) x1 = f->size - 1;
+  if (y1 >= f->size) y1 = f->size - 1;
+  const unsigned char red = (unsigned char)(rgb >> 16), green = (unsigned char)(rgb >> 8), blue = (unsigned char)rgb;
+  for (int py = y0; py <= y1; py++)
+    for (int px = x0; px <= x1; px++) {
+      const double dx = px + 0.5 - cx, dy = py + 0.5 - cy;   /* pixel centres */
+      if (dx * dx + dy * dy > r * r) continue;
+      unsigned char *q = f->rgb + ((size_t)py * f->size + px) * 3;
+      q[0] = red; q[1] = green; q[2] = blue;
+    }
+}
+
+int abl_host_frame_end(abl_frame *f, const char *path) {
+  int rc = 1;
+  FILE *out = fopen(path, "wb");
+  if (out) {
+    fprintf(out, "P6\n%d %d\n255\n", f->size, f->size);
+    rc = fwrite(f->rgb, 3, (size_t)f->size * f->size, out) == (size_t)f->size * f->size ? 0 : 1;
+    if (fclose(out) != 0) rc = 1;
+  }
+  free(f->rgb);
+  f->rgb = NULL;
+  return rc;
+}

@@ -69,6 +69,16 @@ class Model:
         """Runs the model's own initialisation code (statements of main() before simulate)."""
         self.lib.abl_model_populate()
 
+    def write_frame(self, path):
+        """`-C visualize=true` builds only: one picture (binary PPM) of the host arrays as they are — after
+        populate() or download_host() — painted with the model's getColor / getSize hooks."""
+        if not hasattr(self.lib, "abl_model_write_frame"):
+            raise AblError("model was not generated with -C visualize=true")
+        self.lib.abl_model_write_frame.argtypes = [C.c_char_p]
+        self.lib.abl_model_write_frame.restype = C.c_int
+        if self.lib.abl_model_write_frame(os.fsencode(path)) != 0:
+            raise AblError("could not write frame %s" % path)
+
     def host_agents(self, t):
         """Copy of the host records of agent type index `t` as a structured array."""
         arr = self._types[t].agents.contents

@@ -241,6 +241,8 @@ private:
   void storeMember(const AgentDecl &a, int m, const std::string &cols, const std::string &idx,
                    const std::string &value);
   void hostSimulate();
+  void hostVisualize();
+  bool visualize() const { return config.getBool("visualize", false); }
   void hostSeqSupport();
 };
 
@@ -1794,6 +1796,7 @@ std::string CudaPrinter::hostSource() {
     w.nl();
   }
   w.nl();
+  hostVisualize();
   hostSimulate();
 
   // main(): whole user main as abl_model_main, plus the pre-simulate part on its own
@@ -1827,6 +1830,54 @@ std::string CudaPrinter::hostSource() {
   w << "int main(void) { return abl_model_main(); }"; w.nl();
   w << "#endif"; w.nl();
   return w.str();
+}
+
+// `-C visualize=true` (the reference's option name, FlameGPUBackend.cpp:277; its JVM back ends draw the model in a
+// window, MasonPrinter.cpp:704-827): the model's getColor / getSize hooks — analysed by every back end, dropped by all
+// but mason / dmason (AnalysisVisitor.cpp:215-222, src/Sema.cpp) — are printed as host functions, and the `simulate`
+// statement writes one picture per frame interval: frames/frame_<timestep>.ppm (abl_host_frame_*, asset/cuda/abl_host.c).
+void CudaPrinter::hostVisualize() {
+  if (!visualize()) return;
+  std::map<const AgentDecl *, std::string> colorOf, sizeOf;
+  for (Decl &d : script.decls) {
+    if (d.kind != Decl::Func || !d.func || !d.func->skipped) continue;
+    FuncDecl &f = *d.func;
+    if ((f.name != "getColor" && f.name != "getSize") || f.params.size() != 1 || !f.params[0].type.isAgent() ||
+        !f.params[0].type.agent)
+      continue;
+    const AgentDecl *a = f.params[0].type.agent;
+    const std::string name = "abl_vis_" + f.name + "_" + a->name;
+    (f.name == "getColor" ? colorOf : sizeOf)[a] = name;
+    curFn = &f;
+    // (agent-typed variables are pointers to records in host code)
+    w << "static " << typeName(f.retTy) << " " << name << "(const " << a->name << " *" << f.params[0].name << ") {";
+    w.indent(); stmts(f.body); w.outdent();
+    w.nl();
+    w << "}"; w.nl();
+    curFn = nullptr;
+  }
+  EnvDecl *env = script.env;
+  char buf[256];
+  w << "/* one picture of the host arrays as they are (after abl_model_populate or abl_model_download) */"; w.nl();
+  w << "int abl_model_write_frame(const char *path) {"; w.nl();
+  w << "    abl_frame fr;"; w.nl();
+  snprintf(buf, sizeof buf, "    if (abl_host_frame_begin(&fr, 500, %.17g, %.17g, %.17g, %.17g)) return 1;",
+           env ? env->envMin.v[0] : 0.0, env ? env->envMin.v[1] : 0.0, env ? env->envMax.v[0] : 1.0, env ? env->envMax.v[1] : 1.0);
+  w << buf; w.nl();
+  for (AgentDecl *a : script.agents) {
+    AgentMember *pos = a->position();
+    if (!pos) continue;
+    w << "    for (size_t i = 0; i < agents_" << a->name << ".len; i++) {"; w.nl();
+    w << "        const " << a->name << " *a = (const " << a->name << " *)agents_" << a->name << ".data + i;"; w.nl();
+    w << "        abl_host_frame_dot(&fr, (double)a->" << pos->name << ".x, (double)a->" << pos->name << ".y, ";
+    if (colorOf.count(a)) w << "(int)" << colorOf[a] << "(a)"; else w << "0";
+    w << ", ";
+    if (sizeOf.count(a)) w << "(double)" << sizeOf[a] << "(a)"; else w << "1.0";
+    w << ");"; w.nl();
+    w << "    }"; w.nl();
+  }
+  w << "    return abl_host_frame_end(&fr, path);"; w.nl();
+  w << "}"; w.nl(); w.nl();
 }
 
 void CudaPrinter::hostSeqSupport() {
@@ -1914,6 +1965,7 @@ void CudaPrinter::hostSimulate() {
   // FlameMainPrinter.cpp:40-41 `mpirun -np 4`); the runtime does the work (abl_cuda_group_simulate).
   const int gpus = config.getInt("cuda.gpus", 1);
   if (gpus < 1) throw BackendError("cuda backend: cuda.gpus must be at least 1");
+  if (gpus > 1 && visualize()) throw BackendError("cuda backend: visualize=true is not supported with cuda.gpus > 1");
   bool addsAtRunTime = false;
   for (const StepInfo &si : steps) addsAtRunTime = addsAtRunTime || si.fn->addedAgent != nullptr;
   if (gpus > 1 && (seq || addsAtRunTime))
@@ -1938,6 +1990,7 @@ void CudaPrinter::hostSimulate() {
   w << "    int gpus = " << gpus << ";   /* -C cuda.gpus */"; w.nl();
   w << "    if (getenv(\"ABL_CUDA_GPUS\")) gpus = atoi(getenv(\"ABL_CUDA_GPUS\"));"; w.nl();
   w << "    if (gpus > 1) {"; w.nl();
+  if (visualize()) { w << "        fprintf(stderr, \"ABL_CUDA_GPUS > 1: no frames are written (visualize=true draws single-device runs)\\n\");"; w.nl(); }
   if (seq || addsAtRunTime) {
     w << "        fprintf(stderr, \"ABL_CUDA_GPUS > 1 is not supported for this model (sequential step or run-time add())\\n\");"; w.nl();
     w << "        exit(1);"; w.nl();
@@ -1960,7 +2013,24 @@ void CudaPrinter::hostSimulate() {
   w << "    abl_host_check(abl_cuda_create(&rt, &cfg), \"create\");"; w.nl();
   w << "    abl_host_check(abl_model_setup(rt), \"setup\");"; w.nl();
   w << "    abl_model_upload(rt);"; w.nl();
-  w << "    for (int t = 0; t < timesteps; t++) abl_model_timestep(rt);"; w.nl();
+  if (visualize()) {
+    const int every = config.getInt("cuda.frame_interval", 1);
+    if (every < 1) throw BackendError("cuda backend: cuda.frame_interval must be at least 1");
+    w << "    /* -C visualize=true: frames/frame_<timestep>.ppm of the initial state and after every " << every << " timestep(s) */"; w.nl();
+    w << "    abl_host_make_dir(\"frames\");"; w.nl();
+    w << "    abl_model_write_frame(\"frames/frame_00000.ppm\");"; w.nl();
+    w << "    for (int t = 0; t < timesteps; t++) {"; w.nl();
+    w << "        abl_model_timestep(rt);"; w.nl();
+    w << "        if ((t + 1) % " << every << " == 0 || t + 1 == timesteps) {"; w.nl();
+    w << "            char frame_path[64];"; w.nl();
+    w << "            abl_model_download(rt);"; w.nl();
+    w << "            snprintf(frame_path, sizeof frame_path, \"frames/frame_%05d.ppm\", t + 1);"; w.nl();
+    w << "            abl_model_write_frame(frame_path);"; w.nl();
+    w << "        }"; w.nl();
+    w << "    }"; w.nl();
+  } else {
+    w << "    for (int t = 0; t < timesteps; t++) abl_model_timestep(rt);"; w.nl();
+  }
   w << "    abl_model_download(rt);"; w.nl();
   w << "    abl_model_unpin(rt);"; w.nl();
   w << "    abl_rt = NULL;"; w.nl();

@@ -107,6 +107,8 @@ static void printHelp() {
                " * bool cuda.unroll     (default: false) unroll the for-near candidate loop by two\n"
                " * str  cuda.save_format (default: json) save() output: json, flame_xml or flamegpu_xml\n"
                " * int  cuda.dump_state (default: 0)     also write raw binary state on save()\n"
+               " * bool visualize       (default: false) write frames/frame_<timestep>.ppm, agents painted by the model's\n"
+               "                                          getColor / getSize (every cuda.frame_interval timesteps, default 1)\n"
             << std::flush;
 }
 
