@@ -329,6 +329,12 @@ static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim
 __constant__ int c_pdl_trigger;
 // ABL_CUDA_BIN_PREFETCH (default 1): k_bin_rank_move requests the lines of a record before it ranks it
 __constant__ int c_bin_prefetch;
+// ABL_CUDA_BIN_SEGINFO=1 (default 0): k_bin_scatter leaves begin and size of every agent's cell segment per agent
+// (coalesced), so that k_bin_rank_move reaches the segment's ids after one round trip instead of two
+// (key -> cell_start -> ids becomes {begin, size} -> ids).  Same-box A/B on a B200, boids2d 1 M: 0.0916 / 0.0912 ms
+// per timestep with the L2 flushed, 0.0828 / 0.0836 ms steady — the 8 bytes per agent cost what the round trip
+// saves; off.
+__constant__ int c_bin_seginfo;
 
 static const int kScanBlock = 256;
 static const int kScanItems = 16;                      // per thread
@@ -736,7 +742,7 @@ __global__ void k_bin_count(const void *px, const void *py, const void *pz, u32 
 // rather than from the scan, whose few short blocks would all wait for the two round trips to host memory of
 // the reporting threads (device timeline on 2 B200: scan 9 -> 16 us); this kernel runs longer than the report.
 __global__ void k_bin_scatter(const u32 *key, u32 *local, const u32 *ids, u32 n, u32 src_begin,
-                              const u32 *cell_start, u32 *seg_ids, u32 *cell_count, ScanReport report) {
+                              const u32 *cell_start, u32 *seg_ids, u32 *cell_count, ScanReport report, u32 *seg_begin) {
   if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   u32 t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -759,8 +765,17 @@ __global__ void k_bin_scatter(const u32 *key, u32 *local, const u32 *ids, u32 n,
   // instruction iterates over the distinct keys of the warp — nearly 32 here — and the kernel went from 11 to
   // 20 us at 1 M agents.)
   const u32 l = atomicSub(&cell_count[c], 1u) - 1u;
-  local[t] = l;
-  seg_ids[cell_start[c] + l] = ids[src_begin + t];
+  const u32 b = cell_start[c];
+  const u32 id = ids[src_begin + t];
+  seg_ids[b + l] = id;
+  if (c_bin_seginfo) {
+    // for k_bin_rank_move: where the agent's cell segment begins and how many ids it holds (padding records of a
+    // halo exchange keep their slot instead: any distinct slot will do for them)
+    seg_begin[t] = b;
+    local[t] = id == ABL_SENTINEL_ID ? l : cell_start[c + 1] - b;
+  } else {
+    local[t] = l;
+  }
 }
 
 __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src, size_t si, int elem) {
@@ -785,15 +800,14 @@ __device__ __forceinline__ void copy_elem(void *dst, size_t di, const void *src,
 // the step kernel.
 static const u32 kRankCoop = 128;
 __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, const u32 *local,
-                                const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start) {
+                                const u32 *ids, u32 n, u32 src_begin, const u32 *cell_start, const u32 *seg_begin) {
   if (c_pdl_trigger) cudaTriggerProgrammaticLaunchCompletion();
   cudaGridDependencySynchronize();
   const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;            // (no early return: whole warps reach the collectives below)
   const u32 src = src_begin + (valid ? i : 0u);
-  u32 mine = ABL_SENTINEL_ID, b = 0, e = 0;
+  u32 mine = ABL_SENTINEL_ID, b = 0, e = 0, slot = 0;
   if (valid) {
-    const u32 c = key[i];
     mine = ids[src];
     // the record itself is needed only after three dependent round trips (key -> cell_start -> seg_ids): request
     // its lines now (one lane per 128-byte line and column)
@@ -804,12 +818,21 @@ __global__ void k_bin_rank_move(ColTable t, const u32 *seg_ids, const u32 *key, 
           asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
       }
     }
-    b = cell_start[c];
-    e = cell_start[c + 1];
+    if (c_bin_seginfo) {
+      b = seg_begin[i];
+      const u32 x = local[i];            // size of the segment; the drawn slot for padding records
+      e = b + (mine == ABL_SENTINEL_ID ? 0u : x);
+      slot = x;
+    } else {
+      const u32 c = key[i];
+      b = cell_start[c];
+      e = cell_start[c + 1];
+      if (mine == ABL_SENTINEL_ID) slot = local[i];
+    }
   }
   u32 rank = 0;
   const bool crowded = valid && mine != ABL_SENTINEL_ID && e - b > kRankCoop;
-  if (valid && mine == ABL_SENTINEL_ID) rank = local[i];  // padding records: any distinct slot will do
+  if (valid && mine == ABL_SENTINEL_ID) rank = slot;  // padding records: any distinct slot will do
   else if (valid && !crowded) for (u32 q = b; q < e; q++) rank += (seg_ids[q] < mine) ? 1u : 0u;  // ids are unique
   unsigned todo = __ballot_sync(0xffffffffu, crowded);
   const u32 lane = threadIdx.x & 31u;
@@ -1191,6 +1214,9 @@ extern "C" int abl_cuda_create(abl_runtime **out, const abl_config *cfg) {
     const char *bp = getenv("ABL_CUDA_BIN_PREFETCH");
     const int pre = bp ? (atoi(bp) != 0 ? 1 : 0) : 1;
     CU(cudaMemcpyToSymbol(c_bin_prefetch, &pre, sizeof pre));
+    const char *bsi = getenv("ABL_CUDA_BIN_SEGINFO");
+    const int seginfo = bsi ? (atoi(bsi) != 0 ? 1 : 0) : 0;
+    CU(cudaMemcpyToSymbol(c_bin_seginfo, &seginfo, sizeof seginfo));
   }
   if (const char *fl = getenv("ABL_CUDA_FLAT")) rt->flat_loop = atoi(fl) != 0 ? 1 : 0;
   if (const char *tn = getenv("ABL_CUDA_TUNE")) { if (atoi(tn) != 0) rt->flat_loop = -1; }
@@ -1856,11 +1882,11 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
     u32 *seg_ids = (u32 *)p.pairs;
     u32 nb = blocks_for(n, bs);
     CU(launch_pdl(rt->pdl, k_bin_scatter, dim3(nb), dim3(bs), 0, rt->stream, (const u32 *)p.key, p.local, ids, n,
-                  p.src_begin, (const u32 *)p.cell_start, seg_ids, p.cell_count, scatter_rep));
+                  p.src_begin, (const u32 *)p.cell_start, seg_ids, p.cell_count, scatter_rep, seg_ids + p.cap));
     ColTable t;
     fill_table(p, t, true);
     CU(launch_pdl(rt->pdl, k_bin_rank_move, dim3(nb), dim3(bs), 0, rt->stream, t, (const u32 *)seg_ids, (const u32 *)p.key,
-                  (const u32 *)p.local, ids, n, p.src_begin, (const u32 *)p.cell_start));
+                  (const u32 *)p.local, ids, n, p.src_begin, (const u32 *)p.cell_start, (const u32 *)(seg_ids + p.cap)));
     rt->launches += 2;
     CU(cudaGetLastError());
     flip_all(p);
