@@ -48,13 +48,33 @@ def build_reference_program(model, params, use_float, out_dir, threads_flag=True
     return os.path.join(out_dir, "main")
 
 
-def run_reference(model, params, use_float=False, keep=None):
+def strip_lifecycle(source):
+    """predator_prey.abl without what the reference's `c` back end cannot print (CBackend.cpp:30-32 rejects run-time
+    add / remove; CPrinter has no count / sum / log_csv): removeCurrent() and the add() calls of the step functions
+    become empty blocks, the sequential step goes.  main() — the population set-up — is untouched, which is all the
+    `_t0` fixture of this model pins."""
+    import re
+    cut = source.index("void main()")
+    head, tail = source[:cut], source[cut:]
+    head = head.replace("removeCurrent();", "{ }")
+    head = re.sub(r"add\((Prey|Predator) \{.*?\}\s*\);", "{ }", head, flags=re.S)
+    head = re.sub(r"sequential step gather_stats\(\) \{.*?\n\}\n", "", head, flags=re.S)
+    tail = tail.replace("grass_growth,\n    gather_stats", "grass_growth")
+    return head + tail
+
+
+def run_reference(model, params, use_float=False, keep=None, transform=None):
     """-> (list of structured arrays per agent type, json text)"""
     tmp = keep or tempfile.mkdtemp(prefix="ablref_")
     try:
         with open(model) as f:
             source = f.read()
-        if "save(" not in source:
+        if transform is not None:
+            scratch = os.path.join(tmp, "scratch_" + os.path.basename(model))
+            with open(scratch, "w") as f:
+                f.write(transform(source))
+            exe = build_reference_program(scratch, params, use_float, tmp)
+        elif "save(" not in source:
             # a model that never writes its state (sugarscape.abl): the reference runs a scratch copy whose main()
             # ends with save(); the device side is compared through abl_cuda_download, the model itself is untouched
             cut = source.rstrip().rfind("}")
@@ -65,8 +85,7 @@ def run_reference(model, params, use_float=False, keep=None):
         else:
             exe = build_reference_program(model, params, use_float, tmp)
         subprocess.run([exe], cwd=tmp, check=True)
-        with open(model) as f:
-            agents = parse_agents(f.read())
+        agents = parse_agents(source)
         dtypes = [agent_dtype(m, use_float) for _, m in agents]
         raw = [p for p in os.listdir(tmp) if p.endswith(".bin")]
         assert len(raw) == 1, raw
@@ -135,6 +154,13 @@ EXTRA_FIXTURES.update({
     "sugarscape_n4096_t0": ("sugarscape.abl", {"num_agents": 4096, "num_timesteps": 0}, False),
 })
 
+# predator_prey.abl: run-time add / remove keep the reference's `c` back end from generating anything; its INITIAL
+# population (three agent types, randomDirection(), randomInt) is pinned through a scratch copy without them.
+TRANSFORMS = {"predator_prey_n32000_t0": strip_lifecycle}
+EXTRA_FIXTURES.update({
+    "predator_prey_n32000_t0": ("predator_prey.abl", {"num_agents": 32000, "num_timesteps": 0}, False),
+})
+
 # save() text of the reference (libabl.c:46-124), byte for byte: name -> (model, params, use_float, output file).
 # Stored under tests/golden/text/<name>.txt; tests/test_gpu_save_text.py compares the file the generated
 # ./main writes with it (integer / bool models byte-identical, floating point within the last printed digit).
@@ -178,7 +204,7 @@ def main():
         if only and name not in only:
             continue
         path = model_path(model)
-        state, text = run_reference(path, params, use_float)
+        state, text = run_reference(path, params, use_float, transform=TRANSFORMS.get(name))
         npz, meta = fixture_paths(name)
         np.savez_compressed(npz, **{"type%d" % i: s for i, s in enumerate(state)})
         with open(meta, "w") as f:

@@ -68,7 +68,7 @@ def test_initial_state_roundtrip_is_bit_exact():
 
 
 @pytest.mark.parametrize("name", ["two_species_n3000_t0", "boids2d_n4000_t0", "circle3d_n2000_t0", "game_of_life_n4096_t0",
-                                  "ants_n500_t0", "boids2d_flockers_n2000_t0", "sugarscape_n4096_t0"])
+                                  "ants_n500_t0", "boids2d_flockers_n2000_t0", "sugarscape_n4096_t0", "predator_prey_n32000_t0"])
 def test_generated_host_program_builds_the_reference_population(name):
     """CPU: the initialisation code of the generated host program (gcc-compiled C, the same
     xorshift128+ stream and argument evaluation order as the reference's main.c) produces the
