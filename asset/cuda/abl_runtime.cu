@@ -309,8 +309,7 @@ struct abl_runtime {
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                               cudaStream_t stream, Args... args) {
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof cfg);
+  cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
@@ -1435,7 +1434,7 @@ static int halo_finish(abl_runtime *rt, Pool &p, bool published, bool dev_range,
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n);
 
 extern "C" int abl_cuda_pool_size(abl_runtime *rt, int pool, size_t *n) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   if (rt->slab && p->pos_member >= 0) {
     TRY(slab_bin_if_needed(rt, *p));
@@ -1488,7 +1487,7 @@ __global__ void k_set_ids(u32 *dst, const u32 *src, u32 n) {
 
 static int upload_impl(abl_runtime *rt, int pool, const void *host_aos, const unsigned *ids, size_t n,
                        unsigned next_id) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
   if (n > 0x7fffffffu) return fail(ABL_ERR_ARGUMENT, "pool too large");
@@ -1594,7 +1593,7 @@ __global__ void k_transit_to_soa(ColTable t, const u8 *transit, u32 stride, u32 
 }
 
 extern "C" int abl_cuda_transit_record_bytes(abl_runtime *rt, int pool, size_t *bytes) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   if (p->stride % 4u) return fail(ABL_ERR_STATE, "pool %s: record size %u is not a multiple of 4", p->name.c_str(), p->stride);
   if (bytes) *bytes = (size_t)transit_bytes(p->stride);
@@ -1605,7 +1604,7 @@ extern "C" int abl_cuda_transit_record_bytes(abl_runtime *rt, int pool, size_t *
 // runtime's GPU, room for n transit records): grouped by owning slab, counts[s] records for slab s.
 extern "C" int abl_cuda_partition_upload(abl_runtime *rt, int pool, const void *host_aos, size_t n, unsigned first_id,
                                          void *dev_out, unsigned *counts) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!rt->slab) return fail(ABL_ERR_STATE, "partition_upload requires abl_cuda_set_slab");
@@ -1662,7 +1661,7 @@ extern "C" int abl_cuda_partition_upload(abl_runtime *rt, int pool, const void *
 // n transit records in device memory (all of them owned by this slab) become the pool's population;
 // next_id: first id a run-time add() may hand out (the size of the whole population).
 extern "C" int abl_cuda_adopt_records(abl_runtime *rt, int pool, const void *dev_records, size_t n, unsigned next_id) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (p.stride % 4u) return fail(ABL_ERR_STATE, "pool %s: record size %u is not a multiple of 4", p.name.c_str(), p.stride);
@@ -1698,7 +1697,7 @@ extern "C" int abl_cuda_adopt_records(abl_runtime *rt, int pool, const void *dev
 
 extern "C" int abl_cuda_download(abl_runtime *rt, int pool, void *host_aos, size_t capacity,
                                  size_t *n_out) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
   // slab mode: only the owned agents are this rank's to report
@@ -1752,7 +1751,7 @@ __global__ void k_ids_sorted(const u32 *ids, const u32 *rank, u32 n, u32 *out) {
 // ids of the agents abl_cuda_download returns, in the same (ascending) order
 extern "C" int abl_cuda_download_ids(abl_runtime *rt, int pool, unsigned *ids_out, size_t capacity,
                                      size_t *n_out) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
   u32 first = 0;
@@ -1924,7 +1923,7 @@ static int bin_pool(abl_runtime *rt, Pool &p, bool defer_report) {
 }
 
 extern "C" int abl_cuda_bin(abl_runtime *rt, int pool) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   CU(cudaSetDevice(rt->device));
   if (rt->timing) CU(cudaEventRecord(rt->ev[0], rt->stream));
@@ -1939,7 +1938,7 @@ extern "C" int abl_cuda_bin(abl_runtime *rt, int pool) {
 
 extern "C" int abl_cuda_debug_binning(abl_runtime *rt, int pool, unsigned *cell_start,
                                       size_t n_cells_plus_1, unsigned *ids, size_t n_ids) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   if (!p->binned) return fail(ABL_ERR_STATE, "pool is not binned");
   CU(cudaStreamSynchronize(rt->stream));
@@ -1960,16 +1959,16 @@ extern "C" int abl_cuda_debug_binning(abl_runtime *rt, int pool, unsigned *cell_
 // ---------------------------------------------------------------------------------------
 extern "C" int abl_cuda_register_step(abl_runtime *rt, const abl_step_desc *desc, int *step) {
   if (!rt || !desc || !desc->launch) return fail(ABL_ERR_ARGUMENT, "bad step descriptor");
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, desc->self_pool, &p));
   if (desc->nbr_pool >= 0) {
-    Pool *q;
+    Pool *q = nullptr;
     TRY(get_pool(rt, desc->nbr_pool, &q));
     if (q->pos_member < 0) return fail(ABL_ERR_ARGUMENT, "step %s: neighbour pool has no position", desc->name);
     if (!rt->env_set) return fail(ABL_ERR_STATE, "register_step before set_environment");
   }
   if (desc->added_pool >= 0) {
-    Pool *q;
+    Pool *q = nullptr;
     TRY(get_pool(rt, desc->added_pool, &q));
   }
   Step s;
@@ -2673,7 +2672,7 @@ static int combine_real(abl_runtime *rt, double *v) {
 }
 
 extern "C" int abl_cuda_count(abl_runtime *rt, int pool, int *result) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   size_t n = 0;
   TRY(abl_cuda_pool_size(rt, pool, &n));  // owned agents only under slab decomposition
@@ -2730,7 +2729,7 @@ static int reduce_int(abl_runtime *rt, Pool &p, Member &m, int kind, int value, 
 }
 
 extern "C" int abl_cuda_sum_int(abl_runtime *rt, int pool, int member, int *result) {
-  Pool *p; Member *m;
+  Pool *p = nullptr; Member *m = nullptr;
   TRY(get_member(rt, pool, member, &p, &m));
   if (m->type == ABL_TYPE_INT) return reduce_int(rt, *p, *m, 0, 0, result);
   if (m->type == ABL_TYPE_BOOL) return reduce_int(rt, *p, *m, 1, 0, result);
@@ -2738,7 +2737,7 @@ extern "C" int abl_cuda_sum_int(abl_runtime *rt, int pool, int member, int *resu
 }
 
 extern "C" int abl_cuda_count_member_int(abl_runtime *rt, int pool, int member, int value, int *result) {
-  Pool *p; Member *m;
+  Pool *p = nullptr; Member *m = nullptr;
   TRY(get_member(rt, pool, member, &p, &m));
   if (m->type == ABL_TYPE_INT) return reduce_int(rt, *p, *m, 2, value, result);
   if (m->type == ABL_TYPE_BOOL) return reduce_int(rt, *p, *m, 3, value ? 1 : 0, result);
@@ -2746,7 +2745,7 @@ extern "C" int abl_cuda_count_member_int(abl_runtime *rt, int pool, int member, 
 }
 
 extern "C" int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member, double value, int *result) {
-  Pool *p; Member *m;
+  Pool *p = nullptr; Member *m = nullptr;
   TRY(get_member(rt, pool, member, &p, &m));
   if (m->type != ABL_TYPE_FLOAT) return fail(ABL_ERR_ARGUMENT, "count_member_float on non-float member");
   int *d = (int *)rt->d_scalar;
@@ -2770,7 +2769,7 @@ extern "C" int abl_cuda_count_member_float(abl_runtime *rt, int pool, int member
 }
 
 extern "C" int abl_cuda_sum_float(abl_runtime *rt, int pool, int member, int component, double *result) {
-  Pool *p; Member *m;
+  Pool *p = nullptr; Member *m = nullptr;
   TRY(get_member(rt, pool, member, &p, &m));
   int col_index = m->first_col, stride = 1, comp = 0;
   if (m->type == ABL_TYPE_FLOAT2) { stride = 2; comp = component; }
@@ -3165,7 +3164,7 @@ extern "C" int abl_cuda_set_slab(abl_runtime *rt, const int *layer_bounds, int n
 }
 
 extern "C" int abl_cuda_owned_size(abl_runtime *rt, int pool, size_t *n) {
-  Pool *p;
+  Pool *p = nullptr;
   TRY(get_pool(rt, pool, &p));
   if (rt->slab && p->pos_member >= 0) {
     TRY(slab_settle(rt, *p));
@@ -3646,7 +3645,7 @@ static int halo_exchange_standalone(abl_runtime *rt, Pool &p) {
 }
 
 extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_records, void *handle_out) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!rt->slab) return fail(ABL_ERR_STATE, "halo_setup requires abl_cuda_set_slab");
@@ -3684,7 +3683,7 @@ extern "C" int abl_cuda_halo_setup(abl_runtime *rt, int pool, size_t capacity_re
 }
 
 extern "C" int abl_cuda_halo_connect(abl_runtime *rt, int pool, const void *lower_handle, const void *upper_handle) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!p.halo_recv) return fail(ABL_ERR_STATE, "halo_connect before halo_setup");
@@ -3703,14 +3702,14 @@ extern "C" int abl_cuda_halo_connect(abl_runtime *rt, int pool, const void *lowe
 }
 
 extern "C" int abl_cuda_halo_connect_local(abl_runtime *rt, int pool, abl_runtime *lower, abl_runtime *upper) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!p.halo_recv) return fail(ABL_ERR_STATE, "halo_connect before halo_setup");
   abl_runtime *peers[2] = {lower, upper};
   for (int d = 0; d < 2; d++) {
     if (!peers[d]) continue;
-    Pool *q;
+    Pool *q = nullptr;
     TRY(get_pool(peers[d], pool, &q));
     if (!q->halo_recv || q->halo_block != p.halo_block)
       return fail(ABL_ERR_STATE, "halo_connect_local: the peer has no matching receive area");
@@ -3729,7 +3728,7 @@ extern "C" int abl_cuda_halo_connect_local(abl_runtime *rt, int pool, abl_runtim
 }
 
 extern "C" int abl_cuda_exchange(abl_runtime *rt, int pool) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!rt->slab || p.pos_member < 0) return ABL_OK;
@@ -3829,7 +3828,7 @@ extern "C" int abl_cuda_set_local_peers(abl_runtime *rt, abl_runtime *lower, abl
 }
 
 extern "C" int abl_cuda_exchange_begin(abl_runtime *rt, int pool) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   if (!rt->slab || pp->pos_member < 0) return ABL_OK;
   CU(cudaSetDevice(rt->device));
@@ -3845,7 +3844,7 @@ extern "C" int abl_cuda_exchange_begin(abl_runtime *rt, int pool) {
 }
 
 extern "C" int abl_cuda_exchange_end(abl_runtime *rt, int pool) {
-  Pool *pp;
+  Pool *pp = nullptr;
   TRY(get_pool(rt, pool, &pp));
   Pool &p = *pp;
   if (!rt->slab || p.pos_member < 0) return ABL_OK;
