@@ -2491,7 +2491,8 @@ extern "C" int abl_cuda_step(abl_runtime *rt, int step) {
     // reads another pool or every member is rewritten, i.e. arrivals land in output buffers)
     const unsigned all_members = self.members.size() >= 32 ? 0xffffffffu : ((1u << self.members.size()) - 1u);
     const bool arrivals_hit_outputs = nbr != &self || (s.desc.written_members & all_members) == all_members;
-    const bool fork_exchange = direct && !use_dev_range && rt->halo_async && !rt->timing && !rt->trace &&
+    // (stage timing keeps the fork: the commit interval then shows what the step really waits for — the join)
+    const bool fork_exchange = direct && !use_dev_range && rt->halo_async && !rt->trace &&
                                a.slab.active && a.slab.boundary_first && a.self.n && arrivals_hit_outputs;
     if (fork_exchange) {
       if (!rt->side_stream) {

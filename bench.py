@@ -377,6 +377,9 @@ def measure(args, workload, env, strong, steps, warmup, with_cpu_baseline):
                 "kernel_ms": stage["kernel_ms"], "kernel_ms_source": kernel_src,
                 "kernel_ms_stage_events": stage["kernel_ms_stage_events"],
                 "bin_ms": stage["bin_ms"], "commit_ms": stage["commit_ms"],
+                "commit_ms_definition": ("what the stream waits for after the step kernel: the halo exchange kernel runs next to the "
+                                         "step kernel on a side stream (ABL_CUDA_HALO_ASYNC), this is the join" if world > 1 and args.transport == "direct"
+                                         else "interval between the event behind the step kernel and the end of the step function"),
                 "stage_pass_timesteps": reps,
                 "whole_step_algorithmic_bytes_per_agent": whole_step_bytes(workload),
                 "whole_step_frac": step_bytes * steps / (ms_max / 1e3) / 1e9 / peak}

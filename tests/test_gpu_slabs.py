@@ -65,6 +65,32 @@ def test_decomposed_run_is_bit_identical(model_file, params, use_float, slabs, s
 
 
 @pytest.mark.gpu
+def test_stage_timing_keeps_the_forked_exchange_and_the_results():
+    """abl_cuda_enable_timing brackets the stages of every step with events while the halo exchange still runs next
+    to the step kernel on its side stream: results stay bit-identical, and every stage reports a time."""
+    model_file, params, use_float, slabs, steps = CASES[0]
+    m = Model(os.path.join(REPO, "examples", model_file), params, use_float=use_float)
+    m.populate()
+    host = [m.host_agents(t) for t in range(m.n_types)]
+    single = single_run(m, steps)
+    ls = LocalSlabs(m, slabs, transport="direct")
+    ls.upload(host)
+    for rt in ls.rts:
+        rt.enable_timing(True)
+    for _ in range(steps):
+        ls.timestep()
+    for rt in ls.rts:
+        t = rt.last_timing()
+        assert t["kernel_ms"] > 0 and t["bin_ms"] > 0 and t["commit_ms"] >= 0
+        rt.enable_timing(False)
+    ids, rec = ls.download(0)
+    ls.close()
+    assert np.array_equal(ids, np.arange(len(single), dtype=ids.dtype))
+    for f in single.dtype.names:
+        assert np.array_equal(rec[f], single[f])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("model_file,params,use_float,slabs,steps", [CASES[0], CASES[3], CASES[4]],
                          ids=["%s-%dslabs" % (c[0][:-4], c[3]) for c in (CASES[0], CASES[3], CASES[4])])
 def test_scalable_upload_is_bit_identical(model_file, params, use_float, slabs, steps):
